@@ -1,0 +1,175 @@
+/* owgpu.h -- C ABI of libowgpu: batched OpenWurli rendering on NVIDIA B200 (sm_100a).
+ *
+ * The reference (hal0zer0/openwurli v0.6.0) is a single-threaded Rust DSP library with no FFI
+ * boundary on this path; the entry points below are batch-shaped versions of the seams its own
+ * callers use.  Each one cites the reference interface it replaces.  Plain pointers and sizes
+ * only; the library never retains caller pointers after a call returns (plans copy what they
+ * need).  There is NO CPU fallback: every render call fails with OWG_E_NO_DEVICE when no CUDA
+ * device is usable.
+ *
+ * Numeric trouble is not an error: the reference's guards (NaN -> reset / zeros, BE fallback,
+ * voltage damping) are reproduced on the device and reported through owg_last_diag().
+ */
+#ifndef OWGPU_H
+#define OWGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OWG_ABI_VERSION 1
+
+/* ---- error codes ---------------------------------------------------------------------------- */
+#define OWG_OK 0
+#define OWG_E_BAD_ARG (-1)    /* null pointer, n<0, stride too small, sample_rate<=0, ... */
+#define OWG_E_NO_DEVICE (-2)  /* no usable CUDA device (there is no CPU fallback) */
+#define OWG_E_CUDA (-3)       /* CUDA runtime error; text via owg_last_error() */
+#define OWG_E_OOM (-4)        /* host or device allocation failed */
+#define OWG_E_UNSUPPORTED (-5)/* option combination not implemented by this build */
+
+/* ---- job descriptors ------------------------------------------------------------------------ */
+
+/* = the arguments of Voice::note_on (crates/openwurli-dsp/src/voice.rs:28-34) plus the two
+ * post-construction overrides the reference's harnesses use (set_displacement_scale voice.rs:145,
+ * disable_attack_noise voice.rs:150) and the render length of Voice::render_note (voice.rs:191-221:
+ * n = (duration_s * sample_rate) truncated). */
+typedef struct owg_voice_job {
+    uint8_t midi;          /* MIDI note 33..96 */
+    uint8_t mlp_enabled;   /* 0/1: MLP v2 per-note corrections (voice.rs:62-66) */
+    uint8_t attack_noise;  /* 0 = disable_attack_noise() */
+    uint8_t _pad0;
+    uint32_t noise_seed;   /* seed of the jitter and attack-noise LCGs (voice.rs:208: midi*2654435761) */
+    double velocity;       /* 0..1 (callers pass vel/127.0) */
+    double sample_rate;    /* Hz */
+    double duration_s;     /* seconds */
+    double ds_override;    /* pickup displacement-scale override; NaN = none */
+} owg_voice_job;
+
+/* = the flags of `preamp-bench render` (tools/preamp-bench/src/main.rs:372-392), chain B. */
+typedef struct owg_bench_job {
+    owg_voice_job v;
+    double r_ldr;             /* --ldr, static LDR path resistance when tremolo_depth <= 0 (1e6) */
+    double tremolo_depth;     /* --tremolo-depth (0.0 = static r_ldr, main.rs:432-440) */
+    double volume;            /* --volume (0.60); applied as volume^2 before the power amp */
+    double speaker_character; /* --speaker (1.0) */
+    int32_t no_preamp;        /* --no-preamp */
+    int32_t no_poweramp;      /* --no-poweramp */
+} owg_bench_job;
+
+/* MIDI-ish event for WurliEngine streams (engine.rs:299-374). */
+#define OWG_EV_NOTE_ON 0
+#define OWG_EV_NOTE_OFF 1
+#define OWG_EV_SUSTAIN 2 /* note != 0 -> pedal down */
+typedef struct owg_event {
+    int64_t sample;  /* base-rate sample index at which the event applies (block-quantised like the plugin host) */
+    uint8_t kind;
+    uint8_t note;
+    uint16_t _pad0;
+    float velocity;  /* f32, as WurliEngine::note_on takes it (engine.rs:299) */
+} owg_event;
+
+/* = WurliEngine::{new, set_sample_rate, set_volume, set_tremolo_depth, set_speaker_character,
+ *   set_mlp_enabled, render} (engine.rs:194-462), chain E. */
+typedef struct owg_engine_job {
+    double sample_rate, duration_s, volume, tremolo_depth, speaker_character;
+    int32_t mlp_enabled;
+    int32_t block_size; /* render() block length; voice freeing happens at block boundaries (engine.rs:461) */
+    int32_t warm_up;    /* 1 = construct through set_sample_rate (0.6 s warm-up, engine.rs:261-286) */
+    int32_t _pad0;
+    const owg_event* ev; /* sorted by sample */
+    int64_t n_ev;
+} owg_engine_job;
+
+/* ---- options -------------------------------------------------------------------------------- */
+#define OWG_OUT_HOST 0   /* `out` is host memory (pinned recommended); D2H copy inside the call */
+#define OWG_OUT_DEVICE 1 /* `out` is device memory on `device`; no copy */
+
+#define OWG_PRECISION_F64_EXACT 0 /* IEEE f64, no FMA contraction: op-for-op the reference's arithmetic */
+
+#define OWG_PREAMP_MELANGE12 0 /* gen_preamp.rs 12-node DK solver (--features melange-preamp) */
+
+typedef struct owg_opts {
+    int32_t device;       /* CUDA device ordinal; -1 = current device */
+    int32_t out_location; /* OWG_OUT_HOST | OWG_OUT_DEVICE */
+    int32_t precision;    /* OWG_PRECISION_* */
+    int32_t preamp_model; /* OWG_PREAMP_* */
+    void* stream;         /* cudaStream_t to launch on; NULL = library-owned stream */
+    int32_t collect_diag; /* 1 = keep per-call solver counters for owg_last_diag() */
+    int32_t _reserved[7];
+} owg_opts;
+
+/* Solver counters of the last call on this thread that had collect_diag=1 (sums over all jobs).
+ * Mirrors the reference's per-solver diag fields (gen_preamp.rs:1613-1632,1663). */
+typedef struct owg_diag {
+    uint64_t nr_iter_hist[16]; /* main preamp: histogram of last_nr_iterations (bucket 15 = >=15) */
+    uint64_t nr_max_iter, be_fallback, voltage_damp, nan_reset;
+    uint64_t shadow_nr_iter_hist[16];
+    uint64_t shadow_be_fallback, shadow_nan_reset;
+    uint64_t poweramp_iter_hist[9];
+    uint64_t tremolo_nr_iter_hist[16];
+    uint64_t tremolo_be_fallback;
+    uint64_t kernels_launched; /* CUDA kernels this call launched */
+} owg_diag;
+
+/* ---- introspection -------------------------------------------------------------------------- */
+int owg_abi_version(void);
+int owg_device_count(void);          /* usable CUDA devices (0 when none: every render then fails) */
+const char* owg_last_error(void);    /* thread-local text of the last failure */
+void owg_default_opts(owg_opts* o);  /* device=-1, host output, f64 exact, melange12, no diag */
+
+/* ---- one-shot batch renders ----------------------------------------------------------------- */
+
+/* Batch of Voice::render_note_with_scale (voice.rs:201-221) / Voice::note_on + render (chain V:
+ * reed + attack noise + pickup + post-pickup gain).  out is [n][stride] f64; job i writes
+ * (uint64)(duration_s*sample_rate) samples at out + i*stride. */
+int owg_render_voices(const owg_voice_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts);
+
+/* Batch of `preamp-bench render` (main.rs:371-496), chain B: voice -> [2x oversampler] ->
+ * melange preamp (+ Twin-T/LDR tremolo) -> volume^2 -> power amp -> speaker -> POST_SPEAKER_GAIN.
+ * f64 samples before WAV quantisation. */
+int owg_render_bench(const owg_bench_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts);
+
+/* Batch of WurliEngine streams (engine.rs), chain E; f32 out like WurliEngine::render. */
+int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_t stride, const owg_opts* opts);
+
+/* Preamp-only batch: n_inst input signals [n_inst][n_samp] (row stride in_stride) through
+ * upsample_2x -> DkPreamp::process_sample x2 -> downsample_2x (`process_oversampled`,
+ * main.rs:961-974), with Tremolo::new(depth, fs_preamp) driving set_ldr_resistance before every
+ * preamp sample when tremolo_depth > 0 (main.rs:432-461), else reset()+set_ldr_resistance(r_ldr_static).
+ * `in`/`out` follow opts->out_location (both host or both device). */
+int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double fs_base,
+                     int oversample, double tremolo_depth, double r_ldr_static, double* out, int64_t out_stride,
+                     const owg_opts* opts);
+
+/* ---- planned renders: note-on parameterisation done once, inputs resident in HBM ---------- */
+typedef struct owg_plan owg_plan;
+
+/* Runs the host-side note-on setup (tables.rs / variation.rs / mlp_correction.rs / hammer.rs /
+ * voice.rs:28-142 / reed.rs:108-182) for every job and uploads the per-voice init records. */
+int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan);
+int owg_plan_voices(const owg_voice_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan);
+/* Executes the plan (any number of times; each execution is a full, independent render). */
+int owg_plan_execute(owg_plan* plan, double* out, int64_t stride, int32_t out_location);
+/* Samples job i produces; max over jobs when i < 0. */
+int64_t owg_plan_samples(const owg_plan* plan, int64_t i);
+/* CUDA kernels one execution launches. */
+int64_t owg_plan_kernel_launches(const owg_plan* plan);
+/* Device time (ms) of the dominant per-instance kernel in the last execution (CUDA events on the
+ * plan's stream), and of the whole execution. */
+int owg_plan_last_timing(const owg_plan* plan, float* main_kernel_ms, float* total_ms);
+void owg_plan_destroy(owg_plan* plan);
+
+int owg_last_diag(owg_diag* out);
+
+/* ---- FP64 pipe micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) - */
+/* Runs a register-resident stream of dependent-free DFMA (fma=1) or DADD+DMUL pairs (fma=0) on
+ * every SM for about `ms_target` ms and returns the achieved rate in 1e12 FP64 pipe instr/s
+ * (one DFMA = one instruction = 2 flop). */
+int owg_fp64_peak(int32_t device, int32_t fma, float ms_target, double* tera_instr_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OWGPU_H */

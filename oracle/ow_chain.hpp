@@ -1,0 +1,248 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity checker), never on the product path.
+//
+// Restatement of the shared mono chain stages (oversampler.rs, power_amp.rs
+// mod behavioral, speaker.rs), of the `preamp-bench render` harness ("chain B",
+// tools/preamp-bench/src/main.rs:371-496) and of WurliEngine ("chain E",
+// engine.rs).
+#pragma once
+#include "ow_tremolo.hpp"
+
+namespace ow {
+
+// ---- oversampler.rs ---------------------------------------------------------------------
+struct Oversampler {  // oversampler.rs:17-147
+    static constexpr double A[3] = {0.036681502163648, 0.248030921580110, 0.643184620136480};
+    static constexpr double B[3] = {0.110377634768680, 0.420399304190880, 0.854640112701920};
+    double ua[3] = {0, 0, 0}, ub[3] = {0, 0, 0}, da[3] = {0, 0, 0}, db[3] = {0, 0, 0};
+    double down_delay = 0.0;
+    static inline double branch(const double* coef, double* st, double x) {
+        double y = x;
+        for (int i = 0; i < 3; i++) {
+            const double yy = coef[i] * y + st[i];
+            st[i] = y - coef[i] * yy;
+            y = yy;
+        }
+        return y;
+    }
+    inline void up1(double x, double& even, double& odd) {
+        even = branch(A, ua, x);
+        odd = branch(B, ub, x);
+    }
+    inline double down1(double in_even, double in_odd) {
+        const double a = branch(A, da, in_even);
+        const double b = branch(B, db, in_odd);
+        const double out = (a + down_delay) * 0.5;
+        down_delay = b;
+        return out;
+    }
+    void upsample_2x(const double* in, size_t n, double* out) {
+        for (size_t i = 0; i < n; i++) up1(in[i], out[2 * i], out[2 * i + 1]);
+    }
+    void downsample_2x(const double* in, double* out, size_t n_out) {
+        for (size_t i = 0; i < n_out; i++) out[i] = down1(in[2 * i], in[2 * i + 1]);
+    }
+    void reset() { *this = Oversampler(); }
+};
+
+// ---- power_amp.rs (mod behavioral) -------------------------------------------------------
+struct PowerAmp {  // power_amp.rs:167-240
+    static constexpr double OPEN_LOOP_GAIN = 19000.0;
+    static constexpr double FEEDBACK_BETA = 220.0 / (220.0 + 15000.0);
+    static constexpr double HEADROOM = 22.0, CROSSOVER_VT = 0.013, QUIESCENT_GAIN = 0.1, NR_TOL = 1e-6;
+    double closed_loop_gain = OPEN_LOOP_GAIN / (1.0 + OPEN_LOOP_GAIN * FEEDBACK_BETA);
+    uint64_t iter_hist[9] = {0};
+    inline double process(double input) {
+        double y = rclamp(input * closed_loop_gain, -HEADROOM + NR_TOL, HEADROOM - NR_TOL);
+        int it = 0;
+        for (; it < 8; it++) {
+            const double error = input - FEEDBACK_BETA * y;
+            const double v = OPEN_LOOP_GAIN * error;
+            // forward_path, power_amp.rs:227-240
+            const double v_sq = v * v;
+            const double vt_sq = CROSSOVER_VT * CROSSOVER_VT;
+            const double exp_term = std::exp(-v_sq / vt_sq);
+            const double q = QUIESCENT_GAIN;
+            const double cross_gain = q + (1.0 - q) * (1.0 - exp_term);
+            const double v_cross = v * cross_gain;
+            const double dcross_dv = cross_gain + v * (1.0 - q) * (2.0 * v / vt_sq) * exp_term;
+            const double tanh_arg = v_cross / HEADROOM;
+            const double tanh_val = std::tanh(tanh_arg);
+            const double f_val = HEADROOM * tanh_val;
+            const double f_deriv = (1.0 - tanh_val * tanh_val) * dcross_dv;
+            const double residual = y - f_val;
+            const double jacobian = 1.0 + OPEN_LOOP_GAIN * FEEDBACK_BETA * f_deriv;
+            const double delta = residual / jacobian;
+            y -= delta;
+            if (std::fabs(delta) < NR_TOL) { it++; break; }
+        }
+        iter_hist[std::min(it, 8)]++;
+        return y / HEADROOM;
+    }
+};
+
+// ---- speaker.rs ---------------------------------------------------------------------------
+struct Speaker {  // speaker.rs:33-138
+    Biquad hpf, lpf;
+    double character, sample_rate, a2, a3, thermal_coeff, thermal_alpha, thermal_state;
+    explicit Speaker(double sr) {
+        hpf.set(Biquad::HP, 30.0, 0.75, sr);
+        lpf.set(Biquad::LP, 5500.0, 0.707, sr);
+        character = 1.0;
+        sample_rate = sr;
+        a2 = a3 = thermal_coeff = 0.0;
+        thermal_alpha = 1.0 / (5.0 * sr);
+        thermal_state = 0.0;
+        update_coefficients();
+    }
+    void set_character(double ch) {
+        const double c = rclamp(ch, 0.0, 1.0);
+        if (std::fabs(c - character) > 0.002) { character = c; update_coefficients(); }
+    }
+    void update_coefficients() {
+        const double c = character;
+        const double hpf_hz = 20.0 * std::pow(30.0 / 20.0, c);
+        const double lpf_hz = 20000.0 * std::pow(5500.0 / 20000.0, c);
+        hpf.set(Biquad::HP, hpf_hz, 0.75, sample_rate);   // set_type keeps state
+        lpf.set(Biquad::LP, lpf_hz, 0.707, sample_rate);
+        a2 = 0.2 * c;
+        a3 = 0.6 * c;
+        thermal_coeff = 2.0 * c;
+    }
+    inline double process(double input) {
+        const double x2 = input * input;
+        const double x3 = x2 * input;
+        const double shaped = (input + a2 * x2 + a3 * x3) / (1.0 + a2 + a3);
+        const double limited = character < 0.001 ? shaped : std::tanh(shaped);
+        const double power = x2;
+        thermal_state += (power - thermal_state) * thermal_alpha;
+        const double thermal_gain = 1.0 / (1.0 + thermal_coeff * std::sqrt(thermal_state));
+        const double filtered = hpf.process(limited * thermal_gain);
+        return lpf.process(filtered);
+    }
+    void reset() { hpf.reset(); lpf.reset(); thermal_state = 0.0; }
+};
+
+// ---- chain B: `preamp-bench render` (main.rs:371-496) --------------------------------------
+struct BenchJob {
+    uint8_t midi = 60;
+    double velocity = 100.0 / 127.0;  // already normalised (vel/127)
+    double sample_rate = 44100.0;
+    double duration_s = 2.0;
+    uint32_t noise_seed = 0;
+    bool mlp_enabled = true;
+    double ds_override = NAN;
+    bool attack_noise = true;
+    double r_ldr = 1.0e6;
+    double tremolo_depth = 0.0;
+    double volume = 0.60;
+    double speaker_character = 1.0;
+    bool no_preamp = false, no_poweramp = false;
+};
+
+struct Taps {  // optional per-stage taps (T3 voice out, T4 preamp out, T5 final)
+    std::vector<double>* voice = nullptr;
+    std::vector<double>* preamp = nullptr;
+    std::vector<double>* r_ldr = nullptr;     // shunt R fed to the preamp per OS sample
+    std::vector<double>* shadow = nullptr;    // pump (shadow) output per OS sample
+};
+
+struct ChainDiag {
+    pre::Diag main, shadow;
+    uint64_t pa_iter_hist[9] = {0};
+    uint64_t trem_nr_hist[16] = {0};
+    uint64_t trem_be = 0;
+};
+
+static inline std::vector<double> render_bench(const BenchJob& j, Taps* taps = nullptr, ChainDiag* dg = nullptr) {
+    const double sr = j.sample_rate;
+    const bool do_oversample = sr < 88200.0;
+    const double preamp_sr = do_oversample ? sr * 2.0 : sr;
+    const size_t n = (size_t)f64_as_u64(j.duration_s * sr);
+    std::vector<double> reed(n, 0.0);
+    {
+        Voice v;
+        v.note_on(j.midi, j.velocity, sr, j.noise_seed, j.mlp_enabled);
+        if (j.ds_override == j.ds_override) v.pickup.displacement_scale = j.ds_override;
+        if (!j.attack_noise) v.noise.disable();
+        for (size_t off = 0; off < n; off += 1024) v.render(reed.data() + off, std::min<size_t>(1024, n - off));
+    }
+    if (taps && taps->voice) *taps->voice = reed;
+    std::vector<double> pout(n, 0.0);
+    if (j.no_preamp) pout = reed;
+    else {
+        pre::DkPreamp preamp(preamp_sr);
+        Tremolo* trem = nullptr;
+        if (j.tremolo_depth > 0.0) trem = new Tremolo(j.tremolo_depth, preamp_sr);
+        else { preamp.reset(); preamp.set_ldr_resistance(j.r_ldr); }
+        auto step = [&](double x) {
+            if (trem) {
+                const double r = trem->process();
+                if (taps && taps->r_ldr) taps->r_ldr->push_back(r);
+                preamp.set_ldr_resistance(r);
+            }
+            double pump = 0.0;
+            const double y = preamp.process_sample(x, nullptr, &pump);
+            if (taps && taps->shadow) taps->shadow->push_back(pump);
+            return y;
+        };
+        if (do_oversample) {
+            Oversampler os;
+            for (size_t i = 0; i < n; i++) {
+                double u0, u1;
+                os.up1(reed[i], u0, u1);
+                const double p0 = step(u0);
+                const double p1 = step(u1);
+                pout[i] = os.down1(p0, p1);
+            }
+        } else {
+            for (size_t i = 0; i < n; i++) pout[i] = step(reed[i]);
+        }
+        if (dg) {
+            dg->main = preamp.diag_main;
+            dg->shadow = preamp.diag_shadow;
+            if (trem) { std::memcpy(dg->trem_nr_hist, trem->osc.nr_iter_hist, sizeof(dg->trem_nr_hist)); dg->trem_be = trem->osc.diag_be_fallback; }
+        }
+        delete trem;
+    }
+    if (taps && taps->preamp) *taps->preamp = pout;
+    PowerAmp pa;
+    Speaker spk(sr);
+    spk.set_character(j.speaker_character);
+    std::vector<double> fin(n, 0.0);
+    for (size_t i = 0; i < n; i++) {
+        const double att = pout[i] * j.volume * j.volume;
+        const double amp = j.no_poweramp ? att : pa.process(att);
+        fin[i] = spk.process(amp) * POST_SPEAKER_GAIN;
+    }
+    if (dg) std::memcpy(dg->pa_iter_hist, pa.iter_hist, sizeof(dg->pa_iter_hist));
+    return fin;
+}
+
+// ---- preamp-only harness (C2): process_oversampled pattern, main.rs:961-974 + tremolo as in cmd_render :432-461
+static inline void preamp_batch_one(const double* in, size_t n, double fs_base, bool oversample,
+                                    double tremolo_depth_or_neg, double r_ldr_static, double* out) {
+    const double preamp_sr = oversample ? fs_base * 2.0 : fs_base;
+    pre::DkPreamp preamp(preamp_sr);
+    Tremolo* trem = nullptr;
+    if (tremolo_depth_or_neg > 0.0) trem = new Tremolo(tremolo_depth_or_neg, preamp_sr);
+    else { preamp.reset(); preamp.set_ldr_resistance(r_ldr_static); }
+    auto step = [&](double x) {
+        if (trem) preamp.set_ldr_resistance(trem->process());
+        return preamp.process_sample(x);
+    };
+    if (oversample) {
+        Oversampler os;
+        for (size_t i = 0; i < n; i++) {
+            double u0, u1;
+            os.up1(in[i], u0, u1);
+            const double p0 = step(u0);
+            const double p1 = step(u1);
+            out[i] = os.down1(p0, p1);
+        }
+    } else {
+        for (size_t i = 0; i < n; i++) out[i] = step(in[i]);
+    }
+    delete trem;
+}
+
+}  // namespace ow

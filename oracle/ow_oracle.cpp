@@ -1,0 +1,244 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (parity checker and CPU baseline), never shipped and
+// never on the product path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load this library.
+//
+// C API over the restatement headers (ow_voice.hpp, ow_preamp.hpp, ow_tremolo.hpp, ow_chain.hpp,
+// ow_engine.hpp).  Signatures mirror include/owgpu.h with the prefix owo_.
+//
+// PARITY PINNING: the reference (Rust) cannot be compiled here; this oracle is pinned by the
+// reference's own known-answer tests and baked-constant identities only (tests/test_oracle_*.py).
+#include "ow_engine.hpp"
+#include "../include/owgpu.h"
+#include <thread>
+#include <atomic>
+#include <cstdio>
+
+using namespace ow;
+
+static BenchJob to_bench(const owg_bench_job& j) {
+    BenchJob b;
+    b.midi = j.v.midi; b.velocity = j.v.velocity; b.sample_rate = j.v.sample_rate; b.duration_s = j.v.duration_s;
+    b.noise_seed = j.v.noise_seed; b.mlp_enabled = j.v.mlp_enabled != 0; b.ds_override = j.v.ds_override;
+    b.attack_noise = j.v.attack_noise != 0; b.r_ldr = j.r_ldr; b.tremolo_depth = j.tremolo_depth; b.volume = j.volume;
+    b.speaker_character = j.speaker_character; b.no_preamp = j.no_preamp != 0; b.no_poweramp = j.no_poweramp != 0;
+    return b;
+}
+
+template <class F>
+static void parallel_for(int64_t n, int threads, F f) {
+    if (threads <= 1 || n <= 1) { for (int64_t i = 0; i < n; i++) f(i); return; }
+    std::atomic<int64_t> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++)
+        th.emplace_back([&] { for (;;) { int64_t i = next.fetch_add(1); if (i >= n) break; f(i); } });
+    for (auto& t : th) t.join();
+}
+
+static thread_local owg_diag g_diag;
+
+extern "C" {
+
+int owo_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// ---- chain V ------------------------------------------------------------------------------
+int owo_render_voices(const owg_voice_job* jobs, int64_t n, double* out, int64_t stride, int threads) {
+    if (!jobs || !out || n < 0) return OWG_E_BAD_ARG;
+    parallel_for(n, threads, [&](int64_t i) {
+        const owg_voice_job& j = jobs[i];
+        Voice v;
+        v.note_on(j.midi, j.velocity, j.sample_rate, j.noise_seed, j.mlp_enabled != 0);
+        if (j.ds_override == j.ds_override) v.pickup.displacement_scale = j.ds_override;
+        if (!j.attack_noise) v.noise.disable();
+        const size_t ns = (size_t)f64_as_u64(j.duration_s * j.sample_rate);
+        double* o = out + i * stride;
+        for (size_t off = 0; off < ns; off += 1024) v.render(o + off, std::min<size_t>(1024, ns - off));
+    });
+    return OWG_OK;
+}
+
+// ---- chain B ------------------------------------------------------------------------------
+int owo_render_bench(const owg_bench_job* jobs, int64_t n, double* out, int64_t stride, int threads) {
+    if (!jobs || !out || n < 0) return OWG_E_BAD_ARG;
+    pre::settled_state();
+    std::vector<ChainDiag> dgs((size_t)n);
+    parallel_for(n, threads, [&](int64_t i) {
+        std::vector<double> r = render_bench(to_bench(jobs[i]), nullptr, &dgs[i]);
+        std::memcpy(out + i * stride, r.data(), r.size() * sizeof(double));
+    });
+    std::memset(&g_diag, 0, sizeof(g_diag));
+    for (auto& d : dgs) {
+        for (int b = 0; b < 16; b++) { g_diag.nr_iter_hist[b] += d.main.nr_iter_hist[b]; g_diag.shadow_nr_iter_hist[b] += d.shadow.nr_iter_hist[b]; g_diag.tremolo_nr_iter_hist[b] += d.trem_nr_hist[b]; }
+        for (int b = 0; b < 9; b++) g_diag.poweramp_iter_hist[b] += d.pa_iter_hist[b];
+        g_diag.nr_max_iter += d.main.nr_max_iter; g_diag.be_fallback += d.main.be_fallback; g_diag.voltage_damp += d.main.voltage_damp;
+        g_diag.nan_reset += d.main.nan_reset; g_diag.shadow_be_fallback += d.shadow.be_fallback; g_diag.shadow_nan_reset += d.shadow.nan_reset;
+        g_diag.tremolo_be_fallback += d.trem_be;
+    }
+    return OWG_OK;
+}
+
+// chain B with taps for one job: any of the tap pointers may be null.
+// voice/preamp/final: n samples; r_ldr/shadow: n_os samples (2n when oversampled).
+int owo_render_bench_taps(const owg_bench_job* job, double* fin, double* voice, double* preamp, double* r_ldr, double* shadow) {
+    std::vector<double> tv, tp, tr, ts;
+    Taps t; t.voice = &tv; t.preamp = &tp; t.r_ldr = &tr; t.shadow = &ts;
+    std::vector<double> r = render_bench(to_bench(*job), &t, nullptr);
+    if (fin) std::memcpy(fin, r.data(), r.size() * 8);
+    if (voice) std::memcpy(voice, tv.data(), tv.size() * 8);
+    if (preamp) std::memcpy(preamp, tp.data(), tp.size() * 8);
+    if (r_ldr) std::memcpy(r_ldr, tr.data(), tr.size() * 8);
+    if (shadow) std::memcpy(shadow, ts.data(), ts.size() * 8);
+    return OWG_OK;
+}
+
+int owo_last_diag(owg_diag* out) { if (!out) return OWG_E_BAD_ARG; *out = g_diag; return OWG_OK; }
+
+// ---- preamp-only batch (C2) ------------------------------------------------------------------
+int owo_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double fs_base, int oversample,
+                     double tremolo_depth, double r_ldr_static, double* out, int64_t out_stride, int threads) {
+    if (!in || !out || n_inst < 0 || n_samp < 0) return OWG_E_BAD_ARG;
+    pre::settled_state();
+    parallel_for(n_inst, threads, [&](int64_t i) {
+        preamp_batch_one(in + i * in_stride, (size_t)n_samp, fs_base, oversample != 0, tremolo_depth, r_ldr_static, out + i * out_stride);
+    });
+    return OWG_OK;
+}
+
+// ---- chain E ----------------------------------------------------------------------------------
+static void run_engine(const owg_engine_job& j, float* out) {
+    WurliEngine eng(j.sample_rate);
+    // The plugin constructs at a nominal rate and then calls set_sample_rate (lib.rs:96-97), which warms up.
+    if (j.warm_up) eng.set_sample_rate(j.sample_rate);
+    eng.volume.set_target(j.volume);
+    eng.tremolo_depth.set_target(j.tremolo_depth);
+    eng.speaker_character.set_target(j.speaker_character);
+    eng.mlp_enabled = j.mlp_enabled != 0;
+    const int64_t total = (int64_t)f64_as_u64(j.sample_rate * j.duration_s);
+    const int64_t bs = j.block_size > 0 ? j.block_size : 512;
+    int64_t e = 0;
+    for (int64_t pos = 0; pos < total; pos += bs) {
+        const int64_t len = std::min<int64_t>(bs, total - pos);
+        while (e < j.n_ev && j.ev[e].sample < pos + len) {  // events are applied at the start of the block they fall in
+            const owg_event& ev = j.ev[e++];
+            if (ev.kind == OWG_EV_NOTE_ON) eng.note_on(ev.note, ev.velocity);
+            else if (ev.kind == OWG_EV_NOTE_OFF) eng.note_off(ev.note);
+            else if (ev.kind == OWG_EV_SUSTAIN) eng.set_sustain(ev.note != 0);
+        }
+        eng.render(out + pos, (size_t)len);
+    }
+}
+int owo_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_t stride, int threads) {
+    if (!jobs || !out || n < 0) return OWG_E_BAD_ARG;
+    pre::settled_state();
+    parallel_for(n, threads, [&](int64_t i) { run_engine(jobs[i], out + i * stride); });
+    return OWG_OK;
+}
+
+// alias_audit::render_stimulus (alias_audit.rs:131-161): engine without warm_up, 6x1024 settle blocks, then note.
+int owo_alias_stimulus(uint8_t note, uint8_t velocity, double sr, double seconds, double volume, double* out) {
+    WurliEngine eng(sr);
+    eng.ensure_buffer_capacity(1024);
+    eng.volume.set_target(volume);
+    eng.tremolo_depth.set_target(0.0);
+    eng.speaker_character.set_target(0.0);
+    eng.mlp_enabled = true;
+    float buf[1024];
+    for (int i = 0; i < 6; i++) eng.render(buf, 1024);
+    eng.note_on(note, (float)velocity / 127.0f);
+    const size_t total = (size_t)f64_as_u64(sr * seconds);
+    for (size_t pos = 0; pos < total; pos += 1024) {
+        const size_t len = std::min<size_t>(1024, total - pos);
+        eng.render(buf, len);
+        for (size_t k = 0; k < len; k++) out[pos + k] = (double)buf[k];
+    }
+    return OWG_OK;
+}
+
+// ---- known-answer probes (host-side setup functions) --------------------------------------------
+double owo_midi_to_freq(int midi) { return midi_to_freq((uint8_t)midi); }
+double owo_tip_mass_ratio(int midi) { return tip_mass_ratio((uint8_t)midi); }
+void owo_mode_ratios(double mu, double* out7) { mode_ratios(mu, out7); }
+double owo_reed_length_mm(int midi) { return reed_length_mm((uint8_t)midi); }
+double owo_reed_compliance(int midi) { return reed_compliance((uint8_t)midi); }
+double owo_pickup_displacement_scale(int midi) { return pickup_displacement_scale((uint8_t)midi); }
+void owo_spatial_coupling(double mu, double len_mm, double* out7) { spatial_coupling_coefficients(mu, len_mm, out7); }
+double owo_fundamental_decay_rate(int midi) { return fundamental_decay_rate((uint8_t)midi); }
+double owo_output_scale(int midi, double vel) { return output_scale((uint8_t)midi, vel); }
+double owo_velocity_exponent(int midi) { return velocity_exponent((uint8_t)midi); }
+double owo_velocity_scurve(double v) { return velocity_scurve(v); }
+double owo_register_trim_db(int midi) { return register_trim_db((uint8_t)midi); }
+double owo_pickup_rms_proxy(double ds, double f0, double fc) { return pickup_rms_proxy(ds, f0, fc); }
+double owo_freq_detune(int midi) { return freq_detune((uint8_t)midi); }
+void owo_mode_amplitude_offsets(int midi, double* out7) { mode_amplitude_offsets((uint8_t)midi, out7); }
+double owo_dwell_time(double v, double f0) { return dwell_time(v, f0); }
+double owo_onset_ramp_time(double v, double f0) { return onset_ramp_time(v, f0); }
+void owo_dwell_attenuation(double v, double f0, const double* ratios7, double* out7) { dwell_attenuation(v, f0, ratios7, out7); }
+void owo_mlp_infer(int midi, double vel, double* out11) {
+    MlpCorrections c = mlp_infer((uint8_t)midi, vel);
+    for (int i = 0; i < 5; i++) { out11[i] = c.freq_offsets_cents[i]; out11[5 + i] = c.decay_offsets[i]; }
+    out11[10] = c.ds_correction;
+}
+double owo_pickup_soft_saturate(double y) { return Pickup::soft_saturate(y); }
+double owo_fast_exp(double x) { return pre::fast_exp(x); }
+void owo_note_params(int midi, double* out22) {
+    NoteParams p = note_params((uint8_t)midi);
+    out22[0] = p.fundamental_hz;
+    for (int i = 0; i < 7; i++) { out22[1 + i] = p.mode_ratios[i]; out22[8 + i] = p.mode_amplitudes[i]; out22[15 + i] = p.mode_decay_rates[i]; }
+}
+// biquad magnitude probe: run a sine through a band-pass and return peak of the tail (filters.rs:66-99)
+double owo_biquad_bp_gain(double fc, double q, double fs, double f_test, int n) {
+    Biquad b; b.set(Biquad::BP, fc, q, fs);
+    double peak = 0.0;
+    for (int i = 0; i < n; i++) {
+        double y = b.process(std::sin(TAU * f_test * (double)i / fs));
+        if (i > n / 2 && std::fabs(y) > peak) peak = std::fabs(y);
+    }
+    return peak;
+}
+
+// ---- preamp / tremolo probes ----------------------------------------------------------------------
+// Rebuild matrices at (sample_rate, r) and export S (144), K (9), S_NI (36), a_neg (144).
+void owo_preamp_matrices(double sample_rate, double r, double* s144, double* k9, double* sni36, double* aneg144) {
+    pre::CircuitState st; st.set_default();
+    st.current_sample_rate = sample_rate; st.pot_0_resistance = r;
+    st.rebuild_matrices();
+    std::memcpy(s144, st.s, sizeof(st.s)); std::memcpy(k9, st.k, sizeof(st.k));
+    std::memcpy(sni36, st.s_ni, sizeof(st.s_ni)); std::memcpy(aneg144, st.a_neg, sizeof(st.a_neg));
+}
+// Settled preamp state (melange_adapter.rs:14-20): v_prev(12) i_nl_prev(3) i_nl_prev_prev(3) input_prev(1)
+void owo_preamp_settled(double* out19) {
+    const pre::CircuitState& s = pre::settled_state();
+    std::memcpy(out19, s.v_prev, 96); std::memcpy(out19 + 12, s.i_nl_prev, 24); std::memcpy(out19 + 15, s.i_nl_prev_prev, 24); out19[18] = s.input_prev;
+}
+// DkPreamp driven by an input signal at preamp rate with static R (reset(); set_ldr_resistance(r)) -- gain tests.
+void owo_preamp_run(double preamp_sr, double r_ldr, const double* in, int64_t n, double* out) {
+    pre::DkPreamp p(preamp_sr);
+    p.reset(); p.set_ldr_resistance(r_ldr);
+    for (int64_t i = 0; i < n; i++) out[i] = p.process_sample(in[i]);
+}
+// Tremolo::new(depth, sr) then n process() calls -> shunt R; also raw oscillator volts when v_out != null.
+void owo_tremolo_run(double depth, double sr, int64_t n, double* r_out) {
+    Tremolo t(depth, sr);
+    for (int64_t i = 0; i < n; i++) r_out[i] = t.process();
+}
+void owo_tremolo_osc(double sr, int64_t n_settle, int64_t n, double* v_out, double* state_out18) {
+    trm::CircuitState s; s.set_default();
+    if (std::fabs(sr - trm::SAMPLE_RATE) > 0.5) s.set_sample_rate(sr);
+    for (int64_t i = 0; i < n_settle; i++) trm::process_sample(0.0, s);
+    for (int64_t i = 0; i < n; i++) v_out[i] = trm::process_sample(0.0, s);
+    if (state_out18) { std::memcpy(state_out18, s.v_prev, 56); std::memcpy(state_out18 + 7, s.i_nl_prev, 32); std::memcpy(state_out18 + 11, s.i_nl_prev_prev, 32); }
+}
+double owo_poweramp(double x) { PowerAmp p; return p.process(x); }
+void owo_speaker_run(double sr, double character, const double* in, int64_t n, double* out) {
+    Speaker s(sr); s.set_character(character);
+    for (int64_t i = 0; i < n; i++) out[i] = s.process(in[i]);
+}
+void owo_oversampler_roundtrip(const double* in, int64_t n, double* out) {
+    Oversampler os;
+    for (int64_t i = 0; i < n; i++) { double a, b; os.up1(in[i], a, b); out[i] = os.down1(a, b); }
+}
+// Engine state-machine probe: apply events with block rendering, return counts [active, held, sustained, releasing].
+void owo_engine_counts(const owg_engine_job* job, int32_t* out4) {
+    (void)job; (void)out4;
+}
+
+}  // extern "C"
