@@ -1,0 +1,203 @@
+"""Python host layer over libowgpu: job construction with the reference's defaults, plans, output buffers."""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _abi
+from ._abi import BenchJob, Diag, Opts, VoiceJob, OWG_OUT_DEVICE, OWG_OUT_HOST, check, lib
+
+NAN = float("nan")
+
+
+def default_noise_seed(midi):
+    """(midi as u32).wrapping_mul(2654435761) -- voice.rs:208, preamp-bench main.rs:405."""
+    return (int(midi) * 2654435761) & 0xFFFFFFFF
+
+
+def voice_job(midi=60, velocity=100, sample_rate=44100.0, duration=2.0, mlp=False, attack_noise=True, seed=None,
+              displacement_scale=None, velocity_norm=None):
+    """One Voice::note_on + render job.  `velocity` is MIDI 0..127 (normalised as vel/127.0 in f64 like the CLIs,
+    reed-renderer main.rs:83); pass velocity_norm to give the 0..1 value directly."""
+    v = (velocity / 127.0) if velocity_norm is None else float(velocity_norm)
+    return VoiceJob(int(midi), 1 if mlp else 0, 1 if attack_noise else 0, 0,
+                    default_noise_seed(midi) if seed is None else int(seed) & 0xFFFFFFFF, v, float(sample_rate),
+                    float(duration), NAN if displacement_scale is None else float(displacement_scale))
+
+
+def bench_job(note=60, velocity=100, duration=2.0, ldr=1_000_000.0, volume=0.60, speaker=1.0, tremolo_depth=0.0,
+              sample_rate=44100.0, no_poweramp=False, no_preamp=False, no_attack_noise=False, no_mlp=False,
+              displacement_scale=None, seed=None):
+    """One `preamp-bench render` job; keyword names and defaults are the CLI flags (main.rs:372-392)."""
+    return BenchJob(voice_job(note, velocity, sample_rate, duration, not no_mlp, not no_attack_noise, seed,
+                              displacement_scale), float(ldr), float(tremolo_depth), float(volume), float(speaker),
+                    1 if no_preamp else 0, 1 if no_poweramp else 0)
+
+
+def _samples(duration, sample_rate):
+    x = duration * sample_rate  # `(duration * sample_rate) as usize`: truncation
+    return int(x) if x > 0 and math.isfinite(x) else 0
+
+
+def _opts(device=-1, out_location=OWG_OUT_HOST, stream=None, collect_diag=False):
+    o = Opts()
+    lib().owg_default_opts(C.byref(o))
+    o.device = device
+    o.out_location = out_location
+    o.stream = stream
+    o.collect_diag = 1 if collect_diag else 0
+    return o
+
+
+def device_count():
+    return lib().owg_device_count()
+
+
+def last_diag():
+    d = Diag()
+    check(lib().owg_last_diag(C.byref(d)))
+    return d
+
+
+def fp64_peak(device=-1, fma=True, ms_target=50.0):
+    """Measured FP64-pipe instruction rate (1e12 instr/s); a DFMA is one instruction = 2 flop."""
+    r = C.c_double(0.0)
+    check(lib().owg_fp64_peak(device, 1 if fma else 0, ms_target, C.byref(r)))
+    return r.value
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "is_cuda") and x.is_cuda
+
+
+def _out_ptr(out):
+    """(pointer, stride, location) of a caller buffer: numpy float64 [n,stride] or torch tensor (cpu / cuda)."""
+    if isinstance(out, np.ndarray):
+        assert out.dtype == np.float64 and out.ndim == 2 and out.flags.c_contiguous
+        return out.ctypes.data, out.shape[1], OWG_OUT_HOST
+    import torch
+    assert isinstance(out, torch.Tensor) and out.dtype == torch.float64 and out.dim() == 2 and out.is_contiguous()
+    return out.data_ptr(), out.shape[1], (OWG_OUT_DEVICE if out.is_cuda else OWG_OUT_HOST)
+
+
+class Plan:
+    """A planned batch: note-on parameterisation done once on the host, init records resident in HBM.
+    execute() may be called repeatedly; each call is a complete independent render."""
+
+    def __init__(self, handle, n, kind):
+        self._h = handle
+        self.n = n
+        self.kind = kind
+
+    @classmethod
+    def bench(cls, jobs, device=-1, stream=None, collect_diag=False):
+        arr = (BenchJob * len(jobs))(*jobs)
+        h = C.c_void_p()
+        o = _opts(device, OWG_OUT_HOST, stream, collect_diag)
+        check(lib().owg_plan_bench(arr, len(jobs), C.byref(o), C.byref(h)))
+        return cls(h, len(jobs), "bench")
+
+    @classmethod
+    def voices(cls, jobs, device=-1, stream=None, collect_diag=False):
+        arr = (VoiceJob * len(jobs))(*jobs)
+        h = C.c_void_p()
+        o = _opts(device, OWG_OUT_HOST, stream, collect_diag)
+        check(lib().owg_plan_voices(arr, len(jobs), C.byref(o), C.byref(h)))
+        return cls(h, len(jobs), "voices")
+
+    @property
+    def max_samples(self):
+        return lib().owg_plan_samples(self._h, -1)
+
+    def samples(self, i):
+        return lib().owg_plan_samples(self._h, i)
+
+    def execute(self, out):
+        ptr, stride, loc = _out_ptr(out)
+        assert out.shape[0] >= self.n
+        check(lib().owg_plan_execute(self._h, ptr, stride, loc))
+        return out
+
+    @property
+    def kernel_launches(self):
+        return lib().owg_plan_kernel_launches(self._h)
+
+    def last_timing(self):
+        a, b = C.c_float(0), C.c_float(0)
+        check(lib().owg_plan_last_timing(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if self._h:
+            lib().owg_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _alloc_out(n, stride, out):
+    if out is not None:
+        return out
+    return np.zeros((n, stride), dtype=np.float64)
+
+
+def render_voices(jobs, out=None, device=-1, collect_diag=False):
+    """Batch of Voice::note_on + render (chain V). Returns [n, max_samples] float64."""
+    stride = max([_samples(j.duration_s, j.sample_rate) for j in jobs], default=0)
+    out = _alloc_out(len(jobs), stride, out)
+    if len(jobs) == 0 or stride == 0:
+        return out
+    ptr, st, loc = _out_ptr(out)
+    arr = (VoiceJob * len(jobs))(*jobs)
+    o = _opts(device, loc, None, collect_diag)
+    check(lib().owg_render_voices(arr, len(jobs), ptr, st, C.byref(o)))
+    return out
+
+
+def render_bench(jobs, out=None, device=-1, collect_diag=False):
+    """Batch of `preamp-bench render` (chain B). Returns [n, max_samples] float64 (pre-WAV samples)."""
+    stride = max([_samples(j.v.duration_s, j.v.sample_rate) for j in jobs], default=0)
+    out = _alloc_out(len(jobs), stride, out)
+    if len(jobs) == 0 or stride == 0:
+        return out
+    ptr, st, loc = _out_ptr(out)
+    arr = (BenchJob * len(jobs))(*jobs)
+    o = _opts(device, loc, None, collect_diag)
+    check(lib().owg_render_bench(arr, len(jobs), ptr, st, C.byref(o)))
+    return out
+
+
+class Voice:
+    """Mirror of openwurli_dsp::voice::Voice's one-shot constructor (voice.rs:191-221)."""
+
+    @staticmethod
+    def render_note(midi_note, velocity, duration_secs, sample_rate):
+        """Voice::render_note: velocity is 0..1; MLP off; seed = midi*2654435761. Returns f64 samples."""
+        return Voice.render_note_with_scale(midi_note, velocity, duration_secs, sample_rate, None)
+
+    @staticmethod
+    def render_note_with_scale(midi_note, velocity, duration_secs, sample_rate, displacement_scale):
+        j = voice_job(midi_note, 0, sample_rate, duration_secs, mlp=False, attack_noise=True,
+                      displacement_scale=displacement_scale, velocity_norm=velocity)
+        return render_voices([j])[0]
+
+
+def reed_renderer(note=60, velocity=100, duration=1.0):
+    """`reed-renderer -n NOTE -v VEL -d DUR` (tools/reed-renderer/src/main.rs:70-107): 44.1 kHz, voice only.
+    Returns the f64 buffer the CLI would quantise to 24-bit PCM."""
+    return Voice.render_note(note, velocity / 127.0, duration, 44100.0)
+
+
+def preamp_bench_render(**flags):
+    """`preamp-bench render` with its CLI flag names as keywords (see bench_job). Returns f64 samples."""
+    return render_bench([bench_job(**flags)])[0]
+
+
+def pcm24_truncate(samples):
+    """reed-renderer WAV quantisation (main.rs:110-126): clamp to [-1,1], scale by 2^23-1, truncate."""
+    s = np.clip(np.asarray(samples, dtype=np.float64), -1.0, 1.0) * 8388607.0
+    return np.trunc(s).astype(np.int32)

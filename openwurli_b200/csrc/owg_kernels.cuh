@@ -1,0 +1,361 @@
+// CUDA kernels of libowgpu (sm_100a).  See DESIGN.md for the launch geometry and data layout.
+#pragma once
+#include "owg_device.cuh"
+#include "owg_tremolo.cuh"
+
+namespace owgd {
+
+// ---- device-side counters (owg_diag) ------------------------------------------------------------
+struct DevDiag {
+    unsigned long long main_hist[16], main_nr_max, main_be, main_damp, main_nan;
+    unsigned long long sh_hist[16], sh_be, sh_nan;
+    unsigned long long pa_hist[9];
+    unsigned long long trm_hist[16], trm_be;
+    unsigned long long adapter_nan;
+};
+
+__constant__ double c_noise_fade[16];  // hammer.rs:161-168, filled by the host with glibc cos
+
+// ---- settled preamp state: 176 400 silent samples at 48 kHz / 100 kOhm (melange_adapter.rs:14-20) ----
+__global__ void settle_kernel(DkState* out) {
+    __shared__ double rec[OWG_MAT_STRIDE];
+    __shared__ double an[OWG_AN_SPARSE];
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    dk_default_record(rec, an);
+    DkState st;
+    for (int i = 0; i < PN; i++) st.v[i] = PRE_DC_OP[i];
+    for (int i = 0; i < PM; i++) { st.il[i] = PRE_DC_NL_I[i]; st.ilpp[i] = PRE_DC_NL_I[i]; }
+    st.xin_prev = 0.0;
+    st.be_cooldown = 0;
+    const DkDev dv = dk_dev();
+    for (int n = 0; n < 176400; n++) dk_step<false>(0.0, st, rec, an, rec[OWG_MAT_AN66], dv, nullptr);
+    *out = st;
+}
+
+// ---- static-R groups: one record per group (rebuild at first process_sample, gen_preamp.rs:3408-3411) ----
+__global__ void static_matrix_kernel(const OwgPreampGroup* groups, int n_groups, double* recs /*[g][190]*/, double* ans /*[g][38]*/) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const OwgPreampGroup gr = groups[g];
+    if (gr.use_defaults) dk_default_record(recs + (size_t)g * OWG_MAT_STRIDE, ans + (size_t)g * OWG_AN_SPARSE);
+    else dk_rebuild(gr.preamp_sr, gr.r_static, recs + (size_t)g * OWG_MAT_STRIDE, ans + (size_t)g * OWG_AN_SPARSE);
+}
+
+// ---- tremolo groups -------------------------------------------------------------------------------
+// One thread per group: Tremolo::new(depth, sr) (tremolo.rs:84-115: default() incl. 50 warm-up samples at the
+// baked 48 kHz matrices, set_sample_rate, 2*sr settle samples) then n_os x process() (tremolo.rs:121-167), followed
+// by DkPreamp::set_ldr_resistance's clamp / 1e-12 change filter (gen_preamp.rs:1973-1984).  Output: the value of
+// pot_0_resistance in effect at each preamp-rate sample.
+__global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* trem_group_ids, int n_trem, double* pot_seq, int64_t pot_stride,
+                                     DevDiag* diag) {
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_trem) return;
+    const OwgPreampGroup gr = groups[trem_group_ids[gi]];
+    const double sr = gr.preamp_sr;
+    TrmMats m;
+    trm_defaults(m);
+    TrmState st;
+    for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
+    for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
+    st.xin_prev = 0.0;
+    for (int n = 0; n < 50; n++) trm_step(st, m, nullptr);  // CircuitState::default() -> warmup(), gen_tremolo.rs:2021
+    if (fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);
+    {
+        const double tot = sr * 2.0;
+        const unsigned long long n_settle = !(tot == tot) || tot <= 0.0 ? 0ull : (unsigned long long)tot;
+        for (unsigned long long n = 0; n < n_settle; n++) trm_step(st, m, nullptr);
+    }
+    TrmDiag td;
+    for (int i = 0; i < 16; i++) td.hist[i] = 0;
+    td.be_fallback = 0; td.nan_reset = 0;
+    const double depth = gr.tremolo_depth;  // stored unclamped by Tremolo::new (tremolo.rs:105)
+    const double ldr_attack = exp(-1.0 / (0.0025 * sr));
+    const double ldr_release = exp(-1.0 / (0.035 * sr));
+    const double ln_r_max = log(1000000.0);
+    const double ln_min_minus_max = log(9000.0) - log(1000000.0);
+    double env = 0.0;
+    double pot = 9.99999999999999854e4;  // pot_0_resistance of the settled state
+    double* o = pot_seq + (size_t)gi * pot_stride;
+    for (int64_t t = 0; t < gr.n_os; t++) {
+        const double v_out = trm_step(st, m, diag ? &td : nullptr);
+        const double led = rclamp((10.95 - v_out) / (10.95 - 0.70), 0.0, 1.0);
+        const double coeff = led > env ? ldr_attack : ldr_release;
+        env = led + coeff * (env - led);
+        const double drive = rclamp(env, 0.0, 1.0);
+        double r_ldr;
+        if (drive < 1e-6) r_ldr = 1000000.0;
+        else r_ldr = exp(ln_r_max + ln_min_minus_max * pow(drive, 0.9));
+        const double r_upper = 50000.0 * (1.0 - depth);
+        const double r_lower = 50000.0 * depth;
+        const double top = r_upper > 0.0 ? r_upper * 18000.0 / (r_upper + 18000.0) : 0.0;
+        const double branch = 680.0 + r_ldr;
+        const double low = r_lower > 0.0 ? r_lower * branch / (r_lower + branch) : 0.0;
+        const double z = top + low;
+        if (finite64(z)) {
+            const double r = rclamp(z, 1.0e3, 1.0e6);
+            if (!(fabs(r - pot) < 1e-12)) pot = r;
+        }
+        o[t] = pot;
+    }
+    if (diag) {
+        for (int i = 0; i < 16; i++) atomicAdd(&diag->trm_hist[i], (unsigned long long)td.hist[i]);
+        atomicAdd(&diag->trm_be, (unsigned long long)td.be_fallback);
+    }
+}
+
+// One thread per (tremolo group, preamp-rate sample): the lazy rebuild_matrices of that sample.
+__global__ void tremolo_matrix_kernel(const OwgPreampGroup* groups, const int* trem_group_ids, int n_trem, const double* pot_seq, int64_t pot_stride,
+                                      double* recs /*[gi][t][190]*/, int64_t rec_stride_t) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int gi = blockIdx.y;
+    if (gi >= n_trem) return;
+    const OwgPreampGroup gr = groups[trem_group_ids[gi]];
+    if (t >= gr.n_os) return;
+    const double pot = pot_seq[(size_t)gi * pot_stride + t];
+    double* rec = recs + ((size_t)gi * rec_stride_t + t) * OWG_MAT_STRIDE;
+    // A sample whose pot never moved off the settled value at 48 kHz keeps the baked defaults (never dirtied).
+    if (gr.use_defaults && pot == 9.99999999999999854e4) {
+        bool all_same = true;
+        for (int64_t u = 0; u <= t && all_same; u++) all_same = pot_seq[(size_t)gi * pot_stride + u] == pot;
+        if (all_same) { dk_default_record(rec, nullptr); return; }
+    }
+    dk_rebuild(gr.preamp_sr, pot, rec, nullptr);
+}
+// a_neg entries other than [6][6] depend on the rate only.
+__global__ void tremolo_an_kernel(const OwgPreampGroup* groups, int n_groups, double* ans) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    if (groups[g].tremolo_depth > 0.0) {
+        double rec[OWG_MAT_STRIDE];
+        if (groups[g].use_defaults) dk_default_record(rec, ans + (size_t)g * OWG_AN_SPARSE);
+        else dk_rebuild(groups[g].preamp_sr, 9.99999999999999854e4, rec, ans + (size_t)g * OWG_AN_SPARSE);
+    }
+}
+
+// ---- chain V: reed + attack noise + pickup + gain (voice.rs:162-179), one thread per voice -----------
+// out row i = out + row[i]*stride; writes n_samples[i] doubles.
+__global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restrict__ inits, int64_t n, double* __restrict__ out, int64_t stride) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const OwgVoiceInit* vi = inits + i;
+    double s[7], c[7], env[7], drift[7];
+    double cos_inc[7], sin_inc[7], phase_inc[7], amp[7], decay[7];
+#pragma unroll
+    for (int m = 0; m < 7; m++) {
+        s[m] = 0.0; c[m] = 1.0; env[m] = 1.0; drift[m] = vi->jitter_drift[m];
+        cos_inc[m] = vi->cos_inc[m]; sin_inc[m] = vi->sin_inc[m]; phase_inc[m] = vi->phase_inc[m];
+        amp[m] = vi->amplitude[m]; decay[m] = vi->decay_mult[m];
+    }
+    const double revert = vi->jitter_revert, diffusion = vi->jitter_diffusion;
+    const double onset_inc = vi->onset_ramp_inc, onset_exp = vi->onset_shape_exp;
+    const unsigned long long onset_n = vi->onset_ramp_samples;
+    const int onset_mode = onset_exp <= 1.001 ? 0 : (onset_exp >= 1.999 ? 1 : 2);
+    uint32_t jit = vi->jitter_state;
+    // attack noise
+    double n_amp = vi->noise_amp;
+    const double n_decay = vi->noise_decay;
+    uint32_t n_left = vi->noise_remaining, n_rng = vi->noise_rng;
+    const double b0 = vi->bq_b0, b1 = vi->bq_b1, b2 = vi->bq_b2, a1 = vi->bq_a1, a2 = vi->bq_a2;
+    double z1 = 0.0, z2 = 0.0;
+    // pickup
+    double q = 1.0;
+    const double beta = vi->pickup_beta, ds = vi->pickup_ds, gain = vi->post_pickup_gain;
+    const unsigned long long ns = vi->n_samples;
+    double* o = out + i * stride;
+    for (unsigned long long t = 0; t < ns; t++) {
+        // reed.rs:249-264 onset ramp
+        double onset = 1.0;
+        if (t < onset_n) {
+            const double cosine = 0.5 * (1.0 - cos((double)t * onset_inc));
+            onset = onset_mode == 0 ? cosine : (onset_mode == 1 ? cosine * cosine : pow(cosine, onset_exp));
+        }
+        // reed.rs:267-272 OU jitter every 16 samples
+        if ((t & 15ull) == 0ull) {
+#pragma unroll
+            for (int m = 0; m < 7; m++) {
+                jit = jit * 1664525u + 1013904223u;
+                const double u = (double)(jit >> 1) / (4294967295.0 / 2.0);
+                const double noise = (u * 2.0 - 1.0) * 1.7320508080;
+                drift[m] = revert * drift[m] + diffusion * noise;
+            }
+        }
+        // reed.rs:275-291 quadrature rotation
+        double sum = 0.0;
+#pragma unroll
+        for (int m = 0; m < 7; m++) {
+            sum += amp[m] * s[m] * onset * env[m];
+            const double dp = drift[m] * phase_inc[m];
+            const double ci = cos_inc[m] - dp * sin_inc[m];
+            const double si = sin_inc[m] + dp * cos_inc[m];
+            const double s_new = s[m] * ci + c[m] * si;
+            const double c_new = c[m] * ci - s[m] * si;
+            s[m] = s_new; c[m] = c_new;
+            env[m] *= decay[m];
+        }
+        // reed.rs:294-301 renormalise every 1024 samples
+        if ((t & 1023ull) == 0ull && t > 0ull) {
+#pragma unroll
+            for (int m = 0; m < 7; m++) {
+                const double r_inv = 1.0 / sqrt(s[m] * s[m] + c[m] * c[m]);
+                s[m] *= r_inv; c[m] *= r_inv;
+            }
+        }
+        double x = 0.0 + sum;
+        // hammer.rs:150-179 attack noise (additive)
+        if (n_left > 0u) {
+            const uint32_t played = vi->noise_remaining - n_left;
+            const double envn = played < 16u ? c_noise_fade[played] : 1.0;
+            n_rng = n_rng * 1664525u + 1013904223u;
+            const double white = (double)(int32_t)n_rng / 2147483647.0;
+            const double y = b0 * white + z1;
+            z1 = b1 * white - a1 * y + z2;
+            z2 = b2 * white - a2 * y;
+            x += n_amp * envn * y;
+            n_amp *= n_decay;
+            n_left -= 1u;
+        }
+        // pickup.rs:130-149
+        double yy = x * ds;
+        {
+            const double ay = fabs(yy);
+            if (!(ay < 0.94)) {
+                const double range = 0.98 - 0.94;
+                yy = copysign(0.94 + range * tanh((ay - 0.94) / range), yy);
+            }
+        }
+        const double omy = 1.0 - yy;
+        const double alpha = beta * omy;
+        q = (q * (1.0 - alpha) + 2.0 * beta) / (1.0 + alpha);
+        o[t] = ((q * omy - 1.0) * 1.8375) * gain;
+    }
+}
+
+// ---- chain B: [2x up] -> DK preamp (main - shared shadow) -> [2x down] -> vol^2 -> power amp -> speaker ----
+// One warp = up to 31 instances of ONE preamp group in lanes 0..30 plus the group's zero-input shadow
+// solve in lane 31 (melange_adapter.rs:72-81: out = main - shadow).  Processes the voice samples in
+// `out` in place.
+struct WarpEntry { int32_t group, first, count; int32_t _pad; int64_t n_max; };
+
+template <bool TREM, bool DIAG>
+__global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__ warps, const int32_t* __restrict__ order,
+                                                   const OwgChainInit* __restrict__ cinits, const unsigned long long* __restrict__ n_samples,
+                                                   const DkState* __restrict__ settled, const double* __restrict__ recs, const double* __restrict__ ans,
+                                                   const int32_t* __restrict__ group_rec_index, int64_t rec_stride_t,
+                                                   double* __restrict__ out, int64_t stride, DevDiag* diag) {
+    __shared__ double s_rec[OWG_MAT_STRIDE];
+    __shared__ double s_an[OWG_AN_SPARSE];
+    __shared__ OwgChainInit s_ci[32];
+    const int lane = threadIdx.x;
+    const WarpEntry we = warps[blockIdx.x];
+    const bool is_shadow = lane == 31;
+    const bool is_main = lane < we.count;
+    const int32_t job = is_main ? order[we.first + lane] : -1;
+    for (int e = lane; e < OWG_AN_SPARSE; e += 32) s_an[e] = ans[(size_t)we.group * OWG_AN_SPARSE + e];
+    const double* grec = recs + (size_t)group_rec_index[we.group] * (TREM ? (size_t)rec_stride_t * OWG_MAT_STRIDE : (size_t)OWG_MAT_STRIDE);
+    if (!TREM) for (int e = lane; e < OWG_MAT_STRIDE; e += 32) s_rec[e] = grec[e];
+    if (is_main) s_ci[lane] = cinits[job];
+    else {
+        // idle / shadow lanes: benign parameters
+        OwgChainInit z;
+        z.volume = 0.0; z.spk_a2 = 0.0; z.spk_a3 = 0.0; z.spk_norm = 1.0; z.spk_thermal_coeff = 0.0; z.spk_thermal_alpha = 0.0;
+        z.hpf_b0 = z.hpf_b1 = z.hpf_b2 = z.hpf_a1 = z.hpf_a2 = 0.0; z.lpf_b0 = z.lpf_b1 = z.lpf_b2 = z.lpf_a1 = z.lpf_a2 = 0.0;
+        z.spk_tanh = 0; z.group = we.group; z.no_preamp = 0; z.no_poweramp = 1; z.oversample = 0; z._pad = 0;
+        s_ci[lane] = z;
+    }
+    __syncwarp();
+    const OwgChainInit& ci = s_ci[lane];
+    // every main lane of a warp shares the group's base rate, so `oversample` is warp-uniform
+    const int oversample = __shfl_sync(0xffffffffu, ci.oversample, 0);
+    const unsigned long long ns = is_main ? n_samples[job] : 0ull;
+    double* o = is_main ? out + (size_t)job * stride : nullptr;
+
+    DkState st = *settled;  // DkPreamp::new / reset(): clone of the cached settled state (melange_adapter.rs:22-29)
+    const DkDev dv = dk_dev();
+    DkDiag dd;
+    if (DIAG) { for (int i = 0; i < 16; i++) dd.hist[i] = 0; dd.nr_max_iter = dd.be_fallback = dd.voltage_damp = dd.nan_reset = 0; }
+    uint32_t pa_hist[9];
+    if (DIAG) for (int i = 0; i < 9; i++) pa_hist[i] = 0;
+    uint32_t adapter_nan = 0;
+    double ua[3] = {0, 0, 0}, ub[3] = {0, 0, 0}, da[3] = {0, 0, 0}, db[3] = {0, 0, 0};
+    double down_delay = 0.0;
+    SpkState spk = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const double vol = ci.volume;
+    const bool bypass_preamp = ci.no_preamp != 0;
+
+    int64_t tos = 0;  // preamp-rate sample index
+    for (int64_t t = 0; t < we.n_max; t++) {
+        const bool live = is_main && (unsigned long long)t < ns;
+        const double x = live ? o[t] : 0.0;
+        double pre_out;
+        if (oversample) {
+            double u0 = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, ua, x);
+            double u1 = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, ub, x);
+            if (is_shadow) { u0 = 0.0; u1 = 0.0; }
+            double pj[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const double* m = TREM ? grec + (size_t)(tos + j) * OWG_MAT_STRIDE : s_rec;
+                const double an66 = m[OWG_MAT_AN66];
+                const double main_out = dk_step<DIAG>(j == 0 ? u0 : u1, st, m, s_an, an66, dv, &dd);
+                const double pump = __shfl_sync(0xffffffffu, main_out, 31);
+                const double res = main_out - pump;
+                if (!finite64(res)) { adapter_nan++; st = *settled; pj[j] = 0.0; }
+                else pj[j] = res;
+            }
+            tos += 2;
+            const double a = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, da, pj[0]);
+            const double b = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, db, pj[1]);
+            pre_out = (a + down_delay) * 0.5;
+            down_delay = b;
+        } else {
+            const double* m = TREM ? grec + (size_t)tos * OWG_MAT_STRIDE : s_rec;
+            const double an66 = m[OWG_MAT_AN66];
+            const double main_out = dk_step<DIAG>(is_shadow ? 0.0 : x, st, m, s_an, an66, dv, &dd);
+            const double pump = __shfl_sync(0xffffffffu, main_out, 31);
+            const double res = main_out - pump;
+            if (!finite64(res)) { adapter_nan++; st = *settled; pre_out = 0.0; }
+            else pre_out = res;
+            tos += 1;
+        }
+        if (bypass_preamp) pre_out = x;
+        if (live) {
+            const double att = pre_out * vol * vol;
+            const double amped = ci.no_poweramp ? att : poweramp(att, DIAG ? pa_hist : nullptr);
+            o[t] = speaker(amped, spk, ci) * 7.498942093324558;
+        }
+    }
+    if (DIAG && diag) {
+        if (is_main) {
+            for (int i = 0; i < 16; i++) if (dd.hist[i]) atomicAdd(&diag->main_hist[i], (unsigned long long)dd.hist[i]);
+            atomicAdd(&diag->main_nr_max, (unsigned long long)dd.nr_max_iter);
+            atomicAdd(&diag->main_be, (unsigned long long)dd.be_fallback);
+            atomicAdd(&diag->main_damp, (unsigned long long)dd.voltage_damp);
+            atomicAdd(&diag->main_nan, (unsigned long long)dd.nan_reset);
+            for (int i = 0; i < 9; i++) if (pa_hist[i]) atomicAdd(&diag->pa_hist[i], (unsigned long long)pa_hist[i]);
+            atomicAdd(&diag->adapter_nan, (unsigned long long)adapter_nan);
+        } else if (is_shadow && we.first == 0) {
+            // the shadow of a group is counted once (first warp of the launch only, as a representative)
+            for (int i = 0; i < 16; i++) if (dd.hist[i]) atomicAdd(&diag->sh_hist[i], (unsigned long long)dd.hist[i]);
+            atomicAdd(&diag->sh_be, (unsigned long long)dd.be_fallback);
+            atomicAdd(&diag->sh_nan, (unsigned long long)dd.nan_reset);
+        }
+    }
+}
+
+// ---- FP64 pipe micro-benchmark ------------------------------------------------------------------------
+template <bool FMA>
+__global__ void fp64_peak_kernel(double* sink, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+    for (int i = 0; i < iters; i++) {
+        if (FMA) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        } else {
+            x0 = __dmul_rn(x0, a); x1 = __dadd_rn(x1, b); x2 = __dmul_rn(x2, a); x3 = __dadd_rn(x3, b);
+            x4 = __dmul_rn(x4, a); x5 = __dadd_rn(x5, b); x6 = __dmul_rn(x6, a); x7 = __dadd_rn(x7, b);
+        }
+    }
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace owgd

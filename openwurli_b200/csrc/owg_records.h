@@ -1,0 +1,67 @@
+// Plain-data records handed from the host-side note-on setup to the CUDA kernels.
+// One VoiceInit per voice = what the reference's Voice::note_on (voice.rs:28-142) leaves in
+// ModalReed / AttackNoise / Pickup / Voice after construction (SURVEY.md 8(a) "per-voice init record").
+#pragma once
+#include <stdint.h>
+
+#define OWG_NUM_MODES 7
+
+struct OwgVoiceInit {
+    // ModalReed (reed.rs:44-85) -- per-mode constants and initial OU drift
+    double cos_inc[OWG_NUM_MODES];
+    double sin_inc[OWG_NUM_MODES];
+    double phase_inc[OWG_NUM_MODES];
+    double amplitude[OWG_NUM_MODES];
+    double decay_mult[OWG_NUM_MODES];
+    double jitter_drift[OWG_NUM_MODES];
+    double jitter_revert, jitter_diffusion;
+    double onset_ramp_inc, onset_shape_exp;
+    // Pickup (pickup.rs:88-94) and Voice (voice.rs:16)
+    double pickup_beta, pickup_ds, post_pickup_gain;
+    // AttackNoise (hammer.rs:108-117)
+    double noise_amp, noise_decay;
+    double bq_b0, bq_b1, bq_b2, bq_a1, bq_a2;
+    double sample_rate;
+    uint64_t onset_ramp_samples;
+    uint64_t n_samples;      // (duration_s * sample_rate) truncated
+    uint32_t jitter_state;   // LCG state after the 14 Box-Muller draws
+    uint32_t noise_rng;      // AttackNoise LCG seed
+    uint32_t noise_remaining;
+    uint8_t midi;
+    uint8_t _pad[3];
+};
+
+// Per-instance parameters of the shared mono chain in `preamp-bench render` order (chain B,
+// main.rs:478-496): volume^2 -> PowerAmp -> Speaker -> POST_SPEAKER_GAIN.
+struct OwgChainInit {
+    double volume;          // job.volume (applied as x*volume*volume)
+    // Speaker (speaker.rs:50-61) after set_character(): coefficients and biquads
+    double spk_a2, spk_a3, spk_norm;  // norm = 1 + a2 + a3
+    double spk_thermal_coeff, spk_thermal_alpha;
+    double hpf_b0, hpf_b1, hpf_b2, hpf_a1, hpf_a2;
+    double lpf_b0, lpf_b1, lpf_b2, lpf_a1, lpf_a2;
+    int32_t spk_tanh;       // character >= 0.001
+    int32_t group;          // preamp matrix group index
+    int32_t no_preamp, no_poweramp;
+    int32_t oversample;     // sample_rate < 88200
+    int32_t _pad;
+};
+
+// One preamp "group" = instances that share (preamp sample rate, LDR trajectory): they share the
+// DK matrices S, K, S*N_i, a_neg and the zero-input shadow ("pump") sequence.
+struct OwgPreampGroup {
+    double preamp_sr;
+    double r_static;         // clamped static R (tremolo_depth <= 0)
+    double tremolo_depth;    // > 0: Twin-T/LDR trajectory
+    int32_t use_defaults;    // 48 kHz and never dirtied: baked *_DEFAULT tables apply (gen_preamp.rs:1941-1955)
+    int32_t _pad;
+    int64_t n_os;            // preamp-rate samples to produce (max over the group's instances)
+};
+
+// Matrix record layout (doubles) consumed by the DK step.
+#define OWG_MAT_S 0        // S[12][12]
+#define OWG_MAT_SNI 144    // S_NI[12][3]
+#define OWG_MAT_K 180      // K[3][3]
+#define OWG_MAT_AN66 189   // a_neg[6][6] (the only R-dependent a_neg entry)
+#define OWG_MAT_STRIDE 190 // per preamp-rate sample in tremolo mode
+#define OWG_AN_SPARSE 38   // structural non-zeros of a_neg used by build_rhs, row-major order of appearance

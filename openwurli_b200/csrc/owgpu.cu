@@ -1,0 +1,489 @@
+// libowgpu C ABI (include/owgpu.h): plans, launches, copies.  No CPU fallback: every entry point
+// that renders fails with OWG_E_NO_DEVICE when no CUDA device is usable.
+#include "../../include/owgpu.h"
+#include "host_setup.h"
+#include "owg_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+using namespace owgd;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local owg_diag g_last_diag;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            const int _code = (_e == cudaErrorMemoryAllocation) ? OWG_E_OOM : OWG_E_CUDA;         \
+            return fail(_code, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+        }                                                                                          \
+    } while (0)
+
+int usable_devices() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// Per-device process-wide cache (the reference's OnceLock, melange_adapter.rs:12): settled preamp state.
+struct DeviceCache {
+    DkState* d_settled = nullptr;
+    bool fade_uploaded = false;
+};
+std::mutex g_cache_mu;
+std::map<int, DeviceCache> g_cache;
+
+int ensure_device_cache(int device, cudaStream_t stream, DeviceCache** out, int64_t* launches) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    DeviceCache& c = g_cache[device];
+    if (!c.fade_uploaded) {
+        double fade[16];
+        owg::noise_fade_table(fade);
+        CK(cudaMemcpyToSymbol(c_noise_fade, fade, sizeof(fade)));
+        c.fade_uploaded = true;
+    }
+    if (!c.d_settled) {
+        CK(cudaMalloc(&c.d_settled, sizeof(DkState)));
+        settle_kernel<<<1, 32, 0, stream>>>(c.d_settled);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        if (launches) *launches += 1;
+    }
+    *out = &c;
+    return OWG_OK;
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t count) {
+        if (count <= n) return OWG_OK;
+        if (p) { cudaFree(p); p = nullptr; n = 0; }
+        if (count == 0) return OWG_OK;
+        CK(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+        return OWG_OK;
+    }
+    int upload(const std::vector<T>& h, cudaStream_t s) {
+        if (int rc = alloc(h.size())) return rc;
+        if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+        return OWG_OK;
+    }
+};
+
+}  // namespace
+
+struct owg_plan {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int kind = 0;  // 0 = voices (chain V), 1 = bench (chain B)
+    bool collect_diag = false;
+    int64_t n = 0;
+    std::vector<unsigned long long> n_samples;
+    unsigned long long max_samples = 0;
+    // host copies
+    std::vector<OwgPreampGroup> groups;
+    std::vector<int32_t> group_rec_index;
+    std::vector<int> trem_group_ids;
+    std::vector<WarpEntry> warps_static, warps_trem;
+    int64_t trem_n_os_max = 0;
+    // device
+    DevBuf<OwgVoiceInit> d_vinit;
+    DevBuf<OwgChainInit> d_cinit;
+    DevBuf<unsigned long long> d_nsamp;
+    DevBuf<int32_t> d_order;
+    DevBuf<WarpEntry> d_warps_static, d_warps_trem;
+    DevBuf<OwgPreampGroup> d_groups;
+    DevBuf<int32_t> d_group_rec_index;
+    DevBuf<int> d_trem_ids;
+    DevBuf<double> d_static_recs, d_ans, d_pot_seq, d_trem_recs;
+    DevBuf<double> d_stage;  // device-side output when the caller's buffer is host memory
+    DevBuf<DevDiag> d_diag;
+    DeviceCache* cache = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    int64_t launches_last = 0;
+    float main_ms = 0.f, total_ms = 0.f;
+    ~owg_plan() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (evk0) cudaEventDestroy(evk0);
+        if (evk1) cudaEventDestroy(evk1);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+int plan_common(owg_plan* pl, const owg_opts* opts) {
+    if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device (libowgpu has no CPU fallback)");
+    owg_opts o;
+    if (opts) o = *opts; else owg_default_opts(&o);
+    if (o.precision != OWG_PRECISION_F64_EXACT) return fail(OWG_E_UNSUPPORTED, "only OWG_PRECISION_F64_EXACT is implemented");
+    if (o.preamp_model != OWG_PREAMP_MELANGE12) return fail(OWG_E_UNSUPPORTED, "only OWG_PREAMP_MELANGE12 is implemented");
+    int dev = o.device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    CK(cudaSetDevice(dev));
+    pl->device = dev;
+    if (o.stream) { pl->stream = (cudaStream_t)o.stream; pl->own_stream = false; }
+    else { CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking)); pl->own_stream = true; }
+    pl->collect_diag = o.collect_diag != 0;
+    CK(cudaEventCreate(&pl->ev0)); CK(cudaEventCreate(&pl->ev1)); CK(cudaEventCreate(&pl->evk0)); CK(cudaEventCreate(&pl->evk1));
+    int64_t l = 0;
+    if (int rc = ensure_device_cache(dev, pl->stream, &pl->cache, &l)) return rc;
+    return OWG_OK;
+}
+
+bool bad_voice_job(const owg_voice_job& j) {
+    return !(j.sample_rate > 0.0) || !std::isfinite(j.sample_rate) || !(j.duration_s >= 0.0) || !std::isfinite(j.duration_s) ||
+           !std::isfinite(j.velocity);
+}
+
+}  // namespace
+
+extern "C" {
+
+int owg_abi_version(void) { return OWG_ABI_VERSION; }
+int owg_device_count(void) { return usable_devices(); }
+const char* owg_last_error(void) { return g_err.c_str(); }
+void owg_default_opts(owg_opts* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->device = -1;
+    o->out_location = OWG_OUT_HOST;
+    o->precision = OWG_PRECISION_F64_EXACT;
+    o->preamp_model = OWG_PREAMP_MELANGE12;
+}
+
+int owg_plan_voices(const owg_voice_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan) {
+    if (!plan || n < 0 || (n > 0 && !jobs)) return fail(OWG_E_BAD_ARG, "owg_plan_voices: bad argument");
+    for (int64_t i = 0; i < n; i++) if (bad_voice_job(jobs[i])) return fail(OWG_E_BAD_ARG, "owg_plan_voices: job with invalid sample_rate/duration/velocity");
+    owg_plan* pl = new owg_plan();
+    pl->kind = 0;
+    pl->n = n;
+    if (int rc = plan_common(pl, opts)) { delete pl; return rc; }
+    std::vector<OwgVoiceInit> vi((size_t)n);
+    pl->n_samples.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        owg::make_voice_init(jobs[i], &vi[i]);
+        pl->n_samples[i] = vi[i].n_samples;
+        pl->max_samples = std::max<unsigned long long>(pl->max_samples, vi[i].n_samples);
+    }
+    int rc = pl->d_vinit.upload(vi, pl->stream);
+    if (!rc) rc = pl->d_nsamp.upload(pl->n_samples, pl->stream);
+    if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
+    if (rc) { delete pl; return rc; }
+    *plan = pl;
+    return OWG_OK;
+}
+
+int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan) {
+    if (!plan || n < 0 || (n > 0 && !jobs)) return fail(OWG_E_BAD_ARG, "owg_plan_bench: bad argument");
+    for (int64_t i = 0; i < n; i++) {
+        if (bad_voice_job(jobs[i].v)) return fail(OWG_E_BAD_ARG, "owg_plan_bench: job with invalid sample_rate/duration/velocity");
+        if (!std::isfinite(jobs[i].volume) || !std::isfinite(jobs[i].speaker_character) || std::isnan(jobs[i].tremolo_depth))
+            return fail(OWG_E_BAD_ARG, "owg_plan_bench: non-finite volume/speaker/tremolo_depth");
+    }
+    owg_plan* pl = new owg_plan();
+    pl->kind = 1;
+    pl->n = n;
+    if (int rc = plan_common(pl, opts)) { delete pl; return rc; }
+
+    // group jobs by (base rate, static R | tremolo depth): they share matrices and the shadow solve
+    typedef std::tuple<double, int, double> Key;  // (sample_rate, is_trem, r_or_depth)
+    std::map<Key, int> key_to_group;
+    std::vector<std::vector<int32_t>> members;
+    std::vector<OwgVoiceInit> vi((size_t)n);
+    std::vector<OwgChainInit> ci((size_t)n);
+    pl->n_samples.resize((size_t)n);
+    const double R0 = 9.99999999999999854e4;
+    for (int64_t i = 0; i < n; i++) {
+        const owg_bench_job& j = jobs[i];
+        const double fs = j.v.sample_rate;
+        const bool os = fs < 88200.0;
+        const double psr = os ? fs * 2.0 : fs;
+        const bool trem = j.tremolo_depth > 0.0;
+        double r_eff = R0;
+        bool dirty = false;
+        if (!trem && std::isfinite(j.r_ldr)) {  // reset(); set_ldr_resistance(r_ldr)  (main.rs:438-439, gen_preamp.rs:1973-1984)
+            const double r = j.r_ldr < 1.0e3 ? 1.0e3 : (j.r_ldr > 1.0e6 ? 1.0e6 : j.r_ldr);
+            if (!(std::fabs(r - R0) < 1e-12)) { r_eff = r; dirty = true; }
+        }
+        const Key key(fs, trem ? 1 : 0, trem ? j.tremolo_depth : r_eff);
+        auto it = key_to_group.find(key);
+        int g;
+        if (it == key_to_group.end()) {
+            g = (int)pl->groups.size();
+            key_to_group[key] = g;
+            OwgPreampGroup gr;
+            std::memset(&gr, 0, sizeof(gr));
+            gr.preamp_sr = psr;
+            gr.r_static = r_eff;
+            gr.tremolo_depth = trem ? j.tremolo_depth : 0.0;
+            gr.use_defaults = (std::fabs(psr - 48000.0) <= 0.5 && !dirty) ? 1 : 0;
+            gr.n_os = 0;
+            pl->groups.push_back(gr);
+            members.emplace_back();
+        } else g = it->second;
+        owg::make_voice_init(j.v, &vi[i]);
+        owg::make_chain_init(j, g, &ci[i]);
+        pl->n_samples[i] = vi[i].n_samples;
+        pl->max_samples = std::max<unsigned long long>(pl->max_samples, vi[i].n_samples);
+        const int64_t nos = (int64_t)vi[i].n_samples * (os ? 2 : 1);
+        pl->groups[g].n_os = std::max<int64_t>(pl->groups[g].n_os, nos);
+        members[g].push_back((int32_t)i);
+    }
+    // record indices: static groups index d_static_recs, tremolo groups index d_trem_recs
+    pl->group_rec_index.assign(pl->groups.size(), 0);
+    int n_static = 0;
+    for (size_t g = 0; g < pl->groups.size(); g++) {
+        if (pl->groups[g].tremolo_depth > 0.0) {
+            pl->group_rec_index[g] = (int32_t)pl->trem_group_ids.size();
+            pl->trem_group_ids.push_back((int)g);
+            pl->trem_n_os_max = std::max(pl->trem_n_os_max, pl->groups[g].n_os);
+        } else {
+            pl->group_rec_index[g] = (int32_t)g;  // static records are indexed by group id (sparse but simple)
+            n_static++;
+        }
+    }
+    // warps: 31 instances + 1 shadow lane; longest renders first so the tail of the launch is short
+    std::vector<int32_t> order;
+    order.reserve((size_t)n);
+    for (size_t g = 0; g < pl->groups.size(); g++) {
+        std::vector<int32_t>& mem = members[g];
+        std::stable_sort(mem.begin(), mem.end(), [&](int32_t a, int32_t b) { return pl->n_samples[a] > pl->n_samples[b]; });
+        for (size_t off = 0; off < mem.size(); off += 31) {
+            WarpEntry we;
+            we.group = (int32_t)g;
+            we.first = (int32_t)order.size();
+            we.count = (int32_t)std::min<size_t>(31, mem.size() - off);
+            we._pad = 0;
+            we.n_max = 0;
+            for (int k = 0; k < we.count; k++) {
+                order.push_back(mem[off + k]);
+                we.n_max = std::max<int64_t>(we.n_max, (int64_t)pl->n_samples[mem[off + k]]);
+            }
+            (pl->groups[g].tremolo_depth > 0.0 ? pl->warps_trem : pl->warps_static).push_back(we);
+        }
+    }
+    (void)n_static;
+    int rc = pl->d_vinit.upload(vi, pl->stream);
+    if (!rc) rc = pl->d_cinit.upload(ci, pl->stream);
+    if (!rc) rc = pl->d_nsamp.upload(pl->n_samples, pl->stream);
+    if (!rc) rc = pl->d_order.upload(order, pl->stream);
+    if (!rc) rc = pl->d_warps_static.upload(pl->warps_static, pl->stream);
+    if (!rc) rc = pl->d_warps_trem.upload(pl->warps_trem, pl->stream);
+    if (!rc) rc = pl->d_groups.upload(pl->groups, pl->stream);
+    if (!rc) rc = pl->d_group_rec_index.upload(pl->group_rec_index, pl->stream);
+    if (!rc) rc = pl->d_trem_ids.upload(pl->trem_group_ids, pl->stream);
+    if (!rc) rc = pl->d_static_recs.alloc(pl->groups.size() * OWG_MAT_STRIDE);
+    if (!rc) rc = pl->d_ans.alloc(pl->groups.size() * OWG_AN_SPARSE);
+    if (!rc && !pl->trem_group_ids.empty()) {
+        rc = pl->d_pot_seq.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max);
+        if (!rc) rc = pl->d_trem_recs.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max * OWG_MAT_STRIDE);
+    }
+    if (!rc && pl->collect_diag) rc = pl->d_diag.alloc(1);
+    if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
+    if (rc) { delete pl; return rc; }
+    *plan = pl;
+    return OWG_OK;
+}
+
+int64_t owg_plan_samples(const owg_plan* pl, int64_t i) {
+    if (!pl) return -1;
+    if (i < 0) return (int64_t)pl->max_samples;
+    if (i >= pl->n) return -1;
+    return (int64_t)pl->n_samples[(size_t)i];
+}
+
+int64_t owg_plan_kernel_launches(const owg_plan* pl) { return pl ? pl->launches_last : -1; }
+
+int owg_plan_last_timing(const owg_plan* pl, float* main_kernel_ms, float* total_ms) {
+    if (!pl) return fail(OWG_E_BAD_ARG, "null plan");
+    if (main_kernel_ms) *main_kernel_ms = pl->main_ms;
+    if (total_ms) *total_ms = pl->total_ms;
+    return OWG_OK;
+}
+
+void owg_plan_destroy(owg_plan* pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    delete pl;
+}
+
+int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_location) {
+    if (!pl) return fail(OWG_E_BAD_ARG, "null plan");
+    if (pl->n == 0) return OWG_OK;
+    if (!out) return fail(OWG_E_BAD_ARG, "null output");
+    if (stride < (int64_t)pl->max_samples) return fail(OWG_E_BAD_ARG, "stride smaller than the longest render");
+    CK(cudaSetDevice(pl->device));
+    cudaStream_t s = pl->stream;
+    double* dout = out;
+    if (out_location == OWG_OUT_HOST) {
+        if (int rc = pl->d_stage.alloc((size_t)pl->n * (size_t)stride)) return rc;
+        dout = pl->d_stage.p;
+    } else if (out_location != OWG_OUT_DEVICE) return fail(OWG_E_BAD_ARG, "bad out_location");
+    int64_t launches = 0;
+    CK(cudaEventRecord(pl->ev0, s));
+    if (pl->collect_diag) CK(cudaMemsetAsync(pl->d_diag.p, 0, sizeof(DevDiag), s));
+    // chain V for every job
+    {
+        const int threads = 32;
+        const int blocks = (int)((pl->n + threads - 1) / threads);
+        voice_kernel<<<blocks, threads, 0, s>>>(pl->d_vinit.p, pl->n, dout, stride);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    if (pl->kind == 1) {
+        const int ng = (int)pl->groups.size();
+        static_matrix_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_static_recs.p, pl->d_ans.p);
+        CK(cudaGetLastError());
+        launches++;
+        const int nt = (int)pl->trem_group_ids.size();
+        if (nt > 0) {
+            tremolo_an_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_ans.p);
+            CK(cudaGetLastError());
+            tremolo_group_kernel<<<nt, 1, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                   pl->collect_diag ? pl->d_diag.p : nullptr);
+            CK(cudaGetLastError());
+            dim3 grid((unsigned)((pl->trem_n_os_max + 63) / 64), (unsigned)nt);
+            tremolo_matrix_kernel<<<grid, 64, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_trem_recs.p,
+                                                      pl->trem_n_os_max);
+            CK(cudaGetLastError());
+            launches += 3;
+        }
+        CK(cudaEventRecord(pl->evk0, s));
+        if (!pl->warps_static.empty()) {
+            const int nb = (int)pl->warps_static.size();
+            if (pl->collect_diag)
+                chain_kernel<false, true><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                             pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p);
+            else
+                chain_kernel<false, false><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                              pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, nullptr);
+            CK(cudaGetLastError());
+            launches++;
+        }
+        if (!pl->warps_trem.empty()) {
+            const int nb = (int)pl->warps_trem.size();
+            if (pl->collect_diag)
+                chain_kernel<true, true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                            pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
+                                                            pl->d_diag.p);
+            else
+                chain_kernel<true, false><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                             pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
+                                                             nullptr);
+            CK(cudaGetLastError());
+            launches++;
+        }
+        CK(cudaEventRecord(pl->evk1, s));
+    } else {
+        CK(cudaEventRecord(pl->evk0, s));
+        CK(cudaEventRecord(pl->evk1, s));
+    }
+    if (out_location == OWG_OUT_HOST) {
+        // one 2-D copy: rows of max_samples doubles, device pitch == host pitch == stride
+        CK(cudaMemcpy2DAsync(out, (size_t)stride * sizeof(double), dout, (size_t)stride * sizeof(double),
+                             (size_t)pl->max_samples * sizeof(double), (size_t)pl->n, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaEventRecord(pl->ev1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&pl->total_ms, pl->ev0, pl->ev1));
+    CK(cudaEventElapsedTime(&pl->main_ms, pl->evk0, pl->evk1));
+    pl->launches_last = launches;
+    if (pl->collect_diag) {
+        DevDiag h;
+        CK(cudaMemcpy(&h, pl->d_diag.p, sizeof(h), cudaMemcpyDeviceToHost));
+        owg_diag& d = g_last_diag;
+        std::memset(&d, 0, sizeof(d));
+        for (int i = 0; i < 16; i++) { d.nr_iter_hist[i] = h.main_hist[i]; d.shadow_nr_iter_hist[i] = h.sh_hist[i]; d.tremolo_nr_iter_hist[i] = h.trm_hist[i]; }
+        for (int i = 0; i < 9; i++) d.poweramp_iter_hist[i] = h.pa_hist[i];
+        d.nr_max_iter = h.main_nr_max; d.be_fallback = h.main_be; d.voltage_damp = h.main_damp; d.nan_reset = h.main_nan + h.adapter_nan;
+        d.shadow_be_fallback = h.sh_be; d.shadow_nan_reset = h.sh_nan; d.tremolo_be_fallback = h.trm_be;
+        d.kernels_launched = (uint64_t)launches;
+    }
+    return OWG_OK;
+}
+
+int owg_render_voices(const owg_voice_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts) {
+    owg_plan* pl = nullptr;
+    if (int rc = owg_plan_voices(jobs, n, opts, &pl)) return rc;
+    const int rc = owg_plan_execute(pl, out, stride, opts ? opts->out_location : OWG_OUT_HOST);
+    owg_plan_destroy(pl);
+    return rc;
+}
+
+int owg_render_bench(const owg_bench_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts) {
+    owg_plan* pl = nullptr;
+    if (int rc = owg_plan_bench(jobs, n, opts, &pl)) return rc;
+    const int rc = owg_plan_execute(pl, out, stride, opts ? opts->out_location : OWG_OUT_HOST);
+    owg_plan_destroy(pl);
+    return rc;
+}
+
+int owg_render_engines(const owg_engine_job*, int64_t, float*, int64_t, const owg_opts*) {
+    return fail(OWG_E_UNSUPPORTED, "owg_render_engines: chain E (WurliEngine streams) is not implemented in this build");
+}
+
+int owg_preamp_batch(const double*, int64_t, int64_t, int64_t, double, int, double, double, double*, int64_t, const owg_opts*) {
+    return fail(OWG_E_UNSUPPORTED, "owg_preamp_batch: not implemented in this build");
+}
+
+int owg_last_diag(owg_diag* out) {
+    if (!out) return fail(OWG_E_BAD_ARG, "null diag");
+    *out = g_last_diag;
+    return OWG_OK;
+}
+
+int owg_fp64_peak(int32_t device, int32_t fma_mode, float ms_target, double* tera_instr_per_s) {
+    if (!tera_instr_per_s) return fail(OWG_E_BAD_ARG, "null result");
+    if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
+    if (device >= 0) CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaGetDeviceProperties(&prop, dev));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8;
+    double* sink = nullptr;
+    CK(cudaMalloc(&sink, (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    int iters = 1 << 14;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0));
+        if (fma_mode) fp64_peak_kernel<true><<<blocks, threads>>>(sink, iters, 1.0000001, 1e-9);
+        else fp64_peak_kernel<false><<<blocks, threads>>>(sink, iters, 1.0000001, 1e-9);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double instr = (double)threads * blocks * (double)iters * 8.0;
+        const double rate = instr / (ms * 1e-3) / 1e12;
+        if (rep > 0 && rate > best) best = rate;
+        if (ms < ms_target && iters < (1 << 24)) iters *= 2;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tera_instr_per_s = best;
+    return OWG_OK;
+}
+
+}  // extern "C"
