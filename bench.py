@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""bench.py -- audio-seconds rendered per wall-second on the OpenWurli calibration grid (BASELINE.json C3).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--tremolo-depth D] [--duration S]
+
+One "step" = one complete pass of the hot path over the 64-key x 127-velocity grid (8128 `preamp-bench render`
+jobs, chain B, MLP on, 3 s per note, 44.1 kHz).  The default workload has tremolo depth 0.5, i.e. the full
+north_star chain including the Twin-T/LDR coupling; the static-LDR CLI default is measured
+in the same run and reported under "variants".  Under torchrun (N>1) every rank renders its own full grid
+(weak scaling: renders are independent, no data-path collective; seeds are offset per rank).
+
+`value`  : device-timed (CUDA events, max over ranks), init records resident in HBM, output left in HBM.
+`e2e`    : the public API ow.render_bench(jobs, out=pinned_host): host note-on setup + H2D + kernels + D2H of
+           every rendered sample, timed with the host clock around the call.
+--impl reference times the CPU oracle (the reference's algorithm; the Rust reference cannot be built here) with
+all host threads on a bounded sample of the same grid.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+KEYS, VELS, FS = 64, 127, 44100.0
+METRIC = "audio_seconds_rendered_per_second"
+UNIT = "audio-s/s"
+
+
+def grid_jobs(ow, duration, depth, seed_offset=0, stride=1):
+    jobs = []
+    k = 0
+    for key in range(KEYS):
+        for vel in range(1, VELS + 1):
+            if k % stride == 0:
+                midi = 33 + key
+                jobs.append(ow.bench_job(note=midi, velocity=vel, duration=duration, tremolo_depth=depth,
+                                         seed=(ow.default_noise_seed(midi) + seed_offset) & 0xFFFFFFFF))
+            k += 1
+    return jobs
+
+
+def workload_name(duration, depth):
+    trem = f"tremolo_depth {depth:g}" if depth > 0 else "static LDR 1 MOhm (CLI default)"
+    return (f"C3 grid {KEYS} keys x {VELS} velocities = {KEYS * VELS} renders x {duration:g} s, chain B "
+            f"(`preamp-bench render`), MLP on, 44.1 kHz 2x-oversampled melange preamp, {trem}")
+
+
+# ---- algorithmic FLOPs (DESIGN.md "Roofline") ---------------------------------------------------------
+def algorithmic_flops(n_inst, n_samp, mean_nr_iters, depth, n_groups=1):
+    """De-duplicated algorithmic FP64 operations of one pass (+,-,*,/,sqrt = 1 each; fast_exp = 18; libm = 20)."""
+    dk_step = 85 + 288 + 72 + 70 + 220.0 * mean_nr_iters       # rhs + S*rhs + S_NI*i + checks + NR iterations
+    per_sample = 129 + 50 + 2 * dk_step + 200 + 62               # voice + oversampler + 2 DK steps + power amp + speaker
+    inst = n_inst * n_samp * per_sample
+    shared = n_groups * n_samp * 2 * dk_step                     # the shadow solve, once per group
+    if depth > 0:
+        shared += n_groups * n_samp * 2 * (1060 + 5650)          # Twin-T/LDR step + 12x12 LU rebuild per preamp sample
+    return inst + shared
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            self.path = tempfile.mktemp(suffix=".csv")
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1])); smax.append(float(f[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_sample_jobs(O, duration, depth, n_jobs):
+    """Bounded, evenly spread sample of the grid for the CPU arms."""
+    total = KEYS * VELS
+    jobs = []
+    for s in range(n_jobs):
+        k = (s * total) // n_jobs
+        key, vel = k // VELS, k % VELS + 1
+        jobs.append(O.bench_job(33 + key, vel, dur=duration, depth=depth))
+    return jobs
+
+
+def run_cpu(O, duration, depth, n_jobs, threads):
+    import numpy as np
+    jobs = cpu_sample_jobs(O, duration, depth, n_jobs)
+    t0 = time.perf_counter()
+    out = O.render_bench(jobs, threads=threads)
+    dt = time.perf_counter() - t0
+    assert np.all(np.isfinite(out))
+    return n_jobs * duration / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--duration", type=float, default=3.0)
+    ap.add_argument("--tremolo-depth", type=float, default=0.5)
+    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid-stride", type=int, default=1, help="debug: take every k-th grid job")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = {"workload": workload_name(args.duration, args.tremolo_depth), "renders_per_gpu": KEYS * VELS // args.grid_stride,
+           "sample_rate": FS, "duration_s": args.duration, "tremolo_depth": args.tremolo_depth,
+           "cache_policy": "outputs (8.6 GB per pass) and streamed matrices far exceed the 126 MB L2; no flush needed",
+           "parallelism": f"instances sharded over {world} GPU(s), no collective"}
+
+    # ------------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import oracle_lib as O
+        threads = O.lib().owo_hardware_threads() or os.cpu_count() or 1
+        # bounded sample: ~2 jobs per thread, full-length renders
+        n_jobs = max(2 * threads, 8)
+        O.lib().owo_preamp_settled((O.C.c_double * 19)())  # process-wide settled-state cache, like the reference's OnceLock
+        for _ in range(args.warmup):
+            run_cpu(O, min(args.duration, 0.1), args.tremolo_depth, threads, threads)
+        t0 = time.perf_counter()
+        vals = []
+        for _ in range(args.steps):
+            v, dt = run_cpu(O, args.duration, args.tremolo_depth, n_jobs, threads)
+            vals.append(v)
+        wall = time.perf_counter() - t0
+        value = args.steps * n_jobs * args.duration / wall
+        sample = f"{n_jobs} of {KEYS * VELS} grid renders per step (evenly spread keys/velocities), full {args.duration:g} s each"
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "CPU oracle = line-by-line C++ restatement of the reference (Rust toolchain absent; see DESIGN.md)"}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------------ our arm
+    import numpy as np
+    import torch
+    import openwurli_b200 as ow
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.cuda.current_device()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_passes(depth, steps, warm):
+        jobs = grid_jobs(ow, args.duration, depth, seed_offset=rank, stride=args.grid_stride)
+        plan = ow.Plan.bench(jobs, device=dev, stream=stream)
+        out = torch.empty((len(jobs), plan.max_samples), dtype=torch.float64, device="cuda")
+        for _ in range(warm):
+            plan.execute(out)
+        barrier()
+        sampler = ClockSampler(dev)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        main_ms, launches = 0.0, 0
+        for _ in range(steps):
+            plan.execute(out)
+            main_ms += plan.last_timing()[0]
+            launches += plan.kernel_launches
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        finite = bool(torch.isfinite(out[:: max(len(jobs) // 64, 1)]).all().item())
+        peak = float(out.abs().max().item())
+        n_inst, n_samp = len(jobs), plan.max_samples
+        plan.close()
+        del out
+        return dict(ms=ms, main_ms=main_ms, launches=launches, clocks=clocks, finite=finite, peak=peak, n_inst=n_inst, n_samp=n_samp)
+
+    def e2e_passes(depth, steps):
+        jobs = grid_jobs(ow, args.duration, depth, seed_offset=rank, stride=args.grid_stride)
+        n_samp = int(args.duration * FS)
+        host = torch.empty((len(jobs), n_samp), dtype=torch.float64).pin_memory()
+        ow.render_bench(jobs, out=host, device=dev)  # warm-up of the path (allocations, settled-state cache)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ow.render_bench(jobs, out=host, device=dev)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        checksum = float(host[:, ::997].abs().sum().item())
+        probe = ow.Plan.bench(jobs[:64], device=dev)  # init-record bytes per job, as the library counts its uploads
+        h2d = int(probe.h2d_bytes / 64 * len(jobs))
+        probe.close()
+        d2h = len(jobs) * n_samp * 8
+        del host
+        return dict(s=t.item(), h2d=h2d, d2h=d2h, checksum=checksum, n_inst=len(jobs))
+
+    def mean_nr_iterations(depth):
+        """Mean Newton iterations per DK step on a 1-in-64 sample of the grid (device counters), for the FLOP model."""
+        jobs = grid_jobs(ow, args.duration, depth, stride=64)
+        out = torch.empty((len(jobs), int(args.duration * FS)), dtype=torch.float64, device="cuda")
+        pl = ow.Plan.bench(jobs, device=dev, stream=stream, collect_diag=True)
+        pl.execute(out)
+        d = ow.last_diag()
+        pl.close()
+        h = np.array(list(d.nr_iter_hist), dtype=np.float64)
+        # bucket b = last_nr_iterations b -> b+1 iterations ran; bucket 15 (>=15) counted as 16 (lower bound)
+        return float((h * (np.arange(16) + 1)).sum() / max(h.sum(), 1.0))
+
+    main_run = timed_passes(args.tremolo_depth, args.steps, warmup)
+    audio_s = main_run["n_inst"] * args.duration * world
+    value = audio_s * args.steps / (main_run["ms"] * 1e-3)
+    e2e = e2e_passes(args.tremolo_depth, max(1, min(args.steps, 2)))
+    e2e_value = e2e["n_inst"] * args.duration * world * max(1, min(args.steps, 2)) / e2e["s"]
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": main_run["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]},
+            "gpu_launches": main_run["launches"], "clocks": main_run["clocks"],
+            "checks": {"finite": main_run["finite"], "peak_abs": main_run["peak"], "e2e_checksum": e2e["checksum"]}}
+
+    if rank == 0:
+        # roofline of the dominant kernel (chain_kernel): algorithmic FLOPs / its CUDA-event duration inside the timed region
+        fma_peak = ow.fp64_peak(device=dev, fma=True) * 2.0     # TFLOP/s, DFMA = 2 flop
+        unfused_peak = ow.fp64_peak(device=dev, fma=False)      # T instr/s = TFLOP/s for uncontracted code
+        iters = mean_nr_iterations(args.tremolo_depth)
+        flops = algorithmic_flops(main_run["n_inst"], main_run["n_samp"], iters, args.tremolo_depth)
+        kernel_s = main_run["main_ms"] * 1e-3 / args.steps
+        achieved = flops / kernel_s / 1e12
+        line["roofline"] = {"bound": "fp64", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
+                            "traffic": None, "peak_source": "owg_fp64_peak DFMA micro-benchmark measured in this run "
+                            "(MEASURED_PEAKS.json has no FP64 entry; B200 nominal 37 TFLOP/s)",
+                            "peak_unfused_tflops": unfused_peak, "frac_of_unfused": achieved / unfused_peak,
+                            "kernel": "owgd::chain_kernel", "kernel_ms_per_step": kernel_s * 1e3, "mean_nr_iterations": iters,
+                            "algorithmic_gflop_per_step": flops / 1e9}
+        if not args.no_variants:
+            other = 0.0 if args.tremolo_depth > 0 else 0.5
+            v = timed_passes(other, max(1, args.steps - 1), 1) if world == 1 else None
+            if v:
+                line["variants"] = {workload_name(args.duration, other): {
+                    "value": v["n_inst"] * args.duration * max(1, args.steps - 1) / (v["ms"] * 1e-3), "unit": UNIT,
+                    "ms_per_step": v["ms"] / max(1, args.steps - 1)}}
+        if not args.no_cpu_baseline:
+            import oracle_lib as O
+            threads = O.lib().owo_hardware_threads() or os.cpu_count() or 1
+            n_jobs = max(2 * threads, 8)
+            O.lib().owo_preamp_settled((O.C.c_double * 19)())
+            v, dt = run_cpu(O, args.duration, args.tremolo_depth, n_jobs, threads)
+            v1, dt1 = run_cpu(O, args.duration, args.tremolo_depth, 1, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{n_jobs} evenly spread grid renders x {args.duration:g} s, {threads} threads "
+                                              f"({dt:.1f} s); single-thread: {v1:.2f} audio-s/s"}
+        print(json.dumps(line))
+    elif not args.no_variants and world == 1:
+        pass
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -154,6 +154,8 @@ int owg_plan_voices(const owg_voice_job* jobs, int64_t n, const owg_opts* opts, 
 int owg_plan_execute(owg_plan* plan, double* out, int64_t stride, int32_t out_location);
 /* Samples job i produces; max over jobs when i < 0. */
 int64_t owg_plan_samples(const owg_plan* plan, int64_t i);
+/* Bytes of init records / tables the plan uploaded to the device (host->device traffic of the setup). */
+int64_t owg_plan_h2d_bytes(const owg_plan* plan);
 /* CUDA kernels one execution launches. */
 int64_t owg_plan_kernel_launches(const owg_plan* plan);
 /* Device time (ms) of the dominant per-instance kernel in the last execution (CUDA events on the
@@ -162,6 +164,19 @@ int owg_plan_last_timing(const owg_plan* plan, float* main_kernel_ms, float* tot
 void owg_plan_destroy(owg_plan* plan);
 
 int owg_last_diag(owg_diag* out);
+
+/* ---- host-logic probes (no device needed) -------------------------------------------------- */
+/* Flattened per-voice init record the kernels start from (what Voice::note_on leaves behind,
+ * voice.rs:28-142 / reed.rs:108-182): out[0..41] = 7x{cos_inc, sin_inc, phase_inc, amplitude,
+ * decay_mult, jitter_drift}; then jitter_revert, jitter_diffusion, onset_ramp_inc, onset_shape_exp,
+ * pickup_beta, pickup_ds, post_pickup_gain, noise_amp, noise_decay, bq_b0, bq_b1, bq_b2, bq_a1,
+ * bq_a2, onset_ramp_samples, n_samples, jitter_state, noise_rng, noise_remaining (61 doubles). */
+#define OWG_VOICE_INIT_DOUBLES 61
+int owg_host_voice_init(const owg_voice_job* job, double* out61);
+/* Speaker / volume parameters of one bench job: volume, a2, a3, norm, thermal_coeff, thermal_alpha,
+ * hpf b0 b1 b2 a1 a2, lpf b0 b1 b2 a1 a2, tanh flag, oversample flag (18 doubles). */
+#define OWG_CHAIN_INIT_DOUBLES 18
+int owg_host_chain_init(const owg_bench_job* job, double* out18);
 
 /* ---- FP64 pipe micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) - */
 /* Runs a register-resident stream of dependent-free DFMA (fma=1) or DADD+DMUL pairs (fma=0) on

@@ -52,8 +52,8 @@ class Diag(C.Structure):
 
 EXPORTS = ["owg_abi_version", "owg_device_count", "owg_last_error", "owg_default_opts", "owg_render_voices",
            "owg_render_bench", "owg_render_engines", "owg_preamp_batch", "owg_plan_bench", "owg_plan_voices",
-           "owg_plan_execute", "owg_plan_samples", "owg_plan_kernel_launches", "owg_plan_last_timing",
-           "owg_plan_destroy", "owg_last_diag", "owg_fp64_peak"]
+           "owg_plan_execute", "owg_plan_samples", "owg_plan_h2d_bytes", "owg_plan_kernel_launches", "owg_plan_last_timing",
+           "owg_plan_destroy", "owg_last_diag", "owg_fp64_peak", "owg_host_voice_init", "owg_host_chain_init"]
 
 _lib = None
 
@@ -87,6 +87,8 @@ def lib():
         L.owg_plan_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
         L.owg_plan_samples.argtypes = [C.c_void_p, C.c_int64]
         L.owg_plan_samples.restype = C.c_int64
+        L.owg_plan_h2d_bytes.argtypes = [C.c_void_p]
+        L.owg_plan_h2d_bytes.restype = C.c_int64
         L.owg_plan_kernel_launches.argtypes = [C.c_void_p]
         L.owg_plan_kernel_launches.restype = C.c_int64
         L.owg_plan_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -94,6 +96,8 @@ def lib():
         L.owg_plan_destroy.restype = None
         L.owg_last_diag.argtypes = [C.POINTER(Diag)]
         L.owg_fp64_peak.argtypes = [C.c_int32, C.c_int32, C.c_float, dp]
+        L.owg_host_voice_init.argtypes = [C.POINTER(VoiceJob), dp]
+        L.owg_host_chain_init.argtypes = [C.POINTER(BenchJob), dp]
         _lib = L
     return _lib
 

@@ -119,6 +119,10 @@ class Plan:
         return out
 
     @property
+    def h2d_bytes(self):
+        return lib().owg_plan_h2d_bytes(self._h)
+
+    @property
     def kernel_launches(self):
         return lib().owg_plan_kernel_launches(self._h)
 

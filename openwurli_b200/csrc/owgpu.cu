@@ -67,6 +67,8 @@ int ensure_device_cache(int device, cudaStream_t stream, DeviceCache** out, int6
     return OWG_OK;
 }
 
+thread_local int64_t g_h2d_bytes = 0;
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -81,6 +83,7 @@ struct DevBuf {
         return OWG_OK;
     }
     int upload(const std::vector<T>& h, cudaStream_t s) {
+        g_h2d_bytes += h.size() * sizeof(T);
         if (int rc = alloc(h.size())) return rc;
         if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
         return OWG_OK;
@@ -119,6 +122,7 @@ struct owg_plan {
     DeviceCache* cache = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     int64_t launches_last = 0;
+    int64_t h2d_bytes = 0;
     float main_ms = 0.f, total_ms = 0.f;
     ~owg_plan() {
         if (ev0) cudaEventDestroy(ev0);
@@ -175,6 +179,7 @@ int owg_plan_voices(const owg_voice_job* jobs, int64_t n, const owg_opts* opts, 
     if (!plan || n < 0 || (n > 0 && !jobs)) return fail(OWG_E_BAD_ARG, "owg_plan_voices: bad argument");
     for (int64_t i = 0; i < n; i++) if (bad_voice_job(jobs[i])) return fail(OWG_E_BAD_ARG, "owg_plan_voices: job with invalid sample_rate/duration/velocity");
     owg_plan* pl = new owg_plan();
+    g_h2d_bytes = 0;
     pl->kind = 0;
     pl->n = n;
     if (int rc = plan_common(pl, opts)) { delete pl; return rc; }
@@ -189,6 +194,7 @@ int owg_plan_voices(const owg_voice_job* jobs, int64_t n, const owg_opts* opts, 
     if (!rc) rc = pl->d_nsamp.upload(pl->n_samples, pl->stream);
     if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
     if (rc) { delete pl; return rc; }
+    pl->h2d_bytes = g_h2d_bytes;
     *plan = pl;
     return OWG_OK;
 }
@@ -201,6 +207,7 @@ int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, o
             return fail(OWG_E_BAD_ARG, "owg_plan_bench: non-finite volume/speaker/tremolo_depth");
     }
     owg_plan* pl = new owg_plan();
+    g_h2d_bytes = 0;
     pl->kind = 1;
     pl->n = n;
     if (int rc = plan_common(pl, opts)) { delete pl; return rc; }
@@ -301,6 +308,7 @@ int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, o
     if (!rc && pl->collect_diag) rc = pl->d_diag.alloc(1);
     if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
     if (rc) { delete pl; return rc; }
+    pl->h2d_bytes = g_h2d_bytes;
     *plan = pl;
     return OWG_OK;
 }
@@ -311,6 +319,8 @@ int64_t owg_plan_samples(const owg_plan* pl, int64_t i) {
     if (i >= pl->n) return -1;
     return (int64_t)pl->n_samples[(size_t)i];
 }
+
+int64_t owg_plan_h2d_bytes(const owg_plan* pl) { return pl ? pl->h2d_bytes : -1; }
 
 int64_t owg_plan_kernel_launches(const owg_plan* pl) { return pl ? pl->launches_last : -1; }
 
@@ -444,6 +454,30 @@ int owg_render_engines(const owg_engine_job*, int64_t, float*, int64_t, const ow
 
 int owg_preamp_batch(const double*, int64_t, int64_t, int64_t, double, int, double, double, double*, int64_t, const owg_opts*) {
     return fail(OWG_E_UNSUPPORTED, "owg_preamp_batch: not implemented in this build");
+}
+
+int owg_host_voice_init(const owg_voice_job* job, double* o) {
+    if (!job || !o) return fail(OWG_E_BAD_ARG, "owg_host_voice_init: null");
+    OwgVoiceInit v;
+    owg::make_voice_init(*job, &v);
+    int k = 0;
+    for (int m = 0; m < 7; m++) { o[k++] = v.cos_inc[m]; o[k++] = v.sin_inc[m]; o[k++] = v.phase_inc[m]; o[k++] = v.amplitude[m]; o[k++] = v.decay_mult[m]; o[k++] = v.jitter_drift[m]; }
+    o[k++] = v.jitter_revert; o[k++] = v.jitter_diffusion; o[k++] = v.onset_ramp_inc; o[k++] = v.onset_shape_exp;
+    o[k++] = v.pickup_beta; o[k++] = v.pickup_ds; o[k++] = v.post_pickup_gain; o[k++] = v.noise_amp; o[k++] = v.noise_decay;
+    o[k++] = v.bq_b0; o[k++] = v.bq_b1; o[k++] = v.bq_b2; o[k++] = v.bq_a1; o[k++] = v.bq_a2;
+    o[k++] = (double)v.onset_ramp_samples; o[k++] = (double)v.n_samples; o[k++] = (double)v.jitter_state; o[k++] = (double)v.noise_rng;
+    o[k++] = (double)v.noise_remaining;
+    return OWG_OK;
+}
+
+int owg_host_chain_init(const owg_bench_job* job, double* o) {
+    if (!job || !o) return fail(OWG_E_BAD_ARG, "owg_host_chain_init: null");
+    OwgChainInit c;
+    owg::make_chain_init(*job, 0, &c);
+    const double v[18] = {c.volume, c.spk_a2, c.spk_a3, c.spk_norm, c.spk_thermal_coeff, c.spk_thermal_alpha, c.hpf_b0, c.hpf_b1, c.hpf_b2,
+                          c.hpf_a1, c.hpf_a2, c.lpf_b0, c.lpf_b1, c.lpf_b2, c.lpf_a1, c.lpf_a2, (double)c.spk_tanh, (double)c.oversample};
+    for (int i = 0; i < 18; i++) o[i] = v[i];
+    return OWG_OK;
 }
 
 int owg_last_diag(owg_diag* out) {

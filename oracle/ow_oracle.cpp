@@ -236,6 +236,28 @@ void owo_oversampler_roundtrip(const double* in, int64_t n, double* out) {
     Oversampler os;
     for (int64_t i = 0; i < n; i++) { double a, b; os.up1(in[i], a, b); out[i] = os.down1(a, b); }
 }
+// Flattened Voice::note_on state, same layout as owg_host_voice_init (include/owgpu.h).
+void owo_voice_init(const owg_voice_job* j, double* o) {
+    Voice v;
+    v.note_on(j->midi, j->velocity, j->sample_rate, j->noise_seed, j->mlp_enabled != 0);
+    if (j->ds_override == j->ds_override) v.pickup.displacement_scale = j->ds_override;
+    if (!j->attack_noise) v.noise.disable();
+    int k = 0;
+    for (int m = 0; m < 7; m++) { const Mode& q = v.reed.modes[m]; o[k++] = q.cos_inc; o[k++] = q.sin_inc; o[k++] = q.phase_inc; o[k++] = q.amplitude; o[k++] = q.decay_mult; o[k++] = q.jitter_drift; }
+    o[k++] = v.reed.jitter_revert; o[k++] = v.reed.jitter_diffusion; o[k++] = v.reed.onset_ramp_inc; o[k++] = v.reed.onset_shape_exp;
+    o[k++] = v.pickup.beta; o[k++] = v.pickup.displacement_scale; o[k++] = v.post_pickup_gain; o[k++] = v.noise.amplitude; o[k++] = v.noise.decay_per_sample;
+    o[k++] = v.noise.bpf.b0; o[k++] = v.noise.bpf.b1; o[k++] = v.noise.bpf.b2; o[k++] = v.noise.bpf.a1; o[k++] = v.noise.bpf.a2;
+    o[k++] = (double)v.reed.onset_ramp_samples; o[k++] = (double)f64_as_u64(j->duration_s * j->sample_rate); o[k++] = (double)v.reed.jitter_state;
+    o[k++] = (double)v.noise.rng_state; o[k++] = (double)v.noise.remaining;
+}
+void owo_chain_init(const owg_bench_job* j, double* o) {
+    Speaker s(j->v.sample_rate);
+    s.set_character(j->speaker_character);
+    const double v[18] = {j->volume, s.a2, s.a3, 1.0 + s.a2 + s.a3, s.thermal_coeff, s.thermal_alpha, s.hpf.b0, s.hpf.b1, s.hpf.b2, s.hpf.a1, s.hpf.a2,
+                          s.lpf.b0, s.lpf.b1, s.lpf.b2, s.lpf.a1, s.lpf.a2, s.character < 0.001 ? 0.0 : 1.0, j->v.sample_rate < 88200.0 ? 1.0 : 0.0};
+    for (int i = 0; i < 18; i++) o[i] = v[i];
+}
+
 // Engine state-machine probe: apply events with block rendering, return counts [active, held, sustained, releasing].
 void owo_engine_counts(const owg_engine_job* job, int32_t* out4) {
     (void)job; (void)out4;

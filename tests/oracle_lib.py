@@ -106,6 +106,8 @@ def lib():
         L.owo_tremolo_osc.argtypes = [C.c_double, C.c_int64, C.c_int64, dp, dp]
         L.owo_speaker_run.argtypes = [C.c_double, C.c_double, dp, C.c_int64, dp]
         L.owo_oversampler_roundtrip.argtypes = [dp, C.c_int64, dp]
+        L.owo_voice_init.argtypes = [C.POINTER(VoiceJob), dp]
+        L.owo_chain_init.argtypes = [C.POINTER(BenchJob), dp]
         _lib = L
     return _lib
 

@@ -1,0 +1,170 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/owgpu.h declares, argument
+validation and the no-CPU-fallback rule, the product's host-side note-on setup against the oracle
+(bit-exact), and the multi-GPU sharding logic (world_size-2 gloo)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import openwurli_b200 as ow
+from openwurli_b200 import _abi, shard
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAS_GPU = ow.device_count() > 0
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "owgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(owg_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 17
+    L = ow.lib()
+    for name in declared:
+        assert hasattr(L, name), f"libowgpu.so does not export {name}"
+    assert set(declared) == set(_abi.EXPORTS)
+    assert L.owg_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof of every ABI struct as the C compiler sees include/owgpu.h == the ctypes mirrors."""
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "owgpu.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(owg_voice_job), '
+                   'sizeof(owg_bench_job), sizeof(owg_event), sizeof(owg_engine_job), sizeof(owg_opts), sizeof(owg_diag));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(t) for t in (_abi.VoiceJob, _abi.BenchJob, _abi.Event, _abi.EngineJob, _abi.Opts, _abi.Diag)]
+    assert sizes[:2] == [40, 80]
+    assert [C.sizeof(t) for t in (O.VoiceJob, O.BenchJob, O.Diag)] == [sizes[0], sizes[1], sizes[5]]
+
+
+def test_bad_arguments_are_rejected():
+    L = ow.lib()
+    h = C.c_void_p()
+    assert L.owg_plan_bench(None, 3, None, C.byref(h)) == _abi.OWG_E_BAD_ARG
+    bad = ow.bench_job(sample_rate=0.0)
+    arr = (_abi.BenchJob * 1)(bad)
+    assert L.owg_plan_bench(arr, 1, None, C.byref(h)) == _abi.OWG_E_BAD_ARG
+    bad = ow.voice_job(duration=-1.0)
+    arr = (_abi.VoiceJob * 1)(bad)
+    assert L.owg_plan_voices(arr, 1, None, C.byref(h)) == _abi.OWG_E_BAD_ARG
+    assert b"invalid" in L.owg_last_error()
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the behaviour on a machine without a CUDA device")
+def test_no_cpu_fallback_without_device():
+    with pytest.raises(ow.OwgError) as e:
+        ow.Voice.render_note(60, 0.8, 0.1, 44100.0)
+    assert e.value.code == _abi.OWG_E_NO_DEVICE
+    with pytest.raises(ow.OwgError) as e:
+        ow.render_bench([ow.bench_job(duration=0.01)])
+    assert e.value.code == _abi.OWG_E_NO_DEVICE
+
+
+def test_unimplemented_entry_points_fail_loudly():
+    L = ow.lib()
+    assert L.owg_render_engines(None, 0, None, 0, None) in (_abi.OWG_E_UNSUPPORTED, _abi.OWG_E_NO_DEVICE, _abi.OWG_E_BAD_ARG, 0)
+
+
+def _host_init(job):
+    out = np.zeros(61)
+    assert ow.lib().owg_host_voice_init(C.byref(job), O.dptr(out)) == 0
+    return out
+
+
+def _oracle_init(job):
+    oj = O.VoiceJob(job.midi, job.mlp_enabled, job.attack_noise, 0, job.noise_seed, job.velocity, job.sample_rate,
+                    job.duration_s, job.ds_override)
+    out = np.zeros(61)
+    O.lib().owo_voice_init(C.byref(oj), O.dptr(out))
+    return out
+
+
+def test_host_note_on_setup_is_bit_identical_to_oracle():
+    """Every (key, velocity) of the 64 x 127 grid, MLP on and off: the product's host-side parameterisation
+    (openwurli_b200/csrc/host_setup.cpp) must equal the oracle's Voice::note_on restatement bit for bit."""
+    bad = 0
+    for midi in range(33, 97):
+        for vel in range(1, 128, 3):
+            for mlp in (False, True):
+                j = ow.voice_job(midi, vel, 44100.0, 0.25, mlp=mlp)
+                a, b = _host_init(j), _oracle_init(j)
+                if not np.array_equal(a, b):
+                    bad += 1
+                    if bad < 5:
+                        print(midi, vel, mlp, np.nonzero(a != b)[0], (a - b)[a != b])
+    assert bad == 0
+
+
+@pytest.mark.parametrize("sr", [44100.0, 48000.0, 96000.0, 22050.0])
+def test_host_setup_other_rates_and_overrides(sr):
+    for midi, vel, seed, ds, noise in [(33, 1, 0, None, True), (96, 127, 1, 0.3, True), (60, 64, 0xFFFFFFFF, None, False),
+                                       (20, 100, 7, None, True), (110, 50, 9, 0.5, True)]:
+        j = ow.voice_job(midi, vel, sr, 0.1, mlp=True, attack_noise=noise, seed=seed, displacement_scale=ds)
+        assert np.array_equal(_host_init(j), _oracle_init(j)), (midi, vel, seed)
+    j = ow.voice_job(60, 0, sr, 0.1, velocity_norm=0.0)
+    assert np.array_equal(_host_init(j), _oracle_init(j))
+
+
+def test_host_chain_setup_matches_oracle():
+    for sr in (44100.0, 48000.0, 96000.0):
+        for ch in (0.0, 0.0005, 0.001, 0.3, 0.5, 0.9985, 0.999, 1.0, 1.7, -0.2):
+            j = ow.bench_job(speaker=ch, volume=0.37, sample_rate=sr)
+            a, b = np.zeros(18), np.zeros(18)
+            assert ow.lib().owg_host_chain_init(C.byref(j), O.dptr(a)) == 0
+            oj = O.bench_job(sr=sr, speaker=ch, volume=0.37)
+            O.lib().owo_chain_init(C.byref(oj), O.dptr(b))
+            assert np.array_equal(a, b), (sr, ch, a - b)
+
+
+def test_job_defaults_mirror_the_cli():
+    j = ow.bench_job()  # preamp-bench render defaults, main.rs:372-392
+    assert (j.v.midi, j.v.duration_s, j.r_ldr, j.volume, j.speaker_character, j.tremolo_depth, j.v.sample_rate) == \
+        (60, 2.0, 1e6, 0.60, 1.0, 0.0, 44100.0)
+    assert j.v.velocity == 100 / 127.0 and j.v.mlp_enabled == 1 and j.v.attack_noise == 1
+    assert j.v.noise_seed == (60 * 2654435761) % 2 ** 32  # main.rs:405
+    v = ow.voice_job()  # Voice::render_note: MLP off (voice.rs:209)
+    assert v.mlp_enabled == 0
+
+
+def test_shard_partition_properties():
+    jobs = [ow.bench_job(note=33 + k % 64, velocity=1 + k % 127, duration=0.1 + (k % 7) * 0.05,
+                         tremolo_depth=(k % 3) * 0.25) for k in range(500)]
+    for ws in (1, 2, 3, 8):
+        parts = [shard.shard_indices(jobs, ws, r) for r in range(ws)]
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(500))
+        costs = [sum(shard.job_cost(jobs[i]) for i in p) for p in parts]
+        assert max(costs) - min(costs) <= 2 * max(shard.job_cost(j) for j in jobs) + 1
+    assert shard.shard_indices([], 4, 1) == []
+
+
+def test_shard_gloo_world2(tmp_path):
+    """world_size-2 gloo run of the same partition + host-side gather bench.py uses."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import openwurli_b200 as ow\nfrom openwurli_b200 import shard\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "jobs = [ow.bench_job(note=33 + k % 64, velocity=1 + k % 127, duration=0.25) for k in range(101)]\n"
+        "mine = shard.shard_indices(jobs, w, r)\n"
+        "cnt = torch.tensor([len(mine), sum(mine)], dtype=torch.int64)\n"
+        "dist.all_reduce(cnt)\n"
+        "t = torch.tensor([1.0 + r]); dist.all_reduce(t, op=dist.ReduceOp.MAX)\n"
+        "assert cnt[0].item() == 101 and cnt[1].item() == sum(range(101)), cnt\n"
+        "assert t.item() == float(w)\n"
+        "dist.barrier(); dist.destroy_process_group()\n"
+        "print('ok', r)\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
