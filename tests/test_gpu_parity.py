@@ -112,7 +112,8 @@ def _bench_parity(jobs, what, compare_hist=True):
     dc = O.last_diag()
     for i, j in enumerate(jobs):
         n = O.n_samples(j.v.duration_s, j.v.sample_rate)
-        assert_parity(got[i, :n], ref[i, :n], f"{what}[{i}] midi={j.v.midi}")
+        if n:
+            assert_parity(got[i, :n], ref[i, :n], f"{what}[{i}] midi={j.v.midi}")
     if compare_hist:
         # the preamp's Newton iteration counts are decision-for-decision identical
         assert list(dg.nr_iter_hist) == list(dc.nr_iter_hist), what
