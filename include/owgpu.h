@@ -184,6 +184,10 @@ int owg_host_chain_init(const owg_bench_job* job, double* out18);
  * (one DFMA = one instruction = 2 flop). */
 int owg_fp64_peak(int32_t device, int32_t fma, float ms_target, double* tera_instr_per_s);
 
+/* Device self-test: the library's shared-reciprocal division (recip_prepare/div_by, owg_device.cuh) against the
+ * compiler's IEEE-754 f64 division on 303104*n_per_thread pseudo-random operand pairs; *mismatches must be 0. */
+int owg_selftest_division(int64_t n_per_thread, uint64_t seed, uint64_t* mismatches, uint64_t* tested);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,13 @@ def fp64_peak(device=-1, fma=True, ms_target=50.0):
     return r.value
 
 
+def fp64_probe(mode, device=-1):
+    """Raw owg_fp64_peak modes: 10..13 = ns per dependent DADD/DMUL/DFMA/DDIV; 100+k = warp-instr/s (1e12) with k active lanes."""
+    r = C.c_double(0.0)
+    check(lib().owg_fp64_peak(device, int(mode), 20.0, C.byref(r)))
+    return r.value
+
+
 def _is_torch_cuda(x):
     return hasattr(x, "is_cuda") and x.is_cuda
 

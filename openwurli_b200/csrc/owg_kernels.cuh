@@ -20,6 +20,7 @@ __constant__ double c_noise_fade[16];  // hammer.rs:161-168, filled by the host 
 __global__ void settle_kernel(DkState* out) {
     __shared__ double rec[OWG_MAT_STRIDE];
     __shared__ double an[OWG_AN_SPARSE];
+    __shared__ double cold[OWG_COLD_SCRATCH];
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     dk_default_record(rec, an);
     DkState st;
@@ -28,7 +29,7 @@ __global__ void settle_kernel(DkState* out) {
     st.xin_prev = 0.0;
     st.be_cooldown = 0;
     const DkDev dv = dk_dev();
-    for (int n = 0; n < 176400; n++) dk_step<false>(0.0, st, rec, an, rec[OWG_MAT_AN66], dv, nullptr);
+    for (int n = 0; n < 176400; n++) dk_step<false>(0.0, st, rec, an, rec[OWG_MAT_AN66], dv, nullptr, cold, 1);
     *out = st;
 }
 
@@ -48,23 +49,19 @@ __global__ void static_matrix_kernel(const OwgPreampGroup* groups, int n_groups,
 // pot_0_resistance in effect at each preamp-rate sample.
 __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* trem_group_ids, int n_trem, double* pot_seq, int64_t pot_stride,
                                      DevDiag* diag) {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= n_trem) return;
+    const int gi = blockIdx.x;
+    if (gi >= n_trem || threadIdx.x != 0) return;
     const OwgPreampGroup gr = groups[trem_group_ids[gi]];
     const double sr = gr.preamp_sr;
-    TrmMats m;
+    __shared__ TrmMats m;  // one thread per block: the rate-dependent matrices live in shared memory
+    __shared__ TrmK kq;
+    __shared__ double trm_sc[OWG_TRM_SCRATCH];
+    kq = trm_consts();
     trm_defaults(m);
     TrmState st;
     for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
     for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
     st.xin_prev = 0.0;
-    for (int n = 0; n < 50; n++) trm_step(st, m, nullptr);  // CircuitState::default() -> warmup(), gen_tremolo.rs:2021
-    if (fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);
-    {
-        const double tot = sr * 2.0;
-        const unsigned long long n_settle = !(tot == tot) || tot <= 0.0 ? 0ull : (unsigned long long)tot;
-        for (unsigned long long n = 0; n < n_settle; n++) trm_step(st, m, nullptr);
-    }
     TrmDiag td;
     for (int i = 0; i < 16; i++) td.hist[i] = 0;
     td.be_fallback = 0; td.nan_reset = 0;
@@ -73,29 +70,38 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
     const double ldr_release = exp(-1.0 / (0.035 * sr));
     const double ln_r_max = log(1000000.0);
     const double ln_min_minus_max = log(9000.0) - log(1000000.0);
+    const double r_upper = 50000.0 * (1.0 - depth);
+    const double r_lower = 50000.0 * depth;
+    const double top = r_upper > 0.0 ? r_upper * 18000.0 / (r_upper + 18000.0) : 0.0;
     double env = 0.0;
     double pot = 9.99999999999999854e4;  // pot_0_resistance of the settled state
     double* o = pot_seq + (size_t)gi * pot_stride;
-    for (int64_t t = 0; t < gr.n_os; t++) {
-        const double v_out = trm_step(st, m, diag ? &td : nullptr);
-        const double led = rclamp((10.95 - v_out) / (10.95 - 0.70), 0.0, 1.0);
-        const double coeff = led > env ? ldr_attack : ldr_release;
-        env = led + coeff * (env - led);
-        const double drive = rclamp(env, 0.0, 1.0);
-        double r_ldr;
-        if (drive < 1e-6) r_ldr = 1000000.0;
-        else r_ldr = exp(ln_r_max + ln_min_minus_max * pow(drive, 0.9));
-        const double r_upper = 50000.0 * (1.0 - depth);
-        const double r_lower = 50000.0 * depth;
-        const double top = r_upper > 0.0 ? r_upper * 18000.0 / (r_upper + 18000.0) : 0.0;
-        const double branch = 680.0 + r_ldr;
-        const double low = r_lower > 0.0 ? r_lower * branch / (r_lower + branch) : 0.0;
-        const double z = top + low;
-        if (finite64(z)) {
-            const double r = rclamp(z, 1.0e3, 1.0e6);
-            if (!(fabs(r - pot) < 1e-12)) pot = r;
+    const double tot = sr * 2.0;
+    const long long n_settle = !(tot == tot) || tot <= 0.0 ? 0ll : (long long)tot;
+    // One loop, three phases (a single inlined copy of the solver): 50 warm-up samples at the baked 48 kHz matrices
+    // (CircuitState::default() -> warmup(), gen_tremolo.rs:2021), set_sample_rate, 2*sr settle samples, then process().
+    const long long n_pre = 50 + n_settle;
+    for (long long n = 0; n < n_pre + gr.n_os; n++) {
+        if (n == 50 && fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);
+        const bool live = n >= n_pre;
+        const double v_out = trm_step(st, m, kq, (diag && live) ? &td : nullptr, trm_sc);
+        if (live) {
+            const double led = rclamp((10.95 - v_out) / (10.95 - 0.70), 0.0, 1.0);
+            const double coeff = led > env ? ldr_attack : ldr_release;
+            env = led + coeff * (env - led);
+            const double drive = rclamp(env, 0.0, 1.0);
+            double r_ldr;
+            if (drive < 1e-6) r_ldr = 1000000.0;
+            else r_ldr = exp(ln_r_max + ln_min_minus_max * pow(drive, 0.9));
+            const double branch = 680.0 + r_ldr;
+            const double low = r_lower > 0.0 ? r_lower * branch / (r_lower + branch) : 0.0;
+            const double z = top + low;
+            if (finite64(z)) {
+                const double r = rclamp(z, 1.0e3, 1.0e6);
+                if (!(fabs(r - pot) < 1e-12)) pot = r;
+            }
+            o[n - n_pre] = pot;
         }
-        o[t] = pot;
     }
     if (diag) {
         for (int i = 0; i < 16; i++) atomicAdd(&diag->trm_hist[i], (unsigned long long)td.hist[i]);
@@ -245,6 +251,7 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
     __shared__ double s_rec[OWG_MAT_STRIDE];
     __shared__ double s_an[OWG_AN_SPARSE];
     __shared__ OwgChainInit s_ci[32];
+    __shared__ double s_cold[OWG_COLD_SCRATCH * 32];
     const int lane = threadIdx.x;
     const WarpEntry we = warps[blockIdx.x];
     const bool is_shadow = lane == 31;
@@ -283,40 +290,39 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
     const bool bypass_preamp = ci.no_preamp != 0;
 
     int64_t tos = 0;  // preamp-rate sample index
+    const int n_sub = oversample ? 2 : 1;
+    double x_next = (is_main && 0ull < ns) ? o[0] : 0.0;  // software prefetch of the voice sample (hides the L2 latency)
     for (int64_t t = 0; t < we.n_max; t++) {
         const bool live = is_main && (unsigned long long)t < ns;
-        const double x = live ? o[t] : 0.0;
-        double pre_out;
+        const double x = x_next;
+        x_next = (is_main && (unsigned long long)(t + 1) < ns) ? o[t + 1] : 0.0;
+        double u0 = x, u1 = 0.0;
         if (oversample) {
-            double u0 = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, ua, x);
-            double u1 = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, ub, x);
-            if (is_shadow) { u0 = 0.0; u1 = 0.0; }
-            double pj[2];
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const double* m = TREM ? grec + (size_t)(tos + j) * OWG_MAT_STRIDE : s_rec;
-                const double an66 = m[OWG_MAT_AN66];
-                const double main_out = dk_step<DIAG>(j == 0 ? u0 : u1, st, m, s_an, an66, dv, &dd);
-                const double pump = __shfl_sync(0xffffffffu, main_out, 31);
-                const double res = main_out - pump;
-                if (!finite64(res)) { adapter_nan++; st = *settled; pj[j] = 0.0; }
-                else pj[j] = res;
-            }
-            tos += 2;
-            const double a = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, da, pj[0]);
-            const double b = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, db, pj[1]);
-            pre_out = (a + down_delay) * 0.5;
-            down_delay = b;
-        } else {
+            u0 = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, ua, x);
+            u1 = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, ub, x);
+        }
+        if (is_shadow) { u0 = 0.0; u1 = 0.0; }
+        double p0 = 0.0, p1 = 0.0;
+        // One copy of the DK step in the instruction stream (the body is ~2k instructions; two unrolled copies overflow
+        // the instruction cache with a single resident warp per scheduler).
+#pragma unroll 1
+        for (int j = 0; j < n_sub; j++) {
             const double* m = TREM ? grec + (size_t)tos * OWG_MAT_STRIDE : s_rec;
             const double an66 = m[OWG_MAT_AN66];
-            const double main_out = dk_step<DIAG>(is_shadow ? 0.0 : x, st, m, s_an, an66, dv, &dd);
+            const double main_out = dk_step<DIAG>(j == 0 ? u0 : u1, st, m, s_an, an66, dv, &dd, s_cold + lane, 32);
             const double pump = __shfl_sync(0xffffffffu, main_out, 31);
-            const double res = main_out - pump;
-            if (!finite64(res)) { adapter_nan++; st = *settled; pre_out = 0.0; }
-            else pre_out = res;
+            double res = main_out - pump;
+            if (!finite64(res)) { adapter_nan++; st = *settled; res = 0.0; }
+            if (j == 0) p0 = res; else p1 = res;
             tos += 1;
         }
+        double pre_out;
+        if (oversample) {
+            const double a = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, da, p0);
+            const double b = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, db, p1);
+            pre_out = (a + down_delay) * 0.5;
+            down_delay = b;
+        } else pre_out = p0;
         if (bypass_preamp) pre_out = x;
         if (live) {
             const double att = pre_out * vol * vol;
@@ -354,6 +360,51 @@ __global__ void fp64_peak_kernel(double* sink, int iters, double a, double b) {
             x0 = __dmul_rn(x0, a); x1 = __dadd_rn(x1, b); x2 = __dmul_rn(x2, a); x3 = __dadd_rn(x3, b);
             x4 = __dmul_rn(x4, a); x5 = __dadd_rn(x5, b); x6 = __dmul_rn(x6, a); x7 = __dadd_rn(x7, b);
         }
+    }
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// Self-test: recip_prepare()/div_by() against the compiler's IEEE division on pseudo-random operands (full exponent
+// range incl. denormals, zeros, infinities and NaNs every few thousand draws).
+__global__ void division_selftest_kernel(unsigned long long seed, int n, unsigned long long* mismatches) {
+    unsigned long long s = seed + ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1ull) * 0x9E3779B97F4A7C15ull;
+    unsigned long long bad = 0;
+    for (int i = 0; i < n; i++) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        unsigned long long ba = s;
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        unsigned long long bb = s;
+        const int mode = (int)((s >> 40) & 7);
+        if (mode < 6) {  // moderate exponents (the solver's regime): keep exponent within +-64 of the bias
+            ba = (ba & 0x800FFFFFFFFFFFFFull) | ((unsigned long long)(1023 - 64 + (int)((ba >> 52) & 127)) << 52);
+            bb = (bb & 0x800FFFFFFFFFFFFFull) | ((unsigned long long)(1023 - 64 + (int)((bb >> 52) & 127)) << 52);
+        }  // else: raw bit patterns (any exponent, denormals, inf, NaN)
+        if ((i & 4095) == 7) ba = 0ull;
+        if ((i & 4095) == 9) bb = 0x7FF0000000000000ull;
+        const double a = __longlong_as_double((long long)ba), b = __longlong_as_double((long long)bb);
+        const double q1 = div_by(a, recip_prepare(b));
+        const double q2 = a / b;
+        const bool same = (__double_as_longlong(q1) == __double_as_longlong(q2)) || (q1 != q1 && q2 != q2);
+        if (!same) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+// Dependent-chain latency probe (one warp): x = (x + b) * a repeated; and a partial-warp throughput probe.
+__global__ void fp64_latency_kernel(double* sink, int iters, double a, double b, int mode) {
+    double x = threadIdx.x * 1e-3;
+    if (mode == 0) { for (int i = 0; i < iters; i++) { x = __dadd_rn(x, b); x = __dadd_rn(x, b); x = __dadd_rn(x, b); x = __dadd_rn(x, b); } }
+    else if (mode == 1) { for (int i = 0; i < iters; i++) { x = __dmul_rn(x, a); x = __dmul_rn(x, a); x = __dmul_rn(x, a); x = __dmul_rn(x, a); } }
+    else if (mode == 2) { for (int i = 0; i < iters; i++) { x = fma(x, a, b); x = fma(x, a, b); x = fma(x, a, b); x = fma(x, a, b); } }
+    else { for (int i = 0; i < iters; i++) { x = x / a; x = x / a; x = x / a; x = x / a; } }
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+__global__ void fp64_partial_warp_kernel(double* sink, int iters, double a, double b, int active_lanes) {
+    if ((threadIdx.x & 31) >= active_lanes) return;
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+    for (int i = 0; i < iters; i++) {
+        x0 = __dmul_rn(x0, a); x1 = __dadd_rn(x1, b); x2 = __dmul_rn(x2, a); x3 = __dadd_rn(x3, b);
+        x4 = __dmul_rn(x4, a); x5 = __dadd_rn(x5, b); x6 = __dmul_rn(x6, a); x7 = __dadd_rn(x7, b);
     }
     sink[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }

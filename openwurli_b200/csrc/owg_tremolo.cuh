@@ -17,6 +17,8 @@ struct TrmState {
     double v[TN], il[TM], ilpp[TM], xin_prev;
 };
 struct TrmDiag { uint32_t hist[16]; uint32_t be_fallback, nan_reset; };
+struct BjtK;
+
 
 // gen_tremolo.rs:2273-2342; returns false if singular (out untouched)
 __device__ inline bool trm_invert(const double a[TN][TN], double out[TN][TN]) {
@@ -92,7 +94,7 @@ __device__ inline void trm_defaults(TrmMats& m) {  // gen_tremolo.rs:1998-2011
     for (int i = 0; i < TN; i++) for (int j = 0; j < TM; j++) { m.s_ni[i][j] = TRM_S_NI_DEFAULT[i][j]; m.s_ni_be[i][j] = TRM_S_NI_BE_DEFAULT[i][j]; }
 }
 
-__device__ inline void trm_rebuild(TrmMats& m, double rate) {  // gen_tremolo.rs:2139-2222
+__device__ __noinline__ void trm_rebuild(TrmMats& m, double rate) {  // gen_tremolo.rs:2139-2222
     const double alpha = 2.0 * rate, alpha_be = rate;
     double a[TN][TN], a_be[TN][TN];
     for (int i = 0; i < TN; i++)
@@ -108,51 +110,90 @@ __device__ inline void trm_rebuild(TrmMats& m, double rate) {  // gen_tremolo.rs
 }
 
 struct Bjt { double ic, ib, j0, j1, j2, j3; };
+// Loop-invariant sub-expressions of bjt_evaluate (same operations on the same constants the reference
+// re-evaluates on every call, gen_tremolo.rs:1566-1636), computed once.
+struct BjtK { double is, nf_vt, nr_vt, is_bf, is_br, is_nfvt, is_nrvt, is_br_nrvt, is_bf_nfvt; Recip r_nf, r_nr; };
+__device__ __forceinline__ BjtK bjt_consts(double is, double vt, double nf, double nr, double bf, double br) {
+    BjtK k;
+    k.is = is; k.nf_vt = nf * vt; k.nr_vt = nr * vt;
+    k.is_bf = is / bf; k.is_br = is / br;
+    k.is_nfvt = is / k.nf_vt; k.is_nrvt = is / k.nr_vt;
+    k.is_br_nrvt = is / (br * k.nr_vt); k.is_bf_nfvt = is / (bf * k.nf_vt);
+    k.r_nf = recip_prepare(k.nf_vt); k.r_nr = recip_prepare(k.nr_vt);
+    return k;
+}
 // bjt_evaluate Ebers-Moll branch (gen_tremolo.rs:1566-1636) for use_gp=false, ISE=ISC=0, sign=+1.
-__device__ __forceinline__ Bjt bjt_em(double vbe, double vbc, double is, double vt, double nf, double nr, double bf, double br) {
-    const double vbe_eff = 1.0 * vbe, vbc_eff = 1.0 * vbc;
-    const double nf_vt = nf * vt, nr_vt = nr * vt;
-    const double exp_be = fast_exp(vbe_eff / nf_vt);
-    const double exp_bc = fast_exp(vbc_eff / nr_vt);
-    const double i_cc = is * (exp_be - exp_bc);
-    const double ib_fwd = is / bf * (exp_be - 1.0);
-    const double ib_rev = is / br * (exp_bc - 1.0);
+__device__ __forceinline__ Bjt bjt_em(double vbe, double vbc, const BjtK& k) {
+    const double exp_be = fast_exp(div_by(vbe, k.r_nf));
+    const double exp_bc = fast_exp(div_by(vbc, k.r_nr));
+    const double i_cc = k.is * (exp_be - exp_bc);
+    const double ib_fwd = k.is_bf * (exp_be - 1.0);
+    const double ib_rev = k.is_br * (exp_bc - 1.0);
     Bjt o;
-    o.ic = 1.0 * (i_cc - is / br * (exp_bc - 1.0));
-    o.ib = 1.0 * (ib_fwd + ib_rev + 0.0 + 0.0);
-    o.j0 = is / nf_vt * exp_be;
-    o.j1 = -(is / nr_vt) * exp_bc - (is / (br * nr_vt)) * exp_bc;
-    o.j2 = (is / (bf * nf_vt)) * exp_be + 0.0;
-    o.j3 = (is / (br * nr_vt)) * exp_bc + 0.0;
+    o.ic = i_cc - k.is_br * (exp_bc - 1.0);
+    o.ib = ib_fwd + ib_rev;
+    o.j0 = k.is_nfvt * exp_be;
+    o.j1 = -k.is_nrvt * exp_bc - k.is_br_nrvt * exp_bc;
+    o.j2 = k.is_bf_nfvt * exp_be;
+    o.j3 = k.is_br_nrvt * exp_bc;
     return o;
 }
 
+struct TrmK { BjtK q0, q1; double input_conductance; };
+__device__ __forceinline__ TrmK trm_consts() {
+    TrmK k;
+    k.q0 = bjt_consts(TRM_DEVICE_0_IS, TRM_DEVICE_0_VT, TRM_DEVICE_0_NF, TRM_DEVICE_0_NR, TRM_DEVICE_0_BETA_F, TRM_DEVICE_0_BETA_R);
+    k.q1 = bjt_consts(TRM_DEVICE_1_IS, TRM_DEVICE_1_VT, TRM_DEVICE_1_NF, TRM_DEVICE_1_NR, TRM_DEVICE_1_BETA_F, TRM_DEVICE_1_BETA_R);
+    k.input_conductance = 1.0 / TRM_INPUT_RESISTANCE;
+    return k;
+}
 __device__ __forceinline__ double trm_pnjlim(double vnew, double vold, double vt, double vcrit) { return pnjlim(vnew, vold, vt, vcrit); }
 
-__device__ inline void trm_solve4(double a[4][4], double b[4], bool& singular) {  // gen_tremolo.rs:2515-2561
+// gen_tremolo.rs:2515-2561; fully unrolled so that every index is a compile-time constant (registers, no local memory)
+__device__ __forceinline__ void trm_solve4(double a[4][4], double b[4], bool& singular) {
     singular = false;
+    Recip rp[4];
+#pragma unroll
+    for (int col = 0; col < 4; col++) { rp[col].r = 0.0; rp[col].nb = 0.0; rp[col].b = 1.0; }
+#pragma unroll
     for (int col = 0; col < 4; col++) {
-        int max_row = col;
-        double max_val = fabs(a[col][col]);
-        for (int row = col + 1; row < 4; row++) if (fabs(a[row][col]) > max_val) { max_val = fabs(a[row][col]); max_row = row; }
-        if (max_val < 1e-15) { singular = true; break; }
-        if (max_row != col) {
-            for (int j = 0; j < 4; j++) { const double t = a[col][j]; a[col][j] = a[max_row][j]; a[max_row][j] = t; }
-            const double t = b[col]; b[col] = b[max_row]; b[max_row] = t;
-        }
-        const double pivot = a[col][col];
-        for (int row = col + 1; row < 4; row++) {
-            const double factor = a[row][col] / pivot;
-            for (int j = col + 1; j < 4; j++) a[row][j] -= factor * a[col][j];
-            b[row] -= factor * b[col];
+        if (!singular) {
+            int max_row = col;
+            double max_val = fabs(a[col][col]);
+#pragma unroll
+            for (int row = col + 1; row < 4; row++) if (fabs(a[row][col]) > max_val) { max_val = fabs(a[row][col]); max_row = row; }
+            if (max_val < 1e-15) singular = true;
+            else {
+#pragma unroll
+                for (int row = col + 1; row < 4; row++) {
+                    if (max_row == row) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { const double t = a[col][j]; a[col][j] = a[row][j]; a[row][j] = t; }
+                        const double t = b[col]; b[col] = b[row]; b[row] = t;
+                    }
+                }
+                rp[col] = recip_prepare(a[col][col]);  // one reciprocal per pivot, shared by the column's factors and by
+                                                       // the back-substitution (bit-identical to dividing each time)
+#pragma unroll
+                for (int row = col + 1; row < 4; row++) {
+                    const double factor = div_by(a[row][col], rp[col]);
+#pragma unroll
+                    for (int j = col + 1; j < 4; j++) a[row][j] -= factor * a[col][j];
+                    b[row] -= factor * b[col];
+                }
+            }
         }
     }
     if (!singular) {
+#pragma unroll
         for (int i = 3; i >= 0; i--) {
-            double sum = b[i];
-            for (int j = i + 1; j < 4; j++) sum -= a[i][j] * b[j];
-            if (fabs(a[i][i]) < 1e-15) { singular = true; break; }
-            b[i] = sum / a[i][i];
+            if (!singular) {
+                double sum = b[i];
+#pragma unroll
+                for (int j = i + 1; j < 4; j++) sum -= a[i][j] * b[j];
+                if (fabs(a[i][i]) < 1e-15) singular = true;
+                else b[i] = div_by(sum, rp[i]);
+            }
         }
     }
 }
@@ -177,8 +218,15 @@ __device__ __forceinline__ void trm_jac(const Bjt& q0, const Bjt& q1, const doub
 }
 
 // BE fallback of the oscillator (gen_tremolo.rs:2757-3083); v receives the BE voltages.
-__device__ __noinline__ uint32_t trm_be(double input, const TrmState& st, const TrmMats& m, double v[TN], double il[TM]) {
-    const double input_conductance = 1.0 / TRM_INPUT_RESISTANCE;
+// Cold path: state and results travel through a scratch buffer (shared memory) so the hot path's register arrays are
+// never address-taken.  sc: [0..6] v_prev, [7..10] il, [11..14] ilpp  ->  [15..21] v, [22..25] il.
+#define OWG_TRM_SCRATCH 26
+__device__ __noinline__ uint32_t trm_be(double input, double* sc, const TrmMats& m, const TrmK& kq) {
+    TrmState st;
+    for (int i = 0; i < TN; i++) st.v[i] = sc[i];
+    for (int i = 0; i < TM; i++) { st.il[i] = sc[7 + i]; st.ilpp[i] = sc[11 + i]; }
+    double v[TN], il[TM];
+    const double input_conductance = kq.input_conductance;
     const double vt0 = TRM_DEVICE_0_VT, vt1 = TRM_DEVICE_1_VT;
     double rhs_be[TN], v_pred_be[TN], p_be[TM];
     for (int i = 0; i < TN; i++) {
@@ -206,8 +254,8 @@ __device__ __noinline__ uint32_t trm_be(double input, const TrmState& st, const 
         const double v_d1 = p_be[1] + kb[1][0] * il[0] + kb[1][1] * il[1] + kb[1][2] * il[2] + kb[1][3] * il[3];
         const double v_d2 = p_be[2] + kb[2][0] * il[0] + kb[2][1] * il[1] + kb[2][2] * il[2] + kb[2][3] * il[3];
         const double v_d3 = p_be[3] + kb[3][0] * il[0] + kb[3][1] * il[1] + kb[3][2] * il[2] + kb[3][3] * il[3];
-        const Bjt q0 = bjt_em(v_d0, v_d1, TRM_DEVICE_0_IS, vt0, TRM_DEVICE_0_NF, TRM_DEVICE_0_NR, TRM_DEVICE_0_BETA_F, TRM_DEVICE_0_BETA_R);
-        const Bjt q1 = bjt_em(v_d2, v_d3, TRM_DEVICE_1_IS, vt1, TRM_DEVICE_1_NF, TRM_DEVICE_1_NR, TRM_DEVICE_1_BETA_F, TRM_DEVICE_1_BETA_R);
+        const Bjt q0 = bjt_em(v_d0, v_d1, kq.q0);
+        const Bjt q1 = bjt_em(v_d2, v_d3, kq.q1);
         const double f0 = il[0] - q0.ic, f1 = il[1] - q0.ib, f2 = il[2] - q1.ic, f3 = il[3] - q1.ib;
         double a[4][4];
         trm_jac(q0, q1, kb, a);
@@ -261,11 +309,13 @@ __device__ __noinline__ uint32_t trm_be(double input, const TrmState& st, const 
         for (int j = 0; j < TM; j++) acc += m.s_ni_be[i][j] * il[j];
         v[i] = acc;
     }
+    for (int i = 0; i < TN; i++) sc[15 + i] = v[i];
+    for (int i = 0; i < TM; i++) sc[22 + i] = il[i];
     return result;
 }
 
 // process_sample with input 0 (the only way the reference drives it, tremolo.rs:184), gen_tremolo.rs:2353-3116.
-__device__ inline double trm_step(TrmState& st, const TrmMats& m, TrmDiag* dg) {
+__device__ __forceinline__ double trm_step(TrmState& st, const TrmMats& m, const TrmK& kq, TrmDiag* dg, double* sc) {
     const double input = 0.0;
     for (int i = 0; i < TN; i++) st.v[i] = st.v[i] + 1e-25 - 1e-25;
     for (int i = 0; i < TM; i++) st.il[i] = st.il[i] + 1e-25 - 1e-25;
@@ -296,13 +346,15 @@ __device__ inline double trm_step(TrmState& st, const TrmMats& m, TrmDiag* dg) {
     rhs[4] += TRM_N_I[4][0] * st.il[0];
     rhs[4] += TRM_N_I[4][1] * st.il[1];
     rhs[4] += TRM_N_I[4][3] * st.il[3];
-    const double input_conductance = 1.0 / TRM_INPUT_RESISTANCE;
+    const double input_conductance = kq.input_conductance;
     rhs[0] += (input + st.xin_prev) * input_conductance;
     st.xin_prev = input;
 
     double v_pred[TN];
+#pragma unroll
     for (int i = 0; i < TN; i++) {
         double sum = 0.0;
+#pragma unroll
         for (int j = 0; j < TN; j++) sum += m.s[i][j] * rhs[j];
         v_pred[i] = sum;
     }
@@ -321,8 +373,8 @@ __device__ inline double trm_step(TrmState& st, const TrmMats& m, TrmDiag* dg) {
         const double v_d1 = p[1] + k[1][0] * il[0] + k[1][1] * il[1] + k[1][2] * il[2];
         const double v_d2 = p[2] + k[2][0] * il[0] + k[2][1] * il[1] + k[2][3] * il[3];
         const double v_d3 = p[3] + k[3][0] * il[0] + k[3][1] * il[1] + k[3][2] * il[2] + k[3][3] * il[3];
-        const Bjt q0 = bjt_em(v_d0, v_d1, TRM_DEVICE_0_IS, vt0, TRM_DEVICE_0_NF, TRM_DEVICE_0_NR, TRM_DEVICE_0_BETA_F, TRM_DEVICE_0_BETA_R);
-        const Bjt q1 = bjt_em(v_d2, v_d3, TRM_DEVICE_1_IS, vt1, TRM_DEVICE_1_NF, TRM_DEVICE_1_NR, TRM_DEVICE_1_BETA_F, TRM_DEVICE_1_BETA_R);
+        const Bjt q0 = bjt_em(v_d0, v_d1, kq.q0);
+        const Bjt q1 = bjt_em(v_d2, v_d3, kq.q1);
         const double f0 = il[0] - q0.ic, f1 = il[1] - q0.ib, f2 = il[2] - q1.ic, f3 = il[3] - q1.ib;
         double a[4][4];
         trm_jac(q0, q1, k, a);
@@ -375,14 +427,24 @@ __device__ inline double trm_step(TrmState& st, const TrmMats& m, TrmDiag* dg) {
     }
     if (dg) dg->hist[last < 15u ? last : 15u]++;
     double v[TN];
+#pragma unroll
     for (int i = 0; i < TN; i++) {
         double acc = v_pred[i];
+#pragma unroll
         for (int j = 0; j < TM; j++) acc += m.s_ni[i][j] * il[j];
         v[i] = acc;
     }
     if (!(last < (uint32_t)T_MAX_ITER)) {
         if (dg) dg->be_fallback++;
-        trm_be(input, st, m, v, il);
+#pragma unroll
+        for (int i = 0; i < TN; i++) sc[i] = st.v[i];
+#pragma unroll
+        for (int i = 0; i < TM; i++) { sc[7 + i] = st.il[i]; sc[11 + i] = st.ilpp[i]; }
+        trm_be(input, sc, m, kq);
+#pragma unroll
+        for (int i = 0; i < TN; i++) v[i] = sc[15 + i];
+#pragma unroll
+        for (int i = 0; i < TM; i++) il[i] = sc[22 + i];
     }
     bool fin = true;
     for (int i = 0; i < TN; i++) fin = fin && finite64(v[i]);

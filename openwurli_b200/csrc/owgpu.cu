@@ -486,6 +486,23 @@ int owg_last_diag(owg_diag* out) {
     return OWG_OK;
 }
 
+int owg_selftest_division(int64_t n_per_thread, uint64_t seed, uint64_t* mismatches, uint64_t* tested) {
+    if (!mismatches || n_per_thread <= 0) return fail(OWG_E_BAD_ARG, "owg_selftest_division: bad argument");
+    if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(unsigned long long)));
+    CK(cudaMemset(d, 0, sizeof(unsigned long long)));
+    const int blocks = 1184, threads = 256;
+    division_selftest_kernel<<<blocks, threads>>>((unsigned long long)seed, (int)n_per_thread, d);
+    CK(cudaGetLastError());
+    unsigned long long h = 0;
+    CK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches = h;
+    if (tested) *tested = (uint64_t)blocks * threads * (uint64_t)n_per_thread;
+    return OWG_OK;
+}
+
 int owg_fp64_peak(int32_t device, int32_t fma_mode, float ms_target, double* tera_instr_per_s) {
     if (!tera_instr_per_s) return fail(OWG_E_BAD_ARG, "null result");
     if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
@@ -499,6 +516,39 @@ int owg_fp64_peak(int32_t device, int32_t fma_mode, float ms_target, double* ter
     CK(cudaMalloc(&sink, (size_t)threads * blocks * sizeof(double)));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    if (fma_mode >= 10 && fma_mode <= 13) {  // dependent-chain latency: result = ns per dependent op (DADD, DMUL, DFMA, DDIV)
+        const int it = 1 << 16;
+        double best_ns = 1e30;
+        for (int rep = 0; rep < 3; rep++) {
+            CK(cudaEventRecord(e0));
+            fp64_latency_kernel<<<1, 32>>>(sink, it, 1.0000001, 1e-9, fma_mode - 10);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            best_ns = std::min(best_ns, (double)ms * 1e6 / (4.0 * it));
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+        *tera_instr_per_s = best_ns;
+        return OWG_OK;
+    }
+    if (fma_mode >= 100) {  // partial-warp throughput: fma_mode-100 active lanes per warp; result = 1e12 warp-instr-lanes/s (active lanes only)
+        const int lanes = fma_mode - 100;
+        const int it = 1 << 16;
+        double best_rate = 0.0;
+        for (int rep = 0; rep < 3; rep++) {
+            CK(cudaEventRecord(e0));
+            fp64_partial_warp_kernel<<<blocks, threads>>>(sink, it, 1.0000001, 1e-9, lanes);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            best_rate = std::max(best_rate, (double)(threads / 32) * blocks * (double)it * 8.0 / (ms * 1e-3) / 1e12);  // warp-instructions/s
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+        *tera_instr_per_s = best_rate;
+        return OWG_OK;
+    }
     int iters = 1 << 14;
     double best = 0.0;
     for (int rep = 0; rep < 6; rep++) {

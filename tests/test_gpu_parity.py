@@ -213,3 +213,13 @@ def test_fp64_peak_probe_is_sane():
     fma = ow.fp64_peak(fma=True, ms_target=20.0)
     nofma = ow.fp64_peak(fma=False, ms_target=20.0)
     assert 5.0 < fma < 40.0 and 5.0 < nofma < 40.0  # B200: 148 SM x 64 FP64 lanes x ~1.9 GHz ~ 18e12 instr/s
+
+
+def test_shared_reciprocal_division_is_ieee_exact():
+    """recip_prepare()/div_by() (the compiler's own division sequence split so that pivots and constant divisors share
+    one reciprocal) must equal `a / b` bit for bit: ~1.2e9 operand pairs incl. zeros, denormals, infinities, NaNs."""
+    import ctypes as C
+    bad, n = C.c_uint64(1), C.c_uint64(0)
+    for seed in (1, 0xDEADBEEF):
+        assert ow.lib().owg_selftest_division(2048, seed, C.byref(bad), C.byref(n)) == 0
+        assert n.value > 6e8 and bad.value == 0, (bad.value, n.value)

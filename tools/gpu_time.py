@@ -1,0 +1,30 @@
+#!/usr/bin/env python3
+"""Kernel timing probe (CUDA events inside libowgpu): chain/total ms for the grid at a few sizes; FP64 probes."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import openwurli_b200 as ow
+from openwurli_b200.api import fp64_probe
+
+if "--probes" in sys.argv:
+    for name, mode in [("DADD ns/dep-op", 10), ("DMUL ns/dep-op", 11), ("DFMA ns/dep-op", 12), ("DDIV ns/dep-op", 13)]:
+        print(name, round(fp64_probe(mode), 3), flush=True)
+    for lanes in (32, 16, 8, 4):
+        print(f"unfused warp-instr rate with {lanes} active lanes: {fp64_probe(100 + lanes):.3f} T warp-instr/s", flush=True)
+
+def run(depth, dur, stride=1, reps=2):
+    jobs = [ow.bench_job(note=33 + k // 127, velocity=1 + k % 127, duration=dur, tremolo_depth=depth) for k in range(0, 8128, stride)]
+    pl = ow.Plan.bench(jobs)
+    out = torch.empty((len(jobs), pl.max_samples), dtype=torch.float64, device="cuda")
+    best = None
+    for _ in range(reps):
+        pl.execute(out); torch.cuda.synchronize()
+        t = pl.last_timing()
+        best = t if best is None or t[1] < best[1] else best
+    print(f"depth={depth} dur={dur} n={len(jobs)}: chain {best[0]:.1f} ms, total {best[1]:.1f} ms -> {len(jobs)*dur/(best[1]*1e-3):.0f} audio-s/s", flush=True)
+    pl.close()
+
+for depth in (0.0, 0.5):
+    for dur in (0.5, 1.5):
+        run(depth, dur)
