@@ -182,6 +182,59 @@ def render_bench(jobs, out=None, device=-1, collect_diag=False):
     return out
 
 
+def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000.0, out=None, device=-1):
+    """Preamp-only batch (BASELINE config 2): rows of `x` [n_inst, n_samp] (numpy float64, or a torch CUDA tensor)
+    through upsample_2x -> DkPreamp::process_sample x2 -> downsample_2x (`process_oversampled`, preamp-bench main.rs:961-974),
+    LDR driven by Tremolo::new(tremolo_depth, fs_preamp) when tremolo_depth > 0 (main.rs:432-461), else static r_ldr."""
+    if out is None:
+        out = np.zeros_like(x) if isinstance(x, np.ndarray) else x.new_zeros(x.shape)
+    pin, sin, lin = _out_ptr(x)
+    pout, sout, lout = _out_ptr(out)
+    assert lin == lout, "input and output must both be host or both be device buffers"
+    o = _opts(device, lout)
+    check(lib().owg_preamp_batch(pin, sin, x.shape[0], x.shape[1], float(fs_base), 1 if oversample else 0,
+                                 float(tremolo_depth), float(r_ldr), pout, sout, C.byref(o)))
+    return out
+
+
+NOTE_ON, NOTE_OFF, SUSTAIN = 0, 1, 2
+
+
+def engine_job(events, sample_rate=44100.0, duration=1.0, volume=0.5, tremolo_depth=0.5, speaker_character=0.0,
+               mlp=True, block_size=512, warm_up=True):
+    """One WurliEngine stream (engine.rs:194-462).  `events` = [(sample, kind, note, velocity)], sorted by sample;
+    kind in NOTE_ON / NOTE_OFF / SUSTAIN (note != 0 = pedal down); velocity is rounded to f32 like note_on(u8, f32).
+    Defaults are the engine's own (volume 0.5, depth 0.5, character 0.0, MLP on; engine.rs:224-226); warm_up=True
+    constructs through set_sample_rate() as the plugin does (0.6 s warm-up)."""
+    arr = (_abi.Event * max(len(events), 1))()
+    for i, (smp, kind, note, vel) in enumerate(events):
+        arr[i] = _abi.Event(int(smp), int(kind), int(note), 0, float(vel))
+    j = _abi.EngineJob(float(sample_rate), float(duration), float(volume), float(tremolo_depth), float(speaker_character),
+                       1 if mlp else 0, int(block_size), 1 if warm_up else 0, 0, arr, len(events))
+    j._keepalive = arr
+    return j
+
+
+def render_engines(jobs, out=None, device=-1):
+    """Batch of WurliEngine streams (chain E). Returns [n, max_samples] float32 (WurliEngine::render writes f32)."""
+    stride = max([_samples(j.duration_s, j.sample_rate) for j in jobs], default=0)
+    if out is None:
+        out = np.zeros((len(jobs), stride), dtype=np.float32)
+    if len(jobs) == 0 or stride == 0:
+        return out
+    if isinstance(out, np.ndarray):
+        assert out.dtype == np.float32 and out.flags.c_contiguous
+        ptr, st, loc = out.ctypes.data, out.shape[1], OWG_OUT_HOST
+    else:
+        import torch
+        assert out.dtype == torch.float32 and out.is_contiguous()
+        ptr, st, loc = out.data_ptr(), out.shape[1], (OWG_OUT_DEVICE if out.is_cuda else OWG_OUT_HOST)
+    arr = (_abi.EngineJob * len(jobs))(*jobs)
+    o = _opts(device, loc)
+    check(lib().owg_render_engines(arr, len(jobs), ptr, st, C.byref(o)))
+    return out
+
+
 class Voice:
     """Mirror of openwurli_dsp::voice::Voice's one-shot constructor (voice.rs:191-221)."""
 

@@ -389,7 +389,77 @@ void make_chain_init(const owg_bench_job& job, int group, OwgChainInit* out) {
     out->no_preamp = job.no_preamp;
     out->no_poweramp = job.no_poweramp;
     out->oversample = fs < 88200.0 ? 1 : 0;
+    out->pre_only = 0;
 }
+
+void make_damper_rows(double sample_rate, DamperRow* rows) {
+    for (int midi = 0; midi < 128; midi++) {
+        DamperRow& r = rows[midi];
+        std::memset(&r, 0, sizeof(r));
+        if (midi >= 92) { r.enabled = 0; continue; }  // top keys: no damper (reed.rs:193-195)
+        r.enabled = 1;
+        const double base_rate = std::fmax(55.0 * std::pow(2.0, ((double)midi - 60.0) / 24.0), 0.5);
+        double p3 = 1.0;  // 3.0.powi(m): exact
+        for (int m = 0; m < NM; m++) {
+            const double factor = std::fmin(base_rate * p3, 2000.0);
+            r.rate[m] = factor / sample_rate;
+            r.mult[m] = std::exp(-r.rate[m]);
+            p3 *= 3.0;
+        }
+        const double ramp_time = midi < 48 ? 0.050 : (midi < 72 ? 0.025 : 0.008);
+        r.ramp_samples = ramp_time * sample_rate;
+    }
+}
+
+namespace {
+void fill_spk(SpkUpdate* u, int64_t at, double ch, double fs) {
+    const double hpf_hz = 20.0 * std::pow(30.0 / 20.0, ch);
+    const double lpf_hz = 20000.0 * std::pow(5500.0 / 20000.0, ch);
+    const Rbj hp = rbj(1, hpf_hz, 0.75, fs), lp = rbj(0, lpf_hz, 0.707, fs);
+    std::memset(u, 0, sizeof(*u));
+    u->at = at;
+    u->a2 = 0.2 * ch; u->a3 = 0.6 * ch; u->norm = 1.0 + u->a2 + u->a3; u->thermal_coeff = 2.0 * ch;
+    u->hpf_b0 = hp.b0; u->hpf_b1 = hp.b1; u->hpf_b2 = hp.b2; u->hpf_a1 = hp.a1; u->hpf_a2 = hp.a2;
+    u->lpf_b0 = lp.b0; u->lpf_b1 = lp.b1; u->lpf_b2 = lp.b2; u->lpf_a1 = lp.a1; u->lpf_a2 = lp.a2;
+    u->tanh_on = ch < 0.001 ? 0 : 1;
+}
+}  // namespace
+
+int make_speaker_schedule(double fs, double target, int64_t n_warm, int64_t n_total, uint32_t ramp, SpkUpdate* out, int max_out) {
+    int n = 0;
+    double character = 1.0;  // Speaker::new (speaker.rs:63-78)
+    if (n < max_out) fill_spk(&out[n++], -1, character, fs);
+    // LinearSmoother::new(0.0, ramp) (engine.rs:226)
+    double cur = 0.0, tgt = 0.0, step = 0.0;
+    uint32_t remaining = 0;
+    // the smoother is flat except for `ramp` samples after the target is set; simulate sample 0, then the ramp window
+    for (int64_t t = 0; t < n_total; t++) {
+        if (t == n_warm) {  // set_speaker_character(target) -> LinearSmoother::set_target (engine.rs:85-98)
+            if (!(std::fabs(target - tgt) < 1e-9)) {
+                tgt = target;
+                const double delta = tgt - cur;
+                if (ramp == 0) { cur = tgt; remaining = 0; }
+                else { step = delta / (double)ramp; remaining = ramp; }
+            }
+        }
+        if (remaining > 0) {
+            cur += step;
+            remaining -= 1;
+            if (remaining == 0) cur = tgt;
+        }
+        const double c = clampd(cur, 0.0, 1.0);  // Speaker::set_character (speaker.rs:81-87)
+        if (std::fabs(c - character) > 0.002) {
+            character = c;
+            if (n < max_out) fill_spk(&out[n++], t, character, fs);
+            else return -1;
+        }
+        if (remaining == 0 && t > n_warm) break;  // nothing can change any more
+        if (remaining == 0 && t < n_warm) t = n_warm - 1;  // skip the flat part of the warm-up
+    }
+    return n;
+}
+
+double silent_threshold() { return std::pow(10.0, -80.0 / 20.0); }
 
 void noise_fade_table(double* t16) {  // hammer.rs:161-168: 0.5*(1-cos(pi*pos/16)), pos=0..15
     for (int pos = 0; pos < 16; pos++) t16[pos] = 0.5 * (1.0 - std::cos(kPi * ((double)pos / 16.0)));

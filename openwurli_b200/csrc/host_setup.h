@@ -10,4 +10,13 @@ void make_voice_init(const owg_voice_job& job, OwgVoiceInit* out);
 void make_chain_init(const owg_bench_job& job, int group, OwgChainInit* out);
 // Attack-noise raised-cosine fade-in table (hammer.rs:161-168), 16 entries.
 void noise_fade_table(double* t16);
+// ModalReed::start_damper (reed.rs:191-216) for every MIDI key at `sample_rate`: 128 rows.
+void make_damper_rows(double sample_rate, DamperRow* rows128);
+// Host simulation of the engine's speaker-character smoother + Speaker::set_character threshold logic
+// (engine.rs:67-130, 436-439; speaker.rs:63-101): every coefficient update with the render() sample index it takes
+// effect at (entry 0 = the constructor state, at = -1).  The target is applied after `n_warm` samples.
+int make_speaker_schedule(double sample_rate, double character_target, int64_t n_warm, int64_t n_total, uint32_t ramp_samples,
+                          SpkUpdate* out, int max_out);
+// 10^(-80/20): the is_silent threshold (reed.rs:310), through glibc pow like the reference.
+double silent_threshold();
 }  // namespace owg

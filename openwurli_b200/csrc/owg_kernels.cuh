@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
         OwgChainInit z;
         z.volume = 0.0; z.spk_a2 = 0.0; z.spk_a3 = 0.0; z.spk_norm = 1.0; z.spk_thermal_coeff = 0.0; z.spk_thermal_alpha = 0.0;
         z.hpf_b0 = z.hpf_b1 = z.hpf_b2 = z.hpf_a1 = z.hpf_a2 = 0.0; z.lpf_b0 = z.lpf_b1 = z.lpf_b2 = z.lpf_a1 = z.lpf_a2 = 0.0;
-        z.spk_tanh = 0; z.group = we.group; z.no_preamp = 0; z.no_poweramp = 1; z.oversample = 0; z._pad = 0;
+        z.spk_tanh = 0; z.group = we.group; z.no_preamp = 0; z.no_poweramp = 1; z.oversample = 0; z.pre_only = 0;
         s_ci[lane] = z;
     }
     __syncwarp();
@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
             down_delay = b;
         } else pre_out = p0;
         if (bypass_preamp) pre_out = x;
-        if (live) {
+        if (live && ci.pre_only) o[t] = pre_out;
+        else if (live) {
             const double att = pre_out * vol * vol;
             const double amped = ci.no_poweramp ? att : poweramp(att, DIAG ? pa_hist : nullptr);
             o[t] = speaker(amped, spk, ci) * 7.498942093324558;

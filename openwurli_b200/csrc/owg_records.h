@@ -44,7 +44,7 @@ struct OwgChainInit {
     int32_t group;          // preamp matrix group index
     int32_t no_preamp, no_poweramp;
     int32_t oversample;     // sample_rate < 88200
-    int32_t _pad;
+    int32_t pre_only;       // preamp-only harness (owg_preamp_batch): the row holds the input, the preamp output replaces it
 };
 
 // One preamp "group" = instances that share (preamp sample rate, LDR trajectory): they share the
@@ -65,3 +65,40 @@ struct OwgPreampGroup {
 #define OWG_MAT_AN66 189   // a_neg[6][6] (the only R-dependent a_neg entry)
 #define OWG_MAT_STRIDE 190 // per preamp-rate sample in tremolo mode
 #define OWG_AN_SPARSE 38   // structural non-zeros of a_neg used by build_rhs, row-major order of appearance
+
+// ---- chain E (WurliEngine streams) -----------------------------------------------------------------------------------
+struct DamperRow {  // ModalReed::start_damper (reed.rs:191-216) per MIDI key, computed on the host with glibc
+    double rate[7], mult[7];
+    double ramp_samples;
+    int32_t enabled, _pad;
+};
+
+struct SpkUpdate {  // one Speaker::update_coefficients (speaker.rs:89-101) on the host-simulated character ramp
+    int64_t at;   // base-rate sample index (counted from the first render() sample incl. warm-up) at which it takes effect
+    double a2, a3, norm, thermal_coeff;
+    double hpf_b0, hpf_b1, hpf_b2, hpf_a1, hpf_a2, lpf_b0, lpf_b1, lpf_b2, lpf_a1, lpf_a2;
+    int32_t tanh_on, _pad;
+};
+
+struct EngineDesc {  // one WurliEngine stream
+    double sample_rate, volume_target;
+    int64_t n_samples;       // rendered base-rate samples (after the warm-up)
+    int64_t n_warm;          // warm-up base-rate samples (0 or floor(0.6*sr))
+    int32_t block_size, oversample, group, spk_sched, n_spk_updates, ramp_samples;
+    int64_t ev_begin, ev_end; // range in the event array
+};
+
+struct EngineEvent {  // host-prepared: NOTE_ON carries the index of its precomputed OwgVoiceInit
+    int64_t sample;
+    int32_t kind, note;
+    int64_t vinit;
+};
+
+struct EngineGroup {
+    double sample_rate;       // base rate
+    double preamp_sr;
+    double depth_target;      // set_tremolo_depth() target applied right after the warm-up
+    int64_t n_warm_os, n_os; // preamp-rate samples: warm-up, then rendered
+    int32_t oversample, ramp_samples, use_defaults, _pad;
+};
+

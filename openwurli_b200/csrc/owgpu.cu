@@ -3,6 +3,7 @@
 #include "../../include/owgpu.h"
 #include "host_setup.h"
 #include "owg_kernels.cuh"
+#include "owg_engine.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -96,7 +97,9 @@ struct owg_plan {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int kind = 0;  // 0 = voices (chain V), 1 = bench (chain B)
+    int kind = 0;  // 0 = voices (chain V), 1 = bench (chain B), 2 = preamp-only batch (input rows supplied by the caller)
+    const double* in_ptr = nullptr;  // kind 2: caller's input [n][in_stride] (host or device, like `out`)
+    int64_t in_stride = 0;
     bool collect_diag = false;
     int64_t n = 0;
     std::vector<unsigned long long> n_samples;
@@ -152,6 +155,108 @@ int plan_common(owg_plan* pl, const owg_opts* opts) {
     int64_t l = 0;
     if (int rc = ensure_device_cache(dev, pl->stream, &pl->cache, &l)) return rc;
     return OWG_OK;
+}
+
+// One instance of the shared mono chain as the planner sees it.
+struct InstSpec {
+    double fs;            // base sample rate
+    int oversample;       // 2x oversampled preamp
+    unsigned long long n_samples;
+    double depth, r_ldr;  // tremolo depth (>0) or static LDR resistance
+    OwgChainInit ci;
+};
+
+// Group instances by (base rate, oversampling, static R | tremolo depth) -- they share DK matrices and the shadow solve --
+// and pack each group into warps of 31 instances + 1 shadow lane, longest renders first.
+void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vector<int32_t>* order_out) {
+    typedef std::tuple<double, int, int, double> Key;  // (fs, oversample, is_trem, r_or_depth)
+    std::map<Key, int> key_to_group;
+    std::vector<std::vector<int32_t>> members;
+    const double R0 = 9.99999999999999854e4;
+    const size_t n = specs.size();
+    pl->n_samples.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        InstSpec& sp = specs[i];
+        const double psr = sp.oversample ? sp.fs * 2.0 : sp.fs;
+        const bool trem = sp.depth > 0.0;
+        double r_eff = R0;
+        bool dirty = false;
+        if (!trem && std::isfinite(sp.r_ldr)) {  // reset(); set_ldr_resistance(r_ldr)  (main.rs:438-439, gen_preamp.rs:1973-1984)
+            const double r = sp.r_ldr < 1.0e3 ? 1.0e3 : (sp.r_ldr > 1.0e6 ? 1.0e6 : sp.r_ldr);
+            if (!(std::fabs(r - R0) < 1e-12)) { r_eff = r; dirty = true; }
+        }
+        const Key key(sp.fs, sp.oversample, trem ? 1 : 0, trem ? sp.depth : r_eff);
+        auto it = key_to_group.find(key);
+        int g;
+        if (it == key_to_group.end()) {
+            g = (int)pl->groups.size();
+            key_to_group[key] = g;
+            OwgPreampGroup gr;
+            std::memset(&gr, 0, sizeof(gr));
+            gr.preamp_sr = psr;
+            gr.r_static = r_eff;
+            gr.tremolo_depth = trem ? sp.depth : 0.0;
+            gr.use_defaults = (std::fabs(psr - 48000.0) <= 0.5 && !dirty) ? 1 : 0;
+            gr.n_os = 0;
+            pl->groups.push_back(gr);
+            members.emplace_back();
+        } else g = it->second;
+        sp.ci.group = g;
+        sp.ci.oversample = sp.oversample;
+        pl->n_samples[i] = sp.n_samples;
+        pl->max_samples = std::max<unsigned long long>(pl->max_samples, sp.n_samples);
+        const int64_t nos = (int64_t)sp.n_samples * (sp.oversample ? 2 : 1);
+        pl->groups[g].n_os = std::max<int64_t>(pl->groups[g].n_os, nos);
+        members[g].push_back((int32_t)i);
+    }
+    // record indices: static groups index d_static_recs by group id, tremolo groups index d_trem_recs
+    pl->group_rec_index.assign(pl->groups.size(), 0);
+    for (size_t g = 0; g < pl->groups.size(); g++) {
+        if (pl->groups[g].tremolo_depth > 0.0) {
+            pl->group_rec_index[g] = (int32_t)pl->trem_group_ids.size();
+            pl->trem_group_ids.push_back((int)g);
+            pl->trem_n_os_max = std::max(pl->trem_n_os_max, pl->groups[g].n_os);
+        } else pl->group_rec_index[g] = (int32_t)g;
+    }
+    std::vector<int32_t>& order = *order_out;
+    order.reserve(n);
+    for (size_t g = 0; g < pl->groups.size(); g++) {
+        std::vector<int32_t>& mem = members[g];
+        std::stable_sort(mem.begin(), mem.end(), [&](int32_t a, int32_t b) { return pl->n_samples[a] > pl->n_samples[b]; });
+        for (size_t off = 0; off < mem.size(); off += 31) {
+            WarpEntry we;
+            we.group = (int32_t)g;
+            we.first = (int32_t)order.size();
+            we.count = (int32_t)std::min<size_t>(31, mem.size() - off);
+            we._pad = 0;
+            we.n_max = 0;
+            for (int k = 0; k < we.count; k++) {
+                order.push_back(mem[off + k]);
+                we.n_max = std::max<int64_t>(we.n_max, (int64_t)pl->n_samples[mem[off + k]]);
+            }
+            (pl->groups[g].tremolo_depth > 0.0 ? pl->warps_trem : pl->warps_static).push_back(we);
+        }
+    }
+}
+
+int upload_chain_plan(owg_plan* pl, const std::vector<OwgChainInit>& ci, const std::vector<int32_t>& order) {
+    int rc = pl->d_cinit.upload(ci, pl->stream);
+    if (!rc) rc = pl->d_nsamp.upload(pl->n_samples, pl->stream);
+    if (!rc) rc = pl->d_order.upload(order, pl->stream);
+    if (!rc) rc = pl->d_warps_static.upload(pl->warps_static, pl->stream);
+    if (!rc) rc = pl->d_warps_trem.upload(pl->warps_trem, pl->stream);
+    if (!rc) rc = pl->d_groups.upload(pl->groups, pl->stream);
+    if (!rc) rc = pl->d_group_rec_index.upload(pl->group_rec_index, pl->stream);
+    if (!rc) rc = pl->d_trem_ids.upload(pl->trem_group_ids, pl->stream);
+    if (!rc) rc = pl->d_static_recs.alloc(pl->groups.size() * OWG_MAT_STRIDE);
+    if (!rc) rc = pl->d_ans.alloc(pl->groups.size() * OWG_AN_SPARSE);
+    if (!rc && !pl->trem_group_ids.empty()) {
+        rc = pl->d_pot_seq.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max);
+        if (!rc) rc = pl->d_trem_recs.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max * OWG_MAT_STRIDE);
+    }
+    if (!rc && pl->collect_diag) rc = pl->d_diag.alloc(1);
+    if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
+    return rc;
 }
 
 bool bad_voice_job(const owg_voice_job& j) {
@@ -212,101 +317,25 @@ int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, o
     pl->n = n;
     if (int rc = plan_common(pl, opts)) { delete pl; return rc; }
 
-    // group jobs by (base rate, static R | tremolo depth): they share matrices and the shadow solve
-    typedef std::tuple<double, int, double> Key;  // (sample_rate, is_trem, r_or_depth)
-    std::map<Key, int> key_to_group;
-    std::vector<std::vector<int32_t>> members;
+    std::vector<InstSpec> specs((size_t)n);
     std::vector<OwgVoiceInit> vi((size_t)n);
-    std::vector<OwgChainInit> ci((size_t)n);
-    pl->n_samples.resize((size_t)n);
-    const double R0 = 9.99999999999999854e4;
     for (int64_t i = 0; i < n; i++) {
         const owg_bench_job& j = jobs[i];
-        const double fs = j.v.sample_rate;
-        const bool os = fs < 88200.0;
-        const double psr = os ? fs * 2.0 : fs;
-        const bool trem = j.tremolo_depth > 0.0;
-        double r_eff = R0;
-        bool dirty = false;
-        if (!trem && std::isfinite(j.r_ldr)) {  // reset(); set_ldr_resistance(r_ldr)  (main.rs:438-439, gen_preamp.rs:1973-1984)
-            const double r = j.r_ldr < 1.0e3 ? 1.0e3 : (j.r_ldr > 1.0e6 ? 1.0e6 : j.r_ldr);
-            if (!(std::fabs(r - R0) < 1e-12)) { r_eff = r; dirty = true; }
-        }
-        const Key key(fs, trem ? 1 : 0, trem ? j.tremolo_depth : r_eff);
-        auto it = key_to_group.find(key);
-        int g;
-        if (it == key_to_group.end()) {
-            g = (int)pl->groups.size();
-            key_to_group[key] = g;
-            OwgPreampGroup gr;
-            std::memset(&gr, 0, sizeof(gr));
-            gr.preamp_sr = psr;
-            gr.r_static = r_eff;
-            gr.tremolo_depth = trem ? j.tremolo_depth : 0.0;
-            gr.use_defaults = (std::fabs(psr - 48000.0) <= 0.5 && !dirty) ? 1 : 0;
-            gr.n_os = 0;
-            pl->groups.push_back(gr);
-            members.emplace_back();
-        } else g = it->second;
         owg::make_voice_init(j.v, &vi[i]);
-        owg::make_chain_init(j, g, &ci[i]);
-        pl->n_samples[i] = vi[i].n_samples;
-        pl->max_samples = std::max<unsigned long long>(pl->max_samples, vi[i].n_samples);
-        const int64_t nos = (int64_t)vi[i].n_samples * (os ? 2 : 1);
-        pl->groups[g].n_os = std::max<int64_t>(pl->groups[g].n_os, nos);
-        members[g].push_back((int32_t)i);
+        InstSpec& sp = specs[i];
+        sp.fs = j.v.sample_rate;
+        sp.oversample = j.v.sample_rate < 88200.0 ? 1 : 0;
+        sp.n_samples = vi[i].n_samples;
+        sp.depth = j.tremolo_depth;
+        sp.r_ldr = j.r_ldr;
+        owg::make_chain_init(j, 0, &sp.ci);
     }
-    // record indices: static groups index d_static_recs, tremolo groups index d_trem_recs
-    pl->group_rec_index.assign(pl->groups.size(), 0);
-    int n_static = 0;
-    for (size_t g = 0; g < pl->groups.size(); g++) {
-        if (pl->groups[g].tremolo_depth > 0.0) {
-            pl->group_rec_index[g] = (int32_t)pl->trem_group_ids.size();
-            pl->trem_group_ids.push_back((int)g);
-            pl->trem_n_os_max = std::max(pl->trem_n_os_max, pl->groups[g].n_os);
-        } else {
-            pl->group_rec_index[g] = (int32_t)g;  // static records are indexed by group id (sparse but simple)
-            n_static++;
-        }
-    }
-    // warps: 31 instances + 1 shadow lane; longest renders first so the tail of the launch is short
     std::vector<int32_t> order;
-    order.reserve((size_t)n);
-    for (size_t g = 0; g < pl->groups.size(); g++) {
-        std::vector<int32_t>& mem = members[g];
-        std::stable_sort(mem.begin(), mem.end(), [&](int32_t a, int32_t b) { return pl->n_samples[a] > pl->n_samples[b]; });
-        for (size_t off = 0; off < mem.size(); off += 31) {
-            WarpEntry we;
-            we.group = (int32_t)g;
-            we.first = (int32_t)order.size();
-            we.count = (int32_t)std::min<size_t>(31, mem.size() - off);
-            we._pad = 0;
-            we.n_max = 0;
-            for (int k = 0; k < we.count; k++) {
-                order.push_back(mem[off + k]);
-                we.n_max = std::max<int64_t>(we.n_max, (int64_t)pl->n_samples[mem[off + k]]);
-            }
-            (pl->groups[g].tremolo_depth > 0.0 ? pl->warps_trem : pl->warps_static).push_back(we);
-        }
-    }
-    (void)n_static;
+    build_groups_and_warps(pl, specs, &order);
+    std::vector<OwgChainInit> ci((size_t)n);
+    for (int64_t i = 0; i < n; i++) ci[i] = specs[i].ci;
     int rc = pl->d_vinit.upload(vi, pl->stream);
-    if (!rc) rc = pl->d_cinit.upload(ci, pl->stream);
-    if (!rc) rc = pl->d_nsamp.upload(pl->n_samples, pl->stream);
-    if (!rc) rc = pl->d_order.upload(order, pl->stream);
-    if (!rc) rc = pl->d_warps_static.upload(pl->warps_static, pl->stream);
-    if (!rc) rc = pl->d_warps_trem.upload(pl->warps_trem, pl->stream);
-    if (!rc) rc = pl->d_groups.upload(pl->groups, pl->stream);
-    if (!rc) rc = pl->d_group_rec_index.upload(pl->group_rec_index, pl->stream);
-    if (!rc) rc = pl->d_trem_ids.upload(pl->trem_group_ids, pl->stream);
-    if (!rc) rc = pl->d_static_recs.alloc(pl->groups.size() * OWG_MAT_STRIDE);
-    if (!rc) rc = pl->d_ans.alloc(pl->groups.size() * OWG_AN_SPARSE);
-    if (!rc && !pl->trem_group_ids.empty()) {
-        rc = pl->d_pot_seq.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max);
-        if (!rc) rc = pl->d_trem_recs.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max * OWG_MAT_STRIDE);
-    }
-    if (!rc && pl->collect_diag) rc = pl->d_diag.alloc(1);
-    if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
+    if (!rc) rc = upload_chain_plan(pl, ci, order);
     if (rc) { delete pl; return rc; }
     pl->h2d_bytes = g_h2d_bytes;
     *plan = pl;
@@ -352,15 +381,19 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     int64_t launches = 0;
     CK(cudaEventRecord(pl->ev0, s));
     if (pl->collect_diag) CK(cudaMemsetAsync(pl->d_diag.p, 0, sizeof(DevDiag), s));
-    // chain V for every job
-    {
+    if (pl->kind == 2) {
+        // preamp-only batch: the rows start as the caller's input signals
+        CK(cudaMemcpy2DAsync(dout, (size_t)stride * sizeof(double), pl->in_ptr, (size_t)pl->in_stride * sizeof(double),
+                             (size_t)pl->max_samples * sizeof(double), (size_t)pl->n,
+                             out_location == OWG_OUT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    } else {  // chain V for every job
         const int threads = 32;
         const int blocks = (int)((pl->n + threads - 1) / threads);
         voice_kernel<<<blocks, threads, 0, s>>>(pl->d_vinit.p, pl->n, dout, stride);
         CK(cudaGetLastError());
         launches++;
     }
-    if (pl->kind == 1) {
+    if (pl->kind >= 1) {
         const int ng = (int)pl->groups.size();
         static_matrix_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_static_recs.p, pl->d_ans.p);
         CK(cudaGetLastError());
@@ -448,12 +481,221 @@ int owg_render_bench(const owg_bench_job* jobs, int64_t n, double* out, int64_t 
     return rc;
 }
 
-int owg_render_engines(const owg_engine_job*, int64_t, float*, int64_t, const owg_opts*) {
-    return fail(OWG_E_UNSUPPORTED, "owg_render_engines: chain E (WurliEngine streams) is not implemented in this build");
+int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_t stride, const owg_opts* opts) {
+    if (n < 0 || (n > 0 && (!jobs || !out))) return fail(OWG_E_BAD_ARG, "owg_render_engines: bad argument");
+    if (n == 0) return OWG_OK;
+    for (int64_t i = 0; i < n; i++) {
+        const owg_engine_job& j = jobs[i];
+        if (!(j.sample_rate > 0.0) || !std::isfinite(j.sample_rate) || !(j.duration_s >= 0.0) || !std::isfinite(j.duration_s) ||
+            !std::isfinite(j.volume) || !std::isfinite(j.tremolo_depth) || !std::isfinite(j.speaker_character) || j.n_ev < 0 ||
+            (j.n_ev > 0 && !j.ev))
+            return fail(OWG_E_BAD_ARG, "owg_render_engines: invalid job");
+        for (int64_t k = 1; k < j.n_ev; k++)
+            if (j.ev[k].sample < j.ev[k - 1].sample) return fail(OWG_E_BAD_ARG, "owg_render_engines: events must be sorted by sample");
+    }
+    owg_plan pl;  // used for device / stream / cache plumbing only
+    if (int rc = plan_common(&pl, opts)) return rc;
+    cudaStream_t s = pl.stream;
+    const int out_location = opts ? opts->out_location : OWG_OUT_HOST;
+
+    auto trunc_u64 = [](double x) -> unsigned long long { return !(x == x) || x <= 0.0 ? 0ull : (x >= 18446744073709551615.0 ? ~0ull : (unsigned long long)x); };
+    auto trunc_u32 = [](double x) -> uint32_t { return !(x == x) || x <= 0.0 ? 0u : (x >= 4294967295.0 ? 4294967295u : (uint32_t)x); };
+
+    std::vector<EngineDesc> eng((size_t)n);
+    std::vector<EngineGroup> groups;
+    std::vector<EngineEvent> events;
+    std::vector<OwgVoiceInit> vinits;
+    std::vector<DamperRow> dampers;
+    std::vector<int32_t> damper_sched((size_t)n);
+    std::vector<SpkUpdate> spk_updates;
+    std::vector<long long> spk_offsets;
+    std::map<std::tuple<double, double, int>, int> group_key;
+    std::map<double, int> damper_key;
+    std::map<std::tuple<double, double, long long>, std::pair<int, int>> spk_key;  // -> (schedule id, n updates)
+    long long max_samples = 0, max_block = 1, pot_stride = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const owg_engine_job& j = jobs[i];
+        EngineDesc& e = eng[i];
+        const double sr = j.sample_rate;
+        e.sample_rate = sr;
+        e.volume_target = j.volume;
+        e.n_samples = (long long)trunc_u64(sr * j.duration_s);
+        e.n_warm = j.warm_up ? (long long)trunc_u64(sr * 0.6) : 0;
+        e.block_size = j.block_size > 0 ? j.block_size : 512;
+        e.oversample = sr < 88200.0 ? 1 : 0;
+        e.ramp_samples = (int32_t)std::max<uint32_t>(trunc_u32(sr * 0.005), 1u);
+        max_samples = std::max(max_samples, (long long)e.n_samples);
+        max_block = std::max<long long>(max_block, e.block_size);
+        const int sub = e.oversample ? 2 : 1;
+        // shared sequences: (rate, depth target, warm-up)
+        const auto gk = std::make_tuple(sr, j.tremolo_depth, j.warm_up ? 1 : 0);
+        auto git = group_key.find(gk);
+        if (git == group_key.end()) {
+            EngineGroup g;
+            std::memset(&g, 0, sizeof(g));
+            g.sample_rate = sr;
+            g.preamp_sr = e.oversample ? sr * 2.0 : sr;
+            g.depth_target = j.tremolo_depth;
+            g.n_warm_os = e.n_warm * sub;
+            g.n_os = 0;
+            g.oversample = e.oversample;
+            g.ramp_samples = e.ramp_samples;
+            g.use_defaults = std::fabs(g.preamp_sr - 48000.0) <= 0.5 ? 1 : 0;
+            group_key[gk] = (int)groups.size();
+            e.group = (int)groups.size();
+            groups.push_back(g);
+        } else e.group = git->second;
+        groups[e.group].n_os = std::max<int64_t>(groups[e.group].n_os, e.n_samples * sub);
+        // damper table per rate
+        auto dit = damper_key.find(sr);
+        if (dit == damper_key.end()) {
+            damper_key[sr] = (int)(dampers.size() / 128);
+            damper_sched[i] = (int32_t)(dampers.size() / 128);
+            dampers.resize(dampers.size() + 128);
+            owg::make_damper_rows(sr, &dampers[dampers.size() - 128]);
+        } else damper_sched[i] = dit->second;
+        // speaker coefficient schedule per (rate, character target, warm-up length)
+        const auto sk = std::make_tuple(sr, j.speaker_character, (long long)e.n_warm);
+        auto sit = spk_key.find(sk);
+        if (sit == spk_key.end()) {
+            const int cap = e.ramp_samples + 8;
+            std::vector<SpkUpdate> tmp((size_t)cap);
+            const int nu = owg::make_speaker_schedule(sr, j.speaker_character, e.n_warm, e.n_warm + e.n_samples + e.ramp_samples + 2,
+                                                      (uint32_t)e.ramp_samples, tmp.data(), cap);
+            if (nu < 0) return fail(OWG_E_CUDA, "speaker schedule overflow");
+            spk_key[sk] = std::make_pair((int)spk_offsets.size(), nu);
+            e.spk_sched = (int)spk_offsets.size();
+            e.n_spk_updates = nu;
+            spk_offsets.push_back((long long)spk_updates.size());
+            spk_updates.insert(spk_updates.end(), tmp.begin(), tmp.begin() + nu);
+        } else { e.spk_sched = sit->second.first; e.n_spk_updates = sit->second.second; }
+        // events -> voice init records (WurliEngine::note_on, engine.rs:299-338)
+        e.ev_begin = (long long)events.size();
+        unsigned long long age = 0;
+        for (int64_t k = 0; k < j.n_ev; k++) {
+            const owg_event& ev = j.ev[k];
+            EngineEvent d;
+            d.sample = ev.sample;
+            d.kind = ev.kind;
+            d.note = ev.kind == OWG_EV_SUSTAIN ? ev.note : (ev.note < 33 ? 33 : (ev.note > 96 ? 96 : ev.note));
+            d.vinit = -1;
+            if (ev.kind == OWG_EV_NOTE_ON) {
+                age += 1;
+                owg_voice_job vj;
+                std::memset(&vj, 0, sizeof(vj));
+                vj.midi = (uint8_t)d.note;
+                vj.mlp_enabled = j.mlp_enabled ? 1 : 0;
+                vj.attack_noise = 1;
+                vj.noise_seed = (uint32_t)d.note * 2654435761u + (uint32_t)age;
+                vj.velocity = (double)ev.velocity;  // f32 -> f64 (engine.rs:330)
+                vj.sample_rate = sr;
+                vj.duration_s = 0.0;
+                vj.ds_override = NAN;
+                d.vinit = (long long)vinits.size();
+                vinits.emplace_back();
+                owg::make_voice_init(vj, &vinits.back());
+            } else if (ev.kind != OWG_EV_NOTE_OFF && ev.kind != OWG_EV_SUSTAIN) return fail(OWG_E_BAD_ARG, "owg_render_engines: unknown event kind");
+            events.push_back(d);
+        }
+        e.ev_end = (long long)events.size();
+    }
+    if (stride < max_samples) return fail(OWG_E_BAD_ARG, "owg_render_engines: stride smaller than the longest stream");
+    for (auto& g : groups) pot_stride = std::max<long long>(pot_stride, g.n_warm_os + g.n_os);
+    if (events.empty()) events.push_back(EngineEvent{0, OWG_EV_SUSTAIN, 0, -1});
+    if (vinits.empty()) vinits.emplace_back();
+    const int ng = (int)groups.size();
+
+    DevBuf<EngineDesc> d_eng; DevBuf<EngineGroup> d_groups; DevBuf<EngineEvent> d_events; DevBuf<OwgVoiceInit> d_vinits;
+    DevBuf<DamperRow> d_dampers; DevBuf<int32_t> d_dsched; DevBuf<SpkUpdate> d_spk; DevBuf<long long> d_spkoff;
+    DevBuf<double> d_pot, d_recs, d_ans, d_pump, d_scratch; DevBuf<DkState> d_post; DevBuf<VoiceRT> d_pool; DevBuf<float> d_out;
+    DevBuf<EngineDiag> d_diag;
+    int rc = d_eng.upload(eng, s);
+    if (!rc) rc = d_groups.upload(groups, s);
+    if (!rc) rc = d_events.upload(events, s);
+    if (!rc) rc = d_vinits.upload(vinits, s);
+    if (!rc) rc = d_dampers.upload(dampers, s);
+    if (!rc) rc = d_dsched.upload(damper_sched, s);
+    if (!rc) rc = d_spk.upload(spk_updates, s);
+    if (!rc) rc = d_spkoff.upload(spk_offsets, s);
+    if (!rc) rc = d_pot.alloc((size_t)ng * (size_t)pot_stride);
+    if (!rc) rc = d_recs.alloc((size_t)ng * (size_t)pot_stride * OWG_MAT_STRIDE);
+    if (!rc) rc = d_ans.alloc((size_t)ng * OWG_AN_SPARSE);
+    if (!rc) rc = d_pump.alloc((size_t)ng * (size_t)pot_stride);
+    if (!rc) rc = d_post.alloc((size_t)ng);
+    if (!rc) rc = d_pool.alloc((size_t)n * 128);
+    if (!rc) rc = d_scratch.alloc((size_t)max_block * (size_t)n);
+    if (!rc) rc = d_diag.alloc(1);
+    float* dout = out;
+    if (!rc && out_location == OWG_OUT_HOST) { rc = d_out.alloc((size_t)n * (size_t)stride); dout = d_out.p; }
+    if (rc) return rc;
+    CK(cudaMemsetAsync(d_diag.p, 0, sizeof(EngineDiag), s));
+    CK(cudaMemsetAsync(d_pool.p, 0, (size_t)n * 128 * sizeof(VoiceRT), s));
+    engine_tremolo_kernel<<<ng, 32, 0, s>>>(d_groups.p, ng, d_pot.p, pot_stride);
+    CK(cudaGetLastError());
+    {
+        dim3 grid((unsigned)((pot_stride + 63) / 64), (unsigned)ng);
+        engine_matrix_kernel<<<grid, 64, 0, s>>>(d_groups.p, ng, d_pot.p, pot_stride, d_recs.p, pot_stride, d_ans.p);
+        CK(cudaGetLastError());
+    }
+    engine_shadow_kernel<<<ng, 32, 0, s>>>(d_groups.p, ng, pl.cache->d_settled, d_recs.p, pot_stride, d_ans.p, d_pump.p, pot_stride, d_post.p);
+    CK(cudaGetLastError());
+    engine_kernel<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(d_eng.p, (int)n, d_events.p, d_vinits.p, d_dampers.p, d_dsched.p, d_spk.p, d_spkoff.p,
+                                                            d_groups.p, d_post.p, d_recs.p, pot_stride, d_ans.p, d_pump.p, pot_stride, d_pool.p,
+                                                            d_scratch.p, owg::silent_threshold(), dout, stride, d_diag.p);
+    CK(cudaGetLastError());
+    if (out_location == OWG_OUT_HOST)
+        CK(cudaMemcpy2DAsync(out, (size_t)stride * sizeof(float), dout, (size_t)stride * sizeof(float), (size_t)max_samples * sizeof(float),
+                             (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    {
+        EngineDiag h;
+        CK(cudaMemcpy(&h, d_diag.p, sizeof(h), cudaMemcpyDeviceToHost));
+        owg_diag& d = g_last_diag;
+        std::memset(&d, 0, sizeof(d));
+        d.nan_reset = h.nan_guard + h.out_nan;
+        d.kernels_launched = 4;
+        // engine-specific counters are reported through the generic histogram slots: [0]=note-ons, [1]=steals, [2]=voices freed, [3]=max active voices
+        d.nr_iter_hist[0] = h.note_ons; d.nr_iter_hist[1] = h.steals; d.nr_iter_hist[2] = h.voices_freed; d.nr_iter_hist[3] = h.max_active;
+    }
+    return OWG_OK;
 }
 
-int owg_preamp_batch(const double*, int64_t, int64_t, int64_t, double, int, double, double, double*, int64_t, const owg_opts*) {
-    return fail(OWG_E_UNSUPPORTED, "owg_preamp_batch: not implemented in this build");
+int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double fs_base, int oversample,
+                     double tremolo_depth, double r_ldr_static, double* out, int64_t out_stride, const owg_opts* opts) {
+    if (n_inst < 0 || n_samp < 0 || !(fs_base > 0.0) || !std::isfinite(fs_base) || std::isnan(tremolo_depth))
+        return fail(OWG_E_BAD_ARG, "owg_preamp_batch: bad argument");
+    if (n_inst == 0 || n_samp == 0) return OWG_OK;
+    if (!in || !out || in_stride < n_samp || out_stride < n_samp) return fail(OWG_E_BAD_ARG, "owg_preamp_batch: null buffer or stride < n_samp");
+    owg_plan* pl = new owg_plan();
+    g_h2d_bytes = 0;
+    pl->kind = 2;
+    pl->n = n_inst;
+    if (int rc = plan_common(pl, opts)) { delete pl; return rc; }
+    std::vector<InstSpec> specs((size_t)n_inst);
+    for (int64_t i = 0; i < n_inst; i++) {
+        InstSpec& sp = specs[i];
+        sp.fs = fs_base;
+        sp.oversample = oversample ? 1 : 0;
+        sp.n_samples = (unsigned long long)n_samp;
+        sp.depth = tremolo_depth;
+        sp.r_ldr = r_ldr_static;
+        std::memset(&sp.ci, 0, sizeof(sp.ci));
+        sp.ci.spk_norm = 1.0;
+        sp.ci.no_poweramp = 1;
+        sp.ci.pre_only = 1;
+    }
+    std::vector<int32_t> order;
+    build_groups_and_warps(pl, specs, &order);
+    std::vector<OwgChainInit> ci((size_t)n_inst);
+    for (int64_t i = 0; i < n_inst; i++) ci[i] = specs[i].ci;
+    int rc = upload_chain_plan(pl, ci, order);
+    if (!rc) {
+        pl->in_ptr = in;
+        pl->in_stride = in_stride;
+        rc = owg_plan_execute(pl, out, out_stride, opts ? opts->out_location : OWG_OUT_HOST);
+    }
+    owg_plan_destroy(pl);
+    return rc;
 }
 
 int owg_host_voice_init(const owg_voice_job* job, double* o) {

@@ -155,3 +155,21 @@ def last_diag():
     d = Diag()
     lib().owo_last_diag(C.byref(d))
     return d
+
+
+def engine_job(events, sr=44100.0, dur=1.0, volume=0.5, depth=0.5, speaker=0.0, mlp=True, block=512, warm_up=True):
+    arr = (Event * max(len(events), 1))()
+    for i, (smp, kind, note, vel) in enumerate(events):
+        arr[i] = Event(int(smp), int(kind), int(note), 0, float(vel))
+    j = EngineJob(sr, dur, volume, depth, speaker, 1 if mlp else 0, block, 1 if warm_up else 0, 0, arr, len(events))
+    j._keepalive = arr
+    return j
+
+
+def render_engines(jobs, threads=1):
+    n = len(jobs)
+    stride = max([n_samples(j.duration_s, j.sample_rate) for j in jobs], default=0)
+    out = np.zeros((n, stride), dtype=np.float32)
+    arr = (EngineJob * n)(*jobs)
+    assert lib().owo_render_engines(arr, n, out.ctypes.data_as(C.POINTER(C.c_float)), stride, threads) == 0
+    return out

@@ -223,3 +223,95 @@ def test_shared_reciprocal_division_is_ieee_exact():
     for seed in (1, 0xDEADBEEF):
         assert ow.lib().owg_selftest_division(2048, seed, C.byref(bad), C.byref(n)) == 0
         assert n.value > 6e8 and bad.value == 0, (bad.value, n.value)
+
+
+# ---- preamp-only batch (BASELINE config 2) ------------------------------------------------------------------------------
+def _c2_inputs(n_inst, n_samp, fs):
+    """A_i*sin(2*pi*f_i*n/fs + phase), f_i log-spaced 55..2093 Hz over 64 keys, A in {1,2,5,10} mV, 16 phases."""
+    i = np.arange(n_inst)
+    f = 55.0 * (2093.0 / 55.0) ** ((i % 64) / 63.0)
+    amp = np.array([0.001, 0.002, 0.005, 0.010])[(i // 64) % 4]
+    ph = 2 * np.pi * ((i // 256) % 16) / 16.0
+    n = np.arange(n_samp)
+    return amp[:, None] * np.sin(2 * np.pi * f[:, None] * n[None, :] / fs + ph[:, None])
+
+
+def _oracle_preamp_batch(x, fs, oversample, depth, r):
+    y = np.zeros_like(x)
+    O.lib().owo_preamp_batch(O.dptr(x), x.shape[1], x.shape[0], x.shape[1], fs, 1 if oversample else 0, depth, r, O.dptr(y),
+                             x.shape[1], 4)
+    return y
+
+
+@pytest.mark.parametrize("depth,r,fs,oversample", [(0.5, 0.0, 48000.0, True), (0.0, 1e6, 48000.0, True),
+                                                   (0.0, 19000.0, 44100.0, True), (1.0, 0.0, 96000.0, False)])
+def test_preamp_batch_parity(depth, r, fs, oversample):
+    x = _c2_inputs(70, 1500, fs)
+    got = ow.preamp_batch(x, fs, oversample=oversample, tremolo_depth=depth, r_ldr=r)
+    ref = _oracle_preamp_batch(x, fs, oversample, depth, r)
+    for i in range(x.shape[0]):
+        assert_parity(got[i], ref[i], f"preamp batch inst {i}")
+    # main - shadow is a pure AC signal path: a zero input row gives (numerically) zero out
+    z = ow.preamp_batch(np.zeros((2, 400)), fs, oversample=oversample, tremolo_depth=depth, r_ldr=r)
+    assert np.abs(z).max() < 1e-9
+
+
+def test_preamp_batch_device_buffers_and_linearity_in_small_signal():
+    import torch
+    x = _c2_inputs(64, 2000, 48000.0) * 1e-3  # microvolt inputs: the preamp is linear to ~1e-6 relative
+    xd = torch.from_numpy(x).cuda()
+    y1 = ow.preamp_batch(xd, 48000.0, r_ldr=1e6).cpu().numpy()
+    y2 = ow.preamp_batch(torch.from_numpy(2.0 * x).cuda(), 48000.0, r_ldr=1e6).cpu().numpy()
+    assert np.abs(y2 - 2.0 * y1).max() <= 1e-4 * np.abs(y2).max()
+    assert np.array_equal(y1, ow.preamp_batch(x, 48000.0, r_ldr=1e6))
+
+
+# ---- chain E: WurliEngine streams (BASELINE config 5) ---------------------------------------------------------------------
+def _engine_pair(events, **kw):
+    okw = dict(sr=kw.get("sample_rate", 44100.0), dur=kw.get("duration", 1.0), volume=kw.get("volume", 0.5),
+               depth=kw.get("tremolo_depth", 0.5), speaker=kw.get("speaker_character", 0.0), mlp=kw.get("mlp", True),
+               block=kw.get("block_size", 512), warm_up=kw.get("warm_up", True))
+    return ow.engine_job(events, **kw), O.engine_job(events, **okw)
+
+
+def _engine_parity(pairs, what):
+    got = ow.render_engines([p[0] for p in pairs])
+    ref = O.render_engines([p[1] for p in pairs], threads=4)
+    assert got.dtype == np.float32 and got.shape == ref.shape
+    for i in range(len(pairs)):
+        assert np.abs(ref[i]).max() > 0, f"{what}[{i}] reference is silent"
+        assert_parity(got[i].astype(np.float64), ref[i].astype(np.float64), f"{what}[{i}]", MAX_ABS, 1e-6)  # f32 output
+    return got, ref
+
+
+def test_engine_single_notes_warm_and_cold():
+    ev = [(0, ow.NOTE_ON, 60, 100 / 127.0), (9000, ow.NOTE_OFF, 60, 0.0)]
+    pairs = [_engine_pair(ev, duration=0.4, warm_up=True), _engine_pair(ev, duration=0.4, warm_up=False),
+             _engine_pair(ev, duration=0.3, warm_up=True, tremolo_depth=0.0, speaker_character=1.0, volume=0.8),
+             _engine_pair([(100, ow.NOTE_ON, 20, 1.0), (700, ow.NOTE_ON, 120, 0.3)], duration=0.2, warm_up=False, block_size=64)]
+    _engine_parity(pairs, "engine single")
+
+
+def test_engine_polyphony_sustain_restrike_and_stealing():
+    rng = np.random.RandomState(7)
+    ev = []
+    t = 0
+    for k in range(90):  # 90 note-ons in ~0.25 s: exceeds the 64 slots -> stealing with crossfade
+        note = int(33 + rng.randint(0, 64))
+        ev.append((t, ow.NOTE_ON, note, float(np.float32(0.2 + 0.8 * rng.rand()))))
+        if k % 3 == 0:
+            ev.append((t + 40, ow.NOTE_OFF, note, 0.0))
+        if k == 20:
+            ev.append((t + 1, ow.SUSTAIN, 1, 0.0))
+        if k == 60:
+            ev.append((t + 1, ow.SUSTAIN, 0, 0.0))
+        t += 120
+    ev.sort(key=lambda e: e[0])
+    ev2 = [(0, ow.NOTE_ON, 60, 0.9), (10, ow.SUSTAIN, 1, 0.0), (2000, ow.NOTE_OFF, 60, 0.0), (4000, ow.NOTE_ON, 60, 0.7),
+           (9000, ow.SUSTAIN, 0, 0.0)]
+    pairs = [_engine_pair(ev, duration=0.35, warm_up=False, block_size=256),
+             _engine_pair(ev2, duration=0.3, warm_up=False),
+             _engine_pair(ev, duration=0.3, sample_rate=96000.0, warm_up=False, block_size=512)]
+    _engine_parity(pairs, "engine poly")
+    d = ow.last_diag()
+    assert d.nr_iter_hist[0] >= 180 and d.nr_iter_hist[1] > 0  # note-ons and steals counted on the device
