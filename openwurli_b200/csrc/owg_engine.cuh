@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(32) engine_kernel(const EngineDesc* __restrict
                                                     const DkState* __restrict__ post_warm, const double* __restrict__ recs, long long rec_stride_t,
                                                     const double* __restrict__ ans, const double* __restrict__ pump, long long pump_stride,
                                                     VoiceRT* __restrict__ pool /*[engine][128]*/, double* __restrict__ scratch /*[max_block][n_engines]*/,
-                                                    double silent_thr, float* __restrict__ out, long long out_stride, EngineDiag* diag) {
+                                                    double silent_thr, float* __restrict__ out, long long out_stride, long long max_samples, EngineDiag* diag) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_engines) return;
     __shared__ double s_cold[OWG_COLD_SCRATCH * 32];
@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(32) engine_kernel(const EngineDesc* __restrict
             }
         }
     }
+    for (long long t = ed.n_samples; t < max_samples; t++) o[t] = 0.0f;  // ragged batch: rows end in silence
     if (diag) {
         atomicAdd(&diag->nan_guard, d_nan_guard); atomicAdd(&diag->out_nan, d_out_nan); atomicAdd(&diag->steals, d_steals);
         atomicAdd(&diag->note_ons, d_note_ons); atomicAdd(&diag->voices_freed, d_freed); atomicMax(&diag->max_active, d_max_active);

@@ -641,7 +641,7 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     CK(cudaGetLastError());
     engine_kernel<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(d_eng.p, (int)n, d_events.p, d_vinits.p, d_dampers.p, d_dsched.p, d_spk.p, d_spkoff.p,
                                                             d_groups.p, d_post.p, d_recs.p, pot_stride, d_ans.p, d_pump.p, pot_stride, d_pool.p,
-                                                            d_scratch.p, owg::silent_threshold(), dout, stride, d_diag.p);
+                                                            d_scratch.p, owg::silent_threshold(), dout, stride, max_samples, d_diag.p);
     CK(cudaGetLastError());
     if (out_location == OWG_OUT_HOST)
         CK(cudaMemcpy2DAsync(out, (size_t)stride * sizeof(float), dout, (size_t)stride * sizeof(float), (size_t)max_samples * sizeof(float),
