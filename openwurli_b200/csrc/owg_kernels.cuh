@@ -47,8 +47,15 @@ __global__ void static_matrix_kernel(const OwgPreampGroup* groups, int n_groups,
 // baked 48 kHz matrices, set_sample_rate, 2*sr settle samples) then n_os x process() (tremolo.rs:121-167), followed
 // by DkPreamp::set_ldr_resistance's clamp / 1e-12 change filter (gen_preamp.rs:1973-1984).  Output: the value of
 // pot_0_resistance in effect at each preamp-rate sample.
+struct TrmRun {  // oscillator + LDR state carried between chunk launches
+    TrmState st;
+    double env, pot;
+};
+// Processes absolute step indices [n_begin, n_end) of the sequence  50 warm-up | 2*sr settle | n_os live  (clipped to the
+// group's length); run[] carries the state between launches so that the serial oscillator can be pipelined chunk by chunk
+// with the consumers of its output.
 __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* trem_group_ids, int n_trem, double* pot_seq, int64_t pot_stride,
-                                     DevDiag* diag) {
+                                     TrmRun* run, long long live_begin, long long live_end, DevDiag* diag) {
     const int gi = blockIdx.x;
     if (gi >= n_trem || threadIdx.x != 0) return;
     const OwgPreampGroup gr = groups[trem_group_ids[gi]];
@@ -58,10 +65,24 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
     __shared__ double trm_sc[OWG_TRM_SCRATCH];
     kq = trm_consts();
     trm_defaults(m);
+    const double tot = sr * 2.0;
+    const long long n_settle = !(tot == tot) || tot <= 0.0 ? 0ll : (long long)tot;
+    const long long n_pre = 50 + n_settle;
+    // the first launch (live_begin == 0) also runs the pre-roll; later launches resume from run[]
+    const long long n_begin = live_begin == 0 ? 0 : n_pre + live_begin;
+    const long long n_end = n_pre + (live_end < gr.n_os ? live_end : gr.n_os);
+    if (n_begin >= n_end && live_begin != 0) return;
     TrmState st;
-    for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
-    for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
-    st.xin_prev = 0.0;
+    double env = 0.0;
+    double pot = 9.99999999999999854e4;  // pot_0_resistance of the settled state
+    if (live_begin == 0) {
+        for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
+        for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
+        st.xin_prev = 0.0;
+    } else {
+        st = run[gi].st; env = run[gi].env; pot = run[gi].pot;
+        if (fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);  // same deterministic rebuild as at step 50
+    }
     TrmDiag td;
     for (int i = 0; i < 16; i++) td.hist[i] = 0;
     td.be_fallback = 0; td.nan_reset = 0;
@@ -73,15 +94,10 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
     const double r_upper = 50000.0 * (1.0 - depth);
     const double r_lower = 50000.0 * depth;
     const double top = r_upper > 0.0 ? r_upper * 18000.0 / (r_upper + 18000.0) : 0.0;
-    double env = 0.0;
-    double pot = 9.99999999999999854e4;  // pot_0_resistance of the settled state
     double* o = pot_seq + (size_t)gi * pot_stride;
-    const double tot = sr * 2.0;
-    const long long n_settle = !(tot == tot) || tot <= 0.0 ? 0ll : (long long)tot;
     // One loop, three phases (a single inlined copy of the solver): 50 warm-up samples at the baked 48 kHz matrices
     // (CircuitState::default() -> warmup(), gen_tremolo.rs:2021), set_sample_rate, 2*sr settle samples, then process().
-    const long long n_pre = 50 + n_settle;
-    for (long long n = 0; n < n_pre + gr.n_os; n++) {
+    for (long long n = n_begin; n < n_end; n++) {
         if (n == 50 && fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);
         const bool live = n >= n_pre;
         const double v_out = trm_step(st, m, kq, (diag && live) ? &td : nullptr, trm_sc);
@@ -103,6 +119,7 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
             o[n - n_pre] = pot;
         }
     }
+    run[gi].st = st; run[gi].env = env; run[gi].pot = pot;
     if (diag) {
         for (int i = 0; i < 16; i++) atomicAdd(&diag->trm_hist[i], (unsigned long long)td.hist[i]);
         atomicAdd(&diag->trm_be, (unsigned long long)td.be_fallback);
@@ -111,12 +128,12 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
 
 // One thread per (tremolo group, preamp-rate sample): the lazy rebuild_matrices of that sample.
 __global__ void tremolo_matrix_kernel(const OwgPreampGroup* groups, const int* trem_group_ids, int n_trem, const double* pot_seq, int64_t pot_stride,
-                                      double* recs /*[gi][t][190]*/, int64_t rec_stride_t) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                      double* recs /*[gi][t][190]*/, int64_t rec_stride_t, int64_t t_begin, int64_t t_end) {
+    const int64_t t = t_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int gi = blockIdx.y;
     if (gi >= n_trem) return;
     const OwgPreampGroup gr = groups[trem_group_ids[gi]];
-    if (t >= gr.n_os) return;
+    if (t >= gr.n_os || t >= t_end) return;
     const double pot = pot_seq[(size_t)gi * pot_stride + t];
     double* rec = recs + ((size_t)gi * rec_stride_t + t) * OWG_MAT_STRIDE;
     // A sample whose pot never moved off the settled value at 48 kHz keeps the baked defaults (never dirtied).
@@ -241,13 +258,15 @@ __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restric
 // solve in lane 31 (melange_adapter.rs:72-81: out = main - shadow).  Processes the voice samples in
 // `out` in place.
 struct WarpEntry { int32_t group, first, count; int32_t _pad; int64_t n_max; };
+#define OWG_CARRY 40  // doubles of per-lane state carried between chunk launches (12+3+3+1+1 DK, 12+1 oversampler, 5 speaker)
 
 template <bool TREM, bool DIAG>
 __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__ warps, const int32_t* __restrict__ order,
                                                    const OwgChainInit* __restrict__ cinits, const unsigned long long* __restrict__ n_samples,
                                                    const DkState* __restrict__ settled, const double* __restrict__ recs, const double* __restrict__ ans,
                                                    const int32_t* __restrict__ group_rec_index, int64_t rec_stride_t,
-                                                   double* __restrict__ out, int64_t stride, DevDiag* diag) {
+                                                   double* __restrict__ out, int64_t stride, DevDiag* diag,
+                                                   int64_t t_begin, int64_t t_end, double* __restrict__ carry /*[warp][OWG_CARRY][32]*/) {
     __shared__ double s_rec[OWG_MAT_STRIDE];
     __shared__ double s_an[OWG_AN_SPARSE];
     __shared__ OwgChainInit s_ci[32];
@@ -289,10 +308,27 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
     const double vol = ci.volume;
     const bool bypass_preamp = ci.no_preamp != 0;
 
-    int64_t tos = 0;  // preamp-rate sample index
     const int n_sub = oversample ? 2 : 1;
-    double x_next = (is_main && 0ull < ns) ? o[0] : 0.0;  // software prefetch of the voice sample (hides the L2 latency)
-    for (int64_t t = 0; t < we.n_max; t++) {
+    // Chunked execution (tremolo pipeline): [t_begin, t_end) base-rate samples; the per-lane recurrence state is carried
+    // between launches through `carry`.
+    double* cw = carry ? carry + (size_t)blockIdx.x * OWG_CARRY * 32 + lane : nullptr;
+    if (cw && t_begin > 0) {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < PN; i++) st.v[i] = cw[(k++) * 32];
+#pragma unroll
+        for (int i = 0; i < PM; i++) { st.il[i] = cw[(k++) * 32]; st.ilpp[i] = cw[(k++) * 32]; }
+        st.xin_prev = cw[(k++) * 32];
+        st.be_cooldown = (uint32_t)cw[(k++) * 32];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { ua[i] = cw[(k++) * 32]; ub[i] = cw[(k++) * 32]; da[i] = cw[(k++) * 32]; db[i] = cw[(k++) * 32]; }
+        down_delay = cw[(k++) * 32];
+        spk.thermal = cw[(k++) * 32]; spk.h1 = cw[(k++) * 32]; spk.h2 = cw[(k++) * 32]; spk.l1 = cw[(k++) * 32]; spk.l2 = cw[(k++) * 32];
+    }
+    const int64_t t_stop = t_end < we.n_max ? t_end : we.n_max;
+    int64_t tos = t_begin * n_sub;  // preamp-rate sample index
+    double x_next = (is_main && (unsigned long long)t_begin < ns) ? o[t_begin] : 0.0;  // software prefetch (hides the L2 latency)
+    for (int64_t t = t_begin; t < t_stop; t++) {
         const bool live = is_main && (unsigned long long)t < ns;
         const double x = x_next;
         x_next = (is_main && (unsigned long long)(t + 1) < ns) ? o[t + 1] : 0.0;
@@ -330,6 +366,19 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
             const double amped = ci.no_poweramp ? att : poweramp(att, DIAG ? pa_hist : nullptr);
             o[t] = speaker(amped, spk, ci) * 7.498942093324558;
         }
+    }
+    if (cw && t_stop < we.n_max) {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < PN; i++) cw[(k++) * 32] = st.v[i];
+#pragma unroll
+        for (int i = 0; i < PM; i++) { cw[(k++) * 32] = st.il[i]; cw[(k++) * 32] = st.ilpp[i]; }
+        cw[(k++) * 32] = st.xin_prev;
+        cw[(k++) * 32] = (double)st.be_cooldown;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { cw[(k++) * 32] = ua[i]; cw[(k++) * 32] = ub[i]; cw[(k++) * 32] = da[i]; cw[(k++) * 32] = db[i]; }
+        cw[(k++) * 32] = down_delay;
+        cw[(k++) * 32] = spk.thermal; cw[(k++) * 32] = spk.h1; cw[(k++) * 32] = spk.h2; cw[(k++) * 32] = spk.l1; cw[(k++) * 32] = spk.l2;
     }
     if (DIAG && diag) {
         if (is_main) {

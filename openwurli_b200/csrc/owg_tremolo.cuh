@@ -123,9 +123,10 @@ __device__ __forceinline__ BjtK bjt_consts(double is, double vt, double nf, doub
     return k;
 }
 // bjt_evaluate Ebers-Moll branch (gen_tremolo.rs:1566-1636) for use_gp=false, ISE=ISC=0, sign=+1.
-__device__ __forceinline__ Bjt bjt_em(double vbe, double vbc, const BjtK& k) {
-    const double exp_be = fast_exp(div_by(vbe, k.r_nf));
-    const double exp_bc = fast_exp(div_by(vbc, k.r_nr));
+template <bool EXACT>
+__device__ __forceinline__ Bjt bjt_em(double vbe, double vbc, const BjtK& k, DivPolicy<EXACT>& D) {
+    const double exp_be = fast_exp(EXACT ? vbe / k.nf_vt : D.div(vbe, k.r_nf));
+    const double exp_bc = fast_exp(EXACT ? vbc / k.nr_vt : D.div(vbc, k.r_nr));
     const double i_cc = k.is * (exp_be - exp_bc);
     const double ib_fwd = k.is_bf * (exp_be - 1.0);
     const double ib_rev = k.is_br * (exp_bc - 1.0);
@@ -150,7 +151,8 @@ __device__ __forceinline__ TrmK trm_consts() {
 __device__ __forceinline__ double trm_pnjlim(double vnew, double vold, double vt, double vcrit) { return pnjlim(vnew, vold, vt, vcrit); }
 
 // gen_tremolo.rs:2515-2561; fully unrolled so that every index is a compile-time constant (registers, no local memory)
-__device__ __forceinline__ void trm_solve4(double a[4][4], double b[4], bool& singular) {
+template <bool EXACT>
+__device__ __forceinline__ void trm_solve4(double a[4][4], double b[4], bool& singular, DivPolicy<EXACT>& D) {
     singular = false;
     Recip rp[4];
 #pragma unroll
@@ -162,7 +164,7 @@ __device__ __forceinline__ void trm_solve4(double a[4][4], double b[4], bool& si
             double max_val = fabs(a[col][col]);
 #pragma unroll
             for (int row = col + 1; row < 4; row++) if (fabs(a[row][col]) > max_val) { max_val = fabs(a[row][col]); max_row = row; }
-            if (max_val < 1e-15) singular = true;
+            if (max_val < KC(14)) singular = true;
             else {
 #pragma unroll
                 for (int row = col + 1; row < 4; row++) {
@@ -172,11 +174,11 @@ __device__ __forceinline__ void trm_solve4(double a[4][4], double b[4], bool& si
                         const double t = b[col]; b[col] = b[row]; b[row] = t;
                     }
                 }
-                rp[col] = recip_prepare(a[col][col]);  // one reciprocal per pivot, shared by the column's factors and by
+                rp[col] = D.prep(a[col][col]);  // one reciprocal per pivot, shared by the column's factors and by
                                                        // the back-substitution (bit-identical to dividing each time)
 #pragma unroll
                 for (int row = col + 1; row < 4; row++) {
-                    const double factor = div_by(a[row][col], rp[col]);
+                    const double factor = D.div(a[row][col], rp[col]);
 #pragma unroll
                     for (int j = col + 1; j < 4; j++) a[row][j] -= factor * a[col][j];
                     b[row] -= factor * b[col];
@@ -191,8 +193,8 @@ __device__ __forceinline__ void trm_solve4(double a[4][4], double b[4], bool& si
                 double sum = b[i];
 #pragma unroll
                 for (int j = i + 1; j < 4; j++) sum -= a[i][j] * b[j];
-                if (fabs(a[i][i]) < 1e-15) singular = true;
-                else b[i] = div_by(sum, rp[i]);
+                if (fabs(a[i][i]) < KC(14)) singular = true;
+                else b[i] = D.div(sum, rp[i]);
             }
         }
     }
@@ -220,7 +222,7 @@ __device__ __forceinline__ void trm_jac(const Bjt& q0, const Bjt& q1, const doub
 // BE fallback of the oscillator (gen_tremolo.rs:2757-3083); v receives the BE voltages.
 // Cold path: state and results travel through a scratch buffer (shared memory) so the hot path's register arrays are
 // never address-taken.  sc: [0..6] v_prev, [7..10] il, [11..14] ilpp  ->  [15..21] v, [22..25] il.
-#define OWG_TRM_SCRATCH 26
+#define OWG_TRM_SCRATCH 34
 __device__ __noinline__ uint32_t trm_be(double input, double* sc, const TrmMats& m, const TrmK& kq) {
     TrmState st;
     for (int i = 0; i < TN; i++) st.v[i] = sc[i];
@@ -254,14 +256,15 @@ __device__ __noinline__ uint32_t trm_be(double input, double* sc, const TrmMats&
         const double v_d1 = p_be[1] + kb[1][0] * il[0] + kb[1][1] * il[1] + kb[1][2] * il[2] + kb[1][3] * il[3];
         const double v_d2 = p_be[2] + kb[2][0] * il[0] + kb[2][1] * il[1] + kb[2][2] * il[2] + kb[2][3] * il[3];
         const double v_d3 = p_be[3] + kb[3][0] * il[0] + kb[3][1] * il[1] + kb[3][2] * il[2] + kb[3][3] * il[3];
-        const Bjt q0 = bjt_em(v_d0, v_d1, kq.q0);
-        const Bjt q1 = bjt_em(v_d2, v_d3, kq.q1);
+        DivPolicy<true> D;
+        const Bjt q0 = bjt_em(v_d0, v_d1, kq.q0, D);
+        const Bjt q1 = bjt_em(v_d2, v_d3, kq.q1, D);
         const double f0 = il[0] - q0.ic, f1 = il[1] - q0.ib, f2 = il[2] - q1.ic, f3 = il[3] - q1.ib;
         double a[4][4];
         trm_jac(q0, q1, kb, a);
         double b[4] = {f0, f1, f2, f3};
         bool singular;
-        trm_solve4(a, b, singular);
+        trm_solve4(a, b, singular, D);
         if (!singular) {
             const double d0 = b[0], d1 = b[1], d2 = b[2], d3 = b[3];
             const double dv0 = -(kb[0][0] * d0 + kb[0][1] * d1 + kb[0][2] * d2 + kb[0][3] * d3);
@@ -314,11 +317,93 @@ __device__ __noinline__ uint32_t trm_be(double input, double* sc, const TrmMats&
     return result;
 }
 
+// One iteration of the trapezoidal Newton loop (gen_tremolo.rs:2423-2745). Returns true when converged.
+template <bool EXACT>
+__device__ __forceinline__ bool trm_nr_iter(const double p[TM], const double (*k)[TM], const TrmK& kq, double il[TM], unsigned& bad_out) {
+    DivPolicy<EXACT> D;
+    const double vt0 = TRM_DEVICE_0_VT, vt1 = TRM_DEVICE_1_VT;
+    bool converged = false;
+    {
+        const double v_d0 = p[0] + k[0][0] * il[0] + k[0][1] * il[1] + k[0][2] * il[2] + k[0][3] * il[3];
+        const double v_d1 = p[1] + k[1][0] * il[0] + k[1][1] * il[1] + k[1][2] * il[2];
+        const double v_d2 = p[2] + k[2][0] * il[0] + k[2][1] * il[1] + k[2][3] * il[3];
+        const double v_d3 = p[3] + k[3][0] * il[0] + k[3][1] * il[1] + k[3][2] * il[2] + k[3][3] * il[3];
+        const Bjt q0 = bjt_em(v_d0, v_d1, kq.q0, D);
+        const Bjt q1 = bjt_em(v_d2, v_d3, kq.q1, D);
+        const double f0 = il[0] - q0.ic, f1 = il[1] - q0.ib, f2 = il[2] - q1.ic, f3 = il[3] - q1.ib;
+        double a[4][4];
+        trm_jac(q0, q1, k, a);
+        double b[4] = {f0, f1, f2, f3};
+        bool singular;
+        trm_solve4(a, b, singular, D);
+        if (!singular) {
+            const double d0 = b[0], d1 = b[1], d2 = b[2], d3 = b[3];
+            const double it0 = il[0] - d0, it1 = il[1] - d1, it2 = il[2] - d2, it3 = il[3] - d3;
+            const double vt_0 = p[0] + k[0][0] * it0 + k[0][1] * it1 + k[0][2] * it2 + k[0][3] * it3;
+            const double vt_1 = p[1] + k[1][0] * it0 + k[1][1] * it1 + k[1][2] * it2 + k[1][3] * it3;
+            const double vt_2 = p[2] + k[2][0] * it0 + k[2][1] * it1 + k[2][2] * it2 + k[2][3] * it3;
+            const double vt_3 = p[3] + k[3][0] * it0 + k[3][1] * it1 + k[3][2] * it2 + k[3][3] * it3;
+            bool any_limited = false;
+            const double vds[4] = {v_d0, v_d1, v_d2, v_d3};
+            const double vts[4] = {vt_0, vt_1, vt_2, vt_3};
+            double dvt[4], vlim[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                dvt[q] = vts[q] - vds[q];
+                vlim[q] = fabs(dvt[q]) > KC(13) ? trm_pnjlim(vts[q], vds[q], q < 2 ? vt0 : vt1, q < 2 ? TRM_DEVICE_0_VCRIT : TRM_DEVICE_1_VCRIT) : vts[q];
+            }
+            double ga = 1.0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double dv_lim = vlim[q] - vds[q];
+                if (fabs(dvt[q]) > KC(14)) {
+                    // vlim == vtrial (no limiting) makes dv_lim the very same subtraction as dvt: the ratio is exactly 1
+                    const double r = (vlim[q] == vts[q]) ? 1.0 : ((dvt[q] * dv_lim < 0.0) ? 0.0 : rclamp(dv_lim / dvt[q], 0.0, 1.0));
+                    if (r < ga) { ga = r; any_limited = true; }
+                }
+            }
+            {
+                const double max_dv = fmax(fmax(fmax(fabs(dvt[0] * ga), fabs(dvt[1] * ga)), fabs(dvt[2] * ga)), fabs(dvt[3] * ga));
+                if (max_dv > 3.5) { ga *= fmax(3.5 / max_dv, 0.1); any_limited = true; }
+            }
+            il[0] -= ga * d0; il[1] -= ga * d1; il[2] -= ga * d2; il[3] -= ga * d3;
+            if (!any_limited) {
+                bool conv = true;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double dv = dvt[q] * ga;
+                    const double thr = KC(9) * fmax(fabs(vds[q]), fabs(vds[q] + dv)) + KC(10);
+                    if (fabs(dv) > thr) conv = false;
+                }
+                converged = conv;
+            }
+        } else {
+            { const double c = fmax(fabs(il[0]) * KC(16), KC(15)); il[0] -= rclamp(f0 * KC(7), -c, c); }
+            { const double c = fmax(fabs(il[1]) * KC(16), KC(15)); il[1] -= rclamp(f1 * KC(7), -c, c); }
+            { const double c = fmax(fabs(il[2]) * KC(16), KC(15)); il[2] -= rclamp(f2 * KC(7), -c, c); }
+            { const double c = fmax(fabs(il[3]) * KC(16), KC(15)); il[3] -= rclamp(f3 * KC(7), -c, c); }
+        }
+    }
+    bad_out = D.bad;
+    return converged;
+}
+// Rare path: the same iteration with plain IEEE divisions; il in sc[26..29] (in/out), p in sc[30..33].
+__device__ __noinline__ bool trm_nr_iter_exact(double* sc, const TrmMats& m, const TrmK& kq) {
+    double il[TM], p[TM];
+    for (int q = 0; q < TM; q++) { il[q] = sc[26 + q]; p[q] = sc[30 + q]; }
+    unsigned bad;
+    const bool conv = trm_nr_iter<true>(p, m.k, kq, il, bad);
+    for (int q = 0; q < TM; q++) sc[26 + q] = il[q];
+    return conv;
+}
+
 // process_sample with input 0 (the only way the reference drives it, tremolo.rs:184), gen_tremolo.rs:2353-3116.
 __device__ __forceinline__ double trm_step(TrmState& st, const TrmMats& m, const TrmK& kq, TrmDiag* dg, double* sc) {
     const double input = 0.0;
-    for (int i = 0; i < TN; i++) st.v[i] = st.v[i] + 1e-25 - 1e-25;
-    for (int i = 0; i < TM; i++) st.il[i] = st.il[i] + 1e-25 - 1e-25;
+#pragma unroll
+    for (int i = 0; i < TN; i++) st.v[i] = st.v[i] + KC(8) - KC(8);
+#pragma unroll
+    for (int i = 0; i < TM; i++) st.il[i] = st.il[i] + KC(8) - KC(8);
     double rhs[TN];
     for (int i = 0; i < TN; i++) rhs[i] = TRM_RHS_CONST[i];
     const double (*an)[TN] = m.a_neg;
@@ -366,64 +451,23 @@ __device__ __forceinline__ double trm_step(TrmState& st, const TrmMats& m, const
     double il[TM];
     for (int i = 0; i < TM; i++) il[i] = 2.0 * st.il[i] - st.ilpp[i];
     uint32_t last = T_MAX_ITER;
-    const double vt0 = TRM_DEVICE_0_VT, vt1 = TRM_DEVICE_1_VT;
     const double (*k)[TM] = m.k;
     for (int iter = 0; iter < T_MAX_ITER; iter++) {
-        const double v_d0 = p[0] + k[0][0] * il[0] + k[0][1] * il[1] + k[0][2] * il[2] + k[0][3] * il[3];
-        const double v_d1 = p[1] + k[1][0] * il[0] + k[1][1] * il[1] + k[1][2] * il[2];
-        const double v_d2 = p[2] + k[2][0] * il[0] + k[2][1] * il[1] + k[2][3] * il[3];
-        const double v_d3 = p[3] + k[3][0] * il[0] + k[3][1] * il[1] + k[3][2] * il[2] + k[3][3] * il[3];
-        const Bjt q0 = bjt_em(v_d0, v_d1, kq.q0);
-        const Bjt q1 = bjt_em(v_d2, v_d3, kq.q1);
-        const double f0 = il[0] - q0.ic, f1 = il[1] - q0.ib, f2 = il[2] - q1.ic, f3 = il[3] - q1.ib;
-        double a[4][4];
-        trm_jac(q0, q1, k, a);
-        double b[4] = {f0, f1, f2, f3};
-        bool singular;
-        trm_solve4(a, b, singular);
-        if (!singular) {
-            const double d0 = b[0], d1 = b[1], d2 = b[2], d3 = b[3];
-            const double it0 = il[0] - d0, it1 = il[1] - d1, it2 = il[2] - d2, it3 = il[3] - d3;
-            const double vt_0 = p[0] + k[0][0] * it0 + k[0][1] * it1 + k[0][2] * it2 + k[0][3] * it3;
-            const double vt_1 = p[1] + k[1][0] * it0 + k[1][1] * it1 + k[1][2] * it2 + k[1][3] * it3;
-            const double vt_2 = p[2] + k[2][0] * it0 + k[2][1] * it1 + k[2][2] * it2 + k[2][3] * it3;
-            const double vt_3 = p[3] + k[3][0] * it0 + k[3][1] * it1 + k[3][2] * it2 + k[3][3] * it3;
-            bool any_limited = false;
-            const double vds[4] = {v_d0, v_d1, v_d2, v_d3};
-            const double vts[4] = {vt_0, vt_1, vt_2, vt_3};
-            double dvt[4], vlim[4];
-            for (int q = 0; q < 4; q++) {
-                dvt[q] = vts[q] - vds[q];
-                vlim[q] = fabs(dvt[q]) > 1e-4 ? trm_pnjlim(vts[q], vds[q], q < 2 ? vt0 : vt1, q < 2 ? TRM_DEVICE_0_VCRIT : TRM_DEVICE_1_VCRIT) : vts[q];
-            }
-            double ga = 1.0;
-            for (int q = 0; q < 4; q++) {
-                const double dv_lim = vlim[q] - vds[q];
-                if (fabs(dvt[q]) > 1e-15) {
-                    const double r = (dvt[q] * dv_lim < 0.0) ? 0.0 : rclamp(dv_lim / dvt[q], 0.0, 1.0);
-                    if (r < ga) { ga = r; any_limited = true; }
-                }
-            }
-            {
-                const double max_dv = fmax(fmax(fmax(fabs(dvt[0] * ga), fabs(dvt[1] * ga)), fabs(dvt[2] * ga)), fabs(dvt[3] * ga));
-                if (max_dv > 3.5) { ga *= fmax(3.5 / max_dv, 0.1); any_limited = true; }
-            }
-            il[0] -= ga * d0; il[1] -= ga * d1; il[2] -= ga * d2; il[3] -= ga * d3;
-            if (!any_limited) {
-                bool conv = true;
-                for (int q = 0; q < 4; q++) {
-                    const double dv = dvt[q] * ga;
-                    const double thr = 1e-3 * fmax(fabs(vds[q]), fabs(vds[q] + dv)) + 1e-6;
-                    if (fabs(dv) > thr) conv = false;
-                }
-                if (conv) { last = (uint32_t)iter; break; }
-            }
-        } else {
-            { const double c = fmax(fabs(il[0]) * 0.1, 0.01); il[0] -= rclamp(f0 * 0.5, -c, c); }
-            { const double c = fmax(fabs(il[1]) * 0.1, 0.01); il[1] -= rclamp(f1 * 0.5, -c, c); }
-            { const double c = fmax(fabs(il[2]) * 0.1, 0.01); il[2] -= rclamp(f2 * 0.5, -c, c); }
-            { const double c = fmax(fabs(il[3]) * 0.1, 0.01); il[3] -= rclamp(f3 * 0.5, -c, c); }
+        double nl[TM];
+#pragma unroll
+        for (int q = 0; q < TM; q++) nl[q] = il[q];
+        unsigned bad;
+        bool conv = trm_nr_iter<false>(p, k, kq, nl, bad);
+        if (bad) {  // an operand left the fast division's validated range: redo the iteration with plain IEEE divisions
+#pragma unroll
+            for (int q = 0; q < TM; q++) { sc[26 + q] = il[q]; sc[30 + q] = p[q]; }
+            conv = trm_nr_iter_exact(sc, m, kq);
+#pragma unroll
+            for (int q = 0; q < TM; q++) nl[q] = sc[26 + q];
         }
+#pragma unroll
+        for (int q = 0; q < TM; q++) il[q] = nl[q];
+        if (conv) { last = (uint32_t)iter; break; }
     }
     if (dg) dg->hist[last < 15u ? last : 15u]++;
     double v[TN];

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -119,7 +120,11 @@ struct owg_plan {
     DevBuf<OwgPreampGroup> d_groups;
     DevBuf<int32_t> d_group_rec_index;
     DevBuf<int> d_trem_ids;
-    DevBuf<double> d_static_recs, d_ans, d_pot_seq, d_trem_recs;
+    DevBuf<double> d_static_recs, d_ans, d_pot_seq, d_trem_recs, d_carry;
+    DevBuf<TrmRun> d_trm_run;
+    cudaStream_t stream_trem = nullptr;          // the serial Twin-T oscillator runs here, one chunk ahead of its consumers
+    std::vector<cudaEvent_t> chunk_events;       // oscillator chunk c finished
+    std::vector<cudaEvent_t> chain_ev;           // pairs around every chain launch (device time of the dominant kernel)
     DevBuf<double> d_stage;  // device-side output when the caller's buffer is host memory
     DevBuf<DevDiag> d_diag;
     DeviceCache* cache = nullptr;
@@ -132,6 +137,9 @@ struct owg_plan {
         if (ev1) cudaEventDestroy(ev1);
         if (evk0) cudaEventDestroy(evk0);
         if (evk1) cudaEventDestroy(evk1);
+        for (auto e : chunk_events) cudaEventDestroy(e);
+        for (auto e : chain_ev) cudaEventDestroy(e);
+        if (stream_trem) cudaStreamDestroy(stream_trem);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -218,16 +226,22 @@ void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vec
             pl->trem_n_os_max = std::max(pl->trem_n_os_max, pl->groups[g].n_os);
         } else pl->group_rec_index[g] = (int32_t)g;
     }
+    // Lanes per warp.  A warp's Newton loop runs max-over-lanes iterations, and at small batch sizes the kernel is
+    // latency-bound with idle schedulers, so fewer instances per warp (more warps) shortens every warp's critical path.
+    // Aim for ~1 warp per SM sub-partition (148 SMs x 4; measured optimum), capped at 31 instances + the shadow lane.
+    int lpw = (int)((n + 592 - 1) / 592);
+    lpw = lpw < 1 ? 1 : (lpw > 31 ? 31 : lpw);
+    if (const char* e = getenv("OWG_LANES_PER_WARP")) { const int v = atoi(e); if (v >= 1 && v <= 31) lpw = v; }
     std::vector<int32_t>& order = *order_out;
     order.reserve(n);
     for (size_t g = 0; g < pl->groups.size(); g++) {
         std::vector<int32_t>& mem = members[g];
         std::stable_sort(mem.begin(), mem.end(), [&](int32_t a, int32_t b) { return pl->n_samples[a] > pl->n_samples[b]; });
-        for (size_t off = 0; off < mem.size(); off += 31) {
+        for (size_t off = 0; off < mem.size(); off += (size_t)lpw) {
             WarpEntry we;
             we.group = (int32_t)g;
             we.first = (int32_t)order.size();
-            we.count = (int32_t)std::min<size_t>(31, mem.size() - off);
+            we.count = (int32_t)std::min<size_t>((size_t)lpw, mem.size() - off);
             we._pad = 0;
             we.n_max = 0;
             for (int k = 0; k < we.count; k++) {
@@ -393,48 +407,86 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
         CK(cudaGetLastError());
         launches++;
     }
+    size_t chain_ev_used = 0;
+    auto chain_event = [&]() -> cudaEvent_t {
+        if (chain_ev_used == pl->chain_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); pl->chain_ev.push_back(e); }
+        return pl->chain_ev[chain_ev_used++];
+    };
     if (pl->kind >= 1) {
         const int ng = (int)pl->groups.size();
         static_matrix_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_static_recs.p, pl->d_ans.p);
         CK(cudaGetLastError());
         launches++;
         const int nt = (int)pl->trem_group_ids.size();
+        // Tremolo groups: the Twin-T oscillator is one serial thread per group, so it is pipelined: it runs on its own
+        // stream in chunks of CH preamp-rate samples, and chunk c's matrices + chain run on the main stream while the
+        // oscillator already produces chunk c+1.
+        const int64_t CH_BASE = 8192;  // base-rate samples per chunk
+        int64_t n_chunks = 0;
         if (nt > 0) {
+            if (!pl->stream_trem) CK(cudaStreamCreateWithFlags(&pl->stream_trem, cudaStreamNonBlocking));
+            n_chunks = ((int64_t)pl->max_samples + CH_BASE - 1) / CH_BASE;
+            while ((int64_t)pl->chunk_events.size() < n_chunks + 1) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                pl->chunk_events.push_back(e);
+            }
+            if (int rc = pl->d_trm_run.alloc((size_t)nt)) return rc;
+            if (int rc = pl->d_carry.alloc(pl->warps_trem.size() * (size_t)OWG_CARRY * 32)) return rc;
             tremolo_an_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_ans.p);
             CK(cudaGetLastError());
-            tremolo_group_kernel<<<nt, 1, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                   pl->collect_diag ? pl->d_diag.p : nullptr);
-            CK(cudaGetLastError());
-            dim3 grid((unsigned)((pl->trem_n_os_max + 63) / 64), (unsigned)nt);
-            tremolo_matrix_kernel<<<grid, 64, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_trem_recs.p,
-                                                      pl->trem_n_os_max);
-            CK(cudaGetLastError());
-            launches += 3;
+            launches++;
+            CK(cudaEventRecord(pl->chunk_events[n_chunks], s));               // everything the oscillator stream depends on
+            CK(cudaStreamWaitEvent(pl->stream_trem, pl->chunk_events[n_chunks], 0));
+            for (int64_t c = 0; c < n_chunks; c++) {
+                const int64_t os0 = c * CH_BASE * 2, os1 = (c + 1) * CH_BASE * 2;  // covers 2x-oversampled groups; native-rate groups use half
+                tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                                     pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(pl->chunk_events[c], pl->stream_trem));
+                launches++;
+            }
         }
         CK(cudaEventRecord(pl->evk0, s));
-        if (!pl->warps_static.empty()) {
+        if (!pl->warps_static.empty()) {  // static groups do not depend on the oscillator: they run while it settles
             const int nb = (int)pl->warps_static.size();
+            cudaEvent_t e0 = chain_event(), e1 = chain_event();
+            CK(cudaEventRecord(e0, s));
             if (pl->collect_diag)
                 chain_kernel<false, true><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
-                                                             pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p);
+                                                             pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p,
+                                                             0, INT64_MAX, nullptr);
             else
                 chain_kernel<false, false><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
-                                                              pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, nullptr);
+                                                              pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, nullptr,
+                                                              0, INT64_MAX, nullptr);
             CK(cudaGetLastError());
+            CK(cudaEventRecord(e1, s));
             launches++;
         }
         if (!pl->warps_trem.empty()) {
             const int nb = (int)pl->warps_trem.size();
-            if (pl->collect_diag)
-                chain_kernel<true, true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
-                                                            pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
-                                                            pl->d_diag.p);
-            else
-                chain_kernel<true, false><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
-                                                             pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
-                                                             nullptr);
-            CK(cudaGetLastError());
-            launches++;
+            for (int64_t c = 0; c < n_chunks; c++) {
+                const int64_t b0 = c * CH_BASE, b1 = (c + 1) * CH_BASE;
+                CK(cudaStreamWaitEvent(s, pl->chunk_events[c], 0));
+                dim3 grid((unsigned)((2 * CH_BASE + 63) / 64), (unsigned)nt);
+                tremolo_matrix_kernel<<<grid, 64, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_trem_recs.p,
+                                                          pl->trem_n_os_max, 2 * b0, 2 * b1);
+                CK(cudaGetLastError());
+                cudaEvent_t e0 = chain_event(), e1 = chain_event();
+                CK(cudaEventRecord(e0, s));
+                if (pl->collect_diag)
+                    chain_kernel<true, true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                                pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
+                                                                pl->d_diag.p, b0, b1, pl->d_carry.p);
+                else
+                    chain_kernel<true, false><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                                 pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
+                                                                 nullptr, b0, b1, pl->d_carry.p);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(e1, s));
+                launches += 2;
+            }
         }
         CK(cudaEventRecord(pl->evk1, s));
     } else {
@@ -449,7 +501,13 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     CK(cudaEventRecord(pl->ev1, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&pl->total_ms, pl->ev0, pl->ev1));
-    CK(cudaEventElapsedTime(&pl->main_ms, pl->evk0, pl->evk1));
+    pl->main_ms = 0.f;  // device time of the chain kernel launches (busy time, not the wait for the oscillator)
+    for (size_t k = 0; k + 1 < chain_ev_used; k += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, pl->chain_ev[k], pl->chain_ev[k + 1]));
+        pl->main_ms += ms;
+    }
+    (void)pl->evk0;
     pl->launches_last = launches;
     if (pl->collect_diag) {
         DevDiag h;
