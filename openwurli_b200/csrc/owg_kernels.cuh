@@ -68,14 +68,15 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
     const double tot = sr * 2.0;
     const long long n_settle = !(tot == tot) || tot <= 0.0 ? 0ll : (long long)tot;
     const long long n_pre = 50 + n_settle;
-    // the first launch (live_begin == 0) also runs the pre-roll; later launches resume from run[]
-    const long long n_begin = live_begin == 0 ? 0 : n_pre + live_begin;
-    const long long n_end = n_pre + (live_end < gr.n_os ? live_end : gr.n_os);
-    if (n_begin >= n_end && live_begin != 0) return;
+    // live_begin < 0: constructor only (Tremolo::new: warm-up + settle), run at plan time; live launches resume from run[]
+    const bool ctor = live_begin < 0;
+    const long long n_begin = ctor ? 0 : n_pre + live_begin;
+    const long long n_end = ctor ? n_pre : n_pre + (live_end < gr.n_os ? live_end : gr.n_os);
+    if (n_begin >= n_end) return;
     TrmState st;
     double env = 0.0;
     double pot = 9.99999999999999854e4;  // pot_0_resistance of the settled state
-    if (live_begin == 0) {
+    if (ctor) {
         for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
         for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
         st.xin_prev = 0.0;

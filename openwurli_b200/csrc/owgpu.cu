@@ -121,7 +121,7 @@ struct owg_plan {
     DevBuf<int32_t> d_group_rec_index;
     DevBuf<int> d_trem_ids;
     DevBuf<double> d_static_recs, d_ans, d_pot_seq, d_trem_recs, d_carry;
-    DevBuf<TrmRun> d_trm_run;
+    DevBuf<TrmRun> d_trm_run, d_trm_ctor;       // oscillator state: running / as constructed (Tremolo::new, computed at plan time)
     cudaStream_t stream_trem = nullptr;          // the serial Twin-T oscillator runs here, one chunk ahead of its consumers
     std::vector<cudaEvent_t> chunk_events;       // oscillator chunk c finished
     std::vector<cudaEvent_t> chain_ev;           // pairs around every chain launch (device time of the dominant kernel)
@@ -269,6 +269,19 @@ int upload_chain_plan(owg_plan* pl, const std::vector<OwgChainInit>& ci, const s
         if (!rc) rc = pl->d_trem_recs.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max * OWG_MAT_STRIDE);
     }
     if (!rc && pl->collect_diag) rc = pl->d_diag.alloc(1);
+    if (!rc && !pl->trem_group_ids.empty()) {
+        // Constructors run at plan time, per-sample processing at execute time: Tremolo::new (50 warm-up + 2*sr settle
+        // samples of the Twin-T oscillator, tremolo.rs:84-115) is evaluated here once per tremolo group, like Voice::note_on
+        // on the host and DkPreamp::new's cached settled state.
+        const int nt = (int)pl->trem_group_ids.size();
+        rc = pl->d_trm_run.alloc((size_t)nt);
+        if (!rc) rc = pl->d_trm_ctor.alloc((size_t)nt);
+        if (!rc) {
+            tremolo_group_kernel<<<nt, 32, 0, pl->stream>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_trm_ctor.p,
+                                                            -1, -1, nullptr);
+            if (cudaGetLastError() != cudaSuccess) rc = fail(OWG_E_CUDA, "tremolo constructor kernel launch failed");
+        }
+    }
     if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
     return rc;
 }
@@ -431,8 +444,8 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                 CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 pl->chunk_events.push_back(e);
             }
-            if (int rc = pl->d_trm_run.alloc((size_t)nt)) return rc;
             if (int rc = pl->d_carry.alloc(pl->warps_trem.size() * (size_t)OWG_CARRY * 32)) return rc;
+            CK(cudaMemcpyAsync(pl->d_trm_run.p, pl->d_trm_ctor.p, (size_t)nt * sizeof(TrmRun), cudaMemcpyDeviceToDevice, s));
             tremolo_an_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_ans.p);
             CK(cudaGetLastError());
             launches++;
