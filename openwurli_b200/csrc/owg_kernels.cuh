@@ -18,7 +18,7 @@ __constant__ double c_noise_fade[16];  // hammer.rs:161-168, filled by the host 
 
 // ---- settled preamp state: 176 400 silent samples at 48 kHz / 100 kOhm (melange_adapter.rs:14-20) ----
 __global__ void settle_kernel(DkState* out) {
-    __shared__ double rec[OWG_MAT_STRIDE];
+    __shared__ __align__(16) double rec[OWG_MAT_STRIDE];
     __shared__ double an[OWG_AN_SPARSE];
     __shared__ double cold[OWG_COLD_SCRATCH];
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
                                                    const int32_t* __restrict__ group_rec_index, int64_t rec_stride_t,
                                                    double* __restrict__ out, int64_t stride, DevDiag* diag,
                                                    int64_t t_begin, int64_t t_end, double* __restrict__ carry /*[warp][OWG_CARRY][32]*/) {
-    __shared__ double s_rec[OWG_MAT_STRIDE];
+    __shared__ __align__(16) double s_rec[TREM ? 2 * OWG_MAT_STRIDE : OWG_MAT_STRIDE];  // TREM: double-buffered per-sample records
     __shared__ double s_an[OWG_AN_SPARSE];
     __shared__ OwgChainInit s_ci[32];
     __shared__ double s_cold[OWG_COLD_SCRATCH * 32];
@@ -328,6 +328,18 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
     }
     const int64_t t_stop = t_end < we.n_max ? t_end : we.n_max;
     int64_t tos = t_begin * n_sub;  // preamp-rate sample index
+    const int64_t n_rec = rec_stride_t;  // records available per group (TREM)
+    if (TREM) {
+        if (tos < n_rec) {
+            const double* src = grec + (size_t)tos * OWG_MAT_STRIDE;
+            double* dst = s_rec + (tos & 1) * OWG_MAT_STRIDE;
+            for (int c = lane; c < OWG_MAT_STRIDE / 2; c += 32) {
+                const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 2 * c) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     double x_next = (is_main && (unsigned long long)t_begin < ns) ? o[t_begin] : 0.0;  // software prefetch (hides the L2 latency)
     for (int64_t t = t_begin; t < t_stop; t++) {
         const bool live = is_main && (unsigned long long)t < ns;
@@ -344,7 +356,22 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
         // the instruction cache with a single resident warp per scheduler).
 #pragma unroll 1
         for (int j = 0; j < n_sub; j++) {
-            const double* m = TREM ? grec + (size_t)tos * OWG_MAT_STRIDE : s_rec;
+            if (TREM) {
+                // record `tos` was prefetched into s_rec[tos & 1] during the previous step; now prefetch record tos+1
+                // (cp.async, 95 x 16 B per record) so that its L2 latency hides behind this step's Newton solve
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                if (tos + 1 < n_rec) {
+                    const double* src = grec + (size_t)(tos + 1) * OWG_MAT_STRIDE;
+                    double* dst = s_rec + ((tos + 1) & 1) * OWG_MAT_STRIDE;
+                    for (int c = lane; c < OWG_MAT_STRIDE / 2; c += 32) {
+                        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 2 * c) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            const double* m = TREM ? s_rec + (tos & 1) * OWG_MAT_STRIDE : s_rec;
             const double an66 = m[OWG_MAT_AN66];
             const double main_out = dk_step<DIAG>(j == 0 ? u0 : u1, st, m, s_an, an66, dv, &dd, s_cold + lane, 32);
             const double pump = __shfl_sync(0xffffffffu, main_out, 31);

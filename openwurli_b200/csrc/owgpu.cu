@@ -276,11 +276,16 @@ int upload_chain_plan(owg_plan* pl, const std::vector<OwgChainInit>& ci, const s
         const int nt = (int)pl->trem_group_ids.size();
         rc = pl->d_trm_run.alloc((size_t)nt);
         if (!rc) rc = pl->d_trm_ctor.alloc((size_t)nt);
+        if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
+        if (!rc && !pl->stream_trem && cudaStreamCreateWithFlags(&pl->stream_trem, cudaStreamNonBlocking) != cudaSuccess)
+            rc = fail(OWG_E_CUDA, "stream creation failed");
         if (!rc) {
-            tremolo_group_kernel<<<nt, 32, 0, pl->stream>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_trm_ctor.p,
-                                                            -1, -1, nullptr);
+            // asynchronous: every later oscillator launch goes to the same in-order stream, so nothing has to wait here
+            tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                                 pl->d_trm_ctor.p, -1, -1, nullptr);
             if (cudaGetLastError() != cudaSuccess) rc = fail(OWG_E_CUDA, "tremolo constructor kernel launch failed");
         }
+        return rc;
     }
     if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
     return rc;
@@ -445,7 +450,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                 pl->chunk_events.push_back(e);
             }
             if (int rc = pl->d_carry.alloc(pl->warps_trem.size() * (size_t)OWG_CARRY * 32)) return rc;
-            CK(cudaMemcpyAsync(pl->d_trm_run.p, pl->d_trm_ctor.p, (size_t)nt * sizeof(TrmRun), cudaMemcpyDeviceToDevice, s));
+            CK(cudaMemcpyAsync(pl->d_trm_run.p, pl->d_trm_ctor.p, (size_t)nt * sizeof(TrmRun), cudaMemcpyDeviceToDevice, pl->stream_trem));
             tremolo_an_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_ans.p);
             CK(cudaGetLastError());
             launches++;
