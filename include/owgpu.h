@@ -39,13 +39,15 @@ typedef struct owg_voice_job {
     uint8_t midi;          /* MIDI note 33..96 */
     uint8_t mlp_enabled;   /* 0/1: MLP v2 per-note corrections (voice.rs:62-66) */
     uint8_t attack_noise;  /* 0 = disable_attack_noise() */
-    uint8_t _pad0;
+    uint8_t flags;         /* OWG_VOICE_* bits */
     uint32_t noise_seed;   /* seed of the jitter and attack-noise LCGs (voice.rs:208: midi*2654435761) */
     double velocity;       /* 0..1 (callers pass vel/127.0) */
     double sample_rate;    /* Hz */
     double duration_s;     /* seconds */
     double ds_override;    /* pickup displacement-scale override; NaN = none */
 } owg_voice_job;
+
+#define OWG_VOICE_NO_ONSET 1 /* onset_time = 0.0: the reed is built as run_calibrate does (main.rs:1165-1174) */
 
 /* = the flags of `preamp-bench render` (tools/preamp-bench/src/main.rs:372-392), chain B. */
 typedef struct owg_bench_job {
@@ -142,6 +144,18 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
 int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double fs_base,
                      int oversample, double tremolo_depth, double r_ldr_static, double* out, int64_t out_stride,
                      const owg_opts* opts);
+
+/* Output mode "metrics" (BASELINE config 4): chain B with the `run_calibrate` analysis reduced on the device
+ * instead of returning samples (tools/preamp-bench/src/main.rs:1139-1141, 1215-1223, 893-938): over the window
+ * [window_start_s, window_end_s) of the final (T5) signal, per job:
+ *   metrics[7*i + 0] peak_db   = 20 log10(max|x|)            (-120 below 1e-15)
+ *   metrics[7*i + 1] rms_db    = 10 log10(mean x^2)          (-120 when 0)
+ *   metrics[7*i + 2] h2_h1_db  = 20 log10(|X(2 f0)| / |X(f0)|), f0 = midi_to_freq(midi), single-bin DFT
+ *   metrics[7*i + 3..6]        = raw peak, mean square, |X(f0)|, |X(2 f0)|
+ * All jobs of one call must share sample_rate and cover the window.  `metrics` is host memory [n][7]. */
+#define OWG_METRIC_COLUMNS 7
+int owg_render_bench_metrics(const owg_bench_job* jobs, int64_t n, double window_start_s, double window_end_s, double* metrics,
+                             const owg_opts* opts);
 
 /* ---- planned renders: note-on parameterisation done once, inputs resident in HBM ---------- */
 typedef struct owg_plan owg_plan;

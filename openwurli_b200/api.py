@@ -15,22 +15,26 @@ def default_noise_seed(midi):
     return (int(midi) * 2654435761) & 0xFFFFFFFF
 
 
+VOICE_NO_ONSET = 1
+
+
 def voice_job(midi=60, velocity=100, sample_rate=44100.0, duration=2.0, mlp=False, attack_noise=True, seed=None,
-              displacement_scale=None, velocity_norm=None):
+              displacement_scale=None, velocity_norm=None, no_onset=False):
     """One Voice::note_on + render job.  `velocity` is MIDI 0..127 (normalised as vel/127.0 in f64 like the CLIs,
     reed-renderer main.rs:83); pass velocity_norm to give the 0..1 value directly."""
     v = (velocity / 127.0) if velocity_norm is None else float(velocity_norm)
-    return VoiceJob(int(midi), 1 if mlp else 0, 1 if attack_noise else 0, 0,
+    return VoiceJob(int(midi), 1 if mlp else 0, 1 if attack_noise else 0, VOICE_NO_ONSET if no_onset else 0,
                     default_noise_seed(midi) if seed is None else int(seed) & 0xFFFFFFFF, v, float(sample_rate),
                     float(duration), NAN if displacement_scale is None else float(displacement_scale))
 
 
 def bench_job(note=60, velocity=100, duration=2.0, ldr=1_000_000.0, volume=0.60, speaker=1.0, tremolo_depth=0.0,
               sample_rate=44100.0, no_poweramp=False, no_preamp=False, no_attack_noise=False, no_mlp=False,
-              displacement_scale=None, seed=None):
-    """One `preamp-bench render` job; keyword names and defaults are the CLI flags (main.rs:372-392)."""
+              displacement_scale=None, seed=None, no_onset=False):
+    """One `preamp-bench render` job; keyword names and defaults are the CLI flags (main.rs:372-392).
+    no_onset=True builds the reed with onset_time 0 as `run_calibrate` does (main.rs:1165-1174)."""
     return BenchJob(voice_job(note, velocity, sample_rate, duration, not no_mlp, not no_attack_noise, seed,
-                              displacement_scale), float(ldr), float(tremolo_depth), float(volume), float(speaker),
+                              displacement_scale, no_onset=no_onset), float(ldr), float(tremolo_depth), float(volume), float(speaker),
                     1 if no_preamp else 0, 1 if no_poweramp else 0)
 
 
@@ -195,6 +199,29 @@ def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000
     check(lib().owg_preamp_batch(pin, sin, x.shape[0], x.shape[1], float(fs_base), 1 if oversample else 0,
                                  float(tremolo_depth), float(r_ldr), pout, sout, C.byref(o)))
     return out
+
+
+METRIC_COLUMNS = ("peak_db", "rms_db", "h2_h1_db", "peak", "mean_sq", "h1", "h2")
+
+
+def render_bench_metrics(jobs, window=(0.100, 0.400), device=-1):
+    """Chain B with the `run_calibrate` T5 analysis reduced on the device (output mode "metrics", BASELINE config 4):
+    returns [n, 7] float64 = METRIC_COLUMNS over the window [start_s, end_s) (default 100-400 ms, main.rs:1139-1141)."""
+    out = np.zeros((len(jobs), 7), dtype=np.float64)
+    if len(jobs) == 0:
+        return out
+    arr = (BenchJob * len(jobs))(*jobs)
+    o = _opts(device, OWG_OUT_HOST)
+    check(lib().owg_render_bench_metrics(arr, len(jobs), float(window[0]), float(window[1]),
+                                         out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(o)))
+    return out
+
+
+def calibrate_job(note, velocity, volume=0.60, speaker=1.0, tremolo_depth=0.0):
+    """The render `preamp-bench calibrate` measures (run_calibrate, main.rs:1128-1263): 0.5 s at 44.1 kHz, reed built
+    with onset 0, no attack noise, no MLP, default CalibrationConfig, preamp at a static 1 MOhm."""
+    return bench_job(note=note, velocity=velocity, duration=0.5, volume=volume, speaker=speaker, tremolo_depth=tremolo_depth,
+                     no_mlp=True, no_attack_noise=True, no_onset=True)
 
 
 NOTE_ON, NOTE_OFF, SUSTAIN = 0, 1, 2

@@ -293,7 +293,7 @@ void make_voice_init(const owg_voice_job& job, OwgVoiceInit* out) {
     }
     const double d0 = dwell[0];
     if (d0 > 1e-30) for (int i = 0; i < NM; i++) dwell[i] /= d0;
-    const double onset_s = std::fmax((1.0 + 1.0 * (1.0 - vel)) * (1.0 / k.f_detuned), 0.002);
+    const double onset_s = (job.flags & OWG_VOICE_NO_ONSET) ? 0.0 : std::fmax((1.0 + 1.0 * (1.0 - vel)) * (1.0 / k.f_detuned), 0.002);
 
     // voice.rs:44-57 amplitudes
     const double vel_scale = std::pow(vel_scurve(vel), k.vel_exp);
@@ -458,6 +458,8 @@ int make_speaker_schedule(double fs, double target, int64_t n_warm, int64_t n_to
     }
     return n;
 }
+
+double note_frequency(int midi) { return freq_of_key(midi); }
 
 double silent_threshold() { return std::pow(10.0, -80.0 / 20.0); }
 

@@ -19,4 +19,6 @@ int make_speaker_schedule(double sample_rate, double character_target, int64_t n
                           SpkUpdate* out, int max_out);
 // 10^(-80/20): the is_silent threshold (reed.rs:310), through glibc pow like the reference.
 double silent_threshold();
+// tables::midi_to_freq (tables.rs:34-36)
+double note_frequency(int midi);
 }  // namespace owg

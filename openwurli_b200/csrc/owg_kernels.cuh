@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restric
 // solve in lane 31 (melange_adapter.rs:72-81: out = main - shadow).  Processes the voice samples in
 // `out` in place.
 struct WarpEntry { int32_t group, first, count; int32_t _pad; int64_t n_max; };
+#define OWG_METRICS 6  // per job: peak |x|, sum x^2, re1, im1, re2, im2 over the analysis window (run_calibrate, main.rs:1139-1223)
 #define OWG_CARRY 40  // doubles of per-lane state carried between chunk launches (12+3+3+1+1 DK, 12+1 oversampler, 5 speaker)
 
 template <bool TREM, bool DIAG>
@@ -267,7 +268,9 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
                                                    const DkState* __restrict__ settled, const double* __restrict__ recs, const double* __restrict__ ans,
                                                    const int32_t* __restrict__ group_rec_index, int64_t rec_stride_t,
                                                    double* __restrict__ out, int64_t stride, DevDiag* diag,
-                                                   int64_t t_begin, int64_t t_end, double* __restrict__ carry /*[warp][OWG_CARRY][32]*/) {
+                                                   int64_t t_begin, int64_t t_end, double* __restrict__ carry /*[warp][OWG_CARRY][32]*/,
+                                                   double* __restrict__ metrics /*[job][OWG_METRICS] or null*/, const double* __restrict__ f0s,
+                                                   int64_t w_begin, int64_t w_end) {
     __shared__ __align__(16) double s_rec[TREM ? 2 * OWG_MAT_STRIDE : OWG_MAT_STRIDE];  // TREM: double-buffered per-sample records
     __shared__ double s_an[OWG_AN_SPARSE];
     __shared__ OwgChainInit s_ci[32];
@@ -325,6 +328,13 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
         for (int i = 0; i < 3; i++) { ua[i] = cw[(k++) * 32]; ub[i] = cw[(k++) * 32]; da[i] = cw[(k++) * 32]; db[i] = cw[(k++) * 32]; }
         down_delay = cw[(k++) * 32];
         spk.thermal = cw[(k++) * 32]; spk.h1 = cw[(k++) * 32]; spk.h2 = cw[(k++) * 32]; spk.l1 = cw[(k++) * 32]; spk.l2 = cw[(k++) * 32];
+    }
+    // on-device analysis reduction (output mode "metrics"): accumulators continue sequentially across chunk launches
+    double m_peak = 0.0, m_sq = 0.0, m_re1 = 0.0, m_im1 = 0.0, m_re2 = 0.0, m_im2 = 0.0, m_f0 = 0.0, m_sr = 1.0;
+    if (metrics && is_main) {
+        const double* mj = metrics + (size_t)job * OWG_METRICS;
+        m_peak = mj[0]; m_sq = mj[1]; m_re1 = mj[2]; m_im1 = mj[3]; m_re2 = mj[4]; m_im2 = mj[5];
+        m_f0 = f0s[2 * job]; m_sr = f0s[2 * job + 1];
     }
     const int64_t t_stop = t_end < we.n_max ? t_end : we.n_max;
     int64_t tos = t_begin * n_sub;  // preamp-rate sample index
@@ -392,8 +402,23 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
         else if (live) {
             const double att = pre_out * vol * vol;
             const double amped = ci.no_poweramp ? att : poweramp(att, DIAG ? pa_hist : nullptr);
-            o[t] = speaker(amped, spk, ci) * 7.498942093324558;
+            const double y_final = speaker(amped, spk, ci) * 7.498942093324558;
+            if (metrics) {
+                if (t >= w_begin && t < w_end) {  // peak_abs / rms / single-bin DFT at f0 and 2 f0 (main.rs:893-938)
+                    const double ii = (double)(t - w_begin);
+                    m_peak = fmax(m_peak, fabs(y_final));
+                    m_sq += y_final * y_final;
+                    const double ph1 = 2.0 * 3.14159265358979323846 * m_f0 * ii / m_sr;
+                    const double ph2 = 2.0 * 3.14159265358979323846 * (2.0 * m_f0) * ii / m_sr;
+                    m_re1 += y_final * cos(ph1); m_im1 -= y_final * sin(ph1);
+                    m_re2 += y_final * cos(ph2); m_im2 -= y_final * sin(ph2);
+                }
+            } else o[t] = y_final;
         }
+    }
+    if (metrics && is_main) {
+        double* mj = metrics + (size_t)job * OWG_METRICS;
+        mj[0] = m_peak; mj[1] = m_sq; mj[2] = m_re1; mj[3] = m_im1; mj[4] = m_re2; mj[5] = m_im2;
     }
     if (cw && t_stop < we.n_max) {
         int k = 0;

@@ -99,6 +99,9 @@ struct owg_plan {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int kind = 0;  // 0 = voices (chain V), 1 = bench (chain B), 2 = preamp-only batch (input rows supplied by the caller)
+    double* metrics_ptr = nullptr;   // device [n][OWG_METRICS] accumulators when the output mode is "metrics"
+    int64_t w_begin = 0, w_end = 0;  // analysis window, base-rate samples
+    DevBuf<double> d_f0s;            // per job: nominal fundamental, sample rate
     const double* in_ptr = nullptr;  // kind 2: caller's input [n][in_stride] (host or device, like `out`)
     int64_t in_stride = 0;
     bool collect_diag = false;
@@ -473,11 +476,11 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
             if (pl->collect_diag)
                 chain_kernel<false, true><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                              pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p,
-                                                             0, INT64_MAX, nullptr);
+                                                             0, INT64_MAX, nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
             else
                 chain_kernel<false, false><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                               pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, nullptr,
-                                                              0, INT64_MAX, nullptr);
+                                                              0, INT64_MAX, nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, s));
             launches++;
@@ -496,11 +499,11 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                 if (pl->collect_diag)
                     chain_kernel<true, true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                 pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
-                                                                pl->d_diag.p, b0, b1, pl->d_carry.p);
+                                                                pl->d_diag.p, b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
                 else
                     chain_kernel<true, false><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                  pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
-                                                                 nullptr, b0, b1, pl->d_carry.p);
+                                                                 nullptr, b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(e1, s));
                 launches += 2;
@@ -555,6 +558,63 @@ int owg_render_bench(const owg_bench_job* jobs, int64_t n, double* out, int64_t 
     const int rc = owg_plan_execute(pl, out, stride, opts ? opts->out_location : OWG_OUT_HOST);
     owg_plan_destroy(pl);
     return rc;
+}
+
+int owg_render_bench_metrics(const owg_bench_job* jobs, int64_t n, double window_start_s, double window_end_s, double* metrics,
+                             const owg_opts* opts) {
+    if (n < 0 || (n > 0 && (!jobs || !metrics)) || !(window_end_s > window_start_s) || !(window_start_s >= 0.0))
+        return fail(OWG_E_BAD_ARG, "owg_render_bench_metrics: bad argument");
+    if (n == 0) return OWG_OK;
+    const double sr = jobs[0].v.sample_rate;
+    if (!(sr > 0.0) || !std::isfinite(sr)) return fail(OWG_E_BAD_ARG, "owg_render_bench_metrics: invalid sample_rate");
+    const int64_t w0 = (int64_t)(window_start_s * sr), w1 = (int64_t)(window_end_s * sr);  // `(0.100 * BASE_SR) as usize`
+    for (int64_t i = 0; i < n; i++) {
+        if (jobs[i].v.sample_rate != sr) return fail(OWG_E_BAD_ARG, "owg_render_bench_metrics: all jobs must share one sample_rate");
+        if (!(jobs[i].v.duration_s * sr >= (double)w1)) return fail(OWG_E_BAD_ARG, "owg_render_bench_metrics: analysis window exceeds a job's duration");
+    }
+    owg_opts o;
+    if (opts) o = *opts; else owg_default_opts(&o);
+    o.out_location = OWG_OUT_DEVICE;
+    const int64_t BATCH = 65536;  // bounds the device scratch (voice samples) independently of n
+    DevBuf<double> scratch, d_metrics;
+    std::vector<double> raw;
+    for (int64_t b0 = 0; b0 < n; b0 += BATCH) {
+        const int64_t nb = std::min<int64_t>(BATCH, n - b0);
+        owg_plan* pl = nullptr;
+        if (int rc = owg_plan_bench(jobs + b0, nb, &o, &pl)) return rc;
+        std::vector<double> f0s((size_t)nb * 2);
+        for (int64_t i = 0; i < nb; i++) { f0s[2 * i] = owg::note_frequency(jobs[b0 + i].v.midi); f0s[2 * i + 1] = sr; }
+        int rc = pl->d_f0s.upload(f0s, pl->stream);
+        const int64_t stride = (int64_t)pl->max_samples;
+        if (!rc) rc = scratch.alloc((size_t)nb * (size_t)stride);
+        if (!rc) rc = d_metrics.alloc((size_t)nb * OWG_METRICS);
+        if (!rc && cudaMemsetAsync(d_metrics.p, 0, (size_t)nb * OWG_METRICS * sizeof(double), pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "memset failed");
+        if (!rc) {
+            pl->metrics_ptr = d_metrics.p;
+            pl->w_begin = w0;
+            pl->w_end = w1;
+            rc = owg_plan_execute(pl, scratch.p, stride, OWG_OUT_DEVICE);
+        }
+        if (!rc) {
+            raw.resize((size_t)nb * OWG_METRICS);
+            if (cudaMemcpy(raw.data(), d_metrics.p, raw.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(OWG_E_CUDA, "metrics copy failed");
+        }
+        owg_plan_destroy(pl);
+        if (rc) return rc;
+        const double nwin = (double)(w1 - w0);
+        for (int64_t i = 0; i < nb; i++) {
+            const double* r = &raw[(size_t)i * OWG_METRICS];
+            double* m = metrics + (size_t)(b0 + i) * OWG_METRIC_COLUMNS;
+            const double peak = r[0], mean_sq = r[1] / nwin;
+            const double h1 = 2.0 * std::sqrt((r[2] / nwin) * (r[2] / nwin) + (r[3] / nwin) * (r[3] / nwin));
+            const double h2 = 2.0 * std::sqrt((r[4] / nwin) * (r[4] / nwin) + (r[5] / nwin) * (r[5] / nwin));
+            m[0] = peak > 1e-15 ? 20.0 * std::log10(peak) : -120.0;
+            m[1] = mean_sq > 0.0 ? 10.0 * std::log10(mean_sq) : -120.0;
+            m[2] = h1 > 1e-15 ? 20.0 * std::log10(h2 / h1) : -120.0;
+            m[3] = peak; m[4] = mean_sq; m[5] = h1; m[6] = h2;
+        }
+    }
+    return OWG_OK;
 }
 
 int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_t stride, const owg_opts* opts) {

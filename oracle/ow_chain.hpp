@@ -132,6 +132,7 @@ struct BenchJob {
     bool mlp_enabled = true;
     double ds_override = NAN;
     bool attack_noise = true;
+    bool zero_onset = false;
     double r_ldr = 1.0e6;
     double tremolo_depth = 0.0;
     double volume = 0.60;
@@ -161,7 +162,7 @@ static inline std::vector<double> render_bench(const BenchJob& j, Taps* taps = n
     std::vector<double> reed(n, 0.0);
     {
         Voice v;
-        v.note_on(j.midi, j.velocity, sr, j.noise_seed, j.mlp_enabled);
+        v.note_on(j.midi, j.velocity, sr, j.noise_seed, j.mlp_enabled, j.zero_onset);
         if (j.ds_override == j.ds_override) v.pickup.displacement_scale = j.ds_override;
         if (!j.attack_noise) v.noise.disable();
         for (size_t off = 0; off < n; off += 1024) v.render(reed.data() + off, std::min<size_t>(1024, n - off));

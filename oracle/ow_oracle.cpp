@@ -19,7 +19,7 @@ static BenchJob to_bench(const owg_bench_job& j) {
     BenchJob b;
     b.midi = j.v.midi; b.velocity = j.v.velocity; b.sample_rate = j.v.sample_rate; b.duration_s = j.v.duration_s;
     b.noise_seed = j.v.noise_seed; b.mlp_enabled = j.v.mlp_enabled != 0; b.ds_override = j.v.ds_override;
-    b.attack_noise = j.v.attack_noise != 0; b.r_ldr = j.r_ldr; b.tremolo_depth = j.tremolo_depth; b.volume = j.volume;
+    b.attack_noise = j.v.attack_noise != 0; b.zero_onset = (j.v.flags & OWG_VOICE_NO_ONSET) != 0; b.r_ldr = j.r_ldr; b.tremolo_depth = j.tremolo_depth; b.volume = j.volume;
     b.speaker_character = j.speaker_character; b.no_preamp = j.no_preamp != 0; b.no_poweramp = j.no_poweramp != 0;
     return b;
 }
@@ -46,7 +46,7 @@ int owo_render_voices(const owg_voice_job* jobs, int64_t n, double* out, int64_t
     parallel_for(n, threads, [&](int64_t i) {
         const owg_voice_job& j = jobs[i];
         Voice v;
-        v.note_on(j.midi, j.velocity, j.sample_rate, j.noise_seed, j.mlp_enabled != 0);
+        v.note_on(j.midi, j.velocity, j.sample_rate, j.noise_seed, j.mlp_enabled != 0, (j.flags & OWG_VOICE_NO_ONSET) != 0);
         if (j.ds_override == j.ds_override) v.pickup.displacement_scale = j.ds_override;
         if (!j.attack_noise) v.noise.disable();
         const size_t ns = (size_t)f64_as_u64(j.duration_s * j.sample_rate);
@@ -239,7 +239,7 @@ void owo_oversampler_roundtrip(const double* in, int64_t n, double* out) {
 // Flattened Voice::note_on state, same layout as owg_host_voice_init (include/owgpu.h).
 void owo_voice_init(const owg_voice_job* j, double* o) {
     Voice v;
-    v.note_on(j->midi, j->velocity, j->sample_rate, j->noise_seed, j->mlp_enabled != 0);
+    v.note_on(j->midi, j->velocity, j->sample_rate, j->noise_seed, j->mlp_enabled != 0, (j->flags & OWG_VOICE_NO_ONSET) != 0);
     if (j->ds_override == j->ds_override) v.pickup.displacement_scale = j->ds_override;
     if (!j->attack_noise) v.noise.disable();
     int k = 0;

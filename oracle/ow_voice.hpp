@@ -652,12 +652,13 @@ struct Voice {
     double sample_rate;
     uint8_t midi_note;
 
-    void note_on(uint8_t midi, double velocity, double sr, uint32_t noise_seed, bool mlp_enabled) {  // voice.rs:28-142
+    // zero_onset: onset_time_s = 0.0, as run_calibrate builds its reed directly (preamp-bench main.rs:1165-1174)
+    void note_on(uint8_t midi, double velocity, double sr, uint32_t noise_seed, bool mlp_enabled, bool zero_onset = false) {  // voice.rs:28-142
         const NoteParams params = note_params(midi);
         const double detuned = params.fundamental_hz * freq_detune(midi);
         double dwell[NUM_MODES];
         dwell_attenuation(velocity, detuned, params.mode_ratios, dwell);
-        const double onset_time = onset_ramp_time(velocity, detuned);
+        const double onset_time = zero_onset ? 0.0 : onset_ramp_time(velocity, detuned);
         double amp_offsets[NUM_MODES];
         mode_amplitude_offsets(midi, amp_offsets);
         double amplitudes[NUM_MODES];

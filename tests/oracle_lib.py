@@ -9,7 +9,7 @@ SO = os.path.join(ROOT, "oracle", "_build", "liboworacle.so")
 
 
 class VoiceJob(C.Structure):
-    _fields_ = [("midi", C.c_uint8), ("mlp_enabled", C.c_uint8), ("attack_noise", C.c_uint8), ("_pad0", C.c_uint8),
+    _fields_ = [("midi", C.c_uint8), ("mlp_enabled", C.c_uint8), ("attack_noise", C.c_uint8), ("flags", C.c_uint8),
                 ("noise_seed", C.c_uint32), ("velocity", C.c_double), ("sample_rate", C.c_double),
                 ("duration_s", C.c_double), ("ds_override", C.c_double)]
 

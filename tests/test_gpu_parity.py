@@ -25,7 +25,7 @@ G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "
 
 
 def to_oracle_v(j):
-    return O.VoiceJob(j.midi, j.mlp_enabled, j.attack_noise, 0, j.noise_seed, j.velocity, j.sample_rate, j.duration_s,
+    return O.VoiceJob(j.midi, j.mlp_enabled, j.attack_noise, j.flags, j.noise_seed, j.velocity, j.sample_rate, j.duration_s,
                       j.ds_override)
 
 
@@ -315,3 +315,51 @@ def test_engine_polyphony_sustain_restrike_and_stealing():
     _engine_parity(pairs, "engine poly")
     d = ow.last_diag()
     assert d.nr_iter_hist[0] >= 180 and d.nr_iter_hist[1] > 0  # note-ons and steals counted on the device
+
+
+# ---- output mode "metrics": run_calibrate's T5 analysis reduced on the device (BASELINE config 4) --------------------------
+def _calibrate_metrics_from_samples(x, f0, sr=44100.0, w=(0.100, 0.400)):
+    """peak_db / rms_db / h2_h1_ratio_db exactly as tools/preamp-bench/src/main.rs:893-938 define them."""
+    win = x[int(w[0] * sr):int(w[1] * sr)]
+    n = len(win)
+    i = np.arange(n)
+
+    def dft(f):
+        ph = 2.0 * np.pi * f * i / sr
+        re, im = np.sum(win * np.cos(ph)), -np.sum(win * np.sin(ph))
+        return 2.0 * np.sqrt((re / n) ** 2 + (im / n) ** 2)
+
+    peak, msq = np.abs(win).max(), np.mean(win ** 2)
+    h1, h2 = dft(f0), dft(2.0 * f0)
+    return np.array([20 * np.log10(peak) if peak > 1e-15 else -120.0, 10 * np.log10(msq) if msq > 0 else -120.0,
+                     20 * np.log10(h2 / h1) if h1 > 1e-15 else -120.0, peak, msq, h1, h2])
+
+
+def test_metrics_mode_matches_run_calibrate_analysis_of_oracle_samples():
+    cases = [(60, 100, 0.6, 1.0, 0.0), (33, 127, 1.0, 0.5, 0.0), (96, 40, 0.3, 0.0, 0.0), (72, 100, 0.6, 1.0, 0.5), (48, 80, 0.9, 0.2, 0.5)]
+    jobs = [ow.calibrate_job(n, v, volume=vol, speaker=spk, tremolo_depth=d) for n, v, vol, spk, d in cases]
+    got = ow.render_bench_metrics(jobs)
+    ref_samples = O.render_bench([to_oracle_b(j) for j in jobs], threads=4)
+    for k, (n, v, vol, spk, d) in enumerate(cases):
+        ref = _calibrate_metrics_from_samples(ref_samples[k], O.lib().owo_midi_to_freq(n))
+        assert np.abs(got[k, :3] - ref[:3]).max() < 1e-6, (cases[k], got[k], ref)      # dB columns
+        assert np.allclose(got[k, 3:], ref[3:], rtol=1e-7, atol=1e-15), (cases[k], got[k], ref)
+    # the no-onset reed really differs from the cmd_render voice (onset ramp) and equals the oracle's
+    a = ow.render_bench([ow.calibrate_job(60, 100)])[0]
+    b = ow.render_bench([ow.bench_job(note=60, velocity=100, duration=0.5, no_mlp=True, no_attack_noise=True)])[0]
+    assert np.abs(a - b).max() > 1e-4
+    assert_parity(a, ref_samples[0], "calibrate render")
+
+
+def test_metrics_mode_sweep_slice_properties():
+    """A slice of the C4 sweep (volume x depth x speaker over keys): metrics are finite, louder volume is louder, and the
+    result does not depend on batch composition (the library batches internally)."""
+    jobs = [ow.calibrate_job(40 + 8 * k, 100, volume=a / 3.0, speaker=c / 3.0, tremolo_depth=b / 3.0)
+            for k in range(4) for a in range(1, 4) for b in range(3) for c in range(3)]
+    m = ow.render_bench_metrics(jobs)
+    assert m.shape == (len(jobs), 7) and np.all(np.isfinite(m))
+    m2 = ow.render_bench_metrics(jobs[5:9])
+    assert np.array_equal(m[5:9], m2)
+    by = {(j.v.midi, round(j.volume, 3), round(j.tremolo_depth, 3), round(j.speaker_character, 3)): m[i] for i, j in enumerate(jobs)}
+    for k in range(4):
+        assert by[(40 + 8 * k, 1.0, 0.0, 0.0)][1] > by[(40 + 8 * k, round(1 / 3.0, 3), 0.0, 0.0)][1]

@@ -25,6 +25,21 @@ def run(depth, dur, stride=1, reps=2):
     print(f"depth={depth} dur={dur} n={len(jobs)}: chain {best[0]:.1f} ms, total {best[1]:.1f} ms -> {len(jobs)*dur/(best[1]*1e-3):.0f} audio-s/s", flush=True)
     pl.close()
 
-for depth in (0.0, 0.5):
-    for dur in (0.5, 1.5):
-        run(depth, dur)
+if "--scale" in sys.argv:
+    k = int(sys.argv[sys.argv.index("--scale") + 1])
+    def run_big(depth, dur, k):
+        jobs = [ow.bench_job(note=33 + (i // 127) % 64, velocity=1 + i % 127, duration=dur, tremolo_depth=depth, volume=0.3 + 0.5 * (i // 8128) / max(k, 1))
+                for i in range(8128 * k)]
+        pl = ow.Plan.bench(jobs)
+        out = torch.empty((len(jobs), pl.max_samples), dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            pl.execute(out); torch.cuda.synchronize()
+        t = pl.last_timing()
+        print(f"[throughput regime] depth={depth} dur={dur} n={len(jobs)}: chain {t[0]:.1f} ms, total {t[1]:.1f} ms -> {len(jobs)*dur/(t[1]*1e-3):.0f} audio-s/s", flush=True)
+        pl.close()
+    for depth in (0.0, 0.5):
+        run_big(depth, 0.5, k)
+else:
+    for depth in (0.0, 0.5):
+        for dur in (0.5, 1.5):
+            run(depth, dur)
