@@ -304,6 +304,23 @@ def main():
                 line["variants"] = {workload_name(args.duration, other): {
                     "value": v["n_inst"] * args.duration * max(1, args.steps - 1) / (v["ms"] * 1e-3), "unit": UNIT,
                     "ms_per_step": v["ms"] / max(1, args.steps - 1)}}
+                # machine-filling batch (throughput regime): 4 grids at different volumes, 0.5 s each (the C4 sweep's render length)
+                big = []
+                for g in range(4):
+                    for j in grid_jobs(ow, 0.5, args.tremolo_depth, seed_offset=g):
+                        j.volume = 0.3 + 0.15 * g
+                        big.append(j)
+                plan = ow.Plan.bench(big, device=dev, stream=stream)
+                outb = torch.empty((len(big), plan.max_samples), dtype=torch.float64, device="cuda")
+                plan.execute(outb)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); plan.execute(outb); e1.record(); torch.cuda.synchronize()
+                msb = e0.elapsed_time(e1)
+                line["variants"][f"throughput regime: {len(big)} renders x 0.5 s (4 grids), tremolo_depth {args.tremolo_depth:g}"] = {
+                    "value": len(big) * 0.5 / (msb * 1e-3), "unit": UNIT, "ms_per_step": msb}
+                plan.close()
+                del outb
         if not args.no_cpu_baseline:
             import oracle_lib as O
             threads = O.lib().owo_hardware_threads() or os.cpu_count() or 1

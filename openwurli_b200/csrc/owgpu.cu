@@ -45,6 +45,10 @@ int usable_devices() {
 struct DeviceCache {
     DkState* d_settled = nullptr;
     bool fade_uploaded = false;
+    // grow-only device staging buffer for host-output calls (avoids an 8.6 GB cudaMalloc/cudaFree per one-shot render)
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    bool stage_in_use = false;
 };
 std::mutex g_cache_mu;
 std::map<int, DeviceCache> g_cache;
@@ -125,6 +129,7 @@ struct owg_plan {
     DevBuf<int> d_trem_ids;
     DevBuf<double> d_static_recs, d_ans, d_pot_seq, d_trem_recs, d_carry;
     DevBuf<TrmRun> d_trm_run, d_trm_ctor;       // oscillator state: running / as constructed (Tremolo::new, computed at plan time)
+    cudaStream_t stream_copy = nullptr;          // device->host copy-back of finished chunks
     cudaStream_t stream_trem = nullptr;          // the serial Twin-T oscillator runs here, one chunk ahead of its consumers
     std::vector<cudaEvent_t> chunk_events;       // oscillator chunk c finished
     std::vector<cudaEvent_t> chain_ev;           // pairs around every chain launch (device time of the dominant kernel)
@@ -143,6 +148,7 @@ struct owg_plan {
         for (auto e : chunk_events) cudaEventDestroy(e);
         for (auto e : chain_ev) cudaEventDestroy(e);
         if (stream_trem) cudaStreamDestroy(stream_trem);
+        if (stream_copy) cudaStreamDestroy(stream_copy);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -256,40 +262,44 @@ void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vec
     }
 }
 
+// Tremolo::new for every tremolo group, launched as early as possible on the oscillator stream (it is ~0.9 s of serial
+// device work per 88.2 kHz group and nothing else of the plan depends on it).
+int launch_tremolo_ctor(owg_plan* pl) {
+    if (pl->trem_group_ids.empty()) return OWG_OK;
+    const int nt = (int)pl->trem_group_ids.size();
+    int rc = pl->d_groups.upload(pl->groups, pl->stream);
+    if (!rc) rc = pl->d_trem_ids.upload(pl->trem_group_ids, pl->stream);
+    if (!rc) rc = pl->d_trm_run.alloc((size_t)nt);
+    if (!rc) rc = pl->d_trm_ctor.alloc((size_t)nt);
+    if (!rc) rc = pl->d_pot_seq.alloc((size_t)nt * (size_t)pl->trem_n_os_max);
+    if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
+    if (!rc && !pl->stream_trem && cudaStreamCreateWithFlags(&pl->stream_trem, cudaStreamNonBlocking) != cudaSuccess)
+        rc = fail(OWG_E_CUDA, "stream creation failed");
+    if (!rc) {
+        // Constructors run at plan time, per-sample processing at execute time: Tremolo::new (50 warm-up + 2*sr settle
+        // samples of the Twin-T oscillator, tremolo.rs:84-115) is evaluated once per tremolo group, like Voice::note_on on
+        // the host and DkPreamp::new's cached settled state.  Asynchronous: every later oscillator launch goes to the same
+        // in-order stream, so nothing has to wait here.
+        tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                             pl->d_trm_ctor.p, -1, -1, nullptr);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(OWG_E_CUDA, "tremolo constructor kernel launch failed");
+    }
+    return rc;
+}
+
 int upload_chain_plan(owg_plan* pl, const std::vector<OwgChainInit>& ci, const std::vector<int32_t>& order) {
     int rc = pl->d_cinit.upload(ci, pl->stream);
     if (!rc) rc = pl->d_nsamp.upload(pl->n_samples, pl->stream);
     if (!rc) rc = pl->d_order.upload(order, pl->stream);
     if (!rc) rc = pl->d_warps_static.upload(pl->warps_static, pl->stream);
     if (!rc) rc = pl->d_warps_trem.upload(pl->warps_trem, pl->stream);
-    if (!rc) rc = pl->d_groups.upload(pl->groups, pl->stream);
+    if (!rc && pl->trem_group_ids.empty()) rc = pl->d_groups.upload(pl->groups, pl->stream);  // else uploaded by launch_tremolo_ctor
     if (!rc) rc = pl->d_group_rec_index.upload(pl->group_rec_index, pl->stream);
-    if (!rc) rc = pl->d_trem_ids.upload(pl->trem_group_ids, pl->stream);
     if (!rc) rc = pl->d_static_recs.alloc(pl->groups.size() * OWG_MAT_STRIDE);
     if (!rc) rc = pl->d_ans.alloc(pl->groups.size() * OWG_AN_SPARSE);
-    if (!rc && !pl->trem_group_ids.empty()) {
-        rc = pl->d_pot_seq.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max);
-        if (!rc) rc = pl->d_trem_recs.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max * OWG_MAT_STRIDE);
-    }
+    if (!rc && !pl->trem_group_ids.empty())
+        rc = pl->d_trem_recs.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max * OWG_MAT_STRIDE);
     if (!rc && pl->collect_diag) rc = pl->d_diag.alloc(1);
-    if (!rc && !pl->trem_group_ids.empty()) {
-        // Constructors run at plan time, per-sample processing at execute time: Tremolo::new (50 warm-up + 2*sr settle
-        // samples of the Twin-T oscillator, tremolo.rs:84-115) is evaluated here once per tremolo group, like Voice::note_on
-        // on the host and DkPreamp::new's cached settled state.
-        const int nt = (int)pl->trem_group_ids.size();
-        rc = pl->d_trm_run.alloc((size_t)nt);
-        if (!rc) rc = pl->d_trm_ctor.alloc((size_t)nt);
-        if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
-        if (!rc && !pl->stream_trem && cudaStreamCreateWithFlags(&pl->stream_trem, cudaStreamNonBlocking) != cudaSuccess)
-            rc = fail(OWG_E_CUDA, "stream creation failed");
-        if (!rc) {
-            // asynchronous: every later oscillator launch goes to the same in-order stream, so nothing has to wait here
-            tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                                 pl->d_trm_ctor.p, -1, -1, nullptr);
-            if (cudaGetLastError() != cudaSuccess) rc = fail(OWG_E_CUDA, "tremolo constructor kernel launch failed");
-        }
-        return rc;
-    }
     if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
     return rc;
 }
@@ -353,23 +363,25 @@ int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, o
     if (int rc = plan_common(pl, opts)) { delete pl; return rc; }
 
     std::vector<InstSpec> specs((size_t)n);
-    std::vector<OwgVoiceInit> vi((size_t)n);
     for (int64_t i = 0; i < n; i++) {
         const owg_bench_job& j = jobs[i];
-        owg::make_voice_init(j.v, &vi[i]);
         InstSpec& sp = specs[i];
         sp.fs = j.v.sample_rate;
         sp.oversample = j.v.sample_rate < 88200.0 ? 1 : 0;
-        sp.n_samples = vi[i].n_samples;
+        const double ns = j.v.duration_s * j.v.sample_rate;  // (duration * sample_rate) as usize
+        sp.n_samples = !(ns == ns) || ns <= 0.0 ? 0ull : (unsigned long long)ns;
         sp.depth = j.tremolo_depth;
         sp.r_ldr = j.r_ldr;
         owg::make_chain_init(j, 0, &sp.ci);
     }
     std::vector<int32_t> order;
     build_groups_and_warps(pl, specs, &order);
+    int rc = launch_tremolo_ctor(pl);  // the device settles the oscillators while the host parameterises the voices
+    std::vector<OwgVoiceInit> vi((size_t)n);
+    for (int64_t i = 0; i < n; i++) owg::make_voice_init(jobs[i].v, &vi[i]);
     std::vector<OwgChainInit> ci((size_t)n);
     for (int64_t i = 0; i < n; i++) ci[i] = specs[i].ci;
-    int rc = pl->d_vinit.upload(vi, pl->stream);
+    if (!rc) rc = pl->d_vinit.upload(vi, pl->stream);
     if (!rc) rc = upload_chain_plan(pl, ci, order);
     if (rc) { delete pl; return rc; }
     pl->h2d_bytes = g_h2d_bytes;
@@ -409,10 +421,30 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     CK(cudaSetDevice(pl->device));
     cudaStream_t s = pl->stream;
     double* dout = out;
+    bool borrowed_stage = false;
     if (out_location == OWG_OUT_HOST) {
-        if (int rc = pl->d_stage.alloc((size_t)pl->n * (size_t)stride)) return rc;
-        dout = pl->d_stage.p;
+        const size_t need = (size_t)pl->n * (size_t)stride * sizeof(double);
+        {
+            std::lock_guard<std::mutex> lock(g_cache_mu);
+            DeviceCache& c = *pl->cache;
+            if (!c.stage_in_use) {
+                if (c.stage_bytes < need) {
+                    if (c.stage) cudaFree(c.stage);
+                    c.stage = nullptr; c.stage_bytes = 0;
+                    if (cudaMalloc(&c.stage, need) == cudaSuccess) c.stage_bytes = need; else cudaGetLastError();
+                }
+                if (c.stage_bytes >= need) { c.stage_in_use = true; borrowed_stage = true; dout = (double*)c.stage; }
+            }
+        }
+        if (!borrowed_stage) {
+            if (int rc = pl->d_stage.alloc((size_t)pl->n * (size_t)stride)) return rc;
+            dout = pl->d_stage.p;
+        }
     } else if (out_location != OWG_OUT_DEVICE) return fail(OWG_E_BAD_ARG, "bad out_location");
+    struct StageReturn {  // give the borrowed staging buffer back on every exit path
+        DeviceCache* c; bool on;
+        ~StageReturn() { if (on) { std::lock_guard<std::mutex> lock(g_cache_mu); c->stage_in_use = false; } }
+    } stage_return{pl->cache, borrowed_stage};
     int64_t launches = 0;
     CK(cudaEventRecord(pl->ev0, s));
     if (pl->collect_diag) CK(cudaMemsetAsync(pl->d_diag.p, 0, sizeof(DevDiag), s));
@@ -428,6 +460,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
         CK(cudaGetLastError());
         launches++;
     }
+    bool copied_by_chunks = false;
     size_t chain_ev_used = 0;
     auto chain_event = [&]() -> cudaEvent_t {
         if (chain_ev_used == pl->chain_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); pl->chain_ev.push_back(e); }
@@ -469,21 +502,41 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
             }
         }
         CK(cudaEventRecord(pl->evk0, s));
+        // Host output: the rows of a finished chunk are copied back on a third stream while the next chunk computes
+        // (only when all rows belong to one family of groups, so that a column range is final for every row at once).
+        const bool overlap_d2h = out_location == OWG_OUT_HOST && !pl->metrics_ptr && (pl->warps_static.empty() != pl->warps_trem.empty());
+        if (overlap_d2h && !pl->stream_copy) CK(cudaStreamCreateWithFlags(&pl->stream_copy, cudaStreamNonBlocking));
+        auto copy_columns = [&](int64_t b0, int64_t b1, cudaEvent_t after) -> int {
+            const int64_t hi = std::min<int64_t>(b1, (int64_t)pl->max_samples);
+            if (hi <= b0) return OWG_OK;
+            CK(cudaStreamWaitEvent(pl->stream_copy, after, 0));
+            CK(cudaMemcpy2DAsync(out + b0, (size_t)stride * sizeof(double), dout + b0, (size_t)stride * sizeof(double),
+                                 (size_t)(hi - b0) * sizeof(double), (size_t)pl->n, cudaMemcpyDeviceToHost, pl->stream_copy));
+            return OWG_OK;
+        };
         if (!pl->warps_static.empty()) {  // static groups do not depend on the oscillator: they run while it settles
             const int nb = (int)pl->warps_static.size();
-            cudaEvent_t e0 = chain_event(), e1 = chain_event();
-            CK(cudaEventRecord(e0, s));
-            if (pl->collect_diag)
-                chain_kernel<false, true><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
-                                                             pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p,
-                                                             0, INT64_MAX, nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
-            else
-                chain_kernel<false, false><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
-                                                              pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, nullptr,
-                                                              0, INT64_MAX, nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(e1, s));
-            launches++;
+            const int64_t SCH = overlap_d2h ? 4 * CH_BASE : INT64_MAX / 2;  // chunked only to overlap the copy-back
+            if (overlap_d2h) { if (int rc = pl->d_carry.alloc((size_t)nb * OWG_CARRY * 32)) return rc; }
+            for (int64_t b0 = 0; b0 < (int64_t)pl->max_samples; b0 += SCH) {
+                const int64_t b1 = b0 + SCH;
+                cudaEvent_t e0 = chain_event(), e1 = chain_event();
+                CK(cudaEventRecord(e0, s));
+                if (pl->collect_diag)
+                    chain_kernel<false, true><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                                 pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p,
+                                                                 b0, b1, overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin,
+                                                                 pl->w_end);
+                else
+                    chain_kernel<false, false><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                                  pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, nullptr,
+                                                                  b0, b1, overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin,
+                                                                  pl->w_end);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(e1, s));
+                launches++;
+                if (overlap_d2h) { if (int rc = copy_columns(b0, b1, e1)) return rc; }
+            }
         }
         if (!pl->warps_trem.empty()) {
             const int nb = (int)pl->warps_trem.size();
@@ -507,14 +560,21 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(e1, s));
                 launches += 2;
+                if (overlap_d2h) { if (int rc = copy_columns(b0, b1, e1)) return rc; }
             }
+        }
+        if (overlap_d2h) {  // join the copy stream into the main stream
+            cudaEvent_t ej = chain_event();
+            CK(cudaEventRecord(ej, pl->stream_copy));
+            CK(cudaStreamWaitEvent(s, ej, 0));
+            copied_by_chunks = true;
         }
         CK(cudaEventRecord(pl->evk1, s));
     } else {
         CK(cudaEventRecord(pl->evk0, s));
         CK(cudaEventRecord(pl->evk1, s));
     }
-    if (out_location == OWG_OUT_HOST) {
+    if (out_location == OWG_OUT_HOST && !copied_by_chunks) {
         // one 2-D copy: rows of max_samples doubles, device pitch == host pitch == stride
         CK(cudaMemcpy2DAsync(out, (size_t)stride * sizeof(double), dout, (size_t)stride * sizeof(double),
                              (size_t)pl->max_samples * sizeof(double), (size_t)pl->n, cudaMemcpyDeviceToHost, s));
@@ -523,7 +583,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&pl->total_ms, pl->ev0, pl->ev1));
     pl->main_ms = 0.f;  // device time of the chain kernel launches (busy time, not the wait for the oscillator)
-    for (size_t k = 0; k + 1 < chain_ev_used; k += 2) {
+    for (size_t k = 0; k + 1 < (chain_ev_used & ~(size_t)1); k += 2) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, pl->chain_ev[k], pl->chain_ev[k + 1]));
         pl->main_ms += ms;
@@ -824,7 +884,8 @@ int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_
     build_groups_and_warps(pl, specs, &order);
     std::vector<OwgChainInit> ci((size_t)n_inst);
     for (int64_t i = 0; i < n_inst; i++) ci[i] = specs[i].ci;
-    int rc = upload_chain_plan(pl, ci, order);
+    int rc = launch_tremolo_ctor(pl);
+    if (!rc) rc = upload_chain_plan(pl, ci, order);
     if (!rc) {
         pl->in_ptr = in;
         pl->in_stride = in_stride;
