@@ -288,7 +288,4 @@ def preamp_bench_render(**flags):
     return render_bench([bench_job(**flags)])[0]
 
 
-def pcm24_truncate(samples):
-    """reed-renderer WAV quantisation (main.rs:110-126): clamp to [-1,1], scale by 2^23-1, truncate."""
-    s = np.clip(np.asarray(samples, dtype=np.float64), -1.0, 1.0) * 8388607.0
-    return np.trunc(s).astype(np.int32)
+from .wav import pcm24_round, pcm24_truncate  # noqa: E402,F401  (WAV quantisations of the two reference tools)

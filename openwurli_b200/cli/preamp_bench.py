@@ -1,0 +1,157 @@
+"""`preamp-bench render` mirror (tools/preamp-bench/src/main.rs:371-553): same flags, defaults, report and 24-bit WAV.
+
+    python -m openwurli_b200.cli.preamp_bench render --note 60 --velocity 100 --tremolo-depth 0.5 --output c4.wav
+
+Batch extension (not in the reference): `--note` / `--velocity` accept comma-separated lists; all pairs are rendered in one
+device batch and written to `<output stem>_n<NOTE>_v<VEL>.wav`.  `calibrate` prints the T5 columns of `run_calibrate`
+(main.rs:1127-1260) for a notes x velocities grid through the on-device analysis reductions.
+"""
+import math
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+from .. import api, wav
+
+BASE_SR = 44100.0
+
+
+def parse_flag(args, flag, default):  # main.rs:98-105 (a malformed value falls back to the default)
+    for i in range(max(len(args) - 1, 0)):
+        if args[i] == flag:
+            try:
+                return float(args[i + 1])
+            except ValueError:
+                return default
+    return default
+
+
+def parse_flag_str(args, flag, default):  # main.rs:107-114
+    for i in range(max(len(args) - 1, 0)):
+        if args[i] == flag:
+            return args[i + 1]
+    return default
+
+
+def has_flag(args, flag):  # main.rs:116-118
+    return flag in args
+
+
+def to_dbfs(val):  # main.rs:2241-2247
+    return 20.0 * math.log10(val) if val > 1e-15 else -120.0
+
+
+def _as_u8(x):  # Rust `f64 as u8`: saturating, NaN -> 0
+    if x != x:
+        return 0
+    return int(min(max(math.trunc(x), 0), 255))
+
+
+def _list_flag(args, flag, default):
+    s = parse_flag_str(args, flag, None)
+    if s is None or "," not in s:
+        return [_as_u8(parse_flag(args, flag, default))]
+    return [_as_u8(float(t)) for t in s.split(",")]
+
+
+def cmd_render(args):
+    notes = _list_flag(args, "--note", 60.0)
+    velocities = _list_flag(args, "--velocity", 100.0)
+    duration = parse_flag(args, "--duration", 2.0)
+    r_ldr = parse_flag(args, "--ldr", 1_000_000.0)
+    volume = parse_flag(args, "--volume", 0.60)
+    speaker_char = parse_flag(args, "--speaker", 1.0)
+    tremolo_depth = parse_flag(args, "--tremolo-depth", 0.0)
+    sample_rate = parse_flag(args, "--sample-rate", BASE_SR)
+    no_poweramp = has_flag(args, "--no-poweramp")
+    # --no-rail-sag is accepted and ignored: PowerAmp::set_rail_sag is a no-op on the behavioral path (power_amp.rs:255-257)
+    no_preamp = has_flag(args, "--no-preamp")
+    no_attack_noise = has_flag(args, "--no-attack-noise")
+    no_mlp = has_flag(args, "--no-mlp")
+    normalize = has_flag(args, "--normalize")
+    disp_scale = parse_flag(args, "--displacement-scale", 0.30) if has_flag(args, "--displacement-scale") else None
+    output_path = parse_flag_str(args, "--output", os.path.join(tempfile.gettempdir(), "preamp_render.wav"))
+    do_oversample = sample_rate < 88200.0
+
+    pairs = [(n, v) for n in notes for v in velocities]
+    jobs = [api.bench_job(note=n, velocity=v, duration=duration, ldr=r_ldr, volume=volume, speaker=speaker_char,
+                          tremolo_depth=tremolo_depth, sample_rate=sample_rate, no_poweramp=no_poweramp, no_preamp=no_preamp,
+                          no_attack_noise=no_attack_noise, no_mlp=no_mlp, displacement_scale=disp_scale) for n, v in pairs]
+    out = api.render_bench(jobs)
+    stem, ext = os.path.splitext(output_path)
+    for k, (note, velocity) in enumerate(pairs):
+        final_output = out[k]
+        path = output_path if len(pairs) == 1 else f"{stem}_n{note}_v{velocity}{ext or '.wav'}"
+        peak = float(np.max(np.abs(final_output))) if final_output.size else 0.0
+        peak_dbfs = to_dbfs(peak)
+        scale = wav.normalize_scale(final_output, normalize)
+        if not normalize and peak > 1.0:
+            sys.stderr.write(f"WARNING: Peak exceeds 0 dBFS ({peak_dbfs:.1f} dBFS) — consider reducing --volume\n")
+        wav.write_preamp_bench_wav(path, final_output, sample_rate, scale)
+        print("Render complete")
+        print(f"  Note:      MIDI {note}")
+        print(f"  Velocity:  {velocity}")
+        print(f"  Duration:  {duration:.1f}s")
+        if tremolo_depth > 0.0:
+            print(f"  Tremolo:   depth={tremolo_depth:.2f}")
+        else:
+            print(f"  LDR:       {r_ldr:.0f} Ω (static)")
+        print(f"  Volume:    {volume:.3f} (PA gain: 69x, headroom: 22V)")
+        print(f"  Speaker:   {speaker_char:.1f}")
+        if disp_scale is not None:
+            print(f"  Disp scale: {disp_scale:.3f}")
+        if no_preamp:
+            print("  Preamp:    BYPASSED")
+        if no_poweramp:
+            print("  Power amp: BYPASSED")
+        if normalize:
+            print("  Normalize: ON (-3 dBFS ceiling)")
+        if sample_rate != BASE_SR:
+            print(f"  Sample rate: {sample_rate:.0f} Hz (oversample: {'on' if do_oversample else 'off'})")
+        print(f"  Peak:      {peak_dbfs:.1f} dBFS (raw)")
+        print(f"  Build:     openwurli_b200 (libowgpu ABI {api.lib().owg_abi_version()})")
+        print(f"  Output:    {path}")
+    return 0
+
+
+def cmd_calibrate(args):
+    """T5 (final output) columns of `calibrate` for --notes a,b,c --velocities x,y,z (main.rs:1060-1105 flag names)."""
+    notes = [int(s) for s in parse_flag_str(args, "--notes", "36,48,60,72,84").split(",")]
+    velocities = [int(s) for s in parse_flag_str(args, "--velocities", "40,80,127").split(",")]
+    volume = parse_flag(args, "--volume", 0.60)
+    speaker_char = parse_flag(args, "--speaker", 1.0)
+    jobs = [api.calibrate_job(n, v, volume=volume, speaker=speaker_char) for n in notes for v in velocities]
+    m = api.render_bench_metrics(jobs)
+    print("note,velocity,t5_peak_db,t5_rms_db,t5_h2_h1_db")
+    k = 0
+    for n in notes:
+        for v in velocities:
+            print(f"{n},{v},{m[k, 0]:.3f},{m[k, 1]:.3f},{m[k, 2]:.3f}")
+            k += 1
+    return 0
+
+
+USAGE = """Usage: preamp_bench <render|calibrate> [flags]
+  render     --note N --velocity V --duration S --ldr OHM --volume X --speaker C --tremolo-depth D --sample-rate HZ
+             --no-poweramp --no-rail-sag --no-preamp --no-attack-noise --no-mlp --normalize --displacement-scale DS --output FILE
+  calibrate  --notes a,b,c --velocities x,y,z --volume X --speaker C
+"""
+
+
+def main(argv=None):
+    args = list(sys.argv[1:] if argv is None else argv)
+    if not args:
+        sys.stderr.write(USAGE)
+        return 1
+    if args[0] == "render":
+        return cmd_render(args[1:])
+    if args[0] == "calibrate":
+        return cmd_calibrate(args[1:])
+    sys.stderr.write(f"Unknown subcommand: {args[0]} (only the batched render paths are mirrored)\n{USAGE}")
+    return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

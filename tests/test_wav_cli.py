@@ -1,0 +1,100 @@
+"""WAV output and CLI mirrors: quantisation rules of the two reference tools, RIFF round trip, flag parsing."""
+import os
+import struct
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from openwurli_b200 import wav
+from openwurli_b200.cli import preamp_bench, reed_renderer
+
+
+def test_pcm24_truncate_matches_rust_cast():
+    # reed-renderer main.rs:119-123: (clamp(s,-1,1) * 8388607.0) as i32 -- truncation toward zero
+    x = np.array([0.0, 1.0, -1.0, 2.0, -3.0, 0.5, -0.5, 1e-9, -1e-9, 0.9999999, np.nan])
+    q = wav.pcm24_truncate(x)
+    exp = [0, 8388607, -8388607, 8388607, -8388607, 4194303, -4194303, 0, 0, int(0.9999999 * 8388607.0), 0]
+    assert q.tolist() == exp
+
+
+def test_pcm24_round_half_away_from_zero_and_clamp():
+    # preamp-bench main.rs:950-954: (s*scale*max).round() as i32, clamp(+-max)
+    m = 8388607.0
+    x = np.array([0.5 / m, -0.5 / m, 1.5 / m, -1.5 / m, 2.5 / m, 0.49999 / m, 1.0, -1.0, 1.5, -1.5, 0.0])
+    q = wav.pcm24_round(x)
+    assert q.tolist() == [1, -1, 2, -2, 3, 0, 8388607, -8388607, 8388607, -8388607, 0]
+    # scale is applied before rounding
+    assert wav.pcm24_round(np.array([1.0]), 0.5).tolist() == [4194304]   # 4194303.5 rounds away from zero
+    # random cross-check against Python's decimal-free definition of round-half-away
+    rng = np.random.default_rng(5)
+    y = rng.uniform(-1.2, 1.2, 20000)
+    s = y * m
+    ref = np.clip(np.where(s >= 0, np.floor(s + 0.5), -np.floor(-s + 0.5)), -m, m).astype(np.int64)
+    assert np.array_equal(wav.pcm24_round(y).astype(np.int64), ref)
+
+
+def test_normalize_scale_rule():
+    assert wav.normalize_scale(np.array([0.5, -0.6]), True) == 1.0          # peak <= 0.7: untouched
+    assert wav.normalize_scale(np.array([0.5, -1.4]), True) == 0.7 / 1.4
+    assert wav.normalize_scale(np.array([0.5, -1.4]), False) == 1.0
+
+
+def test_wav_roundtrip_and_header(tmp_path):
+    rng = np.random.default_rng(1)
+    q = rng.integers(-8388607, 8388608, 1001).astype(np.int32)   # odd byte count -> pad byte
+    p = tmp_path / "a.wav"
+    wav.write_wav_pcm24(str(p), q, 44100)
+    raw = p.read_bytes()
+    assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt "
+    fmt = struct.unpack("<IHHIIHH", raw[16:36])
+    assert fmt == (16, 1, 1, 44100, 44100 * 3, 3, 24)
+    assert raw[36:40] == b"data" and struct.unpack("<I", raw[40:44])[0] == 3003
+    assert struct.unpack("<I", raw[4:8])[0] == len(raw) - 8
+    q2, sr = wav.read_wav_pcm24(str(p))
+    assert sr == 44100 and np.array_equal(q, q2)
+    # python's own wave module agrees on the layout
+    import wave
+    with wave.open(str(p), "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 3, 44100, 1001)
+
+
+def test_flag_helpers_follow_reference_semantics():
+    a = ["--note", "72", "--volume", "abc", "--no-mlp", "--output"]
+    assert preamp_bench.parse_flag(a, "--note", 60.0) == 72.0
+    assert preamp_bench.parse_flag(a, "--volume", 0.6) == 0.6        # unparsable -> default (main.rs:101)
+    assert preamp_bench.parse_flag(a, "--output", 1.0) == 1.0        # flag in last position has no value (main.rs:99)
+    assert preamp_bench.has_flag(a, "--no-mlp") and not preamp_bench.has_flag(a, "--normalize")
+    assert preamp_bench._as_u8(300.0) == 255 and preamp_bench._as_u8(-4.0) == 0 and preamp_bench._as_u8(60.9) == 60
+    assert preamp_bench.to_dbfs(0.0) == -120.0 and abs(preamp_bench.to_dbfs(0.1) + 20.0) < 1e-12
+    assert reed_renderer.midi_note_name(60) == "C4" and reed_renderer.midi_note_name(33) == "A1" and reed_renderer.midi_note_name(61) == "Cs4"
+
+
+def test_reed_renderer_cli_rejects_bad_input(capsys):
+    assert reed_renderer.main(["--note", "20"]) == 1
+    assert "out of range" in capsys.readouterr().err
+    assert reed_renderer.main(["--bogus"]) == 1
+    assert reed_renderer.main(["--help"]) == 0
+
+
+@pytest.mark.gpu
+def test_cli_renders_match_oracle_wavs(tmp_path):
+    """End to end through the CLI mirrors: the 24-bit files equal the oracle's samples pushed through the same quantiser
+    (a +-1 LSB slack covers a 1e-9 sample difference landing on a rounding boundary)."""
+    import oracle_lib as ol
+    out = tmp_path / "r"
+    assert reed_renderer.main(["-n", "45,72", "-v", "60,110", "-d", "0.25", "--output-dir", str(out)]) == 0
+    for n, name in ((45, "A2"), (72, "C5")):
+        for v in (60, 110):
+            q, sr = wav.read_wav_pcm24(str(out / f"reed_{name}_v{v}.wav"))
+            ref = ol.render_voices([ol.voice_job(midi=n, vel=v, dur=0.25)])[0]
+            assert sr == 44100 and q.size == ref.size
+            assert np.max(np.abs(q.astype(np.int64) - wav.pcm24_truncate(ref))) <= 1
+    p = tmp_path / "pb.wav"
+    assert preamp_bench.main(["render", "--note", "57", "--velocity", "90", "--duration", "0.2", "--tremolo-depth", "0.4",
+                              "--volume", "0.9", "--normalize", "--output", str(p)]) == 0
+    q, sr = wav.read_wav_pcm24(str(p))
+    ref = ol.render_bench([ol.bench_job(midi=57, vel=90, dur=0.2, depth=0.4, volume=0.9)])[0]
+    sc = wav.normalize_scale(ref, True)
+    assert sr == 44100 and np.max(np.abs(q.astype(np.int64) - wav.pcm24_round(ref, sc))) <= 1

@@ -43,3 +43,20 @@ for (f, ln), s in agg.most_common(topn):
     text = src[f][ln - 1].strip()[:100] if f in src and 0 < ln <= len(src[f]) else ""
     cum += s
     print(f"{100*s/tot:5.2f}% (cum {100*cum/tot:5.1f}%) instr {100*inst[(f,ln)]/tinst:5.2f}%  {f}:{ln}  {text}")
+
+# ---- per-function (stage) aggregation: the enclosing __device__/__global__ function of every source line
+def enclosing(f, ln):
+    if f not in src:
+        return f
+    for i in range(min(ln, len(src[f])) - 1, -1, -1):
+        m = re.match(r"\s*(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:__device__|__global__|__launch_bounds__).*?([A-Za-z_0-9]+)\s*\(", src[f][i])
+        if m and not src[f][i].strip().startswith("//"):
+            return f"{f}:{m.group(1)}"
+    return f
+fagg, finst = collections.Counter(), collections.Counter()
+for (f, ln), s in agg.items():
+    k = enclosing(f, ln)
+    fagg[k] += s; finst[k] += inst[(f, ln)]
+print("\nper function (samples = time share, instr = executed warp-instruction share)")
+for k, s in fagg.most_common(30):
+    print(f"{100*s/tot:5.2f}%  instr {100*finst[k]/tinst:5.2f}%  {k}")
