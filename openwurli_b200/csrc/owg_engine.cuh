@@ -169,7 +169,16 @@ __device__ __forceinline__ void voice_note_off(VoiceRT& v, const DamperRow* __re
 // Tremolo::new(0.5, os_sr) [2 s settle] then one process() per preamp-rate sample with the depth trajectory of the engine's
 // LinearSmoother (engine.rs:67-130, 532-547): 0.5 during the warm-up, then a ramp_samples-long linear ramp to the target.
 // Output: pot_0_resistance in effect per preamp-rate sample (warm-up first).
-__global__ void engine_tremolo_kernel(const EngineGroup* groups, int n_groups, double* pot_seq, long long pot_stride) {
+struct EngTrmRun {  // oscillator + LDR + depth-smoother state between chunk launches
+    TrmState st;
+    double env, pot, sm_current, sm_target, sm_step, depth;
+    uint32_t sm_remaining, _pad;
+    long long n_done;  // steps done so far (50 warm-up + 2*sr settle + live)
+};
+
+// live_end_base: produce pot values for live (warm-up + rendered) preamp-rate samples below n_warm_os + live_end_base*sub.
+__global__ void engine_tremolo_kernel(const EngineGroup* groups, int n_groups, double* pot_seq, long long pot_stride, EngTrmRun* run,
+                                      long long live_end_base) {
     const int gi = blockIdx.x;
     if (gi >= n_groups || threadIdx.x != 0) return;
     const EngineGroup gr = groups[gi];
@@ -179,27 +188,39 @@ __global__ void engine_tremolo_kernel(const EngineGroup* groups, int n_groups, d
     __shared__ double trm_sc[OWG_TRM_SCRATCH];
     kq = trm_consts();
     trm_defaults(m);
-    TrmState st;
-    for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
-    for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
-    st.xin_prev = 0.0;
-    const double ldr_attack = exp(-1.0 / (0.0025 * sr));
-    const double ldr_release = exp(-1.0 / (0.035 * sr));
-    const double ln_r_max = log(1000000.0);
-    const double ln_min_minus_max = log(9000.0) - log(1000000.0);
-    double env = 0.0;
-    double pot = 9.99999999999999854e4;
-    // depth smoother (LinearSmoother): current = target = 0.5 until set_tremolo_depth(target) after the warm-up
-    double sm_current = 0.5, sm_target = 0.5, sm_step = 0.0;
-    uint32_t sm_remaining = 0;
-    double depth = 0.5;  // Tremolo::new(0.5, ..) stores 0.5; set_depth() clamps to [0,1]
-    double* o = pot_seq + (size_t)gi * pot_stride;
     const double tot = sr * 2.0;
     const long long n_settle = !(tot == tot) || tot <= 0.0 ? 0ll : (long long)tot;
     const long long n_pre = 50 + n_settle;
     const long long n_live = gr.n_warm_os + gr.n_os;
     const int sub = gr.oversample ? 2 : 1;
-    for (long long n = 0; n < n_pre + n_live; n++) {
+    long long live_end = gr.n_warm_os + live_end_base * sub;
+    if (live_end > n_live) live_end = n_live;
+    EngTrmRun R = run[gi];
+    const long long n_begin = R.n_done, n_end = n_pre + live_end;
+    if (n_begin >= n_end) return;
+    TrmState st;
+    double env, pot, sm_current, sm_target, sm_step, depth;
+    uint32_t sm_remaining;
+    if (n_begin == 0) {
+        for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
+        for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
+        st.xin_prev = 0.0;
+        env = 0.0;
+        pot = 9.99999999999999854e4;
+        // depth smoother (LinearSmoother): current = target = 0.5 until set_tremolo_depth(target) after the warm-up
+        sm_current = 0.5; sm_target = 0.5; sm_step = 0.0; sm_remaining = 0;
+        depth = 0.5;  // Tremolo::new(0.5, ..) stores 0.5; set_depth() clamps to [0,1]
+    } else {
+        st = R.st; env = R.env; pot = R.pot; sm_current = R.sm_current; sm_target = R.sm_target; sm_step = R.sm_step; depth = R.depth;
+        sm_remaining = R.sm_remaining;
+        if (n_begin > 50 && fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);  // same deterministic rebuild as at step 50
+    }
+    const double ldr_attack = exp(-1.0 / (0.0025 * sr));
+    const double ldr_release = exp(-1.0 / (0.035 * sr));
+    const double ln_r_max = log(1000000.0);
+    const double ln_min_minus_max = log(9000.0) - log(1000000.0);
+    double* o = pot_seq + (size_t)gi * pot_stride;
+    for (long long n = n_begin; n < n_end; n++) {
         if (n == 50 && fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);
         const bool live = n >= n_pre;
         if (live) {
@@ -243,16 +264,24 @@ __global__ void engine_tremolo_kernel(const EngineGroup* groups, int n_groups, d
             o[n - n_pre] = pot;
         }
     }
+    R.st = st; R.env = env; R.pot = pot; R.sm_current = sm_current; R.sm_target = sm_target; R.sm_step = sm_step; R.depth = depth;
+    R.sm_remaining = sm_remaining; R.n_done = n_end;
+    run[gi] = R;
 }
 
 // One thread per (group, preamp-rate sample): rebuild_matrices for that sample's pot value (all samples are dirty: the
 // first set_ldr_resistance moves the pot off the settled 100 kOhm).
 __global__ void engine_matrix_kernel(const EngineGroup* groups, int n_groups, const double* pot_seq, long long pot_stride,
-                                     double* recs, long long rec_stride_t, double* ans) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                     double* recs, long long rec_stride_t, double* ans, long long live_begin_base, long long live_end_base) {
     const int gi = blockIdx.y;
     if (gi >= n_groups) return;
     const EngineGroup gr = groups[gi];
+    const int sub = gr.oversample ? 2 : 1;
+    // chunk = live samples [begin, end): the first chunk also covers the warm-up
+    const long long begin = live_begin_base <= 0 ? 0 : gr.n_warm_os + live_begin_base * sub;
+    const long long end = gr.n_warm_os + live_end_base * sub;
+    const long long t = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= end) return;
     if (t == 0) {
         double rec[OWG_MAT_STRIDE];
         if (gr.use_defaults) dk_default_record(rec, ans + (size_t)gi * OWG_AN_SPARSE);
@@ -269,10 +298,10 @@ __global__ void engine_matrix_kernel(const EngineGroup* groups, int n_groups, co
     dk_rebuild(gr.preamp_sr, pot, rec, nullptr);
 }
 
-// Zero-input solve per group over warm-up + render: during the warm-up main and shadow are the same computation, so
-// this also yields every engine's main state at the end of the warm-up (post_warm).  pump[t] covers the rendered part.
+// Zero-input solve per group over the warm-up: main and shadow are the same computation there, so this yields both
+// states at the end of the warm-up (post_warm).  The rendered part of the shadow runs in lane 31 of the chain warps.
 __global__ void engine_shadow_kernel(const EngineGroup* groups, int n_groups, const DkState* settled, const double* recs,
-                                     long long rec_stride_t, const double* ans, double* pump, long long pump_stride, DkState* post_warm) {
+                                     long long rec_stride_t, const double* ans, DkState* post_warm) {
     const int gi = blockIdx.x;
     if (gi >= n_groups || threadIdx.x != 0) return;
     __shared__ double s_an[OWG_AN_SPARSE];
@@ -282,260 +311,553 @@ __global__ void engine_shadow_kernel(const EngineGroup* groups, int n_groups, co
     DkState st = *settled;
     const DkDev dv = dk_dev();
     const double* grec = recs + (size_t)gi * rec_stride_t * OWG_MAT_STRIDE;
-    const long long n_live = gr.n_warm_os + gr.n_os;
-    if (gr.n_warm_os == 0) post_warm[gi] = st;
-    for (long long t = 0; t < n_live; t++) {
+    for (long long t = 0; t < gr.n_warm_os; t++) {
         const double* m = grec + (size_t)t * OWG_MAT_STRIDE;
-        const double y = dk_step<false>(0.0, st, m, s_an, m[OWG_MAT_AN66], dv, nullptr, cold, 1);
-        if (t >= gr.n_warm_os) pump[(size_t)gi * pump_stride + (t - gr.n_warm_os)] = y;
-        if (t + 1 == gr.n_warm_os) post_warm[gi] = st;
+        (void)dk_step<false>(0.0, st, m, s_an, m[OWG_MAT_AN66], dv, nullptr, cold, 1);
     }
+    post_warm[gi] = st;
 }
 
-// ---- the engine kernel: one thread per WurliEngine stream ----------------------------------------------------------------
+// ---- WurliEngine streams: voice-parallel block pipeline ---------------------------------------------------------------
+// The slot state machine (allocation, stealing, sustain, clean-up) and the NaN guard depend only on the voices' own state,
+// never on the shared chain, so a stream is rendered as
+//   per render() block ("round"):  engine_events_kernel   thread / engine : events of the block -> slot table -> render list
+//                                  engine_voice_mix_kernel  CTA / engine, thread / voice: Voice::render into a shared-memory
+//                                                           tile, ordered (slot-order) sum -> mix[engine][t]  (f64)
+//                                  engine_post_kernel     thread / engine : NaN guard (rare), cleanup_voices
+//   per segment of rounds:         engine_chain_kernel    lane / engine  : oversampler, DK preamp - pump, power amp, speaker,
+//                                                           volume smoother, f32 -- on its own stream, one segment behind.
 struct EngineDiag { unsigned long long nan_guard, out_nan, steals, note_ons, voices_freed, max_active; };
 
 #define OWG_SLOT_FREE 0
 #define OWG_SLOT_HELD 1
 #define OWG_SLOT_SUSTAINED 2
 #define OWG_SLOT_RELEASING 3
+#define OWG_ENGINE_TILE 64
 
-__global__ void __launch_bounds__(32) engine_kernel(const EngineDesc* __restrict__ engines, int n_engines, const EngineEvent* __restrict__ events,
-                                                    const OwgVoiceInit* __restrict__ vinits, const DamperRow* __restrict__ dampers /*[sched][128]*/,
-                                                    const int32_t* __restrict__ damper_sched, const SpkUpdate* __restrict__ spk_updates,
-                                                    const long long* __restrict__ spk_offsets, const EngineGroup* __restrict__ groups,
-                                                    const DkState* __restrict__ post_warm, const double* __restrict__ recs, long long rec_stride_t,
-                                                    const double* __restrict__ ans, const double* __restrict__ pump, long long pump_stride,
-                                                    VoiceRT* __restrict__ pool /*[engine][128]*/, double* __restrict__ scratch /*[max_block][n_engines]*/,
-                                                    double silent_thr, float* __restrict__ out, long long out_stride, long long max_samples, EngineDiag* diag) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_engines) return;
-    __shared__ double s_cold[OWG_COLD_SCRATCH * 32];
-    const EngineDesc ed = engines[e];
-    const EngineGroup gr = groups[ed.group];
-    const double sr = ed.sample_rate;
-    VoiceRT* mypool = pool + (size_t)e * 128;
-    double* acc = scratch + e;                 // acc[t * n_engines]: lane-contiguous
-    const long long acc_stride = n_engines;
-    const DamperRow* drows = dampers + (size_t)damper_sched[e] * 128;
-    const double* grec = recs + (size_t)ed.group * rec_stride_t * OWG_MAT_STRIDE;
-    const double* gan = ans + (size_t)ed.group * OWG_AN_SPARSE;
-    const double* gpump = pump + (size_t)ed.group * pump_stride;
-    const SpkUpdate* sched = spk_updates + spk_offsets[ed.spk_sched];
-
-    // slot table (engine.rs:36-61)
-    uint8_t st_state[64], st_note[64], st_cur[64], st_has_voice[64], st_has_steal[64];
+struct EngineState {  // slot table (engine.rs:36-61) + the current round's render list
     unsigned long long st_age[64];
     uint32_t st_fade[64], st_fade_len[64];
-    for (int i = 0; i < 64; i++) { st_state[i] = OWG_SLOT_FREE; st_note[i] = 0; st_cur[i] = 0; st_has_voice[i] = 0; st_has_steal[i] = 0; st_age[i] = 0; st_fade[i] = 0; st_fade_len[i] = 0; }
-    unsigned long long age_counter = 0;
-    bool sustain_held = false;
+    uint8_t st_state[64], st_note[64], st_cur[64], st_has_voice[64], st_has_steal[64];
+    unsigned long long age_counter;
+    long long ev;               // next event of this engine
+    int32_t sustain_held, n_items, nan_flag, _pad;
+    int32_t item_fade[128];     // steal_fade at the start of the block for steal voices, -1 for slot voices
+    uint32_t item_fade_len[128];
+    uint8_t item_pool[128];     // pool entry of item k (items are in the engine's summation order)
+    unsigned long long d_steals, d_note_ons, d_freed, d_max_active, d_nan_guard;
+};
 
-    // shared mono chain state
-    DkState dk = post_warm[ed.group];
-    const DkDev dv = dk_dev();
-    double ua[3] = {0, 0, 0}, ub[3] = {0, 0, 0}, da[3] = {0, 0, 0}, db[3] = {0, 0, 0}, down_delay = 0.0;
-    SpkState spk = {0.0, 0.0, 0.0, 0.0, 0.0};
-    OwgChainInit sc;  // speaker coefficients in effect
-    sc.spk_a2 = 0.0; sc.spk_a3 = 0.0; sc.spk_norm = 1.0; sc.spk_thermal_coeff = 0.0; sc.spk_thermal_alpha = 1.0 / (5.0 * sr);
-    sc.spk_tanh = 0;
-    int spk_next = 0;
-    long long spk_clock = ed.n_warm;  // the schedule counts from the first render() sample incl. the warm-up
-    while (spk_next < ed.n_spk_updates && sched[spk_next].at < spk_clock) {  // updates that happened during the warm-up
-        const SpkUpdate& u = sched[spk_next++];
-        sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
-        sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
-        sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
-    }
-    // volume smoother: current = target = 0.5, then set_volume(target) before the first rendered block
-    double vol_current = 0.5, vol_target = 0.5, vol_step = 0.0;
-    uint32_t vol_remaining = 0;
-    if (!(fabs(ed.volume_target - vol_target) < 1e-9)) {
-        vol_target = ed.volume_target;
-        const double delta = vol_target - vol_current;
-        if (ed.ramp_samples == 0) vol_current = vol_target;
-        else { vol_step = delta / (double)ed.ramp_samples; vol_remaining = (uint32_t)ed.ramp_samples; }
-    }
-    unsigned long long d_nan_guard = 0, d_out_nan = 0, d_steals = 0, d_note_ons = 0, d_freed = 0, d_max_active = 0;
-    const uint32_t fade_samples = (uint32_t)fmin(fmax(sr * 0.005, 0.0), 4294967295.0);  // (sample_rate * 0.005) as u32
-    long long ev = ed.ev_begin;
-    long long tos = 0;
-    float* o = out + (size_t)e * out_stride;
+struct EngineChainState {  // shared mono chain of one engine between segments
+    DkState dk;
+    double ua[3], ub[3], da[3], db[3], down_delay;
+    SpkState spk;
+    OwgChainInit sc;
+    double vol_current, vol_target, vol_step;
+    uint32_t vol_remaining;
+    int32_t spk_next;
+    long long spk_clock;
+    unsigned long long d_out_nan;
+};
 
-    for (long long pos = 0; pos < ed.n_samples; pos += ed.block_size) {
-        const int len = (int)((ed.n_samples - pos) < (long long)ed.block_size ? (ed.n_samples - pos) : (long long)ed.block_size);
-        // ---- events that fall in this block (applied at its start) ----
-        while (ev < ed.ev_end && events[ev].sample < pos + len) {
-            const EngineEvent evv = events[ev++];
-            if (evv.kind == OWG_EV_NOTE_ON) {  // engine.rs:299-338
-                const uint8_t note = (uint8_t)evv.note;
+struct EngineWarp { int32_t group, first, count, block_size; long long n_max; };  // engines of one (group, block size) in lanes 0..count-1
+
+__global__ void engine_init_kernel(const EngineDesc* __restrict__ engines, int n_engines, const EngineGroup* __restrict__ groups,
+                                   const DkState* __restrict__ post_warm, EngineState* __restrict__ states, EngineChainState* __restrict__ chains) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_engines) return;
+    const EngineDesc ed = engines[e];
+    if (states) {
+    EngineState& S = states[e];
+    for (int i = 0; i < 64; i++) { S.st_state[i] = OWG_SLOT_FREE; S.st_note[i] = 0; S.st_cur[i] = 0; S.st_has_voice[i] = 0; S.st_has_steal[i] = 0; S.st_age[i] = 0; S.st_fade[i] = 0; S.st_fade_len[i] = 0; }
+    S.age_counter = 0; S.ev = ed.ev_begin; S.sustain_held = 0; S.n_items = 0; S.nan_flag = 0;
+    S.d_steals = S.d_note_ons = S.d_freed = S.d_max_active = S.d_nan_guard = 0;
+    }
+    if (chains) {
+        EngineChainState& C = chains[e];
+        C.dk = post_warm[ed.group];
+        for (int k = 0; k < 3; k++) { C.ua[k] = C.ub[k] = C.da[k] = C.db[k] = 0.0; }
+        C.down_delay = 0.0;
+        C.spk.thermal = C.spk.h1 = C.spk.h2 = C.spk.l1 = C.spk.l2 = 0.0;
+        C.sc.spk_a2 = 0.0; C.sc.spk_a3 = 0.0; C.sc.spk_norm = 1.0; C.sc.spk_thermal_coeff = 0.0; C.sc.spk_thermal_alpha = 1.0 / (5.0 * ed.sample_rate);
+        C.sc.spk_tanh = 0;
+        C.sc.hpf_b0 = C.sc.hpf_b1 = C.sc.hpf_b2 = C.sc.hpf_a1 = C.sc.hpf_a2 = 0.0;
+        C.sc.lpf_b0 = C.sc.lpf_b1 = C.sc.lpf_b2 = C.sc.lpf_a1 = C.sc.lpf_a2 = 0.0;
+        C.spk_next = 0;
+        C.spk_clock = ed.n_warm;  // the schedule counts from the first render() sample incl. the warm-up
+        // volume smoother: current = target = 0.5, then set_volume(target) before the first rendered block
+        C.vol_current = 0.5; C.vol_target = 0.5; C.vol_step = 0.0; C.vol_remaining = 0;
+        if (!(fabs(ed.volume_target - C.vol_target) < 1e-9)) {
+            C.vol_target = ed.volume_target;
+            const double delta = C.vol_target - C.vol_current;
+            if (ed.ramp_samples == 0) C.vol_current = C.vol_target;
+            else { C.vol_step = delta / (double)ed.ramp_samples; C.vol_remaining = (uint32_t)ed.ramp_samples; }
+        }
+        C.d_out_nan = 0;
+    }
+}
+
+// Events that fall in round r's block (applied at its start, like the host loop around WurliEngine::render), then the
+// block's render list in the summation order of render_voices_to_preamp_out (engine.rs:466-493).
+__global__ void engine_events_kernel(const EngineDesc* __restrict__ engines, int n_engines, long long round, const EngineEvent* __restrict__ events,
+                                     const OwgVoiceInit* __restrict__ vinits, const DamperRow* __restrict__ dampers /*[sched][128]*/,
+                                     const int32_t* __restrict__ damper_sched, VoiceRT* __restrict__ pool /*[engine][128]*/,
+                                     EngineState* __restrict__ states) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_engines) return;
+    const EngineDesc ed = engines[e];
+    const long long pos = round * (long long)ed.block_size;
+    if (pos >= ed.n_samples) return;
+    const int len = (int)((ed.n_samples - pos) < (long long)ed.block_size ? (ed.n_samples - pos) : (long long)ed.block_size);
+    EngineState& S = states[e];
+    VoiceRT* mypool = pool + (size_t)e * 128;
+    const DamperRow* drows = dampers + (size_t)damper_sched[e] * 128;
+    const uint32_t fade_samples = (uint32_t)fmin(fmax(ed.sample_rate * 0.005, 0.0), 4294967295.0);  // (sample_rate * 0.005) as u32
+    long long ev = S.ev;
+    while (ev < ed.ev_end && events[ev].sample < pos + len) {
+        const EngineEvent evv = events[ev++];
+        if (evv.kind == OWG_EV_NOTE_ON) {  // engine.rs:299-338
+            const uint8_t note = (uint8_t)evv.note;
+            for (int i = 0; i < 64; i++) {
+                if (S.st_state[i] == OWG_SLOT_SUSTAINED && S.st_note[i] == note) {
+                    S.st_state[i] = OWG_SLOT_RELEASING;
+                    if (S.st_has_voice[i]) voice_note_off(mypool[2 * i + S.st_cur[i]], drows);
+                }
+            }
+            int best = 0;
+            {  // allocate_voice, engine.rs:569-590
+                unsigned long long best_pr = 0xFFFFFFFFFFFFFFFFull;
                 for (int i = 0; i < 64; i++) {
-                    if (st_state[i] == OWG_SLOT_SUSTAINED && st_note[i] == note) {
-                        st_state[i] = OWG_SLOT_RELEASING;
-                        if (st_has_voice[i]) voice_note_off(mypool[2 * i + st_cur[i]], drows);
+                    unsigned long long pr;
+                    const uint8_t stt = S.st_state[i];
+                    if (stt == OWG_SLOT_FREE) { best = i; break; }
+                    else if (stt == OWG_SLOT_RELEASING) pr = S.st_age[i];
+                    else if (stt == OWG_SLOT_SUSTAINED) pr = S.st_age[i] + 0xFFFFFFFFFFFFFFFFull / 4;
+                    else pr = S.st_age[i] + 0xFFFFFFFFFFFFFFFFull / 2;
+                    if (pr < best_pr) { best_pr = pr; best = i; }
+                }
+            }
+            if (S.st_state[best] != OWG_SLOT_FREE) {  // steal: the running voice becomes the fading steal voice
+                S.st_has_steal[best] = S.st_has_voice[best];
+                S.st_cur[best] ^= 1;                   // new voice goes to the other pool entry (drops any older steal voice)
+                S.st_fade[best] = fade_samples;
+                S.st_fade_len[best] = fade_samples;
+                S.d_steals++;
+            }
+            // a Free slot may still fade a stolen voice: it lives in the other pool entry and is left alone
+            S.age_counter += 1;
+            voice_from_init(mypool[2 * best + S.st_cur[best]], vinits[evv.vinit]);
+            S.st_has_voice[best] = 1;
+            S.st_state[best] = OWG_SLOT_HELD;
+            S.st_note[best] = note;
+            S.st_age[best] = S.age_counter;
+            S.d_note_ons++;
+        } else if (evv.kind == OWG_EV_NOTE_OFF) {  // engine.rs:340-359
+            const uint8_t note = (uint8_t)evv.note;
+            int oldest = -1;
+            for (int i = 0; i < 64; i++)
+                if (S.st_state[i] == OWG_SLOT_HELD && S.st_note[i] == note && (oldest < 0 || S.st_age[i] < S.st_age[oldest])) oldest = i;
+            if (oldest >= 0) {
+                if (S.sustain_held) S.st_state[oldest] = OWG_SLOT_SUSTAINED;
+                else {
+                    S.st_state[oldest] = OWG_SLOT_RELEASING;
+                    if (S.st_has_voice[oldest]) voice_note_off(mypool[2 * oldest + S.st_cur[oldest]], drows);
+                }
+            }
+        } else if (evv.kind == OWG_EV_SUSTAIN) {  // engine.rs:361-374
+            const bool held = evv.note != 0;
+            if (S.sustain_held && !held) {
+                for (int i = 0; i < 64; i++) {
+                    if (S.st_state[i] == OWG_SLOT_SUSTAINED) {
+                        S.st_state[i] = OWG_SLOT_RELEASING;
+                        if (S.st_has_voice[i]) voice_note_off(mypool[2 * i + S.st_cur[i]], drows);
                     }
                 }
-                int best = 0;
-                {  // allocate_voice, engine.rs:569-590
-                    unsigned long long best_pr = 0xFFFFFFFFFFFFFFFFull;
-                    bool found_free = false;
-                    for (int i = 0; i < 64 && !found_free; i++) {
-                        unsigned long long pr;
-                        if (st_state[i] == OWG_SLOT_FREE) { best = i; found_free = true; break; }
-                        else if (st_state[i] == OWG_SLOT_RELEASING) pr = st_age[i];
-                        else if (st_state[i] == OWG_SLOT_SUSTAINED) pr = st_age[i] + 0xFFFFFFFFFFFFFFFFull / 4;
-                        else pr = st_age[i] + 0xFFFFFFFFFFFFFFFFull / 2;
-                        if (pr < best_pr) { best_pr = pr; best = i; }
-                    }
-                }
-                if (st_state[best] != OWG_SLOT_FREE) {  // steal: the running voice becomes the fading steal voice
-                    st_has_steal[best] = st_has_voice[best];
-                    st_cur[best] ^= 1;                   // new voice goes to the other pool entry (drops any older steal voice)
-                    st_fade[best] = fade_samples;
-                    st_fade_len[best] = fade_samples;
-                    d_steals++;
-                } else if (st_has_steal[best]) {
-                    // Free slot that still fades a stolen voice: the new voice must not overwrite it
-                    // (slot.voice is None here, so the steal voice keeps living in the other entry)
-                }
-                age_counter += 1;
-                // pick the pool entry: st_cur points at the entry of `voice`; the steal voice (if any) lives in the other one
-                voice_from_init(mypool[2 * best + st_cur[best]], vinits[evv.vinit]);
-                st_has_voice[best] = 1;
-                st_state[best] = OWG_SLOT_HELD;
-                st_note[best] = note;
-                st_age[best] = age_counter;
-                d_note_ons++;
-            } else if (evv.kind == OWG_EV_NOTE_OFF) {  // engine.rs:340-359
-                const uint8_t note = (uint8_t)evv.note;
-                int oldest = -1;
-                for (int i = 0; i < 64; i++)
-                    if (st_state[i] == OWG_SLOT_HELD && st_note[i] == note && (oldest < 0 || st_age[i] < st_age[oldest])) oldest = i;
-                if (oldest >= 0) {
-                    if (sustain_held) st_state[oldest] = OWG_SLOT_SUSTAINED;
-                    else {
-                        st_state[oldest] = OWG_SLOT_RELEASING;
-                        if (st_has_voice[oldest]) voice_note_off(mypool[2 * oldest + st_cur[oldest]], drows);
-                    }
-                }
-            } else if (evv.kind == OWG_EV_SUSTAIN) {  // engine.rs:361-374
-                const bool held = evv.note != 0;
-                if (sustain_held && !held) {
-                    for (int i = 0; i < 64; i++) {
-                        if (st_state[i] == OWG_SLOT_SUSTAINED) {
-                            st_state[i] = OWG_SLOT_RELEASING;
-                            if (st_has_voice[i]) voice_note_off(mypool[2 * i + st_cur[i]], drows);
-                        }
-                    }
-                }
-                sustain_held = held;
+            }
+            S.sustain_held = held ? 1 : 0;
+        }
+    }
+    S.ev = ev;
+    // render list + the fade bookkeeping that follows each steal voice's render (engine.rs:480-492)
+    int n_items = 0;
+    unsigned long long active = 0;
+    for (int i = 0; i < 64; i++) {
+        if (S.st_state[i] == OWG_SLOT_FREE && !S.st_has_steal[i]) continue;
+        if (S.st_has_voice[i]) {
+            S.item_pool[n_items] = (uint8_t)(2 * i + S.st_cur[i]); S.item_fade[n_items] = -1; S.item_fade_len[n_items] = 1u;
+            n_items++; active++;
+        }
+        if (S.st_has_steal[i]) {
+            S.item_pool[n_items] = (uint8_t)(2 * i + (S.st_cur[i] ^ 1)); S.item_fade[n_items] = (int32_t)S.st_fade[i]; S.item_fade_len[n_items] = S.st_fade_len[i];
+            n_items++;
+            S.st_fade[i] = S.st_fade[i] > (uint32_t)len ? S.st_fade[i] - (uint32_t)len : 0u;
+            if (S.st_fade[i] == 0) S.st_has_steal[i] = 0;
+        }
+    }
+    S.n_items = n_items;
+    if (active > S.d_max_active) S.d_max_active = active;
+}
+
+// Register-resident Voice (reed + attack noise + pickup + gain); one sample per call, same arithmetic as voice_kernel /
+// voice_render_block (voice.rs:162-179, reed.rs:219-306, hammer.rs:150-179, pickup.rs:130-149).
+struct VoiceRegs {
+    double s[7], c[7], env[7], drift[7], cos_inc[7], sin_inc[7], phase_inc[7], amp[7], decay[7];
+    double revert, diffusion, onset_inc, onset_exp, n_amp, n_decay, b0, b1, b2, a1, a2, z1, z2, q, beta, ds, gain, ramp, release_count;
+    unsigned long long smp, onset_n;
+    uint32_t jit, n_rng, n_left, n_total;
+    int onset_mode;
+    bool damper_active, ramp_done;
+};
+
+__device__ __forceinline__ void voice_regs_load(VoiceRegs& r, const VoiceRT* __restrict__ vp) {
+#pragma unroll
+    for (int m = 0; m < 7; m++) {
+        r.s[m] = vp->s[m]; r.c[m] = vp->c[m]; r.env[m] = vp->env[m]; r.drift[m] = vp->drift[m];
+        r.cos_inc[m] = vp->cos_inc[m]; r.sin_inc[m] = vp->sin_inc[m]; r.phase_inc[m] = vp->phase_inc[m]; r.amp[m] = vp->amp[m]; r.decay[m] = vp->decay[m];
+    }
+    r.revert = vp->revert; r.diffusion = vp->diffusion; r.onset_inc = vp->onset_inc; r.onset_exp = vp->onset_exp;
+    r.onset_mode = r.onset_exp <= 1.001 ? 0 : (r.onset_exp >= 1.999 ? 1 : 2);
+    r.onset_n = vp->onset_n; r.smp = vp->sample; r.jit = vp->jit; r.n_rng = vp->n_rng; r.n_left = vp->n_left; r.n_total = vp->n_total;
+    r.n_amp = vp->n_amp; r.z1 = vp->z1; r.z2 = vp->z2; r.q = vp->q;
+    r.n_decay = vp->n_decay; r.b0 = vp->b0; r.b1 = vp->b1; r.b2 = vp->b2; r.a1 = vp->a1; r.a2 = vp->a2;
+    r.beta = vp->beta; r.ds = vp->ds; r.gain = vp->gain;
+    r.damper_active = vp->damper_active != 0; r.ramp_done = vp->damper_ramp_done != 0;
+    r.release_count = vp->damper_release_count; r.ramp = vp->damper_ramp_samples;
+}
+
+__device__ __forceinline__ void voice_regs_store(const VoiceRegs& r, VoiceRT* __restrict__ vp) {
+#pragma unroll
+    for (int m = 0; m < 7; m++) { vp->s[m] = r.s[m]; vp->c[m] = r.c[m]; vp->env[m] = r.env[m]; vp->drift[m] = r.drift[m]; }
+    vp->sample = r.smp; vp->jit = r.jit; vp->n_rng = r.n_rng; vp->n_left = r.n_left; vp->n_amp = r.n_amp; vp->z1 = r.z1; vp->z2 = r.z2; vp->q = r.q;
+    vp->damper_active = r.damper_active ? 1 : 0; vp->damper_ramp_done = r.ramp_done ? 1 : 0; vp->damper_release_count = r.release_count;
+}
+
+__device__ __forceinline__ double voice_sample(VoiceRegs& r, const VoiceRT* __restrict__ vp) {
+    if (r.damper_active) {  // reed.rs:227-247
+        r.release_count += 1.0;
+        if (!r.ramp_done) {
+            if (r.release_count > r.ramp) r.ramp_done = true;
+            else {
+#pragma unroll
+                for (int m = 0; m < 7; m++) r.env[m] *= exp(-(vp->damper_rate[m] * r.release_count / r.ramp));
             }
         }
-        // ---- render_voices_to_preamp_out (engine.rs:466-521) ----
-        for (int t = 0; t < len; t++) acc[(long long)t * acc_stride] = 0.0;
-        bool all_finite = true;
-        unsigned long long active = 0;
+        if (r.ramp_done) {
+#pragma unroll
+            for (int m = 0; m < 7; m++) r.env[m] *= vp->damper_mult[m];
+        }
+    }
+    double onset = 1.0;
+    if (r.smp < r.onset_n) {
+        const double cosine = 0.5 * (1.0 - cos((double)r.smp * r.onset_inc));
+        onset = r.onset_mode == 0 ? cosine : (r.onset_mode == 1 ? cosine * cosine : pow(cosine, r.onset_exp));
+    }
+    if ((r.smp & 15ull) == 0ull) {
+#pragma unroll
+        for (int m = 0; m < 7; m++) {
+            r.jit = r.jit * 1664525u + 1013904223u;
+            const double u = (double)(r.jit >> 1) / (4294967295.0 / 2.0);
+            r.drift[m] = r.revert * r.drift[m] + r.diffusion * ((u * 2.0 - 1.0) * 1.7320508080);
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int m = 0; m < 7; m++) {
+        sum += r.amp[m] * r.s[m] * onset * r.env[m];
+        const double dp = r.drift[m] * r.phase_inc[m];
+        const double ci = r.cos_inc[m] - dp * r.sin_inc[m];
+        const double si = r.sin_inc[m] + dp * r.cos_inc[m];
+        const double s_new = r.s[m] * ci + r.c[m] * si;
+        const double c_new = r.c[m] * ci - r.s[m] * si;
+        r.s[m] = s_new; r.c[m] = c_new;
+        r.env[m] *= r.decay[m];
+    }
+    if ((r.smp & 1023ull) == 0ull && r.smp > 0ull) {
+#pragma unroll
+        for (int m = 0; m < 7; m++) {
+            const double r_inv = 1.0 / sqrt(r.s[m] * r.s[m] + r.c[m] * r.c[m]);
+            r.s[m] *= r_inv; r.c[m] *= r_inv;
+        }
+    }
+    double x = 0.0 + sum;
+    if (r.n_left > 0u) {
+        const uint32_t played = r.n_total - r.n_left;
+        const double envn = played < 16u ? c_noise_fade[played] : 1.0;
+        r.n_rng = r.n_rng * 1664525u + 1013904223u;
+        const double white = (double)(int32_t)r.n_rng / 2147483647.0;
+        const double y = r.b0 * white + r.z1;
+        r.z1 = r.b1 * white - r.a1 * y + r.z2;
+        r.z2 = r.b2 * white - r.a2 * y;
+        x += r.n_amp * envn * y;
+        r.n_amp *= r.n_decay;
+        r.n_left -= 1u;
+    }
+    double yy = x * r.ds;
+    {
+        const double ay = fabs(yy);
+        if (!(ay < 0.94)) yy = copysign(0.94 + (0.98 - 0.94) * tanh((ay - 0.94) / (0.98 - 0.94)), yy);
+    }
+    const double omy = 1.0 - yy;
+    const double alpha = r.beta * omy;
+    r.q = (r.q * (1.0 - alpha) + 2.0 * r.beta) / (1.0 + alpha);
+    r.smp += 1ull;
+    return ((r.q * omy - 1.0) * 1.8375) * r.gain;
+}
+
+// One CTA (64 threads) per engine, one thread per render-list item: each voice renders a 64-sample tile into shared
+// memory, then thread j sums column j over the items IN LIST ORDER (sum_buf[i] += voice_buf[i] [* gain], engine.rs:476-488)
+// and writes mix[engine][t].  Lists longer than 64 (steal voices) take further passes that continue the running sums.
+__global__ void __launch_bounds__(OWG_ENGINE_TILE) engine_voice_mix_kernel(const EngineDesc* __restrict__ engines, long long round,
+                                                                           VoiceRT* __restrict__ pool, EngineState* __restrict__ states,
+                                                                           double* __restrict__ mix, long long mix_stride, long long seg_round0) {
+    __shared__ double tile[OWG_ENGINE_TILE * (OWG_ENGINE_TILE + 1)];
+    __shared__ int32_t s_fade[OWG_ENGINE_TILE];
+    __shared__ double s_fade_len[OWG_ENGINE_TILE];
+    const int e = blockIdx.x;
+    const int tid = threadIdx.x;
+    const EngineDesc ed = engines[e];
+    const long long pos = round * (long long)ed.block_size;
+    if (pos >= ed.n_samples) return;
+    const int len = (int)((ed.n_samples - pos) < (long long)ed.block_size ? (ed.n_samples - pos) : (long long)ed.block_size);
+    EngineState& S = states[e];
+    const int n_items = S.n_items;
+    double* mrow = mix + (size_t)e * mix_stride + (round - seg_round0) * (long long)ed.block_size;
+    if (n_items == 0) {
+        for (int t = tid; t < len; t += OWG_ENGINE_TILE) mrow[t] = 0.0;
+        return;
+    }
+    bool bad = false;
+    for (int base = 0; base < n_items; base += OWG_ENGINE_TILE) {
+        const int k = base + tid;
+        const int nk = n_items - base < OWG_ENGINE_TILE ? n_items - base : OWG_ENGINE_TILE;
+        const bool act = k < n_items;
+        const bool last_pass = base + OWG_ENGINE_TILE >= n_items;
+        VoiceRT* vp = pool + (size_t)e * 128 + (act ? S.item_pool[k] : 0);
+        VoiceRegs r;
+        if (act) { voice_regs_load(r, vp); s_fade[tid] = S.item_fade[k]; s_fade_len[tid] = (double)S.item_fade_len[k]; }
+        for (int t0 = 0; t0 < len; t0 += OWG_ENGINE_TILE) {
+            const int tl = len - t0 < OWG_ENGINE_TILE ? len - t0 : OWG_ENGINE_TILE;
+            if (act) {
+                double* row = tile + tid * (OWG_ENGINE_TILE + 1);
+                for (int t = 0; t < tl; t++) row[t] = voice_sample(r, vp);
+            }
+            __syncthreads();
+            if (tid < tl) {
+                double a = base == 0 ? 0.0 : mrow[t0 + tid];
+                const int tb = t0 + tid;  // sample index inside the block
+                for (int kk = 0; kk < nk; kk++) {
+                    double v = tile[kk * (OWG_ENGINE_TILE + 1) + tid];
+                    const int32_t f = s_fade[kk];
+                    if (f >= 0) {  // gain = saturating_sub(steal_fade, i) / fade_len (engine.rs:483-486)
+                        const int32_t rem = f - tb;
+                        v = v * ((double)(rem > 0 ? rem : 0) / s_fade_len[kk]);
+                    }
+                    a += v;
+                }
+                mrow[t0 + tid] = a;
+                if (last_pass && !finite64(a)) bad = true;
+            }
+            __syncthreads();
+        }
+        if (act) voice_regs_store(r, vp);
+        __syncthreads();
+    }
+    if (bad) S.nan_flag = 1;
+}
+
+// After the block's voices: the NaN guard (engine.rs:495-521; re-renders every voice to find the culprit) and
+// cleanup_voices (engine.rs:592-602).  The chain of this block runs later but reads neither.
+__global__ void engine_post_kernel(const EngineDesc* __restrict__ engines, int n_engines, long long round, VoiceRT* __restrict__ pool,
+                                   EngineState* __restrict__ states, double* __restrict__ mix, long long mix_stride, long long seg_round0,
+                                   double silent_thr) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_engines) return;
+    const EngineDesc ed = engines[e];
+    const long long pos = round * (long long)ed.block_size;
+    if (pos >= ed.n_samples) return;
+    const int len = (int)((ed.n_samples - pos) < (long long)ed.block_size ? (ed.n_samples - pos) : (long long)ed.block_size);
+    EngineState& S = states[e];
+    VoiceRT* mypool = pool + (size_t)e * 128;
+    if (S.nan_flag) {
+        S.nan_flag = 0;
+        S.d_nan_guard++;
+        double* acc = mix + (size_t)e * mix_stride + (round - seg_round0) * (long long)ed.block_size;
         for (int i = 0; i < 64; i++) {
-            if (st_state[i] == OWG_SLOT_FREE && !st_has_steal[i]) continue;
-            if (st_has_voice[i]) {
-                all_finite = voice_render_block(&mypool[2 * i + st_cur[i]], acc, acc_stride, len, -1, 1.0) && all_finite;
-                active++;
+            if (S.st_state[i] == OWG_SLOT_FREE && !S.st_has_steal[i]) continue;
+            if (S.st_has_voice[i]) {
+                for (int t = 0; t < len; t++) acc[t] = 0.0;
+                if (!voice_render_block(&mypool[2 * i + S.st_cur[i]], acc, 1, len, -1, 1.0)) { S.st_state[i] = OWG_SLOT_FREE; S.st_has_voice[i] = 0; }
             }
-            if (st_has_steal[i]) {
-                all_finite = voice_render_block(&mypool[2 * i + (st_cur[i] ^ 1)], acc, acc_stride, len, (long long)st_fade[i], (double)st_fade_len[i]) && all_finite;
-                st_fade[i] = st_fade[i] > (uint32_t)len ? st_fade[i] - (uint32_t)len : 0u;
-                if (st_fade[i] == 0) st_has_steal[i] = 0;
-            }
-        }
-        if (active > d_max_active) d_max_active = active;
-        {
-            bool sum_finite = true;
-            for (int t = 0; t < len; t++) sum_finite = sum_finite && finite64(acc[(long long)t * acc_stride]);
-            if (!sum_finite) {  // NaN guard, engine.rs:499-521 (re-renders every voice to find the culprit)
-                d_nan_guard++;
-                for (int i = 0; i < 64; i++) {
-                    if (st_state[i] == OWG_SLOT_FREE && !st_has_steal[i]) continue;
-                    if (st_has_voice[i]) {
-                        for (int t = 0; t < len; t++) acc[(long long)t * acc_stride] = 0.0;
-                        if (!voice_render_block(&mypool[2 * i + st_cur[i]], acc, acc_stride, len, -1, 1.0)) { st_state[i] = OWG_SLOT_FREE; st_has_voice[i] = 0; }
-                    }
-                    if (st_has_steal[i]) {
-                        for (int t = 0; t < len; t++) acc[(long long)t * acc_stride] = 0.0;
-                        if (!voice_render_block(&mypool[2 * i + (st_cur[i] ^ 1)], acc, acc_stride, len, -1, 1.0)) { st_has_steal[i] = 0; st_fade[i] = 0; }
-                    }
-                }
-                for (int t = 0; t < len; t++) acc[(long long)t * acc_stride] = 0.0;
+            if (S.st_has_steal[i]) {
+                for (int t = 0; t < len; t++) acc[t] = 0.0;
+                if (!voice_render_block(&mypool[2 * i + (S.st_cur[i] ^ 1)], acc, 1, len, -1, 1.0)) { S.st_has_steal[i] = 0; S.st_fade[i] = 0; }
             }
         }
-        (void)all_finite;
-        // ---- shared chain (engine.rs:523-566) then speaker / volume / f32 (engine.rs:436-459) ----
-        for (int t = 0; t < len; t++) {
-            const double x = acc[(long long)t * acc_stride];
-            double stage_out;
-            if (ed.oversample) {
-                const double u0 = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, ua, x);
-                const double u1 = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, ub, x);
-                double p0 = 0.0, p1 = 0.0;
-#pragma unroll 1
-                for (int j = 0; j < 2; j++) {
-                    const double* m = grec + (size_t)(gr.n_warm_os + tos) * OWG_MAT_STRIDE;
-                    const double main_out = dk_step<false>(j == 0 ? u0 : u1, dk, m, gan, m[OWG_MAT_AN66], dv, nullptr, s_cold + threadIdx.x, 32);
-                    double res = main_out - gpump[tos];
-                    if (!finite64(res)) { dk = post_warm[ed.group]; res = 0.0; }
-                    const double pa = poweramp(res * 0.25, nullptr);
-                    if (j == 0) p0 = pa; else p1 = pa;
-                    tos += 1;
-                }
-                const double a = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, da, p0);
-                const double b = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, db, p1);
-                stage_out = (a + down_delay) * 0.5;
-                down_delay = b;
-            } else {
-                const double* m = grec + (size_t)(gr.n_warm_os + tos) * OWG_MAT_STRIDE;
-                const double main_out = dk_step<false>(x, dk, m, gan, m[OWG_MAT_AN66], dv, nullptr, s_cold + threadIdx.x, 32);
-                double res = main_out - gpump[tos];
-                if (!finite64(res)) { dk = post_warm[ed.group]; res = 0.0; }
-                stage_out = poweramp(res * 0.25, nullptr);
-                tos += 1;
-            }
-            while (spk_next < ed.n_spk_updates && sched[spk_next].at <= spk_clock) {  // set_character() -> update_coefficients()
+        for (int t = 0; t < len; t++) acc[t] = 0.0;
+    }
+    for (int i = 0; i < 64; i++) {
+        if (S.st_state[i] != OWG_SLOT_FREE && S.st_has_voice[i] && voice_is_silent(mypool[2 * i + S.st_cur[i]], ed.sample_rate, silent_thr)) {
+            S.st_state[i] = OWG_SLOT_FREE;
+            S.st_has_voice[i] = 0;
+            S.d_freed++;
+        }
+    }
+}
+
+// Shared mono chain for rounds [round0, round1) (engine.rs:523-566 then 436-459).  One warp = up to 31 engines of one
+// (group, block size) plus the group's zero-input shadow solve in lane 31 (melange_adapter.rs:72-81); the per-sample DK
+// records are staged in shared memory with cp.async one step ahead, as in chain_kernel<TREM>.
+__global__ void __launch_bounds__(32) engine_chain_kernel(const EngineWarp* __restrict__ warps, const int32_t* __restrict__ order,
+                                                          const EngineDesc* __restrict__ engines, long long round0, long long round1,
+                                                          const SpkUpdate* __restrict__ spk_updates, const long long* __restrict__ spk_offsets,
+                                                          const EngineGroup* __restrict__ groups, const DkState* __restrict__ post_warm,
+                                                          const double* __restrict__ recs, long long rec_stride_t, const double* __restrict__ ans,
+                                                          EngineChainState* __restrict__ chains, DkState* __restrict__ shadow_states /*[warp]*/,
+                                                          const double* __restrict__ mix, long long mix_stride, float* __restrict__ out,
+                                                          long long out_stride, long long max_samples, int last_segment) {
+    __shared__ __align__(16) double s_rec[2 * OWG_MAT_STRIDE];
+    __shared__ double s_an[OWG_AN_SPARSE];
+    __shared__ OwgChainInit s_ci[32];
+    __shared__ double s_cold[OWG_COLD_SCRATCH * 32];
+    const int lane = threadIdx.x;
+    const EngineWarp we = warps[blockIdx.x];
+    const bool is_shadow = lane == 31;
+    const bool is_main = lane < we.count;
+    const int e = is_main ? order[we.first + lane] : order[we.first];
+    const EngineDesc ed = engines[e];
+    const EngineGroup gr = groups[we.group];
+    for (int k = lane; k < OWG_AN_SPARSE; k += 32) s_an[k] = ans[(size_t)we.group * OWG_AN_SPARSE + k];
+    const double* grec = recs + (size_t)we.group * rec_stride_t * OWG_MAT_STRIDE;
+    const long long n_rec = gr.n_warm_os + gr.n_os;
+    const long long T0 = round0 * (long long)we.block_size;
+    long long T1 = round1 * (long long)we.block_size;
+    if (T1 > we.n_max) T1 = we.n_max;
+    const long long ns = is_main ? ed.n_samples : 0;
+    float* o = out + (size_t)e * out_stride;
+    if (T0 < T1) {
+        EngineChainState& C = chains[e];
+        const SpkUpdate* sched = spk_updates + spk_offsets[ed.spk_sched];
+        const double* mrow = mix + (size_t)e * mix_stride;
+        DkState dk;
+        if (is_shadow) dk = T0 == 0 ? post_warm[we.group] : shadow_states[blockIdx.x];
+        else dk = C.dk;
+        const DkDev dv = dk_dev();
+        double ua[3], ub[3], da[3], db[3];
+        for (int k = 0; k < 3; k++) { ua[k] = C.ua[k]; ub[k] = C.ub[k]; da[k] = C.da[k]; db[k] = C.db[k]; }
+        double down_delay = C.down_delay;
+        SpkState spk = C.spk;
+        s_ci[lane] = C.sc;
+        __syncwarp();
+        OwgChainInit& sc = s_ci[lane];
+        int spk_next = C.spk_next;
+        long long spk_clock = C.spk_clock;
+        double vol_current = C.vol_current;
+        const double vol_target = C.vol_target, vol_step = C.vol_step;
+        uint32_t vol_remaining = C.vol_remaining;
+        unsigned long long d_out_nan = 0;
+        if (T0 == 0 && is_main) {
+            while (spk_next < ed.n_spk_updates && sched[spk_next].at < spk_clock) {  // updates that happened during the warm-up
                 const SpkUpdate& u = sched[spk_next++];
                 sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
                 sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
                 sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
             }
-            spk_clock += 1;
-            const double shaped = speaker(stage_out, spk, sc);
-            if (vol_remaining > 0) {
-                vol_current += vol_step;
-                vol_remaining -= 1;
-                if (vol_remaining == 0) vol_current = vol_target;
-            }
-            const float smp = (float)(shaped * 7.498942093324558 * vol_current);
-            if (isfinite(smp)) o[pos + t] = smp;
-            else {  // engine.rs:449-458: reset chain, emit 0 (the shared shadow cannot be reset per engine; counted in diag)
-                d_out_nan++;
-                dk = post_warm[ed.group];
-                for (int k = 0; k < 3; k++) { ua[k] = ub[k] = da[k] = db[k] = 0.0; }
-                down_delay = 0.0;
-                spk.thermal = spk.h1 = spk.h2 = spk.l1 = spk.l2 = 0.0;
-                o[pos + t] = 0.0f;
+        }
+        const int n_sub = gr.oversample ? 2 : 1;
+        long long tos = gr.n_warm_os + T0 * n_sub;  // record index (records include the warm-up)
+        if (tos < n_rec) {
+            const double* src = grec + (size_t)tos * OWG_MAT_STRIDE;
+            double* dst = s_rec + (tos & 1) * OWG_MAT_STRIDE;
+            for (int c = lane; c < OWG_MAT_STRIDE / 2; c += 32) {
+                const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 2 * c) : "memory");
             }
         }
-        // ---- cleanup_voices (engine.rs:592-602) ----
-        for (int i = 0; i < 64; i++) {
-            if (st_state[i] != OWG_SLOT_FREE && st_has_voice[i] && voice_is_silent(mypool[2 * i + st_cur[i]], sr, silent_thr)) {
-                st_state[i] = OWG_SLOT_FREE;
-                st_has_voice[i] = 0;
-                d_freed++;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        double x_next = (is_main && T0 < ns) ? mrow[0] : 0.0;
+        for (long long t = T0; t < T1; t++) {
+            const bool live = is_main && t < ns;
+            const double x = x_next;
+            x_next = (is_main && t + 1 < ns && t + 1 < T1) ? mrow[t + 1 - T0] : 0.0;
+            double u0 = x, u1 = 0.0;
+            if (n_sub == 2) {
+                u0 = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, ua, x);
+                u1 = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, ub, x);
+            }
+            if (!is_main) { u0 = 0.0; u1 = 0.0; }
+            double pp0 = 0.0, pp1 = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < n_sub; j++) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                if (tos + 1 < n_rec) {
+                    const double* src = grec + (size_t)(tos + 1) * OWG_MAT_STRIDE;
+                    double* dst = s_rec + ((tos + 1) & 1) * OWG_MAT_STRIDE;
+                    for (int c = lane; c < OWG_MAT_STRIDE / 2; c += 32) {
+                        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 2 * c) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                const double* m = s_rec + (tos & 1) * OWG_MAT_STRIDE;
+                const double main_out = dk_step<false>(j == 0 ? u0 : u1, dk, m, s_an, m[OWG_MAT_AN66], dv, nullptr, s_cold + lane, 32);
+                const double pump = __shfl_sync(0xffffffffu, main_out, 31);
+                double res = main_out - pump;
+                if (!finite64(res)) { if (!is_shadow) dk = post_warm[we.group]; res = 0.0; }
+                const double pa = poweramp(res * 0.25, nullptr);
+                if (j == 0) pp0 = pa; else pp1 = pa;
+                tos += 1;
+            }
+            double stage_out;
+            if (n_sub == 2) {
+                const double a = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, da, pp0);
+                const double b = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, db, pp1);
+                stage_out = (a + down_delay) * 0.5;
+                down_delay = b;
+            } else stage_out = pp0;
+            if (live) {
+                while (spk_next < ed.n_spk_updates && sched[spk_next].at <= spk_clock) {  // set_character() -> update_coefficients()
+                    const SpkUpdate& u = sched[spk_next++];
+                    sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
+                    sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
+                    sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+                }
+                spk_clock += 1;
+                const double shaped = speaker(stage_out, spk, sc);
+                if (vol_remaining > 0) {
+                    vol_current += vol_step;
+                    vol_remaining -= 1;
+                    if (vol_remaining == 0) vol_current = vol_target;
+                }
+                const float smp = (float)(shaped * 7.498942093324558 * vol_current);
+                if (isfinite(smp)) o[t] = smp;
+                else {  // engine.rs:449-458: reset chain, emit 0 (the shared shadow cannot be reset per engine; counted in diag)
+                    d_out_nan++;
+                    dk = post_warm[we.group];
+                    for (int k = 0; k < 3; k++) { ua[k] = ub[k] = da[k] = db[k] = 0.0; }
+                    down_delay = 0.0;
+                    spk.thermal = spk.h1 = spk.h2 = spk.l1 = spk.l2 = 0.0;
+                    o[t] = 0.0f;
+                }
             }
         }
+        if (is_shadow) shadow_states[blockIdx.x] = dk;
+        if (is_main) {
+            C.dk = dk;
+            for (int k = 0; k < 3; k++) { C.ua[k] = ua[k]; C.ub[k] = ub[k]; C.da[k] = da[k]; C.db[k] = db[k]; }
+            C.down_delay = down_delay; C.spk = spk; C.sc = sc; C.spk_next = spk_next; C.spk_clock = spk_clock;
+            C.vol_current = vol_current; C.vol_remaining = vol_remaining; C.d_out_nan += d_out_nan;
+        }
     }
-    for (long long t = ed.n_samples; t < max_samples; t++) o[t] = 0.0f;  // ragged batch: rows end in silence
-    if (diag) {
-        atomicAdd(&diag->nan_guard, d_nan_guard); atomicAdd(&diag->out_nan, d_out_nan); atomicAdd(&diag->steals, d_steals);
-        atomicAdd(&diag->note_ons, d_note_ons); atomicAdd(&diag->voices_freed, d_freed); atomicMax(&diag->max_active, d_max_active);
-    }
+    if (last_segment && is_main)
+        for (long long t = ed.n_samples; t < max_samples; t++) o[t] = 0.0f;  // ragged batch: rows end in silence
+}
+
+__global__ void engine_diag_kernel(const EngineState* __restrict__ states, const EngineChainState* __restrict__ chains, int n_engines, EngineDiag* diag) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_engines) return;
+    atomicAdd(&diag->nan_guard, states[e].d_nan_guard); atomicAdd(&diag->out_nan, chains[e].d_out_nan); atomicAdd(&diag->steals, states[e].d_steals);
+    atomicAdd(&diag->note_ons, states[e].d_note_ons); atomicAdd(&diag->voices_freed, states[e].d_freed); atomicMax(&diag->max_active, states[e].d_max_active);
 }
 
 }  // namespace owgd

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -693,6 +694,8 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     if (int rc = plan_common(&pl, opts)) return rc;
     cudaStream_t s = pl.stream;
     const int out_location = opts ? opts->out_location : OWG_OUT_HOST;
+    const bool timing = getenv("OWG_ENGINE_TIMING") != nullptr;
+    const auto t_host0 = std::chrono::steady_clock::now();
 
     auto trunc_u64 = [](double x) -> unsigned long long { return !(x == x) || x <= 0.0 ? 0ull : (x >= 18446744073709551615.0 ? ~0ull : (unsigned long long)x); };
     auto trunc_u32 = [](double x) -> uint32_t { return !(x == x) || x <= 0.0 ? 0u : (x >= 4294967295.0 ? 4294967295u : (uint32_t)x); };
@@ -801,9 +804,44 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     if (vinits.empty()) vinits.emplace_back();
     const int ng = (int)groups.size();
 
+    // rounds (= render() blocks) and segments (= rounds per chain launch; the mix buffers form a ring, one per segment in flight)
+    long long n_rounds = 0;
+    for (auto& e : eng) n_rounds = std::max<long long>(n_rounds, (e.n_samples + e.block_size - 1) / e.block_size);
+    long long seg_rounds = std::max<long long>(1, 8192 / max_block);
+    while (seg_rounds > 1 && (double)n * (double)seg_rounds * (double)max_block * 16.0 > 6.0e9) seg_rounds /= 2;
+    const long long mix_stride = seg_rounds * max_block;
+    const long long n_segs = (n_rounds + seg_rounds - 1) / seg_rounds;
+    const long long ring = std::max<long long>(1, std::min<long long>(std::min<long long>(n_segs, 64),
+                                                                      (long long)(8.0e9 / ((double)n * (double)mix_stride * 8.0))));
+
+    // chain warps: engines of one (group, block size) share a warp (common record index and round boundaries)
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, pl.device);
+    int lanes = (int)((n + (long long)sm_count * 4 - 1) / ((long long)sm_count * 4));
+    lanes = std::min(31, std::max(1, lanes));
+    if (const char* env = getenv("OWG_ENGINE_LANES")) lanes = std::min(31, std::max(1, atoi(env)));
+    std::vector<int32_t> eorder((size_t)n);
+    for (int64_t i = 0; i < n; i++) eorder[i] = (int32_t)i;
+    std::stable_sort(eorder.begin(), eorder.end(), [&](int32_t a, int32_t b) {
+        if (eng[a].group != eng[b].group) return eng[a].group < eng[b].group;
+        if (eng[a].block_size != eng[b].block_size) return eng[a].block_size < eng[b].block_size;
+        return eng[a].n_samples > eng[b].n_samples;
+    });
+    std::vector<EngineWarp> ewarps;
+    for (int64_t i = 0; i < n;) {
+        EngineWarp w;
+        w.group = eng[eorder[i]].group; w.block_size = eng[eorder[i]].block_size; w.first = (int32_t)i; w.count = 0; w.n_max = 0;
+        while (i < n && w.count < lanes && eng[eorder[i]].group == w.group && eng[eorder[i]].block_size == w.block_size) {
+            w.n_max = std::max<long long>(w.n_max, eng[eorder[i]].n_samples);
+            w.count++; i++;
+        }
+        ewarps.push_back(w);
+    }
+
     DevBuf<EngineDesc> d_eng; DevBuf<EngineGroup> d_groups; DevBuf<EngineEvent> d_events; DevBuf<OwgVoiceInit> d_vinits;
-    DevBuf<DamperRow> d_dampers; DevBuf<int32_t> d_dsched; DevBuf<SpkUpdate> d_spk; DevBuf<long long> d_spkoff;
-    DevBuf<double> d_pot, d_recs, d_ans, d_pump, d_scratch; DevBuf<DkState> d_post; DevBuf<VoiceRT> d_pool; DevBuf<float> d_out;
+    DevBuf<DamperRow> d_dampers; DevBuf<int32_t> d_dsched, d_eorder; DevBuf<SpkUpdate> d_spk; DevBuf<long long> d_spkoff;
+    DevBuf<double> d_pot, d_recs, d_ans, d_mix; DevBuf<DkState> d_post, d_shadow; DevBuf<VoiceRT> d_pool; DevBuf<float> d_out;
+    DevBuf<EngineState> d_states; DevBuf<EngineChainState> d_chains; DevBuf<EngineWarp> d_ewarps; DevBuf<EngTrmRun> d_trmrun;
     DevBuf<EngineDiag> d_diag;
     int rc = d_eng.upload(eng, s);
     if (!rc) rc = d_groups.upload(groups, s);
@@ -813,43 +851,130 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     if (!rc) rc = d_dsched.upload(damper_sched, s);
     if (!rc) rc = d_spk.upload(spk_updates, s);
     if (!rc) rc = d_spkoff.upload(spk_offsets, s);
+    if (!rc) rc = d_eorder.upload(eorder, s);
+    if (!rc) rc = d_ewarps.upload(ewarps, s);
     if (!rc) rc = d_pot.alloc((size_t)ng * (size_t)pot_stride);
     if (!rc) rc = d_recs.alloc((size_t)ng * (size_t)pot_stride * OWG_MAT_STRIDE);
     if (!rc) rc = d_ans.alloc((size_t)ng * OWG_AN_SPARSE);
-    if (!rc) rc = d_pump.alloc((size_t)ng * (size_t)pot_stride);
     if (!rc) rc = d_post.alloc((size_t)ng);
+    if (!rc) rc = d_shadow.alloc(ewarps.size());
+    if (!rc) rc = d_trmrun.alloc((size_t)ng);
     if (!rc) rc = d_pool.alloc((size_t)n * 128);
-    if (!rc) rc = d_scratch.alloc((size_t)max_block * (size_t)n);
+    if (!rc) rc = d_states.alloc((size_t)n);
+    if (!rc) rc = d_chains.alloc((size_t)n);
+    if (!rc) rc = d_mix.alloc((size_t)ring * (size_t)n * (size_t)mix_stride);
     if (!rc) rc = d_diag.alloc(1);
     float* dout = out;
     if (!rc && out_location == OWG_OUT_HOST) { rc = d_out.alloc((size_t)n * (size_t)stride); dout = d_out.p; }
     if (rc) return rc;
+    // three streams: `s` renders voices round by round; `so` runs the serial Twin-T oscillator one chunk ahead; `sc` builds the
+    // chunk's DK matrices and runs the chain (with the shadow solve in lane 31) behind both
+    cudaStream_t sc = nullptr, so = nullptr;
+    CK(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t st; ~StreamGuard() { if (st) cudaStreamDestroy(st); } } sc_guard{sc};
+    CK(cudaStreamCreateWithFlags(&so, cudaStreamNonBlocking));
+    StreamGuard so_guard{so};
+    std::vector<cudaEvent_t> evs;
+    struct EventGuard { std::vector<cudaEvent_t>* v; ~EventGuard() { for (auto e : *v) cudaEventDestroy(e); } } ev_guard{&evs};
+    auto new_event = [&](cudaEvent_t* e) -> cudaError_t { cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming); if (r == cudaSuccess) evs.push_back(*e); return r; };
+    cudaEvent_t ev_up;
+    CK(new_event(&ev_up));
+    cudaEvent_t tv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const auto t_host1 = std::chrono::steady_clock::now();
+    if (timing) for (auto& e : tv) { CK(cudaEventCreate(&e)); evs.push_back(e); }
     CK(cudaMemsetAsync(d_diag.p, 0, sizeof(EngineDiag), s));
+    CK(cudaMemsetAsync(d_trmrun.p, 0, (size_t)ng * sizeof(EngTrmRun), s));
     CK(cudaMemsetAsync(d_pool.p, 0, (size_t)n * 128 * sizeof(VoiceRT), s));
-    engine_tremolo_kernel<<<ng, 32, 0, s>>>(d_groups.p, ng, d_pot.p, pot_stride);
+    CK(cudaEventRecord(ev_up, s));
+    CK(cudaStreamWaitEvent(sc, ev_up, 0));
+    CK(cudaStreamWaitEvent(so, ev_up, 0));
+    if (timing) { CK(cudaEventRecord(tv[0], so)); CK(cudaEventRecord(tv[3], s)); CK(cudaEventRecord(tv[2], sc)); }
+    const unsigned eb = (unsigned)((n + 63) / 64);
+    engine_init_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, d_groups.p, nullptr, d_states.p, nullptr);
     CK(cudaGetLastError());
-    {
-        dim3 grid((unsigned)((pot_stride + 63) / 64), (unsigned)ng);
-        engine_matrix_kernel<<<grid, 64, 0, s>>>(d_groups.p, ng, d_pot.p, pot_stride, d_recs.p, pot_stride, d_ans.p);
+    const double silent_thr = owg::silent_threshold();
+    int64_t launches = 1;
+    const long long n_chunks = std::max<long long>(n_segs, 1);
+    std::vector<cudaEvent_t> ev_voices((size_t)n_chunks), ev_chain((size_t)n_chunks), ev_osc((size_t)n_chunks);
+    // oscillator chunks: chunk 0 = Tremolo::new (warm-up + settle) + the engines' warm-up + segment 0
+    for (long long sg = 0; sg < n_chunks; sg++) {
+        const long long r1 = std::min(n_rounds, (sg + 1) * seg_rounds);
+        engine_tremolo_kernel<<<ng, 32, 0, so>>>(d_groups.p, ng, d_pot.p, pot_stride, d_trmrun.p, r1 * max_block);
         CK(cudaGetLastError());
+        CK(new_event(&ev_osc[sg]));
+        CK(cudaEventRecord(ev_osc[sg], so));
+        launches += 1;
     }
-    engine_shadow_kernel<<<ng, 32, 0, s>>>(d_groups.p, ng, pl.cache->d_settled, d_recs.p, pot_stride, d_ans.p, d_pump.p, pot_stride, d_post.p);
-    CK(cudaGetLastError());
-    engine_kernel<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(d_eng.p, (int)n, d_events.p, d_vinits.p, d_dampers.p, d_dsched.p, d_spk.p, d_spkoff.p,
-                                                            d_groups.p, d_post.p, d_recs.p, pot_stride, d_ans.p, d_pump.p, pot_stride, d_pool.p,
-                                                            d_scratch.p, owg::silent_threshold(), dout, stride, max_samples, d_diag.p);
+    if (timing) CK(cudaEventRecord(tv[1], so));
+    long long max_warm_os = 0;
+    for (auto& g : groups) max_warm_os = std::max<long long>(max_warm_os, g.n_warm_os);
+    for (long long sg = 0; sg < n_chunks; sg++) {
+        const long long r0 = sg * seg_rounds, r1 = std::min(n_rounds, r0 + seg_rounds);
+        double* mixbuf = d_mix.p + (size_t)(sg % ring) * (size_t)n * (size_t)mix_stride;
+        if (sg >= ring) CK(cudaStreamWaitEvent(s, ev_chain[sg - ring], 0));  // the chain has consumed this mix buffer
+        for (long long r = r0; r < r1; r++) {
+            engine_events_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, r, d_events.p, d_vinits.p, d_dampers.p, d_dsched.p, d_pool.p, d_states.p);
+            engine_voice_mix_kernel<<<(unsigned)n, OWG_ENGINE_TILE, 0, s>>>(d_eng.p, r, d_pool.p, d_states.p, mixbuf, mix_stride, r0);
+            engine_post_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, r, d_pool.p, d_states.p, mixbuf, mix_stride, r0, silent_thr);
+            launches += 3;
+        }
+        CK(cudaGetLastError());
+        CK(new_event(&ev_voices[sg]));
+        CK(cudaEventRecord(ev_voices[sg], s));
+        // matrices of this chunk, then (first chunk) the warm-up solve and the chain states
+        CK(cudaStreamWaitEvent(sc, ev_osc[sg], 0));
+        {
+            const long long chunk_len = (sg == 0 ? max_warm_os : 0) + (r1 - r0) * max_block * 2;
+            dim3 grid((unsigned)std::max<long long>(1, (chunk_len + 63) / 64), (unsigned)ng);
+            engine_matrix_kernel<<<grid, 64, 0, sc>>>(d_groups.p, ng, d_pot.p, pot_stride, d_recs.p, pot_stride, d_ans.p, r0 * max_block, r1 * max_block);
+            CK(cudaGetLastError());
+            launches += 1;
+        }
+        if (sg == 0) {
+            engine_shadow_kernel<<<ng, 32, 0, sc>>>(d_groups.p, ng, pl.cache->d_settled, d_recs.p, pot_stride, d_ans.p, d_post.p);
+            CK(cudaGetLastError());
+            engine_init_kernel<<<eb, 64, 0, sc>>>(d_eng.p, (int)n, d_groups.p, d_post.p, nullptr, d_chains.p);
+            CK(cudaGetLastError());
+            launches += 2;
+        }
+        CK(cudaStreamWaitEvent(sc, ev_voices[sg], 0));
+        engine_chain_kernel<<<(unsigned)ewarps.size(), 32, 0, sc>>>(d_ewarps.p, d_eorder.p, d_eng.p, r0, r1, d_spk.p, d_spkoff.p, d_groups.p, d_post.p,
+                                                                   d_recs.p, pot_stride, d_ans.p, d_chains.p, d_shadow.p, mixbuf, mix_stride, dout, stride,
+                                                                   max_samples, sg + 1 == n_chunks ? 1 : 0);
+        CK(cudaGetLastError());
+        launches += 1;
+        CK(new_event(&ev_chain[sg]));
+        CK(cudaEventRecord(ev_chain[sg], sc));
+    }
+    {
+        if (timing) CK(cudaEventRecord(tv[4], s));
+        cudaEvent_t ev_s_done;
+        CK(new_event(&ev_s_done));
+        CK(cudaEventRecord(ev_s_done, s));
+        CK(cudaStreamWaitEvent(sc, ev_s_done, 0));
+    }
+    engine_diag_kernel<<<eb, 64, 0, sc>>>(d_states.p, d_chains.p, (int)n, d_diag.p);
     CK(cudaGetLastError());
     if (out_location == OWG_OUT_HOST)
         CK(cudaMemcpy2DAsync(out, (size_t)stride * sizeof(float), dout, (size_t)stride * sizeof(float), (size_t)max_samples * sizeof(float),
-                             (size_t)n, cudaMemcpyDeviceToHost, s));
+                             (size_t)n, cudaMemcpyDeviceToHost, sc));
+    if (timing) CK(cudaEventRecord(tv[5], sc));
+    CK(cudaStreamSynchronize(sc));
     CK(cudaStreamSynchronize(s));
+    if (timing) {
+        float a = 0, b = 0, c = 0, d = 0;
+        cudaEventElapsedTime(&a, tv[0], tv[1]); cudaEventElapsedTime(&c, tv[3], tv[4]); cudaEventElapsedTime(&d, tv[2], tv[5]);
+        (void)b;
+        fprintf(stderr, "[owg engines] host prep %.1f ms (%zu note-ons), oscillator stream %.1f ms, voices stream %.1f ms, matrices+chain stream (incl. waits, copy) %.1f ms, rounds %lld, segments %lld (ring %lld), lanes %d, warps %zu\n",
+                std::chrono::duration<double, std::milli>(t_host1 - t_host0).count(), vinits.size(), a, c, d, n_rounds, n_segs, ring, lanes, ewarps.size());
+    }
     {
         EngineDiag h;
         CK(cudaMemcpy(&h, d_diag.p, sizeof(h), cudaMemcpyDeviceToHost));
         owg_diag& d = g_last_diag;
         std::memset(&d, 0, sizeof(d));
         d.nan_reset = h.nan_guard + h.out_nan;
-        d.kernels_launched = 4;
+        d.kernels_launched = launches;
         // engine-specific counters are reported through the generic histogram slots: [0]=note-ons, [1]=steals, [2]=voices freed, [3]=max active voices
         d.nr_iter_hist[0] = h.note_ons; d.nr_iter_hist[1] = h.steals; d.nr_iter_hist[2] = h.voices_freed; d.nr_iter_hist[3] = h.max_active;
     }
