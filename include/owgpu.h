@@ -90,7 +90,9 @@ typedef struct owg_engine_job {
 
 #define OWG_PRECISION_F64_EXACT 0 /* IEEE f64, no FMA contraction: op-for-op the reference's arithmetic */
 
-#define OWG_PREAMP_MELANGE12 0 /* gen_preamp.rs 12-node DK solver (--features melange-preamp) */
+#define OWG_PREAMP_MELANGE12 0 /* gen_preamp.rs 12-node DK solver (--features melange-preamp; the north-star path) */
+#define OWG_PREAMP_LEGACY8 1   /* dk_preamp_legacy.rs hand-written 8-node solver: the reference's DEFAULT build
+                                * (openwurli-dsp/Cargo.toml:10-19); chain B, preamp batch and metrics entry points */
 
 typedef struct owg_opts {
     int32_t device;       /* CUDA device ordinal; -1 = current device */
@@ -191,6 +193,11 @@ int owg_host_voice_init(const owg_voice_job* job, double* out61);
  * hpf b0 b1 b2 a1 a2, lpf b0 b1 b2 a1 a2, tanh flag, oversample flag (18 doubles). */
 #define OWG_CHAIN_INIT_DOUBLES 18
 int owg_host_chain_init(const owg_bench_job* job, double* out18);
+/* Plan-time constants of the legacy 8-node preamp (dk_preamp_legacy.rs:269-412) at `preamp_sr`: S_base[64], A_neg_base[64],
+ * 2w[8], S[:,FB][8], S[:,E1]-S[:,C1][8], S[:,E2]-S[:,C2][8], K[4], N_v S_fb[2], S_fb N_i[2], s_fb_fb, g_cin, gc_1pc, c_cin,
+ * DC state at 1 MOhm (v[8], i_nl[2], v_nl[2], j_cin, cin_rhs_prev), g_ldr after set_ldr_resistance(r_static), 1/1e6. */
+#define OWG_LEGACY_GROUP_DOUBLES 188
+int owg_host_legacy_group(double preamp_sr, double r_static, double* out188);
 
 /* ---- FP64 pipe micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) - */
 /* Runs a register-resident stream of dependent-free DFMA (fma=1) or DADD+DMUL pairs (fma=0) on

@@ -43,9 +43,13 @@ def _samples(duration, sample_rate):
     return int(x) if x > 0 and math.isfinite(x) else 0
 
 
-def _opts(device=-1, out_location=OWG_OUT_HOST, stream=None, collect_diag=False):
+MELANGE12, LEGACY8 = 0, 1  # owg_opts.preamp_model: gen_preamp.rs 12-node (north star) | dk_preamp_legacy.rs 8-node (reference default build)
+
+
+def _opts(device=-1, out_location=OWG_OUT_HOST, stream=None, collect_diag=False, preamp_model=MELANGE12):
     o = Opts()
     lib().owg_default_opts(C.byref(o))
+    o.preamp_model = int(preamp_model)
     o.device = device
     o.out_location = out_location
     o.stream = stream
@@ -101,10 +105,10 @@ class Plan:
         self.kind = kind
 
     @classmethod
-    def bench(cls, jobs, device=-1, stream=None, collect_diag=False):
+    def bench(cls, jobs, device=-1, stream=None, collect_diag=False, preamp_model=MELANGE12):
         arr = (BenchJob * len(jobs))(*jobs)
         h = C.c_void_p()
-        o = _opts(device, OWG_OUT_HOST, stream, collect_diag)
+        o = _opts(device, OWG_OUT_HOST, stream, collect_diag, preamp_model)
         check(lib().owg_plan_bench(arr, len(jobs), C.byref(o), C.byref(h)))
         return cls(h, len(jobs), "bench")
 
@@ -173,20 +177,21 @@ def render_voices(jobs, out=None, device=-1, collect_diag=False):
     return out
 
 
-def render_bench(jobs, out=None, device=-1, collect_diag=False):
-    """Batch of `preamp-bench render` (chain B). Returns [n, max_samples] float64 (pre-WAV samples)."""
+def render_bench(jobs, out=None, device=-1, collect_diag=False, preamp_model=MELANGE12):
+    """Batch of `preamp-bench render` (chain B). Returns [n, max_samples] float64 (pre-WAV samples).
+    preamp_model: MELANGE12 (`--features melange-preamp`, the north-star path) or LEGACY8 (the reference's default build)."""
     stride = max([_samples(j.v.duration_s, j.v.sample_rate) for j in jobs], default=0)
     out = _alloc_out(len(jobs), stride, out)
     if len(jobs) == 0 or stride == 0:
         return out
     ptr, st, loc = _out_ptr(out)
     arr = (BenchJob * len(jobs))(*jobs)
-    o = _opts(device, loc, None, collect_diag)
+    o = _opts(device, loc, None, collect_diag, preamp_model)
     check(lib().owg_render_bench(arr, len(jobs), ptr, st, C.byref(o)))
     return out
 
 
-def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000.0, out=None, device=-1):
+def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000.0, out=None, device=-1, preamp_model=MELANGE12):
     """Preamp-only batch (BASELINE config 2): rows of `x` [n_inst, n_samp] (numpy float64, or a torch CUDA tensor)
     through upsample_2x -> DkPreamp::process_sample x2 -> downsample_2x (`process_oversampled`, preamp-bench main.rs:961-974),
     LDR driven by Tremolo::new(tremolo_depth, fs_preamp) when tremolo_depth > 0 (main.rs:432-461), else static r_ldr."""
@@ -195,7 +200,7 @@ def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000
     pin, sin, lin = _out_ptr(x)
     pout, sout, lout = _out_ptr(out)
     assert lin == lout, "input and output must both be host or both be device buffers"
-    o = _opts(device, lout)
+    o = _opts(device, lout, preamp_model=preamp_model)
     check(lib().owg_preamp_batch(pin, sin, x.shape[0], x.shape[1], float(fs_base), 1 if oversample else 0,
                                  float(tremolo_depth), float(r_ldr), pout, sout, C.byref(o)))
     return out
@@ -204,14 +209,14 @@ def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000
 METRIC_COLUMNS = ("peak_db", "rms_db", "h2_h1_db", "peak", "mean_sq", "h1", "h2")
 
 
-def render_bench_metrics(jobs, window=(0.100, 0.400), device=-1):
+def render_bench_metrics(jobs, window=(0.100, 0.400), device=-1, preamp_model=MELANGE12):
     """Chain B with the `run_calibrate` T5 analysis reduced on the device (output mode "metrics", BASELINE config 4):
     returns [n, 7] float64 = METRIC_COLUMNS over the window [start_s, end_s) (default 100-400 ms, main.rs:1139-1141)."""
     out = np.zeros((len(jobs), 7), dtype=np.float64)
     if len(jobs) == 0:
         return out
     arr = (BenchJob * len(jobs))(*jobs)
-    o = _opts(device, OWG_OUT_HOST)
+    o = _opts(device, OWG_OUT_HOST, preamp_model=preamp_model)
     check(lib().owg_render_bench_metrics(arr, len(jobs), float(window[0]), float(window[1]),
                                          out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(o)))
     return out

@@ -74,12 +74,19 @@ def cmd_render(args):
     disp_scale = parse_flag(args, "--displacement-scale", 0.30) if has_flag(args, "--displacement-scale") else None
     output_path = parse_flag_str(args, "--output", os.path.join(tempfile.gettempdir(), "preamp_render.wav"))
     do_oversample = sample_rate < 88200.0
+    # The reference picks the preamp at compile time (cargo feature `melange-preamp`; its default build is the legacy 8-node
+    # solver, openwurli-dsp/Cargo.toml:10-19).  Here it is a flag; the default is the north-star melange 12-node model.
+    model_name = parse_flag_str(args, "--preamp-model", "melange12")
+    if model_name not in ("melange12", "legacy8"):
+        sys.stderr.write(f"Unknown --preamp-model {model_name} (melange12 | legacy8)\n")
+        return 1
+    preamp_model = api.LEGACY8 if model_name == "legacy8" else api.MELANGE12
 
     pairs = [(n, v) for n in notes for v in velocities]
     jobs = [api.bench_job(note=n, velocity=v, duration=duration, ldr=r_ldr, volume=volume, speaker=speaker_char,
                           tremolo_depth=tremolo_depth, sample_rate=sample_rate, no_poweramp=no_poweramp, no_preamp=no_preamp,
                           no_attack_noise=no_attack_noise, no_mlp=no_mlp, displacement_scale=disp_scale) for n, v in pairs]
-    out = api.render_bench(jobs)
+    out = api.render_bench(jobs, preamp_model=preamp_model)
     stem, ext = os.path.splitext(output_path)
     for k, (note, velocity) in enumerate(pairs):
         final_output = out[k]
@@ -136,6 +143,7 @@ def cmd_calibrate(args):
 USAGE = """Usage: preamp_bench <render|calibrate> [flags]
   render     --note N --velocity V --duration S --ldr OHM --volume X --speaker C --tremolo-depth D --sample-rate HZ
              --no-poweramp --no-rail-sag --no-preamp --no-attack-noise --no-mlp --normalize --displacement-scale DS --output FILE
+             --preamp-model melange12|legacy8   (compile-time cargo feature in the reference)
   calibrate  --notes a,b,c --velocities x,y,z --volume X --speaker C
 """
 

@@ -459,6 +459,153 @@ int make_speaker_schedule(double fs, double target, int64_t n_warm, int64_t n_to
     return n;
 }
 
+// ---- legacy 8-node preamp: plan-time constants ----------------------------------------------------------------------
+namespace {
+enum LgNode { N_BASE1 = 0, N_EMIT1, N_COLL1, N_EMIT2, N_EMIT2B, N_COLL2, N_OUT, N_FB, LGN };
+struct LgBranch { int a, b; double value; };  // two-terminal element between nodes a and b (b < 0: to a supply / ground)
+const double LG_VCC = 15.0, LG_IS = 3.03e-14, LG_VT = 0.026, LG_VBE_MAX = 0.85;
+
+// Gauss-Jordan with partial pivoting on [M | I] (dk_preamp_legacy.rs:122-168): the operation order fixes the rounding.
+void lg_invert(const double (*m)[LGN], double (*inv)[LGN]) {
+    double w[LGN][2 * LGN];
+    for (int r = 0; r < LGN; r++)
+        for (int c = 0; c < LGN; c++) { w[r][c] = m[r][c]; w[r][LGN + c] = r == c ? 1.0 : 0.0; }
+    for (int col = 0; col < LGN; col++) {
+        int piv = col;
+        double best = std::fabs(w[col][col]);
+        for (int r = col + 1; r < LGN; r++)
+            if (std::fabs(w[r][col]) > best) { best = std::fabs(w[r][col]); piv = r; }
+        if (piv != col)
+            for (int c = 0; c < 2 * LGN; c++) { const double t = w[col][c]; w[col][c] = w[piv][c]; w[piv][c] = t; }
+        const double p = w[col][col];
+        for (int c = 0; c < 2 * LGN; c++) w[col][c] /= p;
+        for (int r = 0; r < LGN; r++) {
+            if (r == col) continue;
+            const double f = w[r][col];
+            for (int c = 0; c < 2 * LGN; c++) w[r][c] -= f * w[col][c];
+        }
+    }
+    for (int r = 0; r < LGN; r++)
+        for (int c = 0; c < LGN; c++) inv[r][c] = w[r][LGN + c];
+}
+void lg_matvec(const double (*m)[LGN], const double* x, double* y) {
+    for (int r = 0; r < LGN; r++) {
+        double acc = 0.0;
+        for (int c = 0; c < LGN; c++) acc += m[r][c] * x[c];
+        y[r] = acc;
+    }
+}
+// K = N_v S N_i with N_v rows (BASE1-EMIT1, COLL1-EMIT2), N_i columns (EMIT1-COLL1, EMIT2-COLL2)  (:424-435)
+void lg_kernel(const double (*s)[LGN], double* k4) {
+    k4[0] = s[N_BASE1][N_EMIT1] - s[N_BASE1][N_COLL1] - s[N_EMIT1][N_EMIT1] + s[N_EMIT1][N_COLL1];
+    k4[1] = s[N_BASE1][N_EMIT2] - s[N_BASE1][N_COLL2] - s[N_EMIT1][N_EMIT2] + s[N_EMIT1][N_COLL2];
+    k4[2] = s[N_COLL1][N_EMIT1] - s[N_COLL1][N_COLL1] - s[N_EMIT2][N_EMIT1] + s[N_EMIT2][N_COLL1];
+    k4[3] = s[N_COLL1][N_EMIT2] - s[N_COLL1][N_COLL2] - s[N_EMIT2][N_EMIT2] + s[N_EMIT2][N_COLL2];
+}
+double lg_clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+double lg_ic(double vbe) { return LG_IS * (std::exp(lg_clampd(vbe, -1.0, LG_VBE_MAX) / LG_VT) - 1.0); }  // :668-671
+}  // namespace
+
+void make_legacy_group(double fs, double r_static, double* rec) {
+    // circuit (dk_preamp_legacy.rs:24-41, stamps :281-310), in the reference's stamping order (the sums into a diagonal
+    // entry are order-sensitive in the last bit)
+    const LgBranch resistors[] = {
+        {N_BASE1, -2, 2000000.0},  // R2 to Vcc
+        {N_BASE1, -1, 470000.0},   // R3 to ground
+        {N_EMIT1, -1, 33000.0},    // Re1
+        {N_COLL1, -2, 150000.0},   // Rc1 to Vcc
+        {N_EMIT2, N_EMIT2B, 270.0},
+        {N_EMIT2B, -1, 820.0},
+        {N_COLL2, -2, 1800.0},     // Rc2 to Vcc
+        {N_COLL2, N_OUT, 6800.0},  // R9
+        {N_OUT, N_FB, 56000.0},    // R10
+    };
+    const LgBranch caps[] = {{N_COLL1, N_BASE1, 100.0e-12}, {N_COLL2, N_COLL1, 100.0e-12}, {N_EMIT1, N_FB, 4.7e-6}, {N_EMIT2, N_EMIT2B, 22.0e-6}};
+    const double r1 = 22000.0, cin = 0.022e-6;
+    double g[LGN][LGN] = {{0}}, c[LGN][LGN] = {{0}}, w[LGN] = {0};
+    for (const LgBranch& e : resistors) {
+        const double y = 1.0 / e.value;
+        g[e.a][e.a] += y;
+        if (e.b >= 0) { g[e.b][e.b] += y; g[e.a][e.b] -= y; g[e.b][e.a] -= y; }
+        else if (e.b == -2) w[e.a] += LG_VCC / e.value;
+    }
+    for (const LgBranch& e : caps) { c[e.a][e.a] += e.value; c[e.b][e.b] += e.value; c[e.a][e.b] -= e.value; c[e.b][e.a] -= e.value; }
+    double g_dc[LGN][LGN];
+    std::memcpy(g_dc, g, sizeof(g));
+    // Cin in series with R1 as a bilinear companion (:273-277)
+    const double t_s = 1.0 / fs;
+    const double two_over_t = 2.0 / t_s;
+    const double alpha = 2.0 * r1 * cin * fs;
+    const double g_cin = (2.0 * cin * fs) / (1.0 + alpha);
+    const double c_cin = (1.0 - alpha) / (1.0 + alpha);
+    g[N_BASE1][N_BASE1] += g_cin;
+    double a_pos[LGN][LGN], s_base[LGN][LGN];
+    for (int r = 0; r < LGN; r++)
+        for (int k = 0; k < LGN; k++) {
+            const double ct = two_over_t * c[r][k];
+            a_pos[r][k] = ct + g[r][k];
+            rec[OWG_LG_AN + r * LGN + k] = ct - g[r][k];
+        }
+    lg_invert(a_pos, s_base);
+    for (int r = 0; r < LGN; r++) {
+        for (int k = 0; k < LGN; k++) rec[OWG_LG_S + r * LGN + k] = s_base[r][k];
+        rec[OWG_LG_W2 + r] = 2.0 * w[r];
+        rec[OWG_LG_SFB + r] = s_base[r][N_FB];
+        rec[OWG_LG_D0 + r] = s_base[r][N_EMIT1] - s_base[r][N_COLL1];
+        rec[OWG_LG_D1 + r] = s_base[r][N_EMIT2] - s_base[r][N_COLL2];
+    }
+    lg_kernel(s_base, rec + OWG_LG_K);
+    rec[OWG_LG_NVSFB + 0] = s_base[N_BASE1][N_FB] - s_base[N_EMIT1][N_FB];
+    rec[OWG_LG_NVSFB + 1] = s_base[N_COLL1][N_FB] - s_base[N_EMIT2][N_FB];
+    rec[OWG_LG_SFBNI + 0] = s_base[N_FB][N_EMIT1] - s_base[N_FB][N_COLL1];
+    rec[OWG_LG_SFBNI + 1] = s_base[N_FB][N_EMIT2] - s_base[N_FB][N_COLL2];
+    rec[OWG_LG_SFBFB] = s_base[N_FB][N_FB];
+    rec[OWG_LG_GCIN] = g_cin;
+    rec[OWG_LG_GC1PC] = g_cin * (1.0 + c_cin);
+    rec[OWG_LG_CCIN] = c_cin;
+    // DC operating point at R_ldr = 1 MOhm (full_dc_solve, :370-412): Newton on the 2x2 kernel of the resistive network
+    const double r_init = 1000000.0;
+    double g_full[LGN][LGN], s_dc[LGN][LGN], k_dc[4], sv[LGN];
+    std::memcpy(g_full, g_dc, sizeof(g_dc));
+    g_full[N_FB][N_FB] += 1.0 / r_init;
+    lg_invert(g_full, s_dc);
+    lg_kernel(s_dc, k_dc);
+    lg_matvec(s_dc, w, sv);
+    const double p0 = sv[N_BASE1] - sv[N_EMIT1], p1 = sv[N_COLL1] - sv[N_EMIT2];
+    double vbe0 = 0.56, vbe1 = 0.66;
+    for (int it = 0; it < 100; it++) {
+        const double e0 = std::exp(lg_clampd(vbe0, -1.0, LG_VBE_MAX) / LG_VT), e1 = std::exp(lg_clampd(vbe1, -1.0, LG_VBE_MAX) / LG_VT);
+        const double ic0 = LG_IS * (e0 - 1.0), gm0 = (LG_IS / LG_VT) * e0, ic1 = LG_IS * (e1 - 1.0), gm1 = (LG_IS / LG_VT) * e1;
+        const double f0 = vbe0 - p0 - k_dc[0] * ic0 - k_dc[1] * ic1;
+        const double f1 = vbe1 - p1 - k_dc[2] * ic0 - k_dc[3] * ic1;
+        if (std::fabs(f0) < 1e-12 && std::fabs(f1) < 1e-12) break;
+        const double j00 = 1.0 - k_dc[0] * gm0, j01 = -k_dc[1] * gm1, j10 = -k_dc[2] * gm0, j11 = 1.0 - k_dc[3] * gm1;
+        const double inv_det = 1.0 / (j00 * j11 - j01 * j10);
+        const double d0 = inv_det * (j11 * f0 - j01 * f1), d1 = inv_det * (j00 * f1 - j10 * f0);
+        const double lim = 2.0 * LG_VT;
+        vbe0 -= lg_clampd(d0, -lim, lim);
+        vbe1 -= lg_clampd(d1, -lim, lim);
+    }
+    const double ic0 = lg_ic(vbe0), ic1 = lg_ic(vbe1);
+    double rhs[LGN], v_dc[LGN];
+    for (int r = 0; r < LGN; r++) rhs[r] = w[r];
+    rhs[N_EMIT1] += ic0; rhs[N_COLL1] -= ic0; rhs[N_EMIT2] += ic1; rhs[N_COLL2] -= ic1;
+    lg_matvec(s_dc, rhs, v_dc);
+    for (int r = 0; r < LGN; r++) rec[OWG_LG_V0 + r] = v_dc[r];
+    rec[OWG_LG_INL0] = ic0; rec[OWG_LG_INL0 + 1] = ic1;
+    rec[OWG_LG_VNL0] = vbe0; rec[OWG_LG_VNL0 + 1] = vbe1;
+    rec[OWG_LG_JCIN0] = g_cin * v_dc[N_BASE1];
+    rec[OWG_LG_CINPREV0] = g_cin * v_dc[N_BASE1];
+    // `reset(); set_ldr_resistance(r)` (main.rs:438-439; :620-626): f64::max(r, 1000) and the 0.01 Ohm change threshold
+    rec[OWG_LG_GINIT] = 1.0 / r_init;
+    double g_static = 1.0 / r_init;
+    if (r_static == r_static) {
+        const double nr = r_static > 1000.0 ? r_static : 1000.0;
+        if (std::fabs(nr - r_init) > 0.01) g_static = 1.0 / nr;
+    }
+    rec[OWG_LG_GSTATIC] = g_static;
+}
+
 double note_frequency(int midi) { return freq_of_key(midi); }
 
 double silent_threshold() { return std::pow(10.0, -80.0 / 20.0); }

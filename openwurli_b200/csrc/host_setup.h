@@ -17,6 +17,10 @@ void make_damper_rows(double sample_rate, DamperRow* rows128);
 // effect at (entry 0 = the constructor state, at = -1).  The target is applied after `n_warm` samples.
 int make_speaker_schedule(double sample_rate, double character_target, int64_t n_warm, int64_t n_total, uint32_t ramp_samples,
                           SpkUpdate* out, int max_out);
+// Legacy 8-node preamp (dk_preamp_legacy.rs:269-412): R_ldr-independent matrices, Sherman-Morrison vectors, Cin-R1 companion
+// constants and the DC operating point at 1 MOhm for `preamp_sr`; rec = OWG_LG_STRIDE doubles (owg_records.h).
+// `r_static`: the static LDR resistance handed to set_ldr_resistance after reset() (NaN = tremolo group).
+void make_legacy_group(double preamp_sr, double r_static, double* rec);
 // 10^(-80/20): the is_silent threshold (reed.rs:310), through glibc pow like the reference.
 double silent_threshold();
 // tables::midi_to_freq (tables.rs:34-36)

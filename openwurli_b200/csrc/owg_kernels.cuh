@@ -55,7 +55,9 @@ struct TrmRun {  // oscillator + LDR state carried between chunk launches
 // group's length); run[] carries the state between launches so that the serial oscillator can be pipelined chunk by chunk
 // with the consumers of its output.
 __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* trem_group_ids, int n_trem, double* pot_seq, int64_t pot_stride,
-                                     TrmRun* run, long long live_begin, long long live_end, DevDiag* diag) {
+                                     TrmRun* run, long long live_begin, long long live_end, DevDiag* diag, int legacy) {
+    // legacy != 0: the consumer is the 8-node legacy preamp, whose set_ldr_resistance (dk_preamp_legacy.rs:620-626) is
+    // r = max(R, 1000); if |r - r_ldr| > 0.01 { r_ldr = r; g_ldr = 1/r } -- the output sequence is g_ldr, `pot` tracks r_ldr.
     const int gi = blockIdx.x;
     if (gi >= n_trem || threadIdx.x != 0) return;
     const OwgPreampGroup gr = groups[trem_group_ids[gi]];
@@ -75,7 +77,7 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
     if (n_begin >= n_end) return;
     TrmState st;
     double env = 0.0;
-    double pot = 9.99999999999999854e4;  // pot_0_resistance of the settled state
+    double pot = legacy ? 1000000.0 : 9.99999999999999854e4;  // pot_0_resistance of the settled state | r_ldr of DkPreamp::new
     if (ctor) {
         for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
         for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
@@ -113,11 +115,17 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
             const double branch = 680.0 + r_ldr;
             const double low = r_lower > 0.0 ? r_lower * branch / (r_lower + branch) : 0.0;
             const double z = top + low;
-            if (finite64(z)) {
-                const double r = rclamp(z, 1.0e3, 1.0e6);
-                if (!(fabs(r - pot) < 1e-12)) pot = r;
+            if (legacy) {
+                const double r = z > 1000.0 ? z : 1000.0;  // f64::max(z, 1000.0): NaN -> 1000
+                if (fabs(r - pot) > 0.01) pot = r;
+                o[n - n_pre] = 1.0 / pot;
+            } else {
+                if (finite64(z)) {
+                    const double r = rclamp(z, 1.0e3, 1.0e6);
+                    if (!(fabs(r - pot) < 1e-12)) pot = r;
+                }
+                o[n - n_pre] = pot;
             }
-            o[n - n_pre] = pot;
         }
     }
     run[gi].st = st; run[gi].env = env; run[gi].pot = pot;

@@ -66,6 +66,30 @@ struct OwgPreampGroup {
 #define OWG_MAT_STRIDE 190 // per preamp-rate sample in tremolo mode
 #define OWG_AN_SPARSE 38   // structural non-zeros of a_neg used by build_rhs, row-major order of appearance
 
+// ---- legacy 8-node preamp (dk_preamp_legacy.rs, the reference's default build; owg_opts.preamp_model = OWG_PREAMP_LEGACY8) ----
+// One record per preamp group (doubles), computed on the host at plan time: every matrix is R_ldr-independent.
+#define OWG_LG_S 0        // S_base[8][8] = (2C/T + G_base)^-1
+#define OWG_LG_AN 64      // A_neg_base[8][8] = 2C/T - G_base
+#define OWG_LG_W2 128     // 2 w
+#define OWG_LG_SFB 136    // S_base[:,FB]
+#define OWG_LG_D0 144     // S_base[:,EMIT1] - S_base[:,COLL1]
+#define OWG_LG_D1 152     // S_base[:,EMIT2] - S_base[:,COLL2]
+#define OWG_LG_K 160      // K[2][2]
+#define OWG_LG_NVSFB 164  // N_v * S_base[:,FB]  (2)
+#define OWG_LG_SFBNI 166  // S_base[FB,:] * N_i  (2)
+#define OWG_LG_SFBFB 168
+#define OWG_LG_GCIN 169
+#define OWG_LG_GC1PC 170
+#define OWG_LG_CCIN 171
+#define OWG_LG_V0 172     // DkState::at_dc at R_ldr = 1 MOhm: v[8], i_nl[2], v_nl[2], j_cin, cin_rhs_prev
+#define OWG_LG_INL0 180
+#define OWG_LG_VNL0 182
+#define OWG_LG_JCIN0 184
+#define OWG_LG_CINPREV0 185
+#define OWG_LG_GSTATIC 186  // g_ldr after `reset(); set_ldr_resistance(r)` (static groups)
+#define OWG_LG_GINIT 187    // 1 / 1e6: g_ldr_prev seen by the first sample
+#define OWG_LG_STRIDE 188
+
 // ---- chain E (WurliEngine streams) -----------------------------------------------------------------------------------
 struct DamperRow {  // ModalReed::start_damper (reed.rs:191-216) per MIDI key, computed on the host with glibc
     double rate[7], mult[7];

@@ -4,6 +4,7 @@
 #include "host_setup.h"
 #include "owg_kernels.cuh"
 #include "owg_engine.cuh"
+#include "owg_legacy.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -110,6 +111,8 @@ struct owg_plan {
     const double* in_ptr = nullptr;  // kind 2: caller's input [n][in_stride] (host or device, like `out`)
     int64_t in_stride = 0;
     bool collect_diag = false;
+    bool legacy = false;             // owg_opts.preamp_model == OWG_PREAMP_LEGACY8
+    DevBuf<double> d_legacy_recs;    // [group][OWG_LG_STRIDE]
     int64_t n = 0;
     std::vector<unsigned long long> n_samples;
     unsigned long long max_samples = 0;
@@ -161,7 +164,8 @@ int plan_common(owg_plan* pl, const owg_opts* opts) {
     owg_opts o;
     if (opts) o = *opts; else owg_default_opts(&o);
     if (o.precision != OWG_PRECISION_F64_EXACT) return fail(OWG_E_UNSUPPORTED, "only OWG_PRECISION_F64_EXACT is implemented");
-    if (o.preamp_model != OWG_PREAMP_MELANGE12) return fail(OWG_E_UNSUPPORTED, "only OWG_PREAMP_MELANGE12 is implemented");
+    if (o.preamp_model != OWG_PREAMP_MELANGE12 && o.preamp_model != OWG_PREAMP_LEGACY8) return fail(OWG_E_UNSUPPORTED, "unknown preamp_model");
+    pl->legacy = o.preamp_model == OWG_PREAMP_LEGACY8;
     int dev = o.device;
     if (dev < 0) CK(cudaGetDevice(&dev));
     CK(cudaSetDevice(dev));
@@ -199,7 +203,13 @@ void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vec
         const bool trem = sp.depth > 0.0;
         double r_eff = R0;
         bool dirty = false;
-        if (!trem && std::isfinite(sp.r_ldr)) {  // reset(); set_ldr_resistance(r_ldr)  (main.rs:438-439, gen_preamp.rs:1973-1984)
+        if (pl->legacy) {  // legacy: r = max(r_ldr, 1000) with a 0.01 Ohm change threshold against the constructor's 1 MOhm (dk_preamp_legacy.rs:620-626)
+            r_eff = 1.0e6;
+            if (!trem) {
+                const double r = sp.r_ldr > 1000.0 ? sp.r_ldr : 1000.0;
+                if (std::fabs(r - 1.0e6) > 0.01) r_eff = r;
+            }
+        } else if (!trem && std::isfinite(sp.r_ldr)) {  // reset(); set_ldr_resistance(r_ldr)  (main.rs:438-439, gen_preamp.rs:1973-1984)
             const double r = sp.r_ldr < 1.0e3 ? 1.0e3 : (sp.r_ldr > 1.0e6 ? 1.0e6 : sp.r_ldr);
             if (!(std::fabs(r - R0) < 1e-12)) { r_eff = r; dirty = true; }
         }
@@ -282,7 +292,7 @@ int launch_tremolo_ctor(owg_plan* pl) {
         // the host and DkPreamp::new's cached settled state.  Asynchronous: every later oscillator launch goes to the same
         // in-order stream, so nothing has to wait here.
         tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                             pl->d_trm_ctor.p, -1, -1, nullptr);
+                                                             pl->d_trm_ctor.p, -1, -1, nullptr, pl->legacy ? 1 : 0);
         if (cudaGetLastError() != cudaSuccess) rc = fail(OWG_E_CUDA, "tremolo constructor kernel launch failed");
     }
     return rc;
@@ -296,10 +306,17 @@ int upload_chain_plan(owg_plan* pl, const std::vector<OwgChainInit>& ci, const s
     if (!rc) rc = pl->d_warps_trem.upload(pl->warps_trem, pl->stream);
     if (!rc && pl->trem_group_ids.empty()) rc = pl->d_groups.upload(pl->groups, pl->stream);  // else uploaded by launch_tremolo_ctor
     if (!rc) rc = pl->d_group_rec_index.upload(pl->group_rec_index, pl->stream);
-    if (!rc) rc = pl->d_static_recs.alloc(pl->groups.size() * OWG_MAT_STRIDE);
-    if (!rc) rc = pl->d_ans.alloc(pl->groups.size() * OWG_AN_SPARSE);
-    if (!rc && !pl->trem_group_ids.empty())
-        rc = pl->d_trem_recs.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max * OWG_MAT_STRIDE);
+    if (pl->legacy) {
+        std::vector<double> recs(pl->groups.size() * OWG_LG_STRIDE);
+        for (size_t g = 0; g < pl->groups.size(); g++)
+            owg::make_legacy_group(pl->groups[g].preamp_sr, pl->groups[g].tremolo_depth > 0.0 ? NAN : pl->groups[g].r_static, &recs[g * OWG_LG_STRIDE]);
+        if (!rc) rc = pl->d_legacy_recs.upload(recs, pl->stream);
+    } else {
+        if (!rc) rc = pl->d_static_recs.alloc(pl->groups.size() * OWG_MAT_STRIDE);
+        if (!rc) rc = pl->d_ans.alloc(pl->groups.size() * OWG_AN_SPARSE);
+        if (!rc && !pl->trem_group_ids.empty())
+            rc = pl->d_trem_recs.alloc(pl->trem_group_ids.size() * (size_t)pl->trem_n_os_max * OWG_MAT_STRIDE);
+    }
     if (!rc && pl->collect_diag) rc = pl->d_diag.alloc(1);
     if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
     return rc;
@@ -469,9 +486,11 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     };
     if (pl->kind >= 1) {
         const int ng = (int)pl->groups.size();
-        static_matrix_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_static_recs.p, pl->d_ans.p);
-        CK(cudaGetLastError());
-        launches++;
+        if (!pl->legacy) {
+            static_matrix_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_static_recs.p, pl->d_ans.p);
+            CK(cudaGetLastError());
+            launches++;
+        }
         const int nt = (int)pl->trem_group_ids.size();
         // Tremolo groups: the Twin-T oscillator is one serial thread per group, so it is pipelined: it runs on its own
         // stream in chunks of CH preamp-rate samples, and chunk c's matrices + chain run on the main stream while the
@@ -488,15 +507,17 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
             }
             if (int rc = pl->d_carry.alloc(pl->warps_trem.size() * (size_t)OWG_CARRY * 32)) return rc;
             CK(cudaMemcpyAsync(pl->d_trm_run.p, pl->d_trm_ctor.p, (size_t)nt * sizeof(TrmRun), cudaMemcpyDeviceToDevice, pl->stream_trem));
-            tremolo_an_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_ans.p);
-            CK(cudaGetLastError());
-            launches++;
+            if (!pl->legacy) {
+                tremolo_an_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_ans.p);
+                CK(cudaGetLastError());
+                launches++;
+            }
             CK(cudaEventRecord(pl->chunk_events[n_chunks], s));               // everything the oscillator stream depends on
             CK(cudaStreamWaitEvent(pl->stream_trem, pl->chunk_events[n_chunks], 0));
             for (int64_t c = 0; c < n_chunks; c++) {
                 const int64_t os0 = c * CH_BASE * 2, os1 = (c + 1) * CH_BASE * 2;  // covers 2x-oversampled groups; native-rate groups use half
                 tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                                     pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr);
+                                                                     pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr, pl->legacy ? 1 : 0);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(pl->chunk_events[c], pl->stream_trem));
                 launches++;
@@ -523,7 +544,11 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                 const int64_t b1 = b0 + SCH;
                 cudaEvent_t e0 = chain_event(), e1 = chain_event();
                 CK(cudaEventRecord(e0, s));
-                if (pl->collect_diag)
+                if (pl->legacy)
+                    chain_legacy_kernel<false><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->d_legacy_recs.p, nullptr,
+                                                                 pl->d_group_rec_index.p, 0, dout, stride, pl->collect_diag ? pl->d_diag.p : nullptr, b0, b1,
+                                                                 overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
+                else if (pl->collect_diag)
                     chain_kernel<false, true><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                  pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p,
                                                                  b0, b1, overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin,
@@ -544,13 +569,19 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
             for (int64_t c = 0; c < n_chunks; c++) {
                 const int64_t b0 = c * CH_BASE, b1 = (c + 1) * CH_BASE;
                 CK(cudaStreamWaitEvent(s, pl->chunk_events[c], 0));
-                dim3 grid((unsigned)((2 * CH_BASE + 63) / 64), (unsigned)nt);
-                tremolo_matrix_kernel<<<grid, 64, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_trem_recs.p,
-                                                          pl->trem_n_os_max, 2 * b0, 2 * b1);
-                CK(cudaGetLastError());
+                if (!pl->legacy) {
+                    dim3 grid((unsigned)((2 * CH_BASE + 63) / 64), (unsigned)nt);
+                    tremolo_matrix_kernel<<<grid, 64, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_trem_recs.p,
+                                                              pl->trem_n_os_max, 2 * b0, 2 * b1);
+                    CK(cudaGetLastError());
+                }
                 cudaEvent_t e0 = chain_event(), e1 = chain_event();
                 CK(cudaEventRecord(e0, s));
-                if (pl->collect_diag)
+                if (pl->legacy)
+                    chain_legacy_kernel<true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->d_legacy_recs.p, pl->d_pot_seq.p,
+                                                                pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride, pl->collect_diag ? pl->d_diag.p : nullptr,
+                                                                b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
+                else if (pl->collect_diag)
                     chain_kernel<true, true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                 pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
                                                                 pl->d_diag.p, b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
@@ -560,7 +591,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                                                                  nullptr, b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(e1, s));
-                launches += 2;
+                launches += pl->legacy ? 1 : 2;
                 if (overlap_d2h) { if (int rc = copy_columns(b0, b1, e1)) return rc; }
             }
         }
@@ -692,6 +723,7 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     }
     owg_plan pl;  // used for device / stream / cache plumbing only
     if (int rc = plan_common(&pl, opts)) return rc;
+    if (pl.legacy) return fail(OWG_E_UNSUPPORTED, "owg_render_engines: OWG_PREAMP_LEGACY8 is not implemented for engine streams");
     cudaStream_t s = pl.stream;
     const int out_location = opts ? opts->out_location : OWG_OUT_HOST;
     const bool timing = getenv("OWG_ENGINE_TIMING") != nullptr;
@@ -1031,6 +1063,13 @@ int owg_host_voice_init(const owg_voice_job* job, double* o) {
     o[k++] = v.bq_b0; o[k++] = v.bq_b1; o[k++] = v.bq_b2; o[k++] = v.bq_a1; o[k++] = v.bq_a2;
     o[k++] = (double)v.onset_ramp_samples; o[k++] = (double)v.n_samples; o[k++] = (double)v.jitter_state; o[k++] = (double)v.noise_rng;
     o[k++] = (double)v.noise_remaining;
+    return OWG_OK;
+}
+
+int owg_host_legacy_group(double preamp_sr, double r_static, double* o) {
+    if (!o || !(preamp_sr > 0.0) || !std::isfinite(preamp_sr)) return fail(OWG_E_BAD_ARG, "owg_host_legacy_group: bad argument");
+    static_assert(OWG_LG_STRIDE == OWG_LEGACY_GROUP_DOUBLES, "record layout");
+    owg::make_legacy_group(preamp_sr, r_static, o);
     return OWG_OK;
 }
 

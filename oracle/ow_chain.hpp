@@ -6,6 +6,8 @@
 // engine.rs).
 #pragma once
 #include "ow_tremolo.hpp"
+#include "ow_preamp_legacy.hpp"
+#include <memory>
 
 namespace ow {
 
@@ -138,6 +140,20 @@ struct BenchJob {
     double volume = 0.60;
     double speaker_character = 1.0;
     bool no_preamp = false, no_poweramp = false;
+    int preamp_model = 0;  // 0 = melange 12-node (dk_preamp/melange_adapter.rs), 1 = legacy 8-node (dk_preamp_legacy.rs, the default build)
+};
+
+// The two DkPreamp implementations behind the reference's `PreampModel` seam (preamp.rs; dk_preamp/mod.rs:14-20).
+struct AnyPreamp {
+    std::unique_ptr<pre::DkPreamp> mel;
+    std::unique_ptr<leg::DkPreamp> lg;
+    AnyPreamp(int model, double sr) {
+        if (model == 1) lg.reset(new leg::DkPreamp(sr));
+        else mel.reset(new pre::DkPreamp(sr));
+    }
+    void reset() { if (lg) lg->reset(); else mel->reset(); }
+    void set_ldr_resistance(double r) { if (lg) lg->set_ldr_resistance(r); else mel->set_ldr_resistance(r); }
+    double process_sample(double x, double* pump = nullptr) { return lg ? lg->process_sample(x, pump) : mel->process_sample(x, nullptr, pump); }
 };
 
 struct Taps {  // optional per-stage taps (T3 voice out, T4 preamp out, T5 final)
@@ -171,7 +187,7 @@ static inline std::vector<double> render_bench(const BenchJob& j, Taps* taps = n
     std::vector<double> pout(n, 0.0);
     if (j.no_preamp) pout = reed;
     else {
-        pre::DkPreamp preamp(preamp_sr);
+        AnyPreamp preamp(j.preamp_model, preamp_sr);
         Tremolo* trem = nullptr;
         if (j.tremolo_depth > 0.0) trem = new Tremolo(j.tremolo_depth, preamp_sr);
         else { preamp.reset(); preamp.set_ldr_resistance(j.r_ldr); }
@@ -182,7 +198,7 @@ static inline std::vector<double> render_bench(const BenchJob& j, Taps* taps = n
                 preamp.set_ldr_resistance(r);
             }
             double pump = 0.0;
-            const double y = preamp.process_sample(x, nullptr, &pump);
+            const double y = preamp.process_sample(x, &pump);
             if (taps && taps->shadow) taps->shadow->push_back(pump);
             return y;
         };
@@ -199,8 +215,8 @@ static inline std::vector<double> render_bench(const BenchJob& j, Taps* taps = n
             for (size_t i = 0; i < n; i++) pout[i] = step(reed[i]);
         }
         if (dg) {
-            dg->main = preamp.diag_main;
-            dg->shadow = preamp.diag_shadow;
+            if (preamp.mel) { dg->main = preamp.mel->diag_main; dg->shadow = preamp.mel->diag_shadow; }
+            else { for (int b = 0; b < 8; b++) dg->main.nr_iter_hist[b] = preamp.lg->nr_iter_hist[b]; dg->main.nan_reset = preamp.lg->nan_reset; }
             if (trem) { std::memcpy(dg->trem_nr_hist, trem->osc.nr_iter_hist, sizeof(dg->trem_nr_hist)); dg->trem_be = trem->osc.diag_be_fallback; }
         }
         delete trem;
@@ -221,9 +237,9 @@ static inline std::vector<double> render_bench(const BenchJob& j, Taps* taps = n
 
 // ---- preamp-only harness (C2): process_oversampled pattern, main.rs:961-974 + tremolo as in cmd_render :432-461
 static inline void preamp_batch_one(const double* in, size_t n, double fs_base, bool oversample,
-                                    double tremolo_depth_or_neg, double r_ldr_static, double* out) {
+                                    double tremolo_depth_or_neg, double r_ldr_static, double* out, int preamp_model = 0) {
     const double preamp_sr = oversample ? fs_base * 2.0 : fs_base;
-    pre::DkPreamp preamp(preamp_sr);
+    AnyPreamp preamp(preamp_model, preamp_sr);
     Tremolo* trem = nullptr;
     if (tremolo_depth_or_neg > 0.0) trem = new Tremolo(tremolo_depth_or_neg, preamp_sr);
     else { preamp.reset(); preamp.set_ldr_resistance(r_ldr_static); }

@@ -90,6 +90,87 @@ int owo_render_bench_taps(const owg_bench_job* job, double* fin, double* voice, 
     return OWG_OK;
 }
 
+// chain B with the preamp implementation chosen as owg_opts.preamp_model does for the product (0 melange-12, 1 legacy-8)
+int owo_render_bench_model(const owg_bench_job* jobs, int64_t n, double* out, int64_t stride, int threads, int preamp_model) {
+    if (!jobs || !out || n < 0) return OWG_E_BAD_ARG;
+    if (preamp_model == 0) return owo_render_bench(jobs, n, out, stride, threads);
+    std::vector<ChainDiag> dgs((size_t)n);
+    parallel_for(n, threads, [&](int64_t i) {
+        BenchJob b = to_bench(jobs[i]);
+        b.preamp_model = preamp_model;
+        std::vector<double> r = render_bench(b, nullptr, &dgs[i]);
+        std::memcpy(out + i * stride, r.data(), r.size() * sizeof(double));
+    });
+    std::memset(&g_diag, 0, sizeof(g_diag));
+    for (auto& d : dgs) {
+        for (int b = 0; b < 16; b++) { g_diag.nr_iter_hist[b] += d.main.nr_iter_hist[b]; g_diag.tremolo_nr_iter_hist[b] += d.trem_nr_hist[b]; }
+        for (int b = 0; b < 9; b++) g_diag.poweramp_iter_hist[b] += d.pa_iter_hist[b];
+        g_diag.nan_reset += d.main.nan_reset;
+        g_diag.tremolo_be_fallback += d.trem_be;
+    }
+    return OWG_OK;
+}
+
+int owo_preamp_batch_model(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double fs_base, int oversample,
+                           double tremolo_depth, double r_ldr_static, double* out, int64_t out_stride, int threads, int preamp_model) {
+    if (!in || !out || n_inst < 0 || n_samp < 0) return OWG_E_BAD_ARG;
+    if (preamp_model == 0) pre::settled_state();
+    parallel_for(n_inst, threads, [&](int64_t i) {
+        preamp_batch_one(in + i * in_stride, (size_t)n_samp, fs_base, oversample != 0, tremolo_depth, r_ldr_static, out + i * out_stride, preamp_model);
+    });
+    return OWG_OK;
+}
+
+// ---- legacy 8-node preamp probes (dk_preamp_legacy.rs tests) -----------------------------------
+// out[0..7] = v_dc, out[8..9] = v_nl, out[10] = max |S_base * A_base - I| is not available (A is not kept): instead
+// out[10] = s_fb_fb, out[11] = g_cin, out[12] = c_cin, out[13..16] = K
+int owo_legacy_dc(double sample_rate, double* out) {
+    leg::DkPreamp p(sample_rate);
+    for (int i = 0; i < 8; i++) out[i] = p.v_dc[i];
+    out[8] = p.main_st.v_nl[0]; out[9] = p.main_st.v_nl[1];
+    out[10] = p.s_fb_fb; out[11] = p.g_cin; out[12] = p.c_cin;
+    out[13] = p.k[0][0]; out[14] = p.k[0][1]; out[15] = p.k[1][0]; out[16] = p.k[1][1];
+    return OWG_OK;
+}
+// Same layout as owg_host_legacy_group (include/owgpu.h): the product's plan-time constants, from the oracle's DkPreamp.
+int owo_legacy_group(double sample_rate, double r_static, double* o) {
+    leg::DkPreamp p(sample_rate);
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) { o[i * 8 + j] = p.s_base[i][j]; o[64 + i * 8 + j] = p.a_neg_base[i][j]; }
+    for (int i = 0; i < 8; i++) {
+        o[128 + i] = p.two_w[i]; o[136 + i] = p.s_fb_col[i];
+        o[144 + i] = p.s_base[i][leg::EMIT1] - p.s_base[i][leg::COLL1];
+        o[152 + i] = p.s_base[i][leg::EMIT2] - p.s_base[i][leg::COLL2];
+        o[172 + i] = p.main_st.v[i];
+    }
+    o[160] = p.k[0][0]; o[161] = p.k[0][1]; o[162] = p.k[1][0]; o[163] = p.k[1][1];
+    o[164] = p.nv_sfb[0]; o[165] = p.nv_sfb[1]; o[166] = p.sfb_ni[0]; o[167] = p.sfb_ni[1];
+    o[168] = p.s_fb_fb; o[169] = p.g_cin; o[170] = p.gc_1pc; o[171] = p.c_cin;
+    o[180] = p.main_st.i_nl[0]; o[181] = p.main_st.i_nl[1]; o[182] = p.main_st.v_nl[0]; o[183] = p.main_st.v_nl[1];
+    o[184] = p.main_st.j_cin; o[185] = p.main_st.cin_rhs_prev;
+    o[187] = p.g_ldr;
+    p.reset();
+    if (r_static == r_static) p.set_ldr_resistance(r_static);
+    o[186] = p.g_ldr;
+    return OWG_OK;
+}
+// Raw preamp run (no oversampler): x[n] -> y[n] at `sample_rate`, R_ldr set once before the first sample;
+// do_reset != 0 calls reset() first (measure_gain, :878-899); pump (shadow output) optional.
+int owo_legacy_run(double sample_rate, double r_ldr, int do_reset, const double* x, int64_t n, double* y, double* pump) {
+    leg::DkPreamp p(sample_rate);
+    p.set_ldr_resistance(r_ldr);
+    if (do_reset) p.reset();
+    for (int64_t i = 0; i < n; i++) { double pu = 0.0; y[i] = p.process_sample(x[i], &pu); if (pump) pump[i] = pu; }
+    return OWG_OK;
+}
+// test_idle_pump_level (:1966-2025): Tremolo::new(depth, sr) drives set_ldr_resistance, zero input; y = main - shadow.
+int owo_legacy_idle_pump(double sample_rate, double depth, int64_t n, double* y, double* pump) {
+    leg::DkPreamp p(sample_rate);
+    Tremolo t(depth, sample_rate);
+    for (int64_t i = 0; i < n; i++) { p.set_ldr_resistance(t.process()); double pu = 0.0; y[i] = p.process_sample(0.0, &pu); if (pump) pump[i] = pu; }
+    return OWG_OK;
+}
+
 int owo_last_diag(owg_diag* out) { if (!out) return OWG_E_BAD_ARG; *out = g_diag; return OWG_OK; }
 
 // ---- preamp-only batch (C2) ------------------------------------------------------------------

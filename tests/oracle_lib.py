@@ -106,6 +106,13 @@ def lib():
         L.owo_tremolo_osc.argtypes = [C.c_double, C.c_int64, C.c_int64, dp, dp]
         L.owo_speaker_run.argtypes = [C.c_double, C.c_double, dp, C.c_int64, dp]
         L.owo_oversampler_roundtrip.argtypes = [dp, C.c_int64, dp]
+        L.owo_render_bench_model.argtypes = [C.POINTER(BenchJob), C.c_int64, dp, C.c_int64, C.c_int, C.c_int]
+        L.owo_preamp_batch_model.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_double,
+                                             C.c_double, dp, C.c_int64, C.c_int, C.c_int]
+        L.owo_legacy_dc.argtypes = [C.c_double, dp]
+        L.owo_legacy_group.argtypes = [C.c_double, C.c_double, dp]
+        L.owo_legacy_run.argtypes = [C.c_double, C.c_double, C.c_int, dp, C.c_int64, dp, dp]
+        L.owo_legacy_idle_pump.argtypes = [C.c_double, C.c_double, C.c_int64, dp, dp]
         L.owo_voice_init.argtypes = [C.POINTER(VoiceJob), dp]
         L.owo_chain_init.argtypes = [C.POINTER(BenchJob), dp]
         _lib = L
@@ -132,13 +139,16 @@ def render_voices(jobs, threads=1):
     return out
 
 
-def render_bench(jobs, threads=1):
+MELANGE12, LEGACY8 = 0, 1
+
+
+def render_bench(jobs, threads=1, preamp_model=MELANGE12):
     n = len(jobs)
     ns = [n_samples(j.v.duration_s, j.v.sample_rate) for j in jobs]
     stride = max(ns) if ns else 0
     out = np.zeros((n, stride))
     arr = (BenchJob * n)(*jobs)
-    assert lib().owo_render_bench(arr, n, dptr(out), stride, threads) == 0
+    assert lib().owo_render_bench_model(arr, n, dptr(out), stride, threads, preamp_model) == 0
     return out
 
 

@@ -363,3 +363,90 @@ def test_metrics_mode_sweep_slice_properties():
     by = {(j.v.midi, round(j.volume, 3), round(j.tremolo_depth, 3), round(j.speaker_character, 3)): m[i] for i, j in enumerate(jobs)}
     for k in range(4):
         assert by[(40 + 8 * k, 1.0, 0.0, 0.0)][1] > by[(40 + 8 * k, round(1 / 3.0, 3), 0.0, 0.0)][1]
+
+
+# ---- legacy 8-node preamp (owg_opts.preamp_model = OWG_PREAMP_LEGACY8; the reference's default cargo build) -------------------------
+# Parity bound for this model.  The legacy solver skips Newton whenever |f| < 1e-9 V at the warm start (dk_preamp_legacy.rs:516-518);
+# inside that dead zone the step is explicit in the BJT currents with loop gain K*gm >> 1, so a 1-ulp difference (CUDA vs glibc exp)
+# grows ~100x per sample until the 1e-9 V threshold re-engages Newton: every implementation of this algorithm carries its own
+# chaotic +-1e-9 V * gain noise floor (measured: 2e-10 at the preamp output, 3e-9..5e-7 after the 69x power amp, independent of the
+# signal level).  So: max-abs <= 1e-6 full scale always (the north-star bound), relative L2 <= 1e-6 for renders peaking above
+# -30 dBFS; quieter renders are checked on the absolute bound only.  The melange model keeps the 1e-7 relative bound.
+LEGACY_REL_L2 = 1e-6
+
+
+def _legacy_parity(jobs, what):
+    got = ow.render_bench(jobs, collect_diag=True, preamp_model=ow.LEGACY8)
+    dg = ow.last_diag()
+    ref = O.render_bench([to_oracle_b(j) for j in jobs], threads=4, preamp_model=O.LEGACY8)
+    dc = O.last_diag()
+    for i, j in enumerate(jobs):
+        n = O.n_samples(j.v.duration_s, j.v.sample_rate)
+        if n:
+            loud = np.abs(ref[i, :n]).max() >= 0.03
+            assert_parity(got[i, :n], ref[i, :n], f"legacy {what}[{i}] midi={j.v.midi}", rel_l2=LEGACY_REL_L2 if loud else np.inf)
+    # Newton update counts per preamp step (0..6) of the main instances: same totals, and the same distribution up to the dead-zone
+    # flips between 0 and 1 updates
+    a, b = np.array(list(dg.nr_iter_hist)[:8], dtype=np.int64), np.array(list(dc.nr_iter_hist)[:8], dtype=np.int64)
+    assert a.sum() == b.sum() and np.abs(a - b).sum() <= max(8, a.sum() // 100), (what, a, b)
+    assert np.abs(a[2:] - b[2:]).sum() <= max(8, a.sum() // 10000), (what, a, b)
+    assert dg.nan_reset == 0 and dc.nan_reset == 0
+    return got, ref
+
+
+def test_legacy_chain_b_static_parity():
+    jobs = [ow.bench_job(note=m, velocity=v, duration=0.3, ldr=r) for m, v, r in
+            [(60, 100, 1e6), (33, 127, 1e6), (96, 127, 19000.0), (48, 1, 50000.0), (84, 64, 5.0), (57, 90, 2.5e6)]]
+    got, ref = _legacy_parity(jobs, "static")
+    mel = ow.render_bench(jobs[:1])
+    assert np.abs(mel[0] - got[0]).max() > 1e-5   # it really is a different solver
+
+
+def test_legacy_chain_b_tremolo_rates_flags():
+    jobs = [ow.bench_job(note=60, velocity=100, duration=0.25, tremolo_depth=0.5),
+            ow.bench_job(note=40, velocity=127, duration=0.3, tremolo_depth=1.0),
+            ow.bench_job(note=72, velocity=80, duration=0.2, tremolo_depth=0.25, sample_rate=48000.0),
+            ow.bench_job(note=55, velocity=60, duration=0.1, tremolo_depth=0.7, sample_rate=96000.0),   # native rate
+            ow.bench_job(note=55, velocity=60, duration=0.1, sample_rate=96000.0, ldr=30000.0),
+            ow.bench_job(note=45, velocity=120, duration=0.07, volume=1.0, speaker=0.0, tremolo_depth=0.5),
+            ow.bench_job(note=70, velocity=90, duration=0.05, no_poweramp=True, tremolo_depth=0.5),
+            ow.bench_job(note=70, velocity=90, duration=0.05, no_preamp=True),
+            ow.bench_job(note=80, velocity=50, duration=0.0, tremolo_depth=0.5)]
+    _legacy_parity(jobs, "tremolo/flags")
+
+
+def test_legacy_long_render_crosses_chunk_boundaries():
+    # 0.6 s at 44.1 kHz = 26 460 samples: 4 oscillator/chain chunks of 8192 with carried state
+    jobs = [ow.bench_job(note=50, velocity=110, duration=0.6, tremolo_depth=0.8), ow.bench_job(note=77, velocity=70, duration=0.45, tremolo_depth=0.8)]
+    _legacy_parity(jobs, "chunks")
+
+
+def test_legacy_preamp_batch_and_metrics():
+    fs = 48000.0
+    x = _c2_inputs(40, 1500, fs)
+    for depth, r in ((0.5, 0.0), (0.0, 19000.0)):
+        got = ow.preamp_batch(x, fs, oversample=True, tremolo_depth=depth, r_ldr=r, preamp_model=ow.LEGACY8)
+        ref = np.zeros_like(x)
+        O.lib().owo_preamp_batch_model(O.dptr(x), x.shape[1], x.shape[0], x.shape[1], fs, 1, depth, r, O.dptr(ref), x.shape[1], 4, O.LEGACY8)
+        for i in range(x.shape[0]):
+            assert_parity(got[i], ref[i], f"legacy preamp batch inst {i}", rel_l2=LEGACY_REL_L2 if np.abs(ref[i]).max() >= 0.03 else np.inf)
+    cases = [(60, 100, 0.6, 1.0, 0.0), (72, 100, 0.6, 1.0, 0.5)]
+    jobs = [ow.calibrate_job(n, v, volume=vol, speaker=spk, tremolo_depth=d) for n, v, vol, spk, d in cases]
+    got = ow.render_bench_metrics(jobs, preamp_model=ow.LEGACY8)
+    ref_samples = O.render_bench([to_oracle_b(j) for j in jobs], threads=2, preamp_model=O.LEGACY8)
+    for k, c in enumerate(cases):
+        ref = _calibrate_metrics_from_samples(ref_samples[k], O.lib().owo_midi_to_freq(c[0]))
+        assert np.abs(got[k, :3] - ref[:3]).max() < 1e-6, (c, got[k], ref)
+
+
+def test_legacy_engines_are_rejected_loudly():
+    import ctypes as C
+    from openwurli_b200 import _abi
+    ej = ow.engine_job([(0, ow.NOTE_ON, 60, 0.8)], duration=0.01)
+    arr = (_abi.EngineJob * 1)(ej)
+    out = np.zeros((1, 441), dtype=np.float32)
+    o = _abi.Opts()
+    ow.lib().owg_default_opts(C.byref(o))
+    o.preamp_model = ow.LEGACY8
+    rc = ow.lib().owg_render_engines(arr, 1, out.ctypes.data_as(C.POINTER(C.c_float)), 441, C.byref(o))
+    assert rc == _abi.OWG_E_UNSUPPORTED

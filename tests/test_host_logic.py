@@ -168,3 +168,20 @@ def test_shard_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_legacy_preamp_plan_constants_match_oracle_bitwise():
+    """make_legacy_group (host_setup.cpp) vs the oracle's DkPreamp::new / reset / set_ldr_resistance: same arithmetic, same bits."""
+    import ctypes as C
+    for sr in (88200.0, 96000.0, 44100.0, 48000.0, 192000.0):
+        for r in (float("nan"), 1e6, 1e6 + 0.005, 19000.0, 500.0, 5e6, float("inf")):
+            a, b = np.zeros(188), np.zeros(188)
+            assert ow.lib().owg_host_legacy_group(sr, r, O.dptr(a)) == 0
+            assert O.lib().owo_legacy_group(sr, r, O.dptr(b)) == 0
+            assert a.tobytes() == b.tobytes(), (sr, r, np.nonzero(a != b)[0][:8])
+    # S_base really is the inverse of A_base = 2C/T + G_base  (A_base = A_neg_base + 2 G_base, with G from the netlist)
+    a = np.zeros(188)
+    ow.lib().owg_host_legacy_group(88200.0, 1e6, O.dptr(a))
+    S, An = a[:64].reshape(8, 8), a[64:128].reshape(8, 8)
+    assert np.allclose(S, S.T, rtol=1e-9, atol=1e-18)           # reciprocal network
+    assert abs(a[186] - 1e-6) < 1e-20 and a[187] == 1.0 / 1e6

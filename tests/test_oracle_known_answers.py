@@ -252,6 +252,74 @@ def test_preamp_gain_at_ldr_endpoints():
     assert abs(tail.mean()) < 1e-5  # shadow subtraction removes the DC operating point
 
 
+# ---- legacy 8-node preamp (dk_preamp_legacy.rs: the reference's default build) ------------------------------------------------------
+def _legacy_gain_db(r, do_reset, settle_s, measure_s):
+    sr = 88200.0
+    n = int(sr * settle_s) + int(sr * measure_s)
+    x = 0.001 * np.sin(2 * np.pi * 1000.0 * np.arange(n) / sr)
+    y = np.zeros(n)
+    L.owo_legacy_run(sr, r, do_reset, O.dptr(x), n, O.dptr(y), None)
+    return 20 * np.log10(np.abs(y[int(sr * settle_s):]).max() / 0.001), y
+
+
+def test_legacy_preamp_dc_operating_point():  # dk_preamp_legacy.rs:901-947 (SPICE ground truth in the comments)
+    for sr in (88200.0, 96000.0, 44100.0):
+        d = O.vec(L.owo_legacy_dc, 17, sr)
+        v = d[:8]
+        assert abs(v[0] - 2.854) < 0.1 and abs(v[1] - 2.297) < 0.1 and abs(v[2] - 4.556) < 0.5
+        assert abs(v[3] - 3.897) < 0.5 and abs(v[5] - 8.551) < 1.0
+        assert 0.45 < v[0] - v[1] < 0.70 and 0.55 < v[2] - v[3] < 0.75
+        assert abs(d[8] - (v[0] - v[1])) < 1e-9 and abs(d[9] - (v[2] - v[3])) < 1e-9   # v_nl is Vbe at the DC point
+    a, b = O.vec(L.owo_legacy_dc, 17, 88200.0), O.vec(L.owo_legacy_dc, 17, 44100.0)
+    assert np.max(np.abs(a[:10] - b[:10])) < 1e-9   # test_l3_dc_independent_of_sample_rate (:1493-1527)
+
+
+def test_legacy_preamp_gain_and_melange_gate():
+    # test_gain_no_tremolo / test_gain_increases_with_tremolo (:949-981, measure_gain :878-899: reset, 0.3 s settle, 0.2 s peak)
+    g1m, _ = _legacy_gain_db(1e6, 1, 0.3, 0.2)
+    g19k, _ = _legacy_gain_db(19000.0, 1, 0.3, 0.2)
+    assert 3.0 < g1m < 12.0 and 10 ** (g19k / 20) > 1.2 * 10 ** (g1m / 20)
+    # dk_preamp/mod.rs:85-117: leg_gain (no reset, 0.5 s settle, 0.1 s peak) within 2 dB of melange at both endpoints;
+    # CHANGELOG v0.5.2 A/B: "within 0.18 dB"
+    l1m, _ = _legacy_gain_db(1e6, 0, 0.5, 0.1)
+    l19k, y = _legacy_gain_db(19000.0, 0, 0.5, 0.1)
+    m1m, _ = _gain_db(1e6)
+    m19k, _ = _gain_db(19000.0)
+    assert abs(l1m - m1m) < 0.3 and abs(l19k - m19k) < 0.3, (l1m, m1m, l19k, m19k)
+    assert np.all(np.isfinite(y))
+
+
+def test_legacy_preamp_stability_and_pump_cancellation():
+    sr = 88200.0
+    # test_stability (:1009-1028): impulse then 2 s of silence
+    n = int(sr * 2.0) + 1
+    x = np.zeros(n); x[0] = 0.01
+    y = np.zeros(n)
+    L.owo_legacy_run(sr, 1e6, 0, O.dptr(x), n, O.dptr(y), None)
+    assert abs(y[-1]) < 1e-3
+    # test_idle_pump_level (:1966-2025): tremolo depth 1.0, zero input: |main - shadow| < -100 dB after 0.5 s, while the pump itself is volts
+    n = int(sr * 2.0)
+    y, pump = np.zeros(n), np.zeros(n)
+    L.owo_legacy_idle_pump(sr, 1.0, n, O.dptr(y), O.dptr(pump))
+    s0 = int(sr * 0.5)
+    assert np.abs(y[s0:]).max() < 1e-5
+    assert np.ptp(pump[s0:]) > 0.5
+
+
+def test_legacy_render_level_vs_melange():
+    """CHANGELOG v0.5.2 / openwurli-dsp/Cargo.toml:12-15: legacy and melange agree "within 0.18 dB" -- reproduced by the two
+    restatements on a full chain-B render once the legacy model's R_ldr start transient (it starts from the 1 MOhm DC point,
+    dk_preamp_legacy.rs:333-337) has died away."""
+    for depth, ldr in ((0.0, 1e6), (0.0, 19000.0), (0.5, 1e6)):
+        j = O.bench_job(midi=57, vel=90, dur=0.8, depth=depth, r_ldr=ldr)
+        a = O.render_bench([j], preamp_model=O.MELANGE12)[0]
+        b = O.render_bench([j], preamp_model=O.LEGACY8)[0]
+        assert np.all(np.isfinite(b)) and np.abs(a - b).max() > 0
+        s0 = int(0.4 * 44100)
+        db = 20 * np.log10(np.sqrt(np.mean(b[s0:] ** 2)) / np.sqrt(np.mean(a[s0:] ** 2)))
+        assert 0.10 < db < 0.26, (depth, ldr, db)
+
+
 def test_preamp_settled_state_is_dc_operating_point():  # melange_adapter.rs:14-20, gen_preamp.rs:1568-1588
     st = np.zeros(19)
     L.owo_preamp_settled(O.dptr(st))
