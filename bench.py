@@ -46,15 +46,25 @@ def grid_jobs(ow, duration, depth, seed_offset=0, stride=1):
     return jobs
 
 
-def workload_name(duration, depth):
+def workload_name(duration, depth, model="melange12"):
     trem = f"tremolo_depth {depth:g}" if depth > 0 else "static LDR 1 MOhm (CLI default)"
+    pre = "melange 12-node preamp" if model == "melange12" else "legacy 8-node preamp"
     return (f"C3 grid {KEYS} keys x {VELS} velocities = {KEYS * VELS} renders x {duration:g} s, chain B "
-            f"(`preamp-bench render`), MLP on, 44.1 kHz 2x-oversampled melange preamp, {trem}")
+            f"(`preamp-bench render`), MLP on, 44.1 kHz 2x-oversampled {pre}, {trem}")
 
 
 # ---- algorithmic FLOPs (DESIGN.md "Roofline") ---------------------------------------------------------
-def algorithmic_flops(n_inst, n_samp, mean_nr_iters, depth, n_groups=1):
+def algorithmic_flops(n_inst, n_samp, mean_nr_iters, depth, model=0, n_groups=1):
     """De-duplicated algorithmic FP64 operations of one pass (+,-,*,/,sqrt = 1 each; fast_exp = 18; libm = 20)."""
+    if model == 1:
+        # legacy 8-node step (dk_preamp_legacy.rs:447-554): 2 dense 8x8 mat-vec (256) + rhs/SM/K corrections (~60) + node update (56)
+        # + final currents (2 exp, ~46) + per loop pass: 2 exp + residual/Jacobian/2x2 solve (~75); mean_nr_iters = loop passes
+        dk_step = 256 + 60 + 56 + 46 + 75.0 * mean_nr_iters
+        per_sample = 129 + 50 + 2 * dk_step + 200 + 62
+        shared = n_groups * n_samp * 2 * dk_step
+        if depth > 0:
+            shared += n_groups * n_samp * 2 * 1060               # Twin-T/LDR step only: no matrix rebuild in this model
+        return n_inst * n_samp * per_sample + shared
     dk_step = 85 + 288 + 72 + 70 + 220.0 * mean_nr_iters       # rhs + S*rhs + S_NI*i + checks + NR iterations
     per_sample = 129 + 50 + 2 * dk_step + 200 + 62               # voice + oversampler + 2 DK steps + power amp + speaker
     inst = n_inst * n_samp * per_sample
@@ -123,11 +133,11 @@ def cpu_sample_jobs(O, duration, depth, n_jobs):
     return jobs
 
 
-def run_cpu(O, duration, depth, n_jobs, threads):
+def run_cpu(O, duration, depth, n_jobs, threads, model=0):
     import numpy as np
     jobs = cpu_sample_jobs(O, duration, depth, n_jobs)
     t0 = time.perf_counter()
-    out = O.render_bench(jobs, threads=threads)
+    out = O.render_bench(jobs, threads=threads, preamp_model=model)
     dt = time.perf_counter() - t0
     assert np.all(np.isfinite(out))
     return n_jobs * duration / dt, dt
@@ -144,14 +154,17 @@ def main():
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grid-stride", type=int, default=1, help="debug: take every k-th grid job")
+    ap.add_argument("--preamp-model", default="melange12", choices=["melange12", "legacy8"],
+                    help="melange12 = the north-star 12-node DK preamp (cargo feature melange-preamp); legacy8 = the reference's default build")
     args = ap.parse_args()
+    model = 1 if args.preamp_model == "legacy8" else 0
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    cfg = {"workload": workload_name(args.duration, args.tremolo_depth), "renders_per_gpu": KEYS * VELS // args.grid_stride,
-           "sample_rate": FS, "duration_s": args.duration, "tremolo_depth": args.tremolo_depth,
+    cfg = {"workload": workload_name(args.duration, args.tremolo_depth, args.preamp_model), "renders_per_gpu": KEYS * VELS // args.grid_stride,
+           "sample_rate": FS, "duration_s": args.duration, "tremolo_depth": args.tremolo_depth, "preamp_model": args.preamp_model,
            "cache_policy": "outputs (8.6 GB per pass) and streamed matrices far exceed the 126 MB L2; no flush needed",
            "parallelism": f"instances sharded over {world} GPU(s), no collective"}
 
@@ -165,11 +178,11 @@ def main():
         n_jobs = max(2 * threads, 8)
         O.lib().owo_preamp_settled((O.C.c_double * 19)())  # process-wide settled-state cache, like the reference's OnceLock
         for _ in range(args.warmup):
-            run_cpu(O, min(args.duration, 0.1), args.tremolo_depth, threads, threads)
+            run_cpu(O, min(args.duration, 0.1), args.tremolo_depth, threads, threads, model)
         t0 = time.perf_counter()
         vals = []
         for _ in range(args.steps):
-            v, dt = run_cpu(O, args.duration, args.tremolo_depth, n_jobs, threads)
+            v, dt = run_cpu(O, args.duration, args.tremolo_depth, n_jobs, threads, model)
             vals.append(v)
         wall = time.perf_counter() - t0
         value = args.steps * n_jobs * args.duration / wall
@@ -204,9 +217,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_passes(depth, steps, warm):
+    def timed_passes(depth, steps, warm, model=model):
         jobs = grid_jobs(ow, args.duration, depth, seed_offset=rank, stride=args.grid_stride)
-        plan = ow.Plan.bench(jobs, device=dev, stream=stream)
+        plan = ow.Plan.bench(jobs, device=dev, stream=stream, preamp_model=model)
         out = torch.empty((len(jobs), plan.max_samples), dtype=torch.float64, device="cuda")
         for _ in range(warm):
             plan.execute(out)
@@ -236,22 +249,22 @@ def main():
         del out
         return dict(ms=ms, main_ms=main_ms, launches=launches, clocks=clocks, finite=finite, peak=peak, n_inst=n_inst, n_samp=n_samp)
 
-    def e2e_passes(depth, steps):
+    def e2e_passes(depth, steps, model=model):
         jobs = grid_jobs(ow, args.duration, depth, seed_offset=rank, stride=args.grid_stride)
         n_samp = int(args.duration * FS)
         host = torch.empty((len(jobs), n_samp), dtype=torch.float64).pin_memory()
-        ow.render_bench(jobs, out=host, device=dev)  # warm-up of the path (allocations, settled-state cache)
+        ow.render_bench(jobs, out=host, device=dev, preamp_model=model)  # warm-up of the path (allocations, settled-state cache)
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            ow.render_bench(jobs, out=host, device=dev)
+            ow.render_bench(jobs, out=host, device=dev, preamp_model=model)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         checksum = float(host[:, ::997].abs().sum().item())
-        probe = ow.Plan.bench(jobs[:64], device=dev)  # init-record bytes per job, as the library counts its uploads
+        probe = ow.Plan.bench(jobs[:64], device=dev, preamp_model=model)  # init-record bytes per job, as the library counts its uploads
         h2d = int(probe.h2d_bytes / 64 * len(jobs))
         probe.close()
         d2h = len(jobs) * n_samp * 8
@@ -262,11 +275,13 @@ def main():
         """Mean Newton iterations per DK step on a 1-in-64 sample of the grid (device counters), for the FLOP model."""
         jobs = grid_jobs(ow, args.duration, depth, stride=64)
         out = torch.empty((len(jobs), int(args.duration * FS)), dtype=torch.float64, device="cuda")
-        pl = ow.Plan.bench(jobs, device=dev, stream=stream, collect_diag=True)
+        pl = ow.Plan.bench(jobs, device=dev, stream=stream, collect_diag=True, preamp_model=model)
         pl.execute(out)
         d = ow.last_diag()
         pl.close()
         h = np.array(list(d.nr_iter_hist), dtype=np.float64)
+        if model == 1:  # legacy: bucket b = b Newton updates = b + 1 device evaluations in the loop
+            return float((h * (np.arange(16) + 1)).sum() / max(h.sum(), 1.0))
         # bucket b = last_nr_iterations b -> b+1 iterations ran; bucket 15 (>=15) counted as 16 (lower bound)
         return float((h * (np.arange(16) + 1)).sum() / max(h.sum(), 1.0))
 
@@ -288,20 +303,20 @@ def main():
         fma_peak = ow.fp64_peak(device=dev, fma=True) * 2.0     # TFLOP/s, DFMA = 2 flop
         unfused_peak = ow.fp64_peak(device=dev, fma=False)      # T instr/s = TFLOP/s for uncontracted code
         iters = mean_nr_iterations(args.tremolo_depth)
-        flops = algorithmic_flops(main_run["n_inst"], main_run["n_samp"], iters, args.tremolo_depth)
+        flops = algorithmic_flops(main_run["n_inst"], main_run["n_samp"], iters, args.tremolo_depth, model)
         kernel_s = main_run["main_ms"] * 1e-3 / args.steps
         achieved = flops / kernel_s / 1e12
         line["roofline"] = {"bound": "fp64", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
                             "traffic": None, "peak_source": "owg_fp64_peak DFMA micro-benchmark measured in this run "
                             "(MEASURED_PEAKS.json has no FP64 entry; B200 nominal 37 TFLOP/s)",
                             "peak_unfused_tflops": unfused_peak, "frac_of_unfused": achieved / unfused_peak,
-                            "kernel": "owgd::chain_kernel", "kernel_ms_per_step": kernel_s * 1e3, "mean_nr_iterations": iters,
+                            "kernel": "owgd::chain_legacy_kernel" if model == 1 else "owgd::chain_kernel", "kernel_ms_per_step": kernel_s * 1e3, "mean_nr_iterations": iters,
                             "algorithmic_gflop_per_step": flops / 1e9}
         if not args.no_variants:
             other = 0.0 if args.tremolo_depth > 0 else 0.5
             v = timed_passes(other, max(1, args.steps - 1), 1) if world == 1 else None
             if v:
-                line["variants"] = {workload_name(args.duration, other): {
+                line["variants"] = {workload_name(args.duration, other, args.preamp_model): {
                     "value": v["n_inst"] * args.duration * max(1, args.steps - 1) / (v["ms"] * 1e-3), "unit": UNIT,
                     "ms_per_step": v["ms"] / max(1, args.steps - 1)}}
                 # machine-filling batch (throughput regime): 4 grids at different volumes, 0.5 s each (the C4 sweep's render length)
@@ -321,13 +336,24 @@ def main():
                     "value": len(big) * 0.5 / (msb * 1e-3), "unit": UNIT, "ms_per_step": msb}
                 plan.close()
                 del outb
+                if model == 0:  # the reference's default-build preamp (legacy 8-node) on the same grid
+                    lv = timed_passes(args.tremolo_depth, 1, 1, model=1)
+                    le = e2e_passes(args.tremolo_depth, 1, model=1)
+                    entry = {"value": lv["n_inst"] * args.duration / (lv["ms"] * 1e-3), "unit": UNIT, "ms_per_step": lv["ms"],
+                             "e2e": le["n_inst"] * args.duration / le["s"]}
+                    if not args.no_cpu_baseline:
+                        import oracle_lib as O
+                        threads = O.lib().owo_hardware_threads() or os.cpu_count() or 1
+                        vc, dtc = run_cpu(O, args.duration, args.tremolo_depth, max(2 * threads, 8), threads, 1)
+                        entry["cpu_baseline"] = {"value": vc, "unit": UNIT, "cores": threads, "kind": "port"}
+                    line["variants"][f"reference default build: {workload_name(args.duration, args.tremolo_depth, 'legacy8')}"] = entry
         if not args.no_cpu_baseline:
             import oracle_lib as O
             threads = O.lib().owo_hardware_threads() or os.cpu_count() or 1
             n_jobs = max(2 * threads, 8)
             O.lib().owo_preamp_settled((O.C.c_double * 19)())
-            v, dt = run_cpu(O, args.duration, args.tremolo_depth, n_jobs, threads)
-            v1, dt1 = run_cpu(O, args.duration, args.tremolo_depth, 1, 1)
+            v, dt = run_cpu(O, args.duration, args.tremolo_depth, n_jobs, threads, model)
+            v1, dt1 = run_cpu(O, args.duration, args.tremolo_depth, 1, 1, model)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n_jobs} evenly spread grid renders x {args.duration:g} s, {threads} threads "
                                               f"({dt:.1f} s); single-thread: {v1:.2f} audio-s/s"}

@@ -247,8 +247,9 @@ def engine_job(events, sample_rate=44100.0, duration=1.0, volume=0.5, tremolo_de
     return j
 
 
-def render_engines(jobs, out=None, device=-1):
-    """Batch of WurliEngine streams (chain E). Returns [n, max_samples] float32 (WurliEngine::render writes f32)."""
+def render_engines(jobs, out=None, device=-1, preamp_model=MELANGE12):
+    """Batch of WurliEngine streams (chain E). Returns [n, max_samples] float32 (WurliEngine::render writes f32).
+    preamp_model=LEGACY8 renders what the reference's default plugin build (legacy 8-node preamp) produces."""
     stride = max([_samples(j.duration_s, j.sample_rate) for j in jobs], default=0)
     if out is None:
         out = np.zeros((len(jobs), stride), dtype=np.float32)
@@ -262,7 +263,7 @@ def render_engines(jobs, out=None, device=-1):
         assert out.dtype == torch.float32 and out.is_contiguous()
         ptr, st, loc = out.data_ptr(), out.shape[1], (OWG_OUT_DEVICE if out.is_cuda else OWG_OUT_HOST)
     arr = (_abi.EngineJob * len(jobs))(*jobs)
-    o = _opts(device, loc)
+    o = _opts(device, loc, preamp_model=preamp_model)
     check(lib().owg_render_engines(arr, len(jobs), ptr, st, C.byref(o)))
     return out
 

@@ -9,6 +9,7 @@
 // for one render() block at a time.
 #pragma once
 #include "owg_kernels.cuh"
+#include "owg_legacy.cuh"
 
 namespace owgd {
 
@@ -169,14 +170,17 @@ __device__ __forceinline__ void voice_note_off(VoiceRT& v, const DamperRow* __re
 // Tremolo::new(0.5, os_sr) [2 s settle] then one process() per preamp-rate sample with the depth trajectory of the engine's
 // LinearSmoother (engine.rs:67-130, 532-547): 0.5 during the warm-up, then a ramp_samples-long linear ramp to the target.
 // Output: pot_0_resistance in effect per preamp-rate sample (warm-up first).
-struct EngTrmRun {  // oscillator + LDR + depth-smoother state between chunk launches
+struct EngTrmRun {  // oscillator state between chunk launches
     TrmState st;
-    double env, pot, sm_current, sm_target, sm_step, depth;
-    uint32_t sm_remaining, _pad;
     long long n_done;  // steps done so far (50 warm-up + 2*sr settle + live)
 };
+struct EngLdrRun {  // LDR envelope, resistance tracking and depth-smoother state between chunk launches
+    double env, pot, sm_current, sm_target, sm_step, depth;
+    uint32_t sm_remaining, _pad;
+    long long n_done;  // live samples done
+};
 
-// live_end_base: produce pot values for live (warm-up + rendered) preamp-rate samples below n_warm_os + live_end_base*sub.
+// live_end_base: produce oscillator output for live (warm-up + rendered) preamp-rate samples below n_warm_os + live_end_base*sub.
 __global__ void engine_tremolo_kernel(const EngineGroup* groups, int n_groups, double* pot_seq, long long pot_stride, EngTrmRun* run,
                                       long long live_end_base) {
     const int gi = blockIdx.x;
@@ -195,36 +199,61 @@ __global__ void engine_tremolo_kernel(const EngineGroup* groups, int n_groups, d
     const int sub = gr.oversample ? 2 : 1;
     long long live_end = gr.n_warm_os + live_end_base * sub;
     if (live_end > n_live) live_end = n_live;
-    EngTrmRun R = run[gi];
-    const long long n_begin = R.n_done, n_end = n_pre + live_end;
+    const long long n_begin = run[gi].n_done, n_end = n_pre + live_end;
     if (n_begin >= n_end) return;
     TrmState st;
-    double env, pot, sm_current, sm_target, sm_step, depth;
-    uint32_t sm_remaining;
     if (n_begin == 0) {
         for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
         for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
         st.xin_prev = 0.0;
-        env = 0.0;
-        pot = 9.99999999999999854e4;
-        // depth smoother (LinearSmoother): current = target = 0.5 until set_tremolo_depth(target) after the warm-up
-        sm_current = 0.5; sm_target = 0.5; sm_step = 0.0; sm_remaining = 0;
-        depth = 0.5;  // Tremolo::new(0.5, ..) stores 0.5; set_depth() clamps to [0,1]
     } else {
-        st = R.st; env = R.env; pot = R.pot; sm_current = R.sm_current; sm_target = R.sm_target; sm_step = R.sm_step; depth = R.depth;
-        sm_remaining = R.sm_remaining;
+        st = run[gi].st;
         if (n_begin > 50 && fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);  // same deterministic rebuild as at step 50
     }
-    const double ldr_attack = exp(-1.0 / (0.0025 * sr));
-    const double ldr_release = exp(-1.0 / (0.035 * sr));
-    const double ln_r_max = log(1000000.0);
-    const double ln_min_minus_max = log(9000.0) - log(1000000.0);
     double* o = pot_seq + (size_t)gi * pot_stride;
     for (long long n = n_begin; n < n_end; n++) {
         if (n == 50 && fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);
-        const bool live = n >= n_pre;
-        if (live) {
-            const long long tl = n - n_pre;
+        const double v_out = trm_step(st, m, kq, nullptr, trm_sc);
+        if (n >= n_pre) o[n - n_pre] = v_out;
+    }
+    run[gi].st = st;
+    run[gi].n_done = n_end;
+}
+
+// Tremolo::process after the oscillator + the engine's depth smoother (engine.rs:67-130, 532-547: 0.5 during the warm-up, then a
+// ramp_samples-long linear ramp to the target) + the preamp's resistance tracking; in place on seq (volts in, pot_0_resistance
+// out), `dseq` is scratch for the depth trajectory.  One CTA per group; serial recurrences on thread 0, maps on all threads.
+__global__ void __launch_bounds__(256) engine_ldr_kernel(const EngineGroup* groups, int n_groups, double* seq, double* dseq, long long seq_stride,
+                                                         EngLdrRun* run, long long live_end_base, int legacy) {
+    // legacy != 0: the consumer is the 8-node legacy preamp (set_ldr_resistance: max(R, 1000), 0.01 Ohm threshold); output = g_ldr
+    const int gi = blockIdx.x;
+    if (gi >= n_groups) return;
+    const EngineGroup gr = groups[gi];
+    const double sr = gr.preamp_sr;
+    const int sub = gr.oversample ? 2 : 1;
+    const long long n_live = gr.n_warm_os + gr.n_os;
+    long long t1 = gr.n_warm_os + live_end_base * sub;
+    if (t1 > n_live) t1 = n_live;
+    const long long t0 = run[gi].n_done;
+    if (t0 >= t1) return;
+    double* o = seq + (size_t)gi * seq_stride;
+    double* dd = dseq + (size_t)gi * seq_stride;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (long long t = t0 + tid; t < t1; t += nth) o[t] = rclamp((10.95 - o[t]) / (10.95 - 0.70), 0.0, 1.0);
+    __syncthreads();
+    if (tid == 0) {
+        const double ldr_attack = exp(-1.0 / (0.0025 * sr));
+        const double ldr_release = exp(-1.0 / (0.035 * sr));
+        EngLdrRun R = run[gi];
+        if (t0 == 0) {
+            R.env = 0.0;
+            // depth smoother (LinearSmoother): current = target = 0.5 until set_tremolo_depth(target) after the warm-up
+            R.sm_current = 0.5; R.sm_target = 0.5; R.sm_step = 0.0; R.sm_remaining = 0;
+            R.depth = 0.5;  // Tremolo::new(0.5, ..) stores 0.5; set_depth() clamps to [0,1]
+        }
+        double env = R.env, sm_current = R.sm_current, sm_target = R.sm_target, sm_step = R.sm_step, depth = R.depth;
+        uint32_t sm_remaining = R.sm_remaining;
+        for (long long tl = t0; tl < t1; tl++) {
             if (tl == gr.n_warm_os) {  // set_tremolo_depth(target): LinearSmoother::set_target (engine.rs:85-98)
                 if (!(fabs(gr.depth_target - sm_target) < 1e-9)) {
                     sm_target = gr.depth_target;
@@ -241,13 +270,23 @@ __global__ void engine_tremolo_kernel(const EngineGroup* groups, int n_groups, d
                 }
                 depth = rclamp(sm_current, 0.0, 1.0);
             }
-        }
-        const double v_out = trm_step(st, m, kq, nullptr, trm_sc);
-        if (live) {
-            const double led = rclamp((10.95 - v_out) / (10.95 - 0.70), 0.0, 1.0);
+            const double led = o[tl];
             const double coeff = led > env ? ldr_attack : ldr_release;
             env = led + coeff * (env - led);
-            const double drive = rclamp(env, 0.0, 1.0);
+            o[tl] = env;
+            dd[tl] = depth;
+        }
+        R.env = env; R.sm_current = sm_current; R.sm_target = sm_target; R.sm_step = sm_step; R.depth = depth; R.sm_remaining = sm_remaining;
+        run[gi].env = R.env; run[gi].sm_current = R.sm_current; run[gi].sm_target = R.sm_target; run[gi].sm_step = R.sm_step;
+        run[gi].depth = R.depth; run[gi].sm_remaining = R.sm_remaining;
+    }
+    __syncthreads();
+    {
+        const double ln_r_max = log(1000000.0);
+        const double ln_min_minus_max = log(9000.0) - log(1000000.0);
+        for (long long t = t0 + tid; t < t1; t += nth) {
+            const double drive = rclamp(o[t], 0.0, 1.0);
+            const double depth = dd[t];
             double r_ldr;
             if (drive < 1e-6) r_ldr = 1000000.0;
             else r_ldr = exp(ln_r_max + ln_min_minus_max * pow(drive, 0.9));
@@ -256,17 +295,29 @@ __global__ void engine_tremolo_kernel(const EngineGroup* groups, int n_groups, d
             const double top = r_upper > 0.0 ? r_upper * 18000.0 / (r_upper + 18000.0) : 0.0;
             const double branch = 680.0 + r_ldr;
             const double low = r_lower > 0.0 ? r_lower * branch / (r_lower + branch) : 0.0;
-            const double z = top + low;
-            if (finite64(z)) {
-                const double r = rclamp(z, 1.0e3, 1.0e6);
-                if (!(fabs(r - pot) < 1e-12)) pot = r;
-            }
-            o[n - n_pre] = pot;
+            o[t] = top + low;
         }
     }
-    R.st = st; R.env = env; R.pot = pot; R.sm_current = sm_current; R.sm_target = sm_target; R.sm_step = sm_step; R.depth = depth;
-    R.sm_remaining = sm_remaining; R.n_done = n_end;
-    run[gi] = R;
+    __syncthreads();
+    if (tid == 0) {
+        double pot = t0 == 0 ? (legacy ? 1000000.0 : 9.99999999999999854e4) : run[gi].pot;
+        for (long long t = t0; t < t1; t++) {
+            const double z = o[t];
+            if (legacy) {
+                const double r = z > 1000.0 ? z : 1000.0;
+                if (fabs(r - pot) > 0.01) pot = r;
+                o[t] = 1.0 / pot;
+            } else {
+                if (finite64(z)) {
+                    const double r = rclamp(z, 1.0e3, 1.0e6);
+                    if (!(fabs(r - pot) < 1e-12)) pot = r;
+                }
+                o[t] = pot;
+            }
+        }
+        run[gi].pot = pot;
+        run[gi].n_done = t1;
+    }
 }
 
 // One thread per (group, preamp-rate sample): rebuild_matrices for that sample's pot value (all samples are dirty: the
@@ -349,7 +400,9 @@ struct EngineState {  // slot table (engine.rs:36-61) + the current round's rend
 };
 
 struct EngineChainState {  // shared mono chain of one engine between segments
-    DkState dk;
+    DkState dk;   // melange 12-node preamp
+    LgState lg;   // legacy 8-node preamp
+    double g_prev;
     double ua[3], ub[3], da[3], db[3], down_delay;
     SpkState spk;
     OwgChainInit sc;
@@ -363,7 +416,8 @@ struct EngineChainState {  // shared mono chain of one engine between segments
 struct EngineWarp { int32_t group, first, count, block_size; long long n_max; };  // engines of one (group, block size) in lanes 0..count-1
 
 __global__ void engine_init_kernel(const EngineDesc* __restrict__ engines, int n_engines, const EngineGroup* __restrict__ groups,
-                                   const DkState* __restrict__ post_warm, EngineState* __restrict__ states, EngineChainState* __restrict__ chains) {
+                                   const DkState* __restrict__ post_warm, EngineState* __restrict__ states, EngineChainState* __restrict__ chains,
+                                   const LgState* __restrict__ post_warm_lg, const double* __restrict__ g_warm_last) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_engines) return;
     const EngineDesc ed = engines[e];
@@ -375,7 +429,8 @@ __global__ void engine_init_kernel(const EngineDesc* __restrict__ engines, int n
     }
     if (chains) {
         EngineChainState& C = chains[e];
-        C.dk = post_warm[ed.group];
+        if (post_warm_lg) { C.lg = post_warm_lg[ed.group]; C.g_prev = g_warm_last[ed.group]; }
+        else C.dk = post_warm[ed.group];
         for (int k = 0; k < 3; k++) { C.ua[k] = C.ub[k] = C.da[k] = C.db[k] = 0.0; }
         C.down_delay = 0.0;
         C.spk.thermal = C.spk.h1 = C.spk.h2 = C.spk.l1 = C.spk.l2 = 0.0;
@@ -851,6 +906,160 @@ __global__ void __launch_bounds__(32) engine_chain_kernel(const EngineWarp* __re
     }
     if (last_segment && is_main)
         for (long long t = ed.n_samples; t < max_samples; t++) o[t] = 0.0f;  // ragged batch: rows end in silence
+}
+
+// ---- legacy 8-node preamp variants (owg_opts.preamp_model = OWG_PREAMP_LEGACY8) ---------------------------------------------------
+// Warm-up: DkPreamp::new (DC point at 1 MOhm) then n_warm_os zero-input steps under the tremolo's g_ldr sequence; main and shadow
+// are the same computation there.  g_last = g_ldr in effect at the last warm-up step (the first rendered step's g_ldr_prev).
+__global__ void engine_shadow_legacy_kernel(const EngineGroup* groups, int n_groups, const double* lgrecs, const double* g_seq, long long g_stride,
+                                            LgState* post_warm, double* g_last) {
+    const int gi = blockIdx.x;
+    if (gi >= n_groups || threadIdx.x != 0) return;
+    __shared__ double s_m[OWG_LG_STRIDE];
+    const EngineGroup gr = groups[gi];
+    for (int e = 0; e < OWG_LG_STRIDE; e++) s_m[e] = lgrecs[(size_t)gi * OWG_LG_STRIDE + e];
+    LgState st;
+    lg_init(st, s_m);
+    double g_prev = s_m[OWG_LG_GINIT];
+    const double* gs = g_seq + (size_t)gi * g_stride;
+    for (long long t = 0; t < gr.n_warm_os; t++) {
+        int iters;
+        const double g = gs[t];
+        (void)lg_step(st, s_m, 0.0, g, g_prev, &iters);
+        g_prev = g;
+    }
+    post_warm[gi] = st;
+    g_last[gi] = g_prev;
+}
+
+__global__ void __launch_bounds__(32) engine_chain_legacy_kernel(const EngineWarp* __restrict__ warps, const int32_t* __restrict__ order,
+                                                                 const EngineDesc* __restrict__ engines, long long round0, long long round1,
+                                                                 const SpkUpdate* __restrict__ spk_updates, const long long* __restrict__ spk_offsets,
+                                                                 const EngineGroup* __restrict__ groups, const LgState* __restrict__ post_warm,
+                                                                 const double* __restrict__ g_warm_last, const double* __restrict__ lgrecs,
+                                                                 const double* __restrict__ g_seq, long long g_stride,
+                                                                 EngineChainState* __restrict__ chains, LgState* __restrict__ shadow_states /*[warp]*/,
+                                                                 const double* __restrict__ mix, long long mix_stride, float* __restrict__ out,
+                                                                 long long out_stride, long long max_samples, int last_segment) {
+    __shared__ double s_m[OWG_LG_STRIDE];
+    __shared__ OwgChainInit s_ci[32];
+    const int lane = threadIdx.x;
+    const EngineWarp we = warps[blockIdx.x];
+    const bool is_shadow = lane == 31;
+    const bool is_main = lane < we.count;
+    const int e = is_main ? order[we.first + lane] : order[we.first];
+    const EngineDesc ed = engines[e];
+    const EngineGroup gr = groups[we.group];
+    for (int k = lane; k < OWG_LG_STRIDE; k += 32) s_m[k] = lgrecs[(size_t)we.group * OWG_LG_STRIDE + k];
+    const double* gs = g_seq + (size_t)we.group * g_stride;
+    const long long n_rec = gr.n_warm_os + gr.n_os;
+    const long long T0 = round0 * (long long)we.block_size;
+    long long T1 = round1 * (long long)we.block_size;
+    if (T1 > we.n_max) T1 = we.n_max;
+    const long long ns = is_main ? ed.n_samples : 0;
+    float* o = out + (size_t)e * out_stride;
+    __syncwarp();
+    if (T0 < T1) {
+        EngineChainState& C = chains[e];
+        const SpkUpdate* sched = spk_updates + spk_offsets[ed.spk_sched];
+        const double* mrow = mix + (size_t)e * mix_stride;
+        LgState st;
+        if (is_shadow) st = T0 == 0 ? post_warm[we.group] : shadow_states[blockIdx.x];
+        else st = C.lg;
+        double g_prev = T0 == 0 ? g_warm_last[we.group] : C.g_prev;  // warp-uniform (all lanes stepped with the same g sequence)
+        double ua[3], ub[3], da[3], db[3];
+        for (int k = 0; k < 3; k++) { ua[k] = C.ua[k]; ub[k] = C.ub[k]; da[k] = C.da[k]; db[k] = C.db[k]; }
+        double down_delay = C.down_delay;
+        SpkState spk = C.spk;
+        s_ci[lane] = C.sc;
+        __syncwarp();
+        OwgChainInit& sc = s_ci[lane];
+        int spk_next = C.spk_next;
+        long long spk_clock = C.spk_clock;
+        double vol_current = C.vol_current;
+        const double vol_target = C.vol_target, vol_step = C.vol_step;
+        uint32_t vol_remaining = C.vol_remaining;
+        unsigned long long d_out_nan = 0;
+        if (T0 == 0 && is_main) {
+            while (spk_next < ed.n_spk_updates && sched[spk_next].at < spk_clock) {  // updates that happened during the warm-up
+                const SpkUpdate& u = sched[spk_next++];
+                sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
+                sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
+                sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+            }
+        }
+        const int n_sub = gr.oversample ? 2 : 1;
+        long long tos = gr.n_warm_os + T0 * n_sub;
+        double x_next = (is_main && T0 < ns) ? mrow[0] : 0.0;
+        double g_next = tos < n_rec ? gs[tos] : g_prev;
+        for (long long t = T0; t < T1; t++) {
+            const bool live = is_main && t < ns;
+            const double x = x_next;
+            x_next = (is_main && t + 1 < ns && t + 1 < T1) ? mrow[t + 1 - T0] : 0.0;
+            double u0 = x, u1 = 0.0;
+            if (n_sub == 2) {
+                u0 = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, ua, x);
+                u1 = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, ub, x);
+            }
+            if (!is_main) { u0 = 0.0; u1 = 0.0; }
+            double pp0 = 0.0, pp1 = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < n_sub; j++) {
+                const double g_ldr = g_next;
+                g_next = tos + 1 < n_rec ? gs[tos + 1] : g_ldr;
+                int iters;
+                const double main_out = lg_step(st, s_m, j == 0 ? u0 : u1, g_ldr, g_prev, &iters);
+                g_prev = g_ldr;
+                const double pump = __shfl_sync(0xffffffffu, main_out, 31);
+                double res = main_out - pump;
+                if (!finite64(res)) { if (!is_shadow) st = post_warm[we.group]; res = 0.0; }  // see chain_legacy_kernel: deviation from reset()
+                const double pa = poweramp(res * 0.25, nullptr);
+                if (j == 0) pp0 = pa; else pp1 = pa;
+                tos += 1;
+            }
+            double stage_out;
+            if (n_sub == 2) {
+                const double a = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, da, pp0);
+                const double b = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, db, pp1);
+                stage_out = (a + down_delay) * 0.5;
+                down_delay = b;
+            } else stage_out = pp0;
+            if (live) {
+                while (spk_next < ed.n_spk_updates && sched[spk_next].at <= spk_clock) {
+                    const SpkUpdate& u = sched[spk_next++];
+                    sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
+                    sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
+                    sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+                }
+                spk_clock += 1;
+                const double shaped = speaker(stage_out, spk, sc);
+                if (vol_remaining > 0) {
+                    vol_current += vol_step;
+                    vol_remaining -= 1;
+                    if (vol_remaining == 0) vol_current = vol_target;
+                }
+                const float smp = (float)(shaped * 7.498942093324558 * vol_current);
+                if (isfinite(smp)) o[t] = smp;
+                else {
+                    d_out_nan++;
+                    st = post_warm[we.group];
+                    for (int k = 0; k < 3; k++) { ua[k] = ub[k] = da[k] = db[k] = 0.0; }
+                    down_delay = 0.0;
+                    spk.thermal = spk.h1 = spk.h2 = spk.l1 = spk.l2 = 0.0;
+                    o[t] = 0.0f;
+                }
+            }
+        }
+        if (is_shadow) shadow_states[blockIdx.x] = st;
+        if (is_main) {
+            C.lg = st; C.g_prev = g_prev;
+            for (int k = 0; k < 3; k++) { C.ua[k] = ua[k]; C.ub[k] = ub[k]; C.da[k] = da[k]; C.db[k] = db[k]; }
+            C.down_delay = down_delay; C.spk = spk; C.sc = sc; C.spk_next = spk_next; C.spk_clock = spk_clock;
+            C.vol_current = vol_current; C.vol_remaining = vol_remaining; C.d_out_nan += d_out_nan;
+        }
+    }
+    if (last_segment && is_main)
+        for (long long t = ed.n_samples; t < max_samples; t++) o[t] = 0.0f;
 }
 
 __global__ void engine_diag_kernel(const EngineState* __restrict__ states, const EngineChainState* __restrict__ chains, int n_engines, EngineDiag* diag) {

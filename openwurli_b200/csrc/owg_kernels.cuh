@@ -47,17 +47,14 @@ __global__ void static_matrix_kernel(const OwgPreampGroup* groups, int n_groups,
 // baked 48 kHz matrices, set_sample_rate, 2*sr settle samples) then n_os x process() (tremolo.rs:121-167), followed
 // by DkPreamp::set_ldr_resistance's clamp / 1e-12 change filter (gen_preamp.rs:1973-1984).  Output: the value of
 // pot_0_resistance in effect at each preamp-rate sample.
-struct TrmRun {  // oscillator + LDR state carried between chunk launches
+struct TrmRun {  // oscillator state carried between chunk launches
     TrmState st;
-    double env, pot;
 };
 // Processes absolute step indices [n_begin, n_end) of the sequence  50 warm-up | 2*sr settle | n_os live  (clipped to the
 // group's length); run[] carries the state between launches so that the serial oscillator can be pipelined chunk by chunk
 // with the consumers of its output.
 __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* trem_group_ids, int n_trem, double* pot_seq, int64_t pot_stride,
-                                     TrmRun* run, long long live_begin, long long live_end, DevDiag* diag, int legacy) {
-    // legacy != 0: the consumer is the 8-node legacy preamp, whose set_ldr_resistance (dk_preamp_legacy.rs:620-626) is
-    // r = max(R, 1000); if |r - r_ldr| > 0.01 { r_ldr = r; g_ldr = 1/r } -- the output sequence is g_ldr, `pot` tracks r_ldr.
+                                     TrmRun* run, long long live_begin, long long live_end, DevDiag* diag) {
     const int gi = blockIdx.x;
     if (gi >= n_trem || threadIdx.x != 0) return;
     const OwgPreampGroup gr = groups[trem_group_ids[gi]];
@@ -76,62 +73,101 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
     const long long n_end = ctor ? n_pre : n_pre + (live_end < gr.n_os ? live_end : gr.n_os);
     if (n_begin >= n_end) return;
     TrmState st;
-    double env = 0.0;
-    double pot = legacy ? 1000000.0 : 9.99999999999999854e4;  // pot_0_resistance of the settled state | r_ldr of DkPreamp::new
     if (ctor) {
         for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
         for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
         st.xin_prev = 0.0;
     } else {
-        st = run[gi].st; env = run[gi].env; pot = run[gi].pot;
+        st = run[gi].st;
         if (fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);  // same deterministic rebuild as at step 50
     }
     TrmDiag td;
     for (int i = 0; i < 16; i++) td.hist[i] = 0;
     td.be_fallback = 0; td.nan_reset = 0;
-    const double depth = gr.tremolo_depth;  // stored unclamped by Tremolo::new (tremolo.rs:105)
-    const double ldr_attack = exp(-1.0 / (0.0025 * sr));
-    const double ldr_release = exp(-1.0 / (0.035 * sr));
-    const double ln_r_max = log(1000000.0);
-    const double ln_min_minus_max = log(9000.0) - log(1000000.0);
-    const double r_upper = 50000.0 * (1.0 - depth);
-    const double r_lower = 50000.0 * depth;
-    const double top = r_upper > 0.0 ? r_upper * 18000.0 / (r_upper + 18000.0) : 0.0;
     double* o = pot_seq + (size_t)gi * pot_stride;
     // One loop, three phases (a single inlined copy of the solver): 50 warm-up samples at the baked 48 kHz matrices
     // (CircuitState::default() -> warmup(), gen_tremolo.rs:2021), set_sample_rate, 2*sr settle samples, then process().
+    // The live part only records the oscillator output; the LED/LDR law and the preamp's resistance tracking are
+    // evaluated by tremolo_ldr_kernel, off this thread's critical path (they do not feed back into the oscillator).
     for (long long n = n_begin; n < n_end; n++) {
         if (n == 50 && fabs(sr - 48000.0) > 0.5) trm_rebuild(m, sr * 1.0);
         const bool live = n >= n_pre;
         const double v_out = trm_step(st, m, kq, (diag && live) ? &td : nullptr, trm_sc);
-        if (live) {
-            const double led = rclamp((10.95 - v_out) / (10.95 - 0.70), 0.0, 1.0);
+        if (live) o[n - n_pre] = v_out;
+    }
+    run[gi].st = st;
+    if (diag) {
+        for (int i = 0; i < 16; i++) atomicAdd(&diag->trm_hist[i], (unsigned long long)td.hist[i]);
+        atomicAdd(&diag->trm_be, (unsigned long long)td.be_fallback);
+    }
+}
+
+// Tremolo::process after the oscillator (tremolo.rs:121-167): LED drive -> asymmetric LDR envelope -> CdS power law ->
+// shunt network, then the consumer's set_ldr_resistance filter; in place on seq[gi][live_begin, live_end): oscillator output
+// volts in, pot_0_resistance (melange: clamp [1e3, 1e6] + 1e-12 change filter, gen_preamp.rs:1973-1984) or g_ldr (legacy:
+// max(R, 1000), 0.01 Ohm threshold, dk_preamp_legacy.rs:620-626) out.  One CTA per tremolo group: the elementwise maps run on
+// all threads, the two cheap serial recurrences (envelope follower, change filter) on thread 0.
+struct LdrRun { double env, pot; };
+__global__ void __launch_bounds__(256) tremolo_ldr_kernel(const OwgPreampGroup* groups, const int* trem_group_ids, int n_trem, double* seq,
+                                                          int64_t seq_stride, LdrRun* run, long long live_begin, long long live_end, int legacy) {
+    const int gi = blockIdx.x;
+    if (gi >= n_trem) return;
+    const OwgPreampGroup gr = groups[trem_group_ids[gi]];
+    const double sr = gr.preamp_sr;
+    const long long t0 = live_begin, t1 = live_end < gr.n_os ? live_end : gr.n_os;
+    if (t0 >= t1) return;
+    double* o = seq + (size_t)gi * seq_stride;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (long long t = t0 + tid; t < t1; t += nth) o[t] = rclamp((10.95 - o[t]) / (10.95 - 0.70), 0.0, 1.0);  // LED drive
+    __syncthreads();
+    if (tid == 0) {
+        const double ldr_attack = exp(-1.0 / (0.0025 * sr));
+        const double ldr_release = exp(-1.0 / (0.035 * sr));
+        double env = t0 == 0 ? 0.0 : run[gi].env;
+        for (long long t = t0; t < t1; t++) {
+            const double led = o[t];
             const double coeff = led > env ? ldr_attack : ldr_release;
             env = led + coeff * (env - led);
-            const double drive = rclamp(env, 0.0, 1.0);
+            o[t] = env;
+        }
+        run[gi].env = env;
+    }
+    __syncthreads();
+    {
+        const double depth = gr.tremolo_depth;  // stored unclamped by Tremolo::new (tremolo.rs:105)
+        const double ln_r_max = log(1000000.0);
+        const double ln_min_minus_max = log(9000.0) - log(1000000.0);
+        const double r_upper = 50000.0 * (1.0 - depth);
+        const double r_lower = 50000.0 * depth;
+        const double top = r_upper > 0.0 ? r_upper * 18000.0 / (r_upper + 18000.0) : 0.0;
+        for (long long t = t0 + tid; t < t1; t += nth) {
+            const double drive = rclamp(o[t], 0.0, 1.0);
             double r_ldr;
             if (drive < 1e-6) r_ldr = 1000000.0;
             else r_ldr = exp(ln_r_max + ln_min_minus_max * pow(drive, 0.9));
             const double branch = 680.0 + r_ldr;
             const double low = r_lower > 0.0 ? r_lower * branch / (r_lower + branch) : 0.0;
-            const double z = top + low;
+            o[t] = top + low;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double pot = t0 == 0 ? (legacy ? 1000000.0 : 9.99999999999999854e4) : run[gi].pot;  // r_ldr of DkPreamp::new | settled pot_0_resistance
+        for (long long t = t0; t < t1; t++) {
+            const double z = o[t];
             if (legacy) {
                 const double r = z > 1000.0 ? z : 1000.0;  // f64::max(z, 1000.0): NaN -> 1000
                 if (fabs(r - pot) > 0.01) pot = r;
-                o[n - n_pre] = 1.0 / pot;
+                o[t] = 1.0 / pot;
             } else {
                 if (finite64(z)) {
                     const double r = rclamp(z, 1.0e3, 1.0e6);
                     if (!(fabs(r - pot) < 1e-12)) pot = r;
                 }
-                o[n - n_pre] = pot;
+                o[t] = pot;
             }
         }
-    }
-    run[gi].st = st; run[gi].env = env; run[gi].pot = pot;
-    if (diag) {
-        for (int i = 0; i < 16; i++) atomicAdd(&diag->trm_hist[i], (unsigned long long)td.hist[i]);
-        atomicAdd(&diag->trm_be, (unsigned long long)td.be_fallback);
+        run[gi].pot = pot;
     }
 }
 

@@ -3,8 +3,8 @@
 #include "../../include/owgpu.h"
 #include "host_setup.h"
 #include "owg_kernels.cuh"
-#include "owg_engine.cuh"
 #include "owg_legacy.cuh"
+#include "owg_engine.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -133,6 +133,7 @@ struct owg_plan {
     DevBuf<int> d_trem_ids;
     DevBuf<double> d_static_recs, d_ans, d_pot_seq, d_trem_recs, d_carry;
     DevBuf<TrmRun> d_trm_run, d_trm_ctor;       // oscillator state: running / as constructed (Tremolo::new, computed at plan time)
+    DevBuf<LdrRun> d_ldr_run;                   // LDR envelope + resistance-tracking state between chunks
     cudaStream_t stream_copy = nullptr;          // device->host copy-back of finished chunks
     cudaStream_t stream_trem = nullptr;          // the serial Twin-T oscillator runs here, one chunk ahead of its consumers
     std::vector<cudaEvent_t> chunk_events;       // oscillator chunk c finished
@@ -282,6 +283,7 @@ int launch_tremolo_ctor(owg_plan* pl) {
     if (!rc) rc = pl->d_trem_ids.upload(pl->trem_group_ids, pl->stream);
     if (!rc) rc = pl->d_trm_run.alloc((size_t)nt);
     if (!rc) rc = pl->d_trm_ctor.alloc((size_t)nt);
+    if (!rc) rc = pl->d_ldr_run.alloc((size_t)nt);
     if (!rc) rc = pl->d_pot_seq.alloc((size_t)nt * (size_t)pl->trem_n_os_max);
     if (!rc && cudaStreamSynchronize(pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "plan upload failed");
     if (!rc && !pl->stream_trem && cudaStreamCreateWithFlags(&pl->stream_trem, cudaStreamNonBlocking) != cudaSuccess)
@@ -292,7 +294,7 @@ int launch_tremolo_ctor(owg_plan* pl) {
         // the host and DkPreamp::new's cached settled state.  Asynchronous: every later oscillator launch goes to the same
         // in-order stream, so nothing has to wait here.
         tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                             pl->d_trm_ctor.p, -1, -1, nullptr, pl->legacy ? 1 : 0);
+                                                             pl->d_trm_ctor.p, -1, -1, nullptr);
         if (cudaGetLastError() != cudaSuccess) rc = fail(OWG_E_CUDA, "tremolo constructor kernel launch failed");
     }
     return rc;
@@ -517,7 +519,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
             for (int64_t c = 0; c < n_chunks; c++) {
                 const int64_t os0 = c * CH_BASE * 2, os1 = (c + 1) * CH_BASE * 2;  // covers 2x-oversampled groups; native-rate groups use half
                 tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                                     pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr, pl->legacy ? 1 : 0);
+                                                                     pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(pl->chunk_events[c], pl->stream_trem));
                 launches++;
@@ -569,6 +571,11 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
             for (int64_t c = 0; c < n_chunks; c++) {
                 const int64_t b0 = c * CH_BASE, b1 = (c + 1) * CH_BASE;
                 CK(cudaStreamWaitEvent(s, pl->chunk_events[c], 0));
+                // oscillator volts -> LDR law -> the preamp's resistance tracking, in place (off the oscillator's serial thread)
+                tremolo_ldr_kernel<<<nt, 256, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_ldr_run.p,
+                                                      2 * b0, 2 * b1, pl->legacy ? 1 : 0);
+                CK(cudaGetLastError());
+                launches++;
                 if (!pl->legacy) {
                     dim3 grid((unsigned)((2 * CH_BASE + 63) / 64), (unsigned)nt);
                     tremolo_matrix_kernel<<<grid, 64, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_trem_recs.p,
@@ -723,7 +730,7 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     }
     owg_plan pl;  // used for device / stream / cache plumbing only
     if (int rc = plan_common(&pl, opts)) return rc;
-    if (pl.legacy) return fail(OWG_E_UNSUPPORTED, "owg_render_engines: OWG_PREAMP_LEGACY8 is not implemented for engine streams");
+    const bool legacy = pl.legacy;
     cudaStream_t s = pl.stream;
     const int out_location = opts ? opts->out_location : OWG_OUT_HOST;
     const bool timing = getenv("OWG_ENGINE_TIMING") != nullptr;
@@ -873,7 +880,8 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     DevBuf<EngineDesc> d_eng; DevBuf<EngineGroup> d_groups; DevBuf<EngineEvent> d_events; DevBuf<OwgVoiceInit> d_vinits;
     DevBuf<DamperRow> d_dampers; DevBuf<int32_t> d_dsched, d_eorder; DevBuf<SpkUpdate> d_spk; DevBuf<long long> d_spkoff;
     DevBuf<double> d_pot, d_recs, d_ans, d_mix; DevBuf<DkState> d_post, d_shadow; DevBuf<VoiceRT> d_pool; DevBuf<float> d_out;
-    DevBuf<EngineState> d_states; DevBuf<EngineChainState> d_chains; DevBuf<EngineWarp> d_ewarps; DevBuf<EngTrmRun> d_trmrun;
+    DevBuf<EngineState> d_states; DevBuf<EngineChainState> d_chains; DevBuf<EngineWarp> d_ewarps; DevBuf<EngTrmRun> d_trmrun; DevBuf<EngLdrRun> d_ldrrun; DevBuf<double> d_depth, d_lgrecs, d_glast;
+    DevBuf<LgState> d_post_lg, d_shadow_lg;
     DevBuf<EngineDiag> d_diag;
     int rc = d_eng.upload(eng, s);
     if (!rc) rc = d_groups.upload(groups, s);
@@ -886,11 +894,22 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     if (!rc) rc = d_eorder.upload(eorder, s);
     if (!rc) rc = d_ewarps.upload(ewarps, s);
     if (!rc) rc = d_pot.alloc((size_t)ng * (size_t)pot_stride);
-    if (!rc) rc = d_recs.alloc((size_t)ng * (size_t)pot_stride * OWG_MAT_STRIDE);
-    if (!rc) rc = d_ans.alloc((size_t)ng * OWG_AN_SPARSE);
-    if (!rc) rc = d_post.alloc((size_t)ng);
-    if (!rc) rc = d_shadow.alloc(ewarps.size());
+    if (legacy) {
+        std::vector<double> lgrecs((size_t)ng * OWG_LG_STRIDE);
+        for (int g = 0; g < ng; g++) owg::make_legacy_group(groups[g].preamp_sr, NAN, &lgrecs[(size_t)g * OWG_LG_STRIDE]);
+        if (!rc) rc = d_lgrecs.upload(lgrecs, s);
+        if (!rc) rc = d_glast.alloc((size_t)ng);
+        if (!rc) rc = d_post_lg.alloc((size_t)ng);
+        if (!rc) rc = d_shadow_lg.alloc(ewarps.size());
+    } else {
+        if (!rc) rc = d_recs.alloc((size_t)ng * (size_t)pot_stride * OWG_MAT_STRIDE);
+        if (!rc) rc = d_ans.alloc((size_t)ng * OWG_AN_SPARSE);
+        if (!rc) rc = d_post.alloc((size_t)ng);
+        if (!rc) rc = d_shadow.alloc(ewarps.size());
+    }
     if (!rc) rc = d_trmrun.alloc((size_t)ng);
+    if (!rc) rc = d_ldrrun.alloc((size_t)ng);
+    if (!rc) rc = d_depth.alloc((size_t)ng * (size_t)pot_stride);
     if (!rc) rc = d_pool.alloc((size_t)n * 128);
     if (!rc) rc = d_states.alloc((size_t)n);
     if (!rc) rc = d_chains.alloc((size_t)n);
@@ -916,13 +935,14 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     if (timing) for (auto& e : tv) { CK(cudaEventCreate(&e)); evs.push_back(e); }
     CK(cudaMemsetAsync(d_diag.p, 0, sizeof(EngineDiag), s));
     CK(cudaMemsetAsync(d_trmrun.p, 0, (size_t)ng * sizeof(EngTrmRun), s));
+    CK(cudaMemsetAsync(d_ldrrun.p, 0, (size_t)ng * sizeof(EngLdrRun), s));
     CK(cudaMemsetAsync(d_pool.p, 0, (size_t)n * 128 * sizeof(VoiceRT), s));
     CK(cudaEventRecord(ev_up, s));
     CK(cudaStreamWaitEvent(sc, ev_up, 0));
     CK(cudaStreamWaitEvent(so, ev_up, 0));
     if (timing) { CK(cudaEventRecord(tv[0], so)); CK(cudaEventRecord(tv[3], s)); CK(cudaEventRecord(tv[2], sc)); }
     const unsigned eb = (unsigned)((n + 63) / 64);
-    engine_init_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, d_groups.p, nullptr, d_states.p, nullptr);
+    engine_init_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, d_groups.p, nullptr, d_states.p, nullptr, nullptr, nullptr);
     CK(cudaGetLastError());
     const double silent_thr = owg::silent_threshold();
     int64_t launches = 1;
@@ -955,6 +975,28 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
         CK(cudaEventRecord(ev_voices[sg], s));
         // matrices of this chunk, then (first chunk) the warm-up solve and the chain states
         CK(cudaStreamWaitEvent(sc, ev_osc[sg], 0));
+        engine_ldr_kernel<<<ng, 256, 0, sc>>>(d_groups.p, ng, d_pot.p, d_depth.p, pot_stride, d_ldrrun.p, r1 * max_block, legacy ? 1 : 0);
+        CK(cudaGetLastError());
+        launches += 1;
+        if (legacy) {
+            if (sg == 0) {
+                engine_shadow_legacy_kernel<<<ng, 32, 0, sc>>>(d_groups.p, ng, d_lgrecs.p, d_pot.p, pot_stride, d_post_lg.p, d_glast.p);
+                CK(cudaGetLastError());
+                engine_init_kernel<<<eb, 64, 0, sc>>>(d_eng.p, (int)n, d_groups.p, nullptr, nullptr, d_chains.p, d_post_lg.p, d_glast.p);
+                CK(cudaGetLastError());
+                launches += 2;
+            }
+            CK(cudaStreamWaitEvent(sc, ev_voices[sg], 0));
+            engine_chain_legacy_kernel<<<(unsigned)ewarps.size(), 32, 0, sc>>>(d_ewarps.p, d_eorder.p, d_eng.p, r0, r1, d_spk.p, d_spkoff.p, d_groups.p,
+                                                                              d_post_lg.p, d_glast.p, d_lgrecs.p, d_pot.p, pot_stride, d_chains.p,
+                                                                              d_shadow_lg.p, mixbuf, mix_stride, dout, stride, max_samples,
+                                                                              sg + 1 == n_chunks ? 1 : 0);
+            CK(cudaGetLastError());
+            launches += 1;
+            CK(new_event(&ev_chain[sg]));
+            CK(cudaEventRecord(ev_chain[sg], sc));
+            continue;
+        }
         {
             const long long chunk_len = (sg == 0 ? max_warm_os : 0) + (r1 - r0) * max_block * 2;
             dim3 grid((unsigned)std::max<long long>(1, (chunk_len + 63) / 64), (unsigned)ng);
@@ -965,7 +1007,7 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
         if (sg == 0) {
             engine_shadow_kernel<<<ng, 32, 0, sc>>>(d_groups.p, ng, pl.cache->d_settled, d_recs.p, pot_stride, d_ans.p, d_post.p);
             CK(cudaGetLastError());
-            engine_init_kernel<<<eb, 64, 0, sc>>>(d_eng.p, (int)n, d_groups.p, d_post.p, nullptr, d_chains.p);
+            engine_init_kernel<<<eb, 64, 0, sc>>>(d_eng.p, (int)n, d_groups.p, d_post.p, nullptr, d_chains.p, nullptr, nullptr);
             CK(cudaGetLastError());
             launches += 2;
         }

@@ -56,7 +56,8 @@ struct WurliEngine {
     static constexpr int MAX_VOICES = 64;
     std::vector<VoiceSlot> voices;
     uint64_t age_counter = 0;
-    std::unique_ptr<pre::DkPreamp> preamp;
+    std::unique_ptr<AnyPreamp> preamp;
+    int preamp_model = 0;  // 0 melange 12-node, 1 legacy 8-node (the default build)
     std::unique_ptr<Tremolo> tremolo;
     Oversampler oversampler;
     PowerAmp power_amp;
@@ -68,12 +69,12 @@ struct WurliEngine {
     LinearSmoother volume, tremolo_depth, speaker_character;
     uint64_t nan_guard_fires = 0;
 
-    explicit WurliEngine(double sr)  // engine.rs:194-229 (no warm-up)
-        : voices(MAX_VOICES), sample_rate(sr), volume(0.5, ramp_samples_for_rate(sr)),
+    explicit WurliEngine(double sr, int model = 0)  // engine.rs:194-229 (no warm-up)
+        : voices(MAX_VOICES), preamp_model(model), sample_rate(sr), volume(0.5, ramp_samples_for_rate(sr)),
           tremolo_depth(0.5, ramp_samples_for_rate(sr)), speaker_character(0.0, ramp_samples_for_rate(sr)) {
         oversample = sr < 88200.0;
         os_sample_rate = oversample ? sr * 2.0 : sr;
-        preamp.reset(new pre::DkPreamp(os_sample_rate));
+        preamp.reset(new AnyPreamp(preamp_model, os_sample_rate));
         tremolo.reset(new Tremolo(0.5, os_sample_rate));
         speaker.reset(new Speaker(sr));
         voice_buf.assign(8192, 0.0); sum_buf.assign(8192, 0.0); up_buf.assign(16384, 0.0); out_buf.assign(8192, 0.0);
@@ -94,7 +95,7 @@ struct WurliEngine {
         sample_rate = sr;
         oversample = sr < 88200.0;
         os_sample_rate = oversample ? sr * 2.0 : sr;
-        preamp.reset(new pre::DkPreamp(os_sample_rate));
+        preamp.reset(new AnyPreamp(preamp_model, os_sample_rate));
         tremolo.reset(new Tremolo(tremolo_depth.target, os_sample_rate));
         oversampler = Oversampler();
         power_amp = PowerAmp();

@@ -185,8 +185,8 @@ int owo_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_
 }
 
 // ---- chain E ----------------------------------------------------------------------------------
-static void run_engine(const owg_engine_job& j, float* out) {
-    WurliEngine eng(j.sample_rate);
+static void run_engine(const owg_engine_job& j, float* out, int preamp_model = 0) {
+    WurliEngine eng(j.sample_rate, preamp_model);
     // The plugin constructs at a nominal rate and then calls set_sample_rate (lib.rs:96-97), which warms up.
     if (j.warm_up) eng.set_sample_rate(j.sample_rate);
     eng.volume.set_target(j.volume);
@@ -211,6 +211,13 @@ int owo_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     if (!jobs || !out || n < 0) return OWG_E_BAD_ARG;
     pre::settled_state();
     parallel_for(n, threads, [&](int64_t i) { run_engine(jobs[i], out + i * stride); });
+    return OWG_OK;
+}
+
+int owo_render_engines_model(const owg_engine_job* jobs, int64_t n, float* out, int64_t stride, int threads, int preamp_model) {
+    if (!jobs || !out || n < 0) return OWG_E_BAD_ARG;
+    if (preamp_model == 0) pre::settled_state();
+    parallel_for(n, threads, [&](int64_t i) { run_engine(jobs[i], out + i * stride, preamp_model); });
     return OWG_OK;
 }
 

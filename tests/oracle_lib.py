@@ -78,6 +78,7 @@ def lib():
         L.owo_preamp_batch.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_double,
                                        C.c_double, dp, C.c_int64, C.c_int]
         L.owo_render_engines.argtypes = [C.POINTER(EngineJob), C.c_int64, C.POINTER(C.c_float), C.c_int64, C.c_int]
+        L.owo_render_engines_model.argtypes = [C.POINTER(EngineJob), C.c_int64, C.POINTER(C.c_float), C.c_int64, C.c_int, C.c_int]
         L.owo_alias_stimulus.argtypes = [C.c_uint8, C.c_uint8, C.c_double, C.c_double, C.c_double, dp]
         L.owo_last_diag.argtypes = [C.POINTER(Diag)]
         for name, args in [("owo_midi_to_freq", [C.c_int]), ("owo_tip_mass_ratio", [C.c_int]),
@@ -176,10 +177,10 @@ def engine_job(events, sr=44100.0, dur=1.0, volume=0.5, depth=0.5, speaker=0.0, 
     return j
 
 
-def render_engines(jobs, threads=1):
+def render_engines(jobs, threads=1, preamp_model=0):
     n = len(jobs)
     stride = max([n_samples(j.duration_s, j.sample_rate) for j in jobs], default=0)
     out = np.zeros((n, stride), dtype=np.float32)
     arr = (EngineJob * n)(*jobs)
-    assert lib().owo_render_engines(arr, n, out.ctypes.data_as(C.POINTER(C.c_float)), stride, threads) == 0
+    assert lib().owo_render_engines_model(arr, n, out.ctypes.data_as(C.POINTER(C.c_float)), stride, threads, preamp_model) == 0
     return out

@@ -13,9 +13,12 @@ if "--probes" in sys.argv:
     for lanes in (32, 16, 8, 4):
         print(f"unfused warp-instr rate with {lanes} active lanes: {fp64_probe(100 + lanes):.3f} T warp-instr/s", flush=True)
 
+MODEL = int(os.environ.get("GT_MODEL", "0"))  # 0 melange12, 1 legacy8
+
+
 def run(depth, dur, stride=1, reps=2):
     jobs = [ow.bench_job(note=33 + k // 127, velocity=1 + k % 127, duration=dur, tremolo_depth=depth) for k in range(0, 8128, stride)]
-    pl = ow.Plan.bench(jobs)
+    pl = ow.Plan.bench(jobs, preamp_model=MODEL)
     out = torch.empty((len(jobs), pl.max_samples), dtype=torch.float64, device="cuda")
     best = None
     for _ in range(reps):
@@ -30,7 +33,7 @@ if "--scale" in sys.argv:
     def run_big(depth, dur, k):
         jobs = [ow.bench_job(note=33 + (i // 127) % 64, velocity=1 + i % 127, duration=dur, tremolo_depth=depth, volume=0.3 + 0.5 * (i // 8128) / max(k, 1))
                 for i in range(8128 * k)]
-        pl = ow.Plan.bench(jobs)
+        pl = ow.Plan.bench(jobs, preamp_model=MODEL)
         out = torch.empty((len(jobs), pl.max_samples), dtype=torch.float64, device="cuda")
         for _ in range(2):
             pl.execute(out); torch.cuda.synchronize()
