@@ -495,6 +495,231 @@ __global__ void __launch_bounds__(32) chain_kernel(const WarpEntry* __restrict__
     }
 }
 
+// ---- chain B, warp-specialised: the DK preamp in one warp, everything around it in a second warp -----------------------------
+// The grid is a latency problem: a render is a serial recurrence and its time is (samples) x (per-sample latency of one warp).
+// chain_split_kernel cuts that latency by running the two halves of the per-sample work concurrently on two schedulers:
+//   warp A (threads 0..31):   [record staging] -> DK step x n_sub -> main - shadow            (~75 % of chain_kernel's time)
+//   warp B (threads 32..63):  voice sample -> upsampler  ...  downsampler -> volume^2 -> power amp -> speaker -> store/metrics
+// connected by two 2-slot rings in shared memory (U: B -> A, P: A -> B) and four named barriers (bar.arrive on the producer,
+// bar.sync on the consumer; one phase per sample and slot).  Same arithmetic, same order, same carried state layout as
+// chain_kernel (which remains the DIAG path): results are bit-identical between the two kernels.
+#define OWG_BAR_UFULL 1  // + slot
+#define OWG_BAR_PFULL 3  // + slot
+__device__ __forceinline__ void owg_bar_arrive(int id) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void owg_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <bool TREM>
+__global__ void __launch_bounds__(64) chain_split_kernel(const WarpEntry* __restrict__ warps, const int32_t* __restrict__ order,
+                                                         const OwgChainInit* __restrict__ cinits, const unsigned long long* __restrict__ n_samples,
+                                                         const DkState* __restrict__ settled, const double* __restrict__ recs, const double* __restrict__ ans,
+                                                         const int32_t* __restrict__ group_rec_index, int64_t rec_stride_t,
+                                                         double* __restrict__ out, int64_t stride,
+                                                         int64_t t_begin, int64_t t_end, double* __restrict__ carry /*[warp][OWG_CARRY][32]*/,
+                                                         double* __restrict__ metrics /*[job][OWG_METRICS] or null*/, const double* __restrict__ f0s,
+                                                         int64_t w_begin, int64_t w_end, int swap_roles) {
+    __shared__ __align__(16) double s_rec[TREM ? 2 * OWG_MAT_STRIDE : OWG_MAT_STRIDE];
+    __shared__ double s_an[OWG_AN_SPARSE];
+    __shared__ OwgChainInit s_ci[32];
+    __shared__ double s_cold[OWG_COLD_SCRATCH * 32];
+    __shared__ double s_u[2][2][32];  // [slot][sub][lane]: upsampled input of sample t in slot t & 1
+    __shared__ double s_p[2][2][32];  // [slot][sub][lane]: preamp output (main - shadow)
+    __shared__ int s_swap;
+    const int lane = threadIdx.x & 31;
+    // Role placement.  Warps occupy hardware warp slots and slot % 4 selects the scheduler; with two-warp CTAs, CTAs 0 and 2 of an
+    // SM land on schedulers {0,1} and CTAs 1 and 3 on {2,3}.  Swapping the roles in every other pair of slots puts one DK warp
+    // and one (mostly waiting) I/O warp on each scheduler instead of two DK warps on half of them.
+    if (threadIdx.x == 0) {
+        unsigned wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        s_swap = swap_roles ? (int)((wid >> 2) & 1u) : 0;
+    }
+    __syncthreads();
+    const bool warp_a = (threadIdx.x < 32) != (s_swap != 0);
+    const WarpEntry we = warps[blockIdx.x];
+    const bool is_shadow = lane == 31;
+    const bool is_main = lane < we.count;
+    const int32_t job = is_main ? order[we.first + lane] : -1;
+    const double* grec = recs + (size_t)group_rec_index[we.group] * (TREM ? (size_t)rec_stride_t * OWG_MAT_STRIDE : (size_t)OWG_MAT_STRIDE);
+    if (warp_a) {
+        for (int e = lane; e < OWG_AN_SPARSE; e += 32) s_an[e] = ans[(size_t)we.group * OWG_AN_SPARSE + e];
+        if (!TREM) for (int e = lane; e < OWG_MAT_STRIDE; e += 32) s_rec[e] = grec[e];
+    } else {
+        if (is_main) s_ci[lane] = cinits[job];
+        else {
+            OwgChainInit z;
+            z.volume = 0.0; z.spk_a2 = 0.0; z.spk_a3 = 0.0; z.spk_norm = 1.0; z.spk_thermal_coeff = 0.0; z.spk_thermal_alpha = 0.0;
+            z.hpf_b0 = z.hpf_b1 = z.hpf_b2 = z.hpf_a1 = z.hpf_a2 = 0.0; z.lpf_b0 = z.lpf_b1 = z.lpf_b2 = z.lpf_a1 = z.lpf_a2 = 0.0;
+            z.spk_tanh = 0; z.group = we.group; z.no_preamp = 0; z.no_poweramp = 1; z.oversample = 0; z.pre_only = 0;
+            s_ci[lane] = z;
+        }
+    }
+    __syncthreads();
+    const int oversample = s_ci[0].oversample;  // every main lane of a warp shares the group's base rate (lane 0 is always main)
+    const int n_sub = oversample ? 2 : 1;
+    const int64_t t_stop = t_end < we.n_max ? t_end : we.n_max;
+    double* cw = carry ? carry + (size_t)blockIdx.x * OWG_CARRY * 32 + lane : nullptr;
+    const bool resume = cw && t_begin > 0;
+    const bool save = cw && t_stop < we.n_max;
+    if (t_begin >= t_stop) return;
+
+    if (warp_a) {
+        // ================================ warp A: the DK preamp ================================
+        DkState st = *settled;  // DkPreamp::new / reset(): clone of the cached settled state (melange_adapter.rs:22-29)
+        const DkDev dv = dk_dev();
+        if (resume) {
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < PN; i++) st.v[i] = cw[(k++) * 32];
+#pragma unroll
+            for (int i = 0; i < PM; i++) { st.il[i] = cw[(k++) * 32]; st.ilpp[i] = cw[(k++) * 32]; }
+            st.xin_prev = cw[(k++) * 32];
+            st.be_cooldown = (uint32_t)cw[(k++) * 32];
+        }
+        int64_t tos = t_begin * n_sub;
+        const int64_t n_rec = rec_stride_t;
+        if (TREM) {
+            if (tos < n_rec) {
+                const double* src = grec + (size_t)tos * OWG_MAT_STRIDE;
+                double* dst = s_rec + (tos & 1) * OWG_MAT_STRIDE;
+                for (int c = lane; c < OWG_MAT_STRIDE / 2; c += 32) {
+                    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 2 * c) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int64_t t = t_begin; t < t_stop; t++) {
+            const int slot = (int)(t & 1);
+            owg_bar_sync(OWG_BAR_UFULL + slot);
+            double u0 = s_u[slot][0][lane], u1 = s_u[slot][1][lane];
+            if (is_shadow) { u0 = 0.0; u1 = 0.0; }
+            double p0 = 0.0, p1 = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < n_sub; j++) {
+                if (TREM) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    if (tos + 1 < n_rec) {
+                        const double* src = grec + (size_t)(tos + 1) * OWG_MAT_STRIDE;
+                        double* dst = s_rec + ((tos + 1) & 1) * OWG_MAT_STRIDE;
+                        for (int c = lane; c < OWG_MAT_STRIDE / 2; c += 32) {
+                            const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 2 * c);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 2 * c) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                const double* m = TREM ? s_rec + (tos & 1) * OWG_MAT_STRIDE : s_rec;
+                const double an66 = m[OWG_MAT_AN66];
+                const double main_out = dk_step<false>(j == 0 ? u0 : u1, st, m, s_an, an66, dv, nullptr, s_cold + lane, 32);
+                const double pump = __shfl_sync(0xffffffffu, main_out, 31);
+                double res = main_out - pump;
+                if (!finite64(res)) { st = *settled; res = 0.0; }
+                if (j == 0) p0 = res; else p1 = res;
+                tos += 1;
+            }
+            s_p[slot][0][lane] = p0;
+            s_p[slot][1][lane] = p1;
+            owg_bar_arrive(OWG_BAR_PFULL + slot);
+        }
+        if (save) {
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < PN; i++) cw[(k++) * 32] = st.v[i];
+#pragma unroll
+            for (int i = 0; i < PM; i++) { cw[(k++) * 32] = st.il[i]; cw[(k++) * 32] = st.ilpp[i]; }
+            cw[(k++) * 32] = st.xin_prev;
+            cw[(k++) * 32] = (double)st.be_cooldown;
+        }
+        return;
+    }
+
+    // ================================ warp B: input and output stages ================================
+    const OwgChainInit& ci = s_ci[lane];
+    const unsigned long long ns = is_main ? n_samples[job] : 0ull;
+    double* o = is_main ? out + (size_t)job * stride : nullptr;
+    double ua[3] = {0, 0, 0}, ub[3] = {0, 0, 0}, da[3] = {0, 0, 0}, db[3] = {0, 0, 0};
+    double down_delay = 0.0;
+    SpkState spk = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const double vol = ci.volume;
+    const bool bypass_preamp = ci.no_preamp != 0;
+    const int CARRY_B0 = PN + 2 * PM + 2;  // first carried slot of warp B's state (after the DK state)
+    if (resume) {
+        int k = CARRY_B0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { ua[i] = cw[(k++) * 32]; ub[i] = cw[(k++) * 32]; da[i] = cw[(k++) * 32]; db[i] = cw[(k++) * 32]; }
+        down_delay = cw[(k++) * 32];
+        spk.thermal = cw[(k++) * 32]; spk.h1 = cw[(k++) * 32]; spk.h2 = cw[(k++) * 32]; spk.l1 = cw[(k++) * 32]; spk.l2 = cw[(k++) * 32];
+    }
+    double m_peak = 0.0, m_sq = 0.0, m_re1 = 0.0, m_im1 = 0.0, m_re2 = 0.0, m_im2 = 0.0, m_f0 = 0.0, m_sr = 1.0;
+    if (metrics && is_main) {
+        const double* mj = metrics + (size_t)job * OWG_METRICS;
+        m_peak = mj[0]; m_sq = mj[1]; m_re1 = mj[2]; m_im1 = mj[3]; m_re2 = mj[4]; m_im2 = mj[5];
+        m_f0 = f0s[2 * job]; m_sr = f0s[2 * job + 1];
+    }
+    // produce U[t]: the voice sample through the 2x polyphase upsampler (or straight through at native rate)
+    auto produce = [&](int64_t t, double& x_keep) {
+        const double x = (is_main && (unsigned long long)t < ns) ? o[t] : 0.0;
+        double u0 = x, u1 = 0.0;
+        if (oversample) {
+            u0 = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, ua, x);
+            u1 = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, ub, x);
+        }
+        const int slot = (int)(t & 1);
+        s_u[slot][0][lane] = u0;
+        s_u[slot][1][lane] = u1;
+        x_keep = x;
+        owg_bar_arrive(OWG_BAR_UFULL + slot);
+    };
+    double xk0 = 0.0, xk1 = 0.0;  // the voice samples of the two samples in flight (slot-indexed), for --no-preamp
+    produce(t_begin, (t_begin & 1) ? xk1 : xk0);
+    if (t_begin + 1 < t_stop) produce(t_begin + 1, ((t_begin + 1) & 1) ? xk1 : xk0);
+    for (int64_t t = t_begin; t < t_stop; t++) {
+        const int slot = (int)(t & 1);
+        owg_bar_sync(OWG_BAR_PFULL + slot);
+        const double p0 = s_p[slot][0][lane], p1 = s_p[slot][1][lane];
+        const double x = slot ? xk1 : xk0;
+        if (t + 2 < t_stop) produce(t + 2, slot ? xk1 : xk0);  // refill the slot first: warp A never waits on the output stage
+        const bool live = is_main && (unsigned long long)t < ns;
+        double pre_out;
+        if (oversample) {
+            const double a = allpass3(OWG_OS_A0, OWG_OS_A1, OWG_OS_A2, da, p0);
+            const double b = allpass3(OWG_OS_B0, OWG_OS_B1, OWG_OS_B2, db, p1);
+            pre_out = (a + down_delay) * 0.5;
+            down_delay = b;
+        } else pre_out = p0;
+        if (bypass_preamp) pre_out = x;
+        if (live && ci.pre_only) o[t] = pre_out;
+        else if (live) {
+            const double att = pre_out * vol * vol;
+            const double amped = ci.no_poweramp ? att : poweramp(att, nullptr);
+            const double y_final = speaker(amped, spk, ci) * 7.498942093324558;
+            if (metrics) {
+                if (t >= w_begin && t < w_end) {  // peak_abs / rms / single-bin DFT at f0 and 2 f0 (main.rs:893-938)
+                    const double ii = (double)(t - w_begin);
+                    m_peak = fmax(m_peak, fabs(y_final));
+                    m_sq += y_final * y_final;
+                    const double ph1 = 2.0 * 3.14159265358979323846 * m_f0 * ii / m_sr;
+                    const double ph2 = 2.0 * 3.14159265358979323846 * (2.0 * m_f0) * ii / m_sr;
+                    m_re1 += y_final * cos(ph1); m_im1 -= y_final * sin(ph1);
+                    m_re2 += y_final * cos(ph2); m_im2 -= y_final * sin(ph2);
+                }
+            } else o[t] = y_final;
+        }
+    }
+    if (metrics && is_main) {
+        double* mj = metrics + (size_t)job * OWG_METRICS;
+        mj[0] = m_peak; mj[1] = m_sq; mj[2] = m_re1; mj[3] = m_im1; mj[4] = m_re2; mj[5] = m_im2;
+    }
+    if (save) {
+        int k = CARRY_B0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { cw[(k++) * 32] = ua[i]; cw[(k++) * 32] = ub[i]; cw[(k++) * 32] = da[i]; cw[(k++) * 32] = db[i]; }
+        cw[(k++) * 32] = down_delay;
+        cw[(k++) * 32] = spk.thermal; cw[(k++) * 32] = spk.h1; cw[(k++) * 32] = spk.h2; cw[(k++) * 32] = spk.l1; cw[(k++) * 32] = spk.l2;
+    }
+}
+
 // ---- FP64 pipe micro-benchmark ------------------------------------------------------------------------
 template <bool FMA>
 __global__ void fp64_peak_kernel(double* sink, int iters, double a, double b) {

@@ -112,6 +112,7 @@ struct owg_plan {
     int64_t in_stride = 0;
     bool collect_diag = false;
     bool legacy = false;             // owg_opts.preamp_model == OWG_PREAMP_LEGACY8
+    bool use_split = false;          // chain_split_kernel (decided at plan time from the batch size)
     DevBuf<double> d_legacy_recs;    // [group][OWG_LG_STRIDE]
     int64_t n = 0;
     std::vector<unsigned long long> n_samples;
@@ -252,6 +253,16 @@ void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vec
     // Aim for ~1 warp per SM sub-partition (148 SMs x 4; measured optimum), capped at 31 instances + the shadow lane.
     int lpw = (int)((n + 592 - 1) / 592);
     lpw = lpw < 1 ? 1 : (lpw > 31 ? 31 : lpw);
+    // Warp-specialised chain (chain_split_kernel: 2 warps per instance group) when the whole batch still fits in one wave of
+    // 3 CTAs per SM -- the fourth quarter of each register file stays free for the oscillator / matrix / voice kernels that
+    // run concurrently on the other streams.  Larger batches are throughput-bound and keep the one-warp kernel.
+    {
+        const char* split_env = getenv("OWG_CHAIN_SPLIT");
+        const bool allow = !(split_env && split_env[0] == '0') && !pl->collect_diag && !pl->legacy;
+        const int lpw_split = (int)((n + 444 - 1) / 444);
+        pl->use_split = allow && lpw_split <= 31;
+        if (pl->use_split) lpw = lpw_split < 1 ? 1 : lpw_split;
+    }
     if (const char* e = getenv("OWG_LANES_PER_WARP")) { const int v = atoi(e); if (v >= 1 && v <= 31) lpw = v; }
     std::vector<int32_t>& order = *order_out;
     order.reserve(n);
@@ -487,6 +498,10 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
         return pl->chain_ev[chain_ev_used++];
     };
     if (pl->kind >= 1) {
+        // warp-specialised chain (DK preamp | input + output stages) unless counters are collected or it is switched off
+        const char* split_env = getenv("OWG_CHAIN_SPLIT");
+        const bool split_chain = pl->use_split;
+        const int swap_roles = (split_env && split_env[0] == '2') ? 0 : 1;  // OWG_CHAIN_SPLIT=2: split without the role placement (A/B test)
         const int ng = (int)pl->groups.size();
         if (!pl->legacy) {
             static_matrix_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_static_recs.p, pl->d_ans.p);
@@ -550,6 +565,11 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                     chain_legacy_kernel<false><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->d_legacy_recs.p, nullptr,
                                                                  pl->d_group_rec_index.p, 0, dout, stride, pl->collect_diag ? pl->d_diag.p : nullptr, b0, b1,
                                                                  overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
+                else if (!pl->collect_diag && split_chain)
+                    chain_split_kernel<false><<<nb, 64, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                                pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride,
+                                                                b0, b1, overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin,
+                                                                pl->w_end, swap_roles);
                 else if (pl->collect_diag)
                     chain_kernel<false, true><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                  pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p,
@@ -588,6 +608,10 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                     chain_legacy_kernel<true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->d_legacy_recs.p, pl->d_pot_seq.p,
                                                                 pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride, pl->collect_diag ? pl->d_diag.p : nullptr,
                                                                 b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
+                else if (!pl->collect_diag && split_chain)
+                    chain_split_kernel<true><<<nb, 64, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                               pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
+                                                               b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end, swap_roles);
                 else if (pl->collect_diag)
                     chain_kernel<true, true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                 pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,

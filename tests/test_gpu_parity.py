@@ -114,6 +114,10 @@ def _bench_parity(jobs, what, compare_hist=True):
         n = O.n_samples(j.v.duration_s, j.v.sample_rate)
         if n:
             assert_parity(got[i, :n], ref[i, :n], f"{what}[{i}] midi={j.v.midi}")
+    # collect_diag=True runs the single-warp chain_kernel; the default path is the warp-specialised chain_split_kernel:
+    # same arithmetic in the same order, so the two are bit-identical
+    fast = ow.render_bench(jobs)
+    assert np.array_equal(fast, got), f"{what}: split kernel differs from the diag kernel by {np.abs(fast - got).max():.3e}"
     if compare_hist:
         # the preamp's Newton iteration counts are decision-for-decision identical
         assert list(dg.nr_iter_hist) == list(dc.nr_iter_hist), what
