@@ -479,6 +479,35 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     int64_t launches = 0;
     CK(cudaEventRecord(pl->ev0, s));
     if (pl->collect_diag) CK(cudaMemsetAsync(pl->d_diag.p, 0, sizeof(DevDiag), s));
+    // Tremolo groups: the Twin-T oscillator is one serial thread per group, so it is pipelined: it runs on its own stream in
+    // chunks, and chunk c's LDR law + matrices + chain run on the main stream while the oscillator already produces chunk c+1.
+    // It depends on nothing else in this call, so it is enqueued first (before the voice kernel); the first chunk is short so
+    // that the chain can start early.
+    const int64_t CH_BASE = 8192, CH_FIRST = 2048;  // base-rate samples per chunk
+    auto chunk_lo = [&](int64_t c) -> int64_t { return c <= 0 ? 0 : CH_FIRST + (c - 1) * CH_BASE; };
+    int64_t n_chunks = 0;
+    const int nt = pl->kind >= 1 ? (int)pl->trem_group_ids.size() : 0;
+    if (nt > 0) {
+        if (!pl->stream_trem) CK(cudaStreamCreateWithFlags(&pl->stream_trem, cudaStreamNonBlocking));
+        n_chunks = (int64_t)pl->max_samples <= CH_FIRST ? 1 : 1 + ((int64_t)pl->max_samples - CH_FIRST + CH_BASE - 1) / CH_BASE;
+        while ((int64_t)pl->chunk_events.size() < n_chunks + 1) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            pl->chunk_events.push_back(e);
+        }
+        if (int rc = pl->d_carry.alloc(pl->warps_trem.size() * (size_t)OWG_CARRY * 32)) return rc;
+        CK(cudaEventRecord(pl->chunk_events[n_chunks], s));               // orders the oscillator stream after earlier work on `s`
+        CK(cudaStreamWaitEvent(pl->stream_trem, pl->chunk_events[n_chunks], 0));
+        CK(cudaMemcpyAsync(pl->d_trm_run.p, pl->d_trm_ctor.p, (size_t)nt * sizeof(TrmRun), cudaMemcpyDeviceToDevice, pl->stream_trem));
+        for (int64_t c = 0; c < n_chunks; c++) {
+            const int64_t os0 = chunk_lo(c) * 2, os1 = chunk_lo(c + 1) * 2;  // covers 2x-oversampled groups; native-rate groups use half
+            tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                                 pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(pl->chunk_events[c], pl->stream_trem));
+            launches++;
+        }
+    }
     if (pl->kind == 2) {
         // preamp-only batch: the rows start as the caller's input signals
         CK(cudaMemcpy2DAsync(dout, (size_t)stride * sizeof(double), pl->in_ptr, (size_t)pl->in_stride * sizeof(double),
@@ -508,37 +537,10 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
             CK(cudaGetLastError());
             launches++;
         }
-        const int nt = (int)pl->trem_group_ids.size();
-        // Tremolo groups: the Twin-T oscillator is one serial thread per group, so it is pipelined: it runs on its own
-        // stream in chunks of CH preamp-rate samples, and chunk c's matrices + chain run on the main stream while the
-        // oscillator already produces chunk c+1.
-        const int64_t CH_BASE = 8192;  // base-rate samples per chunk
-        int64_t n_chunks = 0;
-        if (nt > 0) {
-            if (!pl->stream_trem) CK(cudaStreamCreateWithFlags(&pl->stream_trem, cudaStreamNonBlocking));
-            n_chunks = ((int64_t)pl->max_samples + CH_BASE - 1) / CH_BASE;
-            while ((int64_t)pl->chunk_events.size() < n_chunks + 1) {
-                cudaEvent_t e;
-                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                pl->chunk_events.push_back(e);
-            }
-            if (int rc = pl->d_carry.alloc(pl->warps_trem.size() * (size_t)OWG_CARRY * 32)) return rc;
-            CK(cudaMemcpyAsync(pl->d_trm_run.p, pl->d_trm_ctor.p, (size_t)nt * sizeof(TrmRun), cudaMemcpyDeviceToDevice, pl->stream_trem));
-            if (!pl->legacy) {
-                tremolo_an_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_ans.p);
-                CK(cudaGetLastError());
-                launches++;
-            }
-            CK(cudaEventRecord(pl->chunk_events[n_chunks], s));               // everything the oscillator stream depends on
-            CK(cudaStreamWaitEvent(pl->stream_trem, pl->chunk_events[n_chunks], 0));
-            for (int64_t c = 0; c < n_chunks; c++) {
-                const int64_t os0 = c * CH_BASE * 2, os1 = (c + 1) * CH_BASE * 2;  // covers 2x-oversampled groups; native-rate groups use half
-                tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                                     pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr);
-                CK(cudaGetLastError());
-                CK(cudaEventRecord(pl->chunk_events[c], pl->stream_trem));
-                launches++;
-            }
+        if (nt > 0 && !pl->legacy) {
+            tremolo_an_kernel<<<(ng + 31) / 32, 32, 0, s>>>(pl->d_groups.p, ng, pl->d_ans.p);
+            CK(cudaGetLastError());
+            launches++;
         }
         CK(cudaEventRecord(pl->evk0, s));
         // Host output: the rows of a finished chunk are copied back on a third stream while the next chunk computes
@@ -589,7 +591,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
         if (!pl->warps_trem.empty()) {
             const int nb = (int)pl->warps_trem.size();
             for (int64_t c = 0; c < n_chunks; c++) {
-                const int64_t b0 = c * CH_BASE, b1 = (c + 1) * CH_BASE;
+                const int64_t b0 = chunk_lo(c), b1 = chunk_lo(c + 1);
                 CK(cudaStreamWaitEvent(s, pl->chunk_events[c], 0));
                 // oscillator volts -> LDR law -> the preamp's resistance tracking, in place (off the oscillator's serial thread)
                 tremolo_ldr_kernel<<<nt, 256, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_ldr_run.p,
