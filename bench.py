@@ -257,7 +257,10 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
+            ts = time.perf_counter()
             ow.render_bench(jobs, out=host, device=dev, preamp_model=model)
+            if os.environ.get("OWG_BENCH_DEBUG"):
+                print(f"[rank {rank}] e2e step {time.perf_counter() - ts:.3f} s", file=sys.stderr, flush=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -310,7 +313,8 @@ def main():
                             "traffic": None, "peak_source": "owg_fp64_peak DFMA micro-benchmark measured in this run "
                             "(MEASURED_PEAKS.json has no FP64 entry; B200 nominal 37 TFLOP/s)",
                             "peak_unfused_tflops": unfused_peak, "frac_of_unfused": achieved / unfused_peak,
-                            "kernel": "owgd::chain_legacy_kernel" if model == 1 else "owgd::chain_kernel", "kernel_ms_per_step": kernel_s * 1e3, "mean_nr_iterations": iters,
+                            "kernel": "owgd::chain_legacy_kernel" if model == 1 else
+                            ("owgd::chain_split_kernel" if main_run["n_inst"] <= 444 * 31 else "owgd::chain_kernel"), "kernel_ms_per_step": kernel_s * 1e3, "mean_nr_iterations": iters,
                             "algorithmic_gflop_per_step": flops / 1e9}
         if not args.no_variants:
             other = 0.0 if args.tremolo_depth > 0 else 0.5
