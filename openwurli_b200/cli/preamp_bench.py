@@ -140,7 +140,56 @@ def cmd_calibrate(args):
     return 0
 
 
-USAGE = """Usage: preamp_bench <render|calibrate> [flags]
+def cmd_render_midi(args):
+    """`render-midi --midi FILE` (main.rs:1603-1895): the SMF front-end is the reference's (smf.py); the audio path is the plugin's
+    WurliEngine (chain E: 64 slots with stealing crossfade, tremolo, f32) instead of the tool's private voice manager, with the
+    tool's event timing (64-sample blocks).  `--tremolo-depth` defaults to 0 like the tool's static 1 MOhm preamp."""
+    from .. import smf
+    midi_path = parse_flag_str(args, "--midi", "")
+    if not midi_path:
+        sys.stderr.write("Usage: preamp_bench render-midi --midi <file.mid> [--output <file.wav>] [--volume V] [--speaker S] [--tail T] [--track N]\n")
+        return 1
+    output_path = parse_flag_str(args, "--output", os.path.join(tempfile.gettempdir(), "preamp_render_midi.wav"))
+    volume = parse_flag(args, "--volume", 0.60)
+    speaker_char = parse_flag(args, "--speaker", 1.0)
+    tail = parse_flag(args, "--tail", 2.0)
+    depth = parse_flag(args, "--tremolo-depth", 0.0)
+    track = int(parse_flag(args, "--track", 0.0)) if has_flag(args, "--track") else None
+    if has_flag(args, "--no-poweramp"):
+        sys.stderr.write("--no-poweramp is not available on the WurliEngine path\n")
+        return 1
+    model = api.LEGACY8 if parse_flag_str(args, "--preamp-model", "melange12") == "legacy8" else api.MELANGE12
+    try:
+        events = smf.timed_events(open(midi_path, "rb").read(), track)
+    except smf.SmfError as e:
+        sys.stderr.write(f"{e}\n")
+        return 1
+    if not events:
+        sys.stderr.write("No note events found in MIDI file\n")
+        return 1
+    n = smf.total_samples(events, tail, BASE_SR)
+    job = api.engine_job(smf.engine_events(events, 64, BASE_SR), sample_rate=BASE_SR, duration=n / BASE_SR + 0.5 / BASE_SR, volume=volume,
+                         tremolo_depth=depth, speaker_character=speaker_char, block_size=64, warm_up=True)
+    out = api.render_engines([job], preamp_model=model)[0][:n].astype(np.float64)
+    peak = float(np.max(np.abs(out))) if out.size else 0.0
+    if peak > 1.0:
+        sys.stderr.write(f"WARNING: Peak exceeds 0 dBFS ({to_dbfs(peak):.1f} dBFS) — consider reducing --volume\n")
+    wav.write_preamp_bench_wav(output_path, out, BASE_SR, 1.0)
+    d = api.last_diag()
+    print("MIDI render complete")
+    print(f"  File:      {midi_path}")
+    print(f"  Notes:     {int(d.nr_iter_hist[0])} note-ons")
+    print(f"  Peak poly: {int(d.nr_iter_hist[3])} voices")
+    print(f"  Duration:  {n / BASE_SR:.1f}s")
+    print(f"  Volume:    {volume:.3f}")
+    print(f"  Speaker:   {speaker_char:.1f}")
+    print(f"  Peak:      {to_dbfs(peak):.1f} dBFS")
+    print(f"  Output:    {output_path}")
+    return 0
+
+
+USAGE = """Usage: preamp_bench <render|calibrate|render-midi> [flags]
+  render-midi --midi FILE --output FILE --volume X --speaker C --tail S --track N --tremolo-depth D --preamp-model M
   render     --note N --velocity V --duration S --ldr OHM --volume X --speaker C --tremolo-depth D --sample-rate HZ
              --no-poweramp --no-rail-sag --no-preamp --no-attack-noise --no-mlp --normalize --displacement-scale DS --output FILE
              --preamp-model melange12|legacy8   (compile-time cargo feature in the reference)
@@ -157,6 +206,8 @@ def main(argv=None):
         return cmd_render(args[1:])
     if args[0] == "calibrate":
         return cmd_calibrate(args[1:])
+    if args[0] == "render-midi":
+        return cmd_render_midi(args[1:])
     sys.stderr.write(f"Unknown subcommand: {args[0]} (only the batched render paths are mirrored)\n{USAGE}")
     return 1
 

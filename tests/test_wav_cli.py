@@ -98,3 +98,68 @@ def test_cli_renders_match_oracle_wavs(tmp_path):
     ref = ol.render_bench([ol.bench_job(midi=57, vel=90, dur=0.2, depth=0.4, volume=0.9)])[0]
     sc = wav.normalize_scale(ref, True)
     assert sr == 44100 and np.max(np.abs(q.astype(np.int64) - wav.pcm24_round(ref, sc))) <= 1
+
+
+# ---- SMF front-end of render-midi (main.rs:1626-1716) ------------------------------------------------------------------------------
+def _vlq(n):
+    out = [n & 0x7F]
+    n >>= 7
+    while n:
+        out.append(0x80 | (n & 0x7F))
+        n >>= 7
+    return bytes(reversed(out))
+
+
+def _smf(tracks, division=480, fmt=1):
+    body = b"MThd" + struct.pack(">IHHH", 6, fmt, len(tracks), division)
+    for t in tracks:
+        body += b"MTrk" + struct.pack(">I", len(t)) + t
+    return body
+
+
+def test_smf_parser_time_map_running_status_and_filters():
+    from openwurli_b200 import smf
+    tempo = lambda us: b"\xFF\x51\x03" + us.to_bytes(3, "big")
+    eot = b"\x00\xFF\x2F\x00"
+    # track 0: tempo 250000 at t=0 (240 BPM), note 60 on at tick 480, running-status note 64, vel-0 note-on = off, CC64 pedal, sysex
+    t0 = (_vlq(0) + tempo(250_000) + _vlq(480) + b"\x90\x3C\x64" + _vlq(0) + b"\x40\x50" + _vlq(240) + b"\x3C\x00"
+          + _vlq(0) + b"\xB0\x40\x7F" + _vlq(120) + b"\xB0\x40\x3F" + _vlq(0) + b"\xF0\x03\x01\x02\xF7" + _vlq(0) + b"\x80\x40\x00"
+          + _vlq(0) + b"\xC0\x05" + eot)
+    # track 1 keeps the default tempo (500000): the reference's time map is per track
+    t1 = _vlq(960) + b"\x91\x30\x7F" + _vlq(960) + b"\x81\x30\x00" + eot
+    data = _smf([t0, t1])
+    ev = smf.timed_events(data)
+    kinds = [(round(t, 9), k, n, v) for t, k, n, v in ev]
+    assert kinds == [(0.25, "on", 60, 100), (0.25, "on", 64, 80), (0.375, "off", 60, 0), (0.375, "pedal", 1, 0),
+                     (0.4375, "pedal", 0, 0), (0.4375, "off", 64, 0), (1.0, "on", 48, 127), (2.0, "off", 48, 0)]
+    assert [e[2] for e in smf.timed_events(data, track_filter=1)] == [48, 48]
+    assert smf.total_samples(ev, 2.0) == int(4.0 * 44100.0)
+    # events apply at the first 64-sample chunk boundary at or after their time
+    assert smf.chunk_of(0.0) == 0 and smf.chunk_of(64 / 44100.0) == 1 and smf.chunk_of(64 / 44100.0 + 1e-12) == 2
+    ee = smf.engine_events(ev)
+    assert ee[0][0] == smf.chunk_of(0.25) * 64 and ee[0][1] == 0 and abs(ee[0][3] - 100 / 127) < 1e-7
+    with pytest.raises(smf.SmfError):
+        smf.timed_events(_smf([t0], division=0xE728))   # SMPTE timing is rejected like main.rs:1633-1636
+    with pytest.raises(smf.SmfError):
+        smf.timed_events(b"RIFFxxxx")
+
+
+@pytest.mark.gpu
+def test_render_midi_cli_matches_oracle_engine(tmp_path):
+    """SMF file -> events -> WurliEngine streams -> 24-bit WAV, against the oracle engine fed with the same event schedule."""
+    import oracle_lib as ol
+    from openwurli_b200 import smf
+    eot = b"\x00\xFF\x2F\x00"
+    trk = (_vlq(0) + b"\xFF\x51\x03" + (300_000).to_bytes(3, "big") + _vlq(0) + b"\x90\x3C\x64" + _vlq(120) + b"\x43\x50" + _vlq(120) + b"\xB0\x40\x7F"
+           + _vlq(120) + b"\x90\x3C\x00" + _vlq(240) + b"\xB0\x40\x00" + _vlq(0) + b"\x80\x43\x00" + eot)
+    mid, out = tmp_path / "a.mid", tmp_path / "a.wav"
+    mid.write_bytes(_smf([trk], division=480, fmt=0))
+    assert preamp_bench.main(["render-midi", "--midi", str(mid), "--output", str(out), "--tail", "0.2", "--volume", "0.7", "--speaker", "0.5"]) == 0
+    q, sr = wav.read_wav_pcm24(str(out))
+    ev = smf.timed_events(mid.read_bytes())
+    n = smf.total_samples(ev, 0.2)
+    assert sr == 44100 and q.size == n
+    ref = ol.render_engines([ol.engine_job(smf.engine_events(ev), sr=44100.0, dur=n / 44100.0 + 0.5 / 44100.0, volume=0.7, depth=0.0, speaker=0.5,
+                                           block=64, warm_up=True)])[0][:n].astype(np.float64)
+    assert np.abs(ref).max() > 1e-3
+    assert np.max(np.abs(q.astype(np.int64) - wav.pcm24_round(ref, 1.0))) <= 2
