@@ -384,7 +384,8 @@ struct EngineDiag { unsigned long long nan_guard, out_nan, steals, note_ons, voi
 #define OWG_SLOT_HELD 1
 #define OWG_SLOT_SUSTAINED 2
 #define OWG_SLOT_RELEASING 3
-#define OWG_ENGINE_TILE 64
+#define OWG_ENGINE_TILE 16   // samples per shared-memory tile of the voice/mix kernel
+#define OWG_ENGINE_ITEMS 64  // threads (= render-list items per pass) of the voice/mix kernel
 
 struct EngineState {  // slot table (engine.rs:36-61) + the current round's render list
     unsigned long long st_age[64];
@@ -555,8 +556,12 @@ __global__ void engine_events_kernel(const EngineDesc* __restrict__ engines, int
 
 // Register-resident Voice (reed + attack noise + pickup + gain); one sample per call, same arithmetic as voice_kernel /
 // voice_render_block (voice.rs:162-179, reed.rs:219-306, hammer.rs:150-179, pickup.rs:130-149).
+// The 35 per-mode constants (cos_inc, sin_inc, phase_inc, amplitude, decay) live in shared memory, one column per thread
+// (kb[(a * 7 + m) * OWG_ENGINE_ITEMS], a = 0..4), which halves the register footprint and doubles the resident warps: the kernel is
+// bound by the latency of one voice sample, so throughput scales with the warps per scheduler.
+#define OWG_VK(a, m) kb[((a) * 7 + (m)) * OWG_ENGINE_ITEMS]
 struct VoiceRegs {
-    double s[7], c[7], env[7], drift[7], cos_inc[7], sin_inc[7], phase_inc[7], amp[7], decay[7];
+    double s[7], c[7], env[7], drift[7];
     double revert, diffusion, onset_inc, onset_exp, n_amp, n_decay, b0, b1, b2, a1, a2, z1, z2, q, beta, ds, gain, ramp, release_count;
     unsigned long long smp, onset_n;
     uint32_t jit, n_rng, n_left, n_total;
@@ -564,11 +569,11 @@ struct VoiceRegs {
     bool damper_active, ramp_done;
 };
 
-__device__ __forceinline__ void voice_regs_load(VoiceRegs& r, const VoiceRT* __restrict__ vp) {
+__device__ __forceinline__ void voice_regs_load(VoiceRegs& r, const VoiceRT* __restrict__ vp, double* __restrict__ kb) {
 #pragma unroll
     for (int m = 0; m < 7; m++) {
         r.s[m] = vp->s[m]; r.c[m] = vp->c[m]; r.env[m] = vp->env[m]; r.drift[m] = vp->drift[m];
-        r.cos_inc[m] = vp->cos_inc[m]; r.sin_inc[m] = vp->sin_inc[m]; r.phase_inc[m] = vp->phase_inc[m]; r.amp[m] = vp->amp[m]; r.decay[m] = vp->decay[m];
+        OWG_VK(0, m) = vp->cos_inc[m]; OWG_VK(1, m) = vp->sin_inc[m]; OWG_VK(2, m) = vp->phase_inc[m]; OWG_VK(3, m) = vp->amp[m]; OWG_VK(4, m) = vp->decay[m];
     }
     r.revert = vp->revert; r.diffusion = vp->diffusion; r.onset_inc = vp->onset_inc; r.onset_exp = vp->onset_exp;
     r.onset_mode = r.onset_exp <= 1.001 ? 0 : (r.onset_exp >= 1.999 ? 1 : 2);
@@ -587,7 +592,7 @@ __device__ __forceinline__ void voice_regs_store(const VoiceRegs& r, VoiceRT* __
     vp->damper_active = r.damper_active ? 1 : 0; vp->damper_ramp_done = r.ramp_done ? 1 : 0; vp->damper_release_count = r.release_count;
 }
 
-__device__ __forceinline__ double voice_sample(VoiceRegs& r, const VoiceRT* __restrict__ vp) {
+__device__ __forceinline__ double voice_sample(VoiceRegs& r, const VoiceRT* __restrict__ vp, const double* __restrict__ kb) {
     if (r.damper_active) {  // reed.rs:227-247
         r.release_count += 1.0;
         if (!r.ramp_done) {
@@ -618,14 +623,15 @@ __device__ __forceinline__ double voice_sample(VoiceRegs& r, const VoiceRT* __re
     double sum = 0.0;
 #pragma unroll
     for (int m = 0; m < 7; m++) {
-        sum += r.amp[m] * r.s[m] * onset * r.env[m];
-        const double dp = r.drift[m] * r.phase_inc[m];
-        const double ci = r.cos_inc[m] - dp * r.sin_inc[m];
-        const double si = r.sin_inc[m] + dp * r.cos_inc[m];
+        const double k_cos = OWG_VK(0, m), k_sin = OWG_VK(1, m);
+        sum += OWG_VK(3, m) * r.s[m] * onset * r.env[m];
+        const double dp = r.drift[m] * OWG_VK(2, m);
+        const double ci = k_cos - dp * k_sin;
+        const double si = k_sin + dp * k_cos;
         const double s_new = r.s[m] * ci + r.c[m] * si;
         const double c_new = r.c[m] * ci - r.s[m] * si;
         r.s[m] = s_new; r.c[m] = c_new;
-        r.env[m] *= r.decay[m];
+        r.env[m] *= OWG_VK(4, m);
     }
     if ((r.smp & 1023ull) == 0ull && r.smp > 0ull) {
 #pragma unroll
@@ -659,15 +665,16 @@ __device__ __forceinline__ double voice_sample(VoiceRegs& r, const VoiceRT* __re
     return ((r.q * omy - 1.0) * 1.8375) * r.gain;
 }
 
-// One CTA (64 threads) per engine, one thread per render-list item: each voice renders a 64-sample tile into shared
+// One CTA (64 threads) per engine, one thread per render-list item: each voice renders a 16-sample tile into shared
 // memory, then thread j sums column j over the items IN LIST ORDER (sum_buf[i] += voice_buf[i] [* gain], engine.rs:476-488)
 // and writes mix[engine][t].  Lists longer than 64 (steal voices) take further passes that continue the running sums.
-__global__ void __launch_bounds__(OWG_ENGINE_TILE) engine_voice_mix_kernel(const EngineDesc* __restrict__ engines, long long round,
-                                                                           VoiceRT* __restrict__ pool, EngineState* __restrict__ states,
-                                                                           double* __restrict__ mix, long long mix_stride, long long seg_round0) {
-    __shared__ double tile[OWG_ENGINE_TILE * (OWG_ENGINE_TILE + 1)];
-    __shared__ int32_t s_fade[OWG_ENGINE_TILE];
-    __shared__ double s_fade_len[OWG_ENGINE_TILE];
+__global__ void __launch_bounds__(OWG_ENGINE_ITEMS, 8) engine_voice_mix_kernel(const EngineDesc* __restrict__ engines, long long round,
+                                                                               VoiceRT* __restrict__ pool, EngineState* __restrict__ states,
+                                                                               double* __restrict__ mix, long long mix_stride, long long seg_round0) {
+    __shared__ double tile[OWG_ENGINE_ITEMS * (OWG_ENGINE_TILE + 1)];
+    __shared__ double s_k[35 * OWG_ENGINE_ITEMS];
+    __shared__ int32_t s_fade[OWG_ENGINE_ITEMS];
+    __shared__ double s_fade_len[OWG_ENGINE_ITEMS];
     const int e = blockIdx.x;
     const int tid = threadIdx.x;
     const EngineDesc ed = engines[e];
@@ -678,23 +685,24 @@ __global__ void __launch_bounds__(OWG_ENGINE_TILE) engine_voice_mix_kernel(const
     const int n_items = S.n_items;
     double* mrow = mix + (size_t)e * mix_stride + (round - seg_round0) * (long long)ed.block_size;
     if (n_items == 0) {
-        for (int t = tid; t < len; t += OWG_ENGINE_TILE) mrow[t] = 0.0;
+        for (int t = tid; t < len; t += OWG_ENGINE_ITEMS) mrow[t] = 0.0;
         return;
     }
+    double* kb = s_k + tid;
     bool bad = false;
-    for (int base = 0; base < n_items; base += OWG_ENGINE_TILE) {
+    for (int base = 0; base < n_items; base += OWG_ENGINE_ITEMS) {
         const int k = base + tid;
-        const int nk = n_items - base < OWG_ENGINE_TILE ? n_items - base : OWG_ENGINE_TILE;
+        const int nk = n_items - base < OWG_ENGINE_ITEMS ? n_items - base : OWG_ENGINE_ITEMS;
         const bool act = k < n_items;
-        const bool last_pass = base + OWG_ENGINE_TILE >= n_items;
+        const bool last_pass = base + OWG_ENGINE_ITEMS >= n_items;
         VoiceRT* vp = pool + (size_t)e * 128 + (act ? S.item_pool[k] : 0);
         VoiceRegs r;
-        if (act) { voice_regs_load(r, vp); s_fade[tid] = S.item_fade[k]; s_fade_len[tid] = (double)S.item_fade_len[k]; }
+        if (act) { voice_regs_load(r, vp, kb); s_fade[tid] = S.item_fade[k]; s_fade_len[tid] = (double)S.item_fade_len[k]; }
         for (int t0 = 0; t0 < len; t0 += OWG_ENGINE_TILE) {
             const int tl = len - t0 < OWG_ENGINE_TILE ? len - t0 : OWG_ENGINE_TILE;
             if (act) {
                 double* row = tile + tid * (OWG_ENGINE_TILE + 1);
-                for (int t = 0; t < tl; t++) row[t] = voice_sample(r, vp);
+                for (int t = 0; t < tl; t++) row[t] = voice_sample(r, vp, kb);
             }
             __syncthreads();
             if (tid < tl) {

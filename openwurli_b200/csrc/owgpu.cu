@@ -833,6 +833,30 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
             spk_offsets.push_back((long long)spk_updates.size());
             spk_updates.insert(spk_updates.end(), tmp.begin(), tmp.begin() + nu);
         } else { e.spk_sched = sit->second.first; e.n_spk_updates = sit->second.second; }
+    }
+    if (stride < max_samples) return fail(OWG_E_BAD_ARG, "owg_render_engines: stride smaller than the longest stream");
+    for (auto& g : groups) pot_stride = std::max<long long>(pot_stride, g.n_warm_os + g.n_os);
+    // The oscillator's constructor (50 + 2*sr settle steps) and the engines' warm-up depend on the groups only: they start on their own
+    // stream now and run while the host parameterises every note-on below.
+    const int ng = (int)groups.size();
+    DevBuf<EngineGroup> d_groups; DevBuf<double> d_pot; DevBuf<EngTrmRun> d_trmrun;
+    cudaStream_t so = nullptr;
+    CK(cudaStreamCreateWithFlags(&so, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t st; ~StreamGuard() { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } } } so_guard{so};
+    {
+        int rc0 = d_groups.upload(groups, so);
+        if (!rc0) rc0 = d_pot.alloc((size_t)ng * (size_t)pot_stride);
+        if (!rc0) rc0 = d_trmrun.alloc((size_t)ng);
+        if (rc0) return rc0;
+        CK(cudaMemsetAsync(d_trmrun.p, 0, (size_t)ng * sizeof(EngTrmRun), so));
+        CK(cudaStreamSynchronize(so));  // the group table is read by kernels on all three streams
+        engine_tremolo_kernel<<<ng, 32, 0, so>>>(d_groups.p, ng, d_pot.p, pot_stride, d_trmrun.p, 0);
+        CK(cudaGetLastError());
+    }
+    for (int64_t i = 0; i < n; i++) {
+        const owg_engine_job& j = jobs[i];
+        EngineDesc& e = eng[i];
+        const double sr = j.sample_rate;
         // events -> voice init records (WurliEngine::note_on, engine.rs:299-338)
         e.ev_begin = (long long)events.size();
         unsigned long long age = 0;
@@ -863,11 +887,8 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
         }
         e.ev_end = (long long)events.size();
     }
-    if (stride < max_samples) return fail(OWG_E_BAD_ARG, "owg_render_engines: stride smaller than the longest stream");
-    for (auto& g : groups) pot_stride = std::max<long long>(pot_stride, g.n_warm_os + g.n_os);
     if (events.empty()) events.push_back(EngineEvent{0, OWG_EV_SUSTAIN, 0, -1});
     if (vinits.empty()) vinits.emplace_back();
-    const int ng = (int)groups.size();
 
     // rounds (= render() blocks) and segments (= rounds per chain launch; the mix buffers form a ring, one per segment in flight)
     long long n_rounds = 0;
@@ -903,14 +924,13 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
         ewarps.push_back(w);
     }
 
-    DevBuf<EngineDesc> d_eng; DevBuf<EngineGroup> d_groups; DevBuf<EngineEvent> d_events; DevBuf<OwgVoiceInit> d_vinits;
+    DevBuf<EngineDesc> d_eng; DevBuf<EngineEvent> d_events; DevBuf<OwgVoiceInit> d_vinits;
     DevBuf<DamperRow> d_dampers; DevBuf<int32_t> d_dsched, d_eorder; DevBuf<SpkUpdate> d_spk; DevBuf<long long> d_spkoff;
-    DevBuf<double> d_pot, d_recs, d_ans, d_mix; DevBuf<DkState> d_post, d_shadow; DevBuf<VoiceRT> d_pool; DevBuf<float> d_out;
-    DevBuf<EngineState> d_states; DevBuf<EngineChainState> d_chains; DevBuf<EngineWarp> d_ewarps; DevBuf<EngTrmRun> d_trmrun; DevBuf<EngLdrRun> d_ldrrun; DevBuf<double> d_depth, d_lgrecs, d_glast;
+    DevBuf<double> d_recs, d_ans, d_mix; DevBuf<DkState> d_post, d_shadow; DevBuf<VoiceRT> d_pool; DevBuf<float> d_out;
+    DevBuf<EngineState> d_states; DevBuf<EngineChainState> d_chains; DevBuf<EngineWarp> d_ewarps; DevBuf<EngLdrRun> d_ldrrun; DevBuf<double> d_depth, d_lgrecs, d_glast;
     DevBuf<LgState> d_post_lg, d_shadow_lg;
     DevBuf<EngineDiag> d_diag;
     int rc = d_eng.upload(eng, s);
-    if (!rc) rc = d_groups.upload(groups, s);
     if (!rc) rc = d_events.upload(events, s);
     if (!rc) rc = d_vinits.upload(vinits, s);
     if (!rc) rc = d_dampers.upload(dampers, s);
@@ -919,7 +939,6 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     if (!rc) rc = d_spkoff.upload(spk_offsets, s);
     if (!rc) rc = d_eorder.upload(eorder, s);
     if (!rc) rc = d_ewarps.upload(ewarps, s);
-    if (!rc) rc = d_pot.alloc((size_t)ng * (size_t)pot_stride);
     if (legacy) {
         std::vector<double> lgrecs((size_t)ng * OWG_LG_STRIDE);
         for (int g = 0; g < ng; g++) owg::make_legacy_group(groups[g].preamp_sr, NAN, &lgrecs[(size_t)g * OWG_LG_STRIDE]);
@@ -933,7 +952,6 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
         if (!rc) rc = d_post.alloc((size_t)ng);
         if (!rc) rc = d_shadow.alloc(ewarps.size());
     }
-    if (!rc) rc = d_trmrun.alloc((size_t)ng);
     if (!rc) rc = d_ldrrun.alloc((size_t)ng);
     if (!rc) rc = d_depth.alloc((size_t)ng * (size_t)pot_stride);
     if (!rc) rc = d_pool.alloc((size_t)n * 128);
@@ -946,11 +964,9 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     if (rc) return rc;
     // three streams: `s` renders voices round by round; `so` runs the serial Twin-T oscillator one chunk ahead; `sc` builds the
     // chunk's DK matrices and runs the chain (with the shadow solve in lane 31) behind both
-    cudaStream_t sc = nullptr, so = nullptr;
+    cudaStream_t sc = nullptr;
     CK(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-    struct StreamGuard { cudaStream_t st; ~StreamGuard() { if (st) cudaStreamDestroy(st); } } sc_guard{sc};
-    CK(cudaStreamCreateWithFlags(&so, cudaStreamNonBlocking));
-    StreamGuard so_guard{so};
+    StreamGuard sc_guard{sc};
     std::vector<cudaEvent_t> evs;
     struct EventGuard { std::vector<cudaEvent_t>* v; ~EventGuard() { for (auto e : *v) cudaEventDestroy(e); } } ev_guard{&evs};
     auto new_event = [&](cudaEvent_t* e) -> cudaError_t { cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming); if (r == cudaSuccess) evs.push_back(*e); return r; };
@@ -960,12 +976,10 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     const auto t_host1 = std::chrono::steady_clock::now();
     if (timing) for (auto& e : tv) { CK(cudaEventCreate(&e)); evs.push_back(e); }
     CK(cudaMemsetAsync(d_diag.p, 0, sizeof(EngineDiag), s));
-    CK(cudaMemsetAsync(d_trmrun.p, 0, (size_t)ng * sizeof(EngTrmRun), s));
     CK(cudaMemsetAsync(d_ldrrun.p, 0, (size_t)ng * sizeof(EngLdrRun), s));
     CK(cudaMemsetAsync(d_pool.p, 0, (size_t)n * 128 * sizeof(VoiceRT), s));
     CK(cudaEventRecord(ev_up, s));
     CK(cudaStreamWaitEvent(sc, ev_up, 0));
-    CK(cudaStreamWaitEvent(so, ev_up, 0));
     if (timing) { CK(cudaEventRecord(tv[0], so)); CK(cudaEventRecord(tv[3], s)); CK(cudaEventRecord(tv[2], sc)); }
     const unsigned eb = (unsigned)((n + 63) / 64);
     engine_init_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, d_groups.p, nullptr, d_states.p, nullptr, nullptr, nullptr);
@@ -992,7 +1006,7 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
         if (sg >= ring) CK(cudaStreamWaitEvent(s, ev_chain[sg - ring], 0));  // the chain has consumed this mix buffer
         for (long long r = r0; r < r1; r++) {
             engine_events_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, r, d_events.p, d_vinits.p, d_dampers.p, d_dsched.p, d_pool.p, d_states.p);
-            engine_voice_mix_kernel<<<(unsigned)n, OWG_ENGINE_TILE, 0, s>>>(d_eng.p, r, d_pool.p, d_states.p, mixbuf, mix_stride, r0);
+            engine_voice_mix_kernel<<<(unsigned)n, OWG_ENGINE_ITEMS, 0, s>>>(d_eng.p, r, d_pool.p, d_states.p, mixbuf, mix_stride, r0);
             engine_post_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, r, d_pool.p, d_states.p, mixbuf, mix_stride, r0, silent_thr);
             launches += 3;
         }
