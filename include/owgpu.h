@@ -86,7 +86,8 @@ typedef struct owg_engine_job {
 
 /* ---- options -------------------------------------------------------------------------------- */
 #define OWG_OUT_HOST 0   /* `out` is host memory (pinned recommended); D2H copy inside the call */
-#define OWG_OUT_DEVICE 1 /* `out` is device memory on `device`; no copy */
+#define OWG_OUT_DEVICE 1 /* `out` is device memory on `device`; no copy.  The library works on opts->stream (or its own
+                          * non-blocking stream): any work the caller queued on OTHER streams for that buffer must be complete. */
 
 #define OWG_PRECISION_F64_EXACT 0 /* IEEE f64, no FMA contraction: op-for-op the reference's arithmetic */
 

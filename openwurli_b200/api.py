@@ -92,6 +92,10 @@ def _out_ptr(out):
         return out.ctypes.data, out.shape[1], OWG_OUT_HOST
     import torch
     assert isinstance(out, torch.Tensor) and out.dtype == torch.float64 and out.dim() == 2 and out.is_contiguous()
+    if out.is_cuda:
+        # The library launches on its own (non-blocking) stream unless one is passed in: work the caller has queued on torch's
+        # current stream for this buffer (fills, copies) must have landed before our kernels touch it.
+        torch.cuda.current_stream(out.device).synchronize()
     return out.data_ptr(), out.shape[1], (OWG_OUT_DEVICE if out.is_cuda else OWG_OUT_HOST)
 
 
@@ -261,6 +265,8 @@ def render_engines(jobs, out=None, device=-1, preamp_model=MELANGE12):
     else:
         import torch
         assert out.dtype == torch.float32 and out.is_contiguous()
+        if out.is_cuda:
+            torch.cuda.current_stream(out.device).synchronize()
         ptr, st, loc = out.data_ptr(), out.shape[1], (OWG_OUT_DEVICE if out.is_cuda else OWG_OUT_HOST)
     arr = (_abi.EngineJob * len(jobs))(*jobs)
     o = _opts(device, loc, preamp_model=preamp_model)

@@ -481,3 +481,55 @@ def test_legacy_engine_streams():
     mel = ow.render_engines(jobs[:1])
     n0 = mel.shape[1]
     assert np.abs(mel[0].astype(np.float64) - got[0, :n0].astype(np.float64)).max() > 1e-5
+
+
+# ---- BASELINE.json's full sizes: parity on a sample of rows + size-independent properties ---------------------------------------
+def test_full_c3_grid_properties():
+    """Config 3 at its full size (64 keys x 127 velocities x 3 s, tremolo depth 0.5, MLP on) rendered on the device:
+    rows sampled across the grid match the oracle, a second execution is bit-identical (determinism), the sampled rows are
+    bit-identical to the same jobs rendered as a small batch (batch-composition invariance: different lanes per warp, different
+    kernel variant), every sample is finite and the loudness ordering over velocity holds for every key."""
+    import torch
+    jobs = [ow.bench_job(note=33 + k, velocity=v, duration=3.0, tremolo_depth=0.5) for k in range(64) for v in range(1, 128)]
+    pl = ow.Plan.bench(jobs)
+    out = torch.empty((len(jobs), pl.max_samples), dtype=torch.float64, device="cuda")
+    pl.execute(out)
+    cs1 = out.sum(dim=1).cpu().numpy()
+    idx = [0, 126, 127 * 13 + 63, 127 * 31 + 100, 127 * 47 + 5, 127 * 63 + 126]
+    rows = out[idx].cpu().numpy()
+    assert bool(torch.isfinite(out).all().item())
+    rms = out[:, 4410:].pow(2).mean(dim=1).sqrt().cpu().numpy().reshape(64, 127)
+    out.zero_()
+    pl.execute(out)
+    assert np.array_equal(out.sum(dim=1).cpu().numpy(), cs1)   # run-to-run determinism (a checksum per row)
+    assert np.array_equal(out[idx].cpu().numpy(), rows)
+    pl.close()
+    del out
+    ref = O.render_bench([to_oracle_b(jobs[i]) for i in idx], threads=6)
+    for k, i in enumerate(idx):
+        assert_parity(rows[k], ref[k], f"full C3 grid row {i}")
+    small = ow.render_bench([jobs[i] for i in idx])
+    assert np.array_equal(small, rows)
+    # harder key strikes are louder for every key (velocity 1 < 64 < 127)
+    assert np.all(rms[:, 63] > rms[:, 0]) and np.all(rms[:, 126] > rms[:, 63]), (rms[:, 0].min(), rms[:, 63].min(), rms[:, 126].min())
+
+
+def test_full_c2_preamp_batch_properties():
+    """Config 2 at its full size (4096 instances, 2 s at 48 kHz base rate, 2x oversampled, tremolo depth 0.5): sampled rows match the
+    oracle; rows with identical input are bit-identical wherever they sit in the batch; a silent row stays silent."""
+    import torch
+    fs, n = 48000.0, 96000
+    x = _c2_inputs(4096, n, fs)
+    x[1000] = 0.0
+    x[3000] = x[7]
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    ow.preamp_batch(xd, fs, oversample=True, tremolo_depth=0.5, out=yd)
+    y = yd.cpu().numpy()
+    assert np.all(np.isfinite(y))
+    assert np.abs(y[1000]).max() < 1e-9
+    assert np.array_equal(y[3000], y[7])
+    idx = [7, 300, 4095]
+    ref = _oracle_preamp_batch(x[idx], fs, True, 0.5, 0.0)
+    for k, i in enumerate(idx):
+        assert_parity(y[i], ref[k], f"full C2 row {i}")
