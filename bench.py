@@ -210,7 +210,8 @@ def main():
     else:
         torch.cuda.set_device(0)
     dev = torch.cuda.current_device()
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)   # the plan launches on this stream and the timing events are recorded on it
+    stream = tstream.cuda_stream
 
     def barrier():
         if dist is not None:
@@ -228,13 +229,13 @@ def main():
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(tstream)
         main_ms, launches = 0.0, 0
         for _ in range(steps):
             plan.execute(out)
             main_ms += plan.last_timing()[0]
             launches += plan.kernel_launches
-        e1.record()
+        e1.record(tstream)
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
@@ -334,7 +335,7 @@ def main():
                 plan.execute(outb)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); plan.execute(outb); e1.record(); torch.cuda.synchronize()
+                e0.record(tstream); plan.execute(outb); e1.record(tstream); torch.cuda.synchronize()
                 msb = e0.elapsed_time(e1)
                 line["variants"][f"throughput regime: {len(big)} renders x 0.5 s (4 grids), tremolo_depth {args.tremolo_depth:g}"] = {
                     "value": len(big) * 0.5 / (msb * 1e-3), "unit": UNIT, "ms_per_step": msb}
