@@ -388,7 +388,10 @@ def _legacy_parity(jobs, what):
         n = O.n_samples(j.v.duration_s, j.v.sample_rate)
         if n:
             loud = np.abs(ref[i, :n]).max() >= 0.03
-            assert_parity(got[i, :n], ref[i, :n], f"legacy {what}[{i}] midi={j.v.midi}", rel_l2=LEGACY_REL_L2 if loud else np.inf)
+            # at the 1 kOhm floor the preamp gain (and with it the dead-zone noise floor) is at its maximum: measured 5.5e-7
+            floor_r = j.tremolo_depth <= 0 and j.r_ldr < 5000.0
+            assert_parity(got[i, :n], ref[i, :n], f"legacy {what}[{i}] midi={j.v.midi}", max_abs=3e-6 if floor_r else MAX_ABS,
+                          rel_l2=LEGACY_REL_L2 if loud else np.inf)
     # Newton update counts per preamp step (0..6) of the main instances: same totals, and the same distribution up to the dead-zone
     # flips between 0 and 1 updates
     a, b = np.array(list(dg.nr_iter_hist)[:8], dtype=np.int64), np.array(list(dc.nr_iter_hist)[:8], dtype=np.int64)
