@@ -160,6 +160,22 @@ int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_
 int owg_render_bench_metrics(const owg_bench_job* jobs, int64_t n, double window_start_s, double window_end_s, double* metrics,
                              const owg_opts* opts);
 
+/* `preamp-bench calibrate` (tools/preamp-bench/src/main.rs:1069-1300): every column of its CSV, reduced on the device at the five tap
+ * points T1 reed, T2 pickup, T3 voice (x output_scale), T4 preamp, T5 final, over [window_start_s, window_end_s).  `cfg` is the
+ * CalibrationConfig the CLI builds (tables.rs:256-277; NULL = CalibrationConfig::default()); the jobs are built the way run_calibrate
+ * builds its reed (OWG_VOICE_NO_ONSET, mlp_enabled 0, attack_noise 0, r_ldr 1e6, tremolo_depth 0).  rows is host memory
+ * [n][OWG_CALIBRATE_COLUMNS]:
+ *   0 ds_at_c4  1 ds_actual  2 y_peak  3 t2_peak_db  4 t2_rms_db  5 t2_h2_h1_db  6 t3_peak_db  7 t3_rms_db  8 t4_peak_db  9 t4_rms_db
+ *   10 t4_h2_h1_db  11 t5_peak_db  12 t5_rms_db  13 t5_h2_h1_db  14 proxy_db  15 trim_db  16 proxy_error_db  17 tanh_compression_db */
+typedef struct owg_calib_cfg {
+    double ds_at_c4, ds_exponent, ds_clamp_lo, ds_clamp_hi, target_db, voicing_slope;
+    int32_t zero_trim, _pad0;
+} owg_calib_cfg;
+void owg_default_calib_cfg(owg_calib_cfg* cfg); /* CalibrationConfig::default(): 0.85, 0.75, (0.02, 0.95), -35, -0.04, false */
+#define OWG_CALIBRATE_COLUMNS 18
+int owg_render_calibrate(const owg_bench_job* jobs, int64_t n, const owg_calib_cfg* cfg, double window_start_s, double window_end_s,
+                         double* rows, const owg_opts* opts);
+
 /* ---- planned renders: note-on parameterisation done once, inputs resident in HBM ---------- */
 typedef struct owg_plan owg_plan;
 

@@ -233,6 +233,40 @@ def calibrate_job(note, velocity, volume=0.60, speaker=1.0, tremolo_depth=0.0):
                      no_mlp=True, no_attack_noise=True, no_onset=True)
 
 
+CALIBRATE_COLUMNS = ("ds_at_c4", "ds_actual", "y_peak", "t2_peak_db", "t2_rms_db", "t2_h2_h1_db", "t3_peak_db", "t3_rms_db", "t4_peak_db",
+                     "t4_rms_db", "t4_h2_h1_db", "t5_peak_db", "t5_rms_db", "t5_h2_h1_db", "proxy_db", "trim_db", "proxy_error_db",
+                     "tanh_compression_db")
+
+
+def calib_cfg(ds_at_c4=None, ds_clamp_max=None, zero_trim=False, **kw):
+    """CalibrationConfig (tables.rs:256-277); defaults = CalibrationConfig::default().  `preamp-bench calibrate` itself defaults to
+    ds_at_c4=0.75, ds_clamp_max=0.82 (main.rs:1072-1078)."""
+    c = _abi.CalibCfg()
+    lib().owg_default_calib_cfg(C.byref(c))
+    if ds_at_c4 is not None:
+        c.ds_at_c4 = float(ds_at_c4)
+    if ds_clamp_max is not None:
+        c.ds_clamp_hi = float(ds_clamp_max)
+    c.zero_trim = 1 if zero_trim else 0
+    for k, v in kw.items():
+        setattr(c, k, float(v))
+    return c
+
+
+def render_calibrate(notes, velocities, cfg=None, volume=0.40, speaker=1.0, window=(0.100, 0.400), device=-1, preamp_model=MELANGE12):
+    """`preamp-bench calibrate` (run_calibrate, main.rs:1127-1260) for notes x velocities: all five taps reduced on the device.
+    Returns [len(notes) * len(velocities), 18] float64 in CALIBRATE_COLUMNS order (note-major like the CSV)."""
+    jobs = [calibrate_job(n, v, volume=volume, speaker=speaker) for n in notes for v in velocities]
+    out = np.zeros((len(jobs), len(CALIBRATE_COLUMNS)), dtype=np.float64)
+    if not jobs:
+        return out
+    arr = (BenchJob * len(jobs))(*jobs)
+    o = _opts(device, OWG_OUT_HOST, preamp_model=preamp_model)
+    check(lib().owg_render_calibrate(arr, len(jobs), C.byref(cfg) if cfg is not None else None, float(window[0]), float(window[1]),
+                                     out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(o)))
+    return out
+
+
 NOTE_ON, NOTE_OFF, SUSTAIN = 0, 1, 2
 
 

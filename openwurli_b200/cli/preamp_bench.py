@@ -123,20 +123,53 @@ def cmd_render(args):
     return 0
 
 
-def cmd_calibrate(args):
-    """T5 (final output) columns of `calibrate` for --notes a,b,c --velocities x,y,z (main.rs:1060-1105 flag names)."""
-    notes = [int(s) for s in parse_flag_str(args, "--notes", "36,48,60,72,84").split(",")]
-    velocities = [int(s) for s in parse_flag_str(args, "--velocities", "40,80,127").split(",")]
-    volume = parse_flag(args, "--volume", 0.60)
-    speaker_char = parse_flag(args, "--speaker", 1.0)
-    jobs = [api.calibrate_job(n, v, volume=volume, speaker=speaker_char) for n in notes for v in velocities]
-    m = api.render_bench_metrics(jobs)
-    print("note,velocity,t5_peak_db,t5_rms_db,t5_h2_h1_db")
+def midi_note_name(note):  # main.rs:666-672 (sharps with '#', unlike reed-renderer's file names)
+    names = ["C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"]
+    return f"{names[note % 12]}{note // 12 - 1}"
+
+
+def _csv_u8_list(args, flag, default):  # parse_csv_list::<u8>: unparsable / out-of-range items are dropped
+    out = []
+    for t in parse_flag_str(args, flag, default).split(","):
+        try:
+            v = int(t.strip())
+        except ValueError:
+            continue
+        if 0 <= v <= 255:
+            out.append(v)
+    return out
+
+
+CALIBRATE_HEADER = ("midi,note_name,velocity,ds_at_c4,ds_actual,y_peak,t2_peak_db,t2_rms_db,t2_h2_h1_db,t3_peak_db,t3_rms_db,"
+                    "t4_peak_db,t4_rms_db,t4_h2_h1_db,t5_peak_db,t5_rms_db,t5_h2_h1_db,proxy_db,trim_db,proxy_error_db,tanh_compression_db")
+
+
+def calibrate_csv_lines(notes, velocities, rows):
+    """write_calibrate_csv (main.rs:1262-1310): 4 decimals for the three scale columns, 2 for the dB columns."""
+    lines = [CALIBRATE_HEADER]
     k = 0
     for n in notes:
         for v in velocities:
-            print(f"{n},{v},{m[k, 0]:.3f},{m[k, 1]:.3f},{m[k, 2]:.3f}")
+            r = rows[k]
             k += 1
+            lines.append(f"{n},{midi_note_name(n)},{v}," + ",".join(f"{x:.4f}" for x in r[:3]) + "," + ",".join(f"{x:.2f}" for x in r[3:]))
+    return lines
+
+
+def cmd_calibrate(args):
+    """`preamp-bench calibrate` (main.rs:1069-1104): same flags and CSV; all rows in one device batch."""
+    notes = _csv_u8_list(args, "--notes", "36,40,44,48,52,56,60,64,68,72,76,80,84")
+    velocities = _csv_u8_list(args, "--velocities", "40,80,127")
+    cfg = api.calib_cfg(ds_at_c4=parse_flag(args, "--ds-at-c4", 0.75), ds_clamp_max=parse_flag(args, "--ds-clamp-max", 0.82),
+                        zero_trim=has_flag(args, "--zero-trim"))
+    volume = parse_flag(args, "--volume", 0.40)
+    speaker_char = parse_flag(args, "--speaker", 1.0)
+    output_path = parse_flag_str(args, "--output", os.path.join(tempfile.gettempdir(), "calibrate.csv"))
+    model = api.LEGACY8 if parse_flag_str(args, "--preamp-model", "melange12") == "legacy8" else api.MELANGE12
+    rows = api.render_calibrate(notes, velocities, cfg, volume=volume, speaker=speaker_char, preamp_model=model)
+    with open(output_path, "w") as f:
+        f.write("\n".join(calibrate_csv_lines(notes, velocities, rows)) + "\n")
+    sys.stderr.write(f"Calibrate: {len(notes)} notes × {len(velocities)} velocities = {len(rows)} rows → {output_path}\n")
     return 0
 
 
@@ -193,7 +226,7 @@ USAGE = """Usage: preamp_bench <render|calibrate|render-midi> [flags]
   render     --note N --velocity V --duration S --ldr OHM --volume X --speaker C --tremolo-depth D --sample-rate HZ
              --no-poweramp --no-rail-sag --no-preamp --no-attack-noise --no-mlp --normalize --displacement-scale DS --output FILE
              --preamp-model melange12|legacy8   (compile-time cargo feature in the reference)
-  calibrate  --notes a,b,c --velocities x,y,z --volume X --speaker C
+  calibrate  --notes a,b,c --velocities x,y,z --ds-at-c4 D --ds-clamp-max M --volume X --speaker C --zero-trim --output FILE
 """
 
 

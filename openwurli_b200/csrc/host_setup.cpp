@@ -606,6 +606,30 @@ void make_legacy_group(double fs, double r_static, double* rec) {
     rec[OWG_LG_GSTATIC] = g_static;
 }
 
+double register_trim_db(int midi) { return key_row(midi).trim_db; }
+
+double calib_displacement_scale(int midi, const owg_calib_cfg& cfg) {  // tables.rs:283-288
+    const double ds = cfg.ds_at_c4 * std::pow(compliance(midi) / compliance(60), cfg.ds_exponent);
+    return clampd(ds, cfg.ds_clamp_lo, cfg.ds_clamp_hi);
+}
+
+double calib_output_scale(int midi, double velocity, const owg_calib_cfg& cfg) {  // tables.rs:578-616
+    const KeyRow& k = key_row(midi);
+    const double ds = calib_displacement_scale(midi, cfg);
+    const double sv = vel_scurve(velocity);
+    const double vs = std::pow(sv, k.vel_exp);
+    const double vs_c4 = std::pow(sv, g_vel_exp_c4);
+    const double eds = std::fmax(ds * vs, 1e-6);
+    const double eds_ref = std::fmax(cfg.ds_at_c4 * vs_c4, 1e-6);
+    const double rms = rms_proxy(eds, k.f_nominal, kPickupFc);
+    const double rms_ref = rms_proxy(eds_ref, g_f_c4, kPickupFc);
+    const double flat_db = -20.0 * std::log10(rms / rms_ref);
+    const double voicing_db = cfg.voicing_slope * std::fmax((double)midi - 60.0, 0.0);
+    const double trim = cfg.zero_trim ? 0.0 : k.trim_db;
+    const double eff_trim = trim * std::pow(velocity, 1.3);
+    return std::pow(10.0, (cfg.target_db + flat_db + voicing_db + eff_trim) / 20.0);
+}
+
 double note_frequency(int midi) { return freq_of_key(midi); }
 
 double silent_threshold() { return std::pow(10.0, -80.0 / 20.0); }

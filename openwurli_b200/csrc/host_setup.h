@@ -21,6 +21,11 @@ int make_speaker_schedule(double sample_rate, double character_target, int64_t n
 // constants and the DC operating point at 1 MOhm for `preamp_sr`; rec = OWG_LG_STRIDE doubles (owg_records.h).
 // `r_static`: the static LDR resistance handed to set_ldr_resistance after reset() (NaN = tremolo group).
 void make_legacy_group(double preamp_sr, double r_static, double* rec);
+// CalibrationConfig-parametrised table functions (tables.rs:256-288, 578-616, 465-503) for `preamp-bench calibrate`, whose CLI
+// defaults (ds_at_c4 0.75, upper clamp 0.82) differ from CalibrationConfig::default().
+double calib_displacement_scale(int midi, const owg_calib_cfg& cfg);
+double calib_output_scale(int midi, double velocity, const owg_calib_cfg& cfg);
+double register_trim_db(int midi);
 // 10^(-80/20): the is_silent threshold (reed.rs:310), through glibc pow like the reference.
 double silent_threshold();
 // tables::midi_to_freq (tables.rs:34-36)

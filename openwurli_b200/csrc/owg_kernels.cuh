@@ -14,6 +14,14 @@ struct DevDiag {
     unsigned long long adapter_nan;
 };
 
+// Per-job analysis accumulators over the window (run_calibrate, main.rs:1139-1223); each 6-tuple = peak |x|, sum x^2, re1, im1, re2, im2:
+//   [0..5] T5 final output   [6..11] T4 preamp output   [12] T1 reed peak   [13..18] T2 pickup output   [19..20] T3 voice output (peak, sum x^2)
+#define OWG_METRICS 21
+#define OWG_MET_T4 6
+#define OWG_MET_T1 12
+#define OWG_MET_T2 13
+#define OWG_MET_T3 19
+
 __constant__ double c_noise_fade[16];  // hammer.rs:161-168, filled by the host with glibc cos
 
 // ---- settled preamp state: 176 400 silent samples at 48 kHz / 100 kOhm (melange_adapter.rs:14-20) ----
@@ -202,9 +210,14 @@ __global__ void tremolo_an_kernel(const OwgPreampGroup* groups, int n_groups, do
 
 // ---- chain V: reed + attack noise + pickup + gain (voice.rs:162-179), one thread per voice -----------
 // out row i = out + row[i]*stride; writes n_samples[i] doubles.
-__global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restrict__ inits, int64_t n, double* __restrict__ out, int64_t stride) {
+// TAPS: also reduce the calibrate taps T1 (reed), T2 (pickup), T3 (x output gain) over [w_begin, w_end) into metrics[i][12..20].
+template <bool TAPS>
+__global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restrict__ inits, int64_t n, double* __restrict__ out, int64_t stride,
+                                                   double* __restrict__ metrics, const double* __restrict__ f0s, int64_t w_begin, int64_t w_end) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    double t1_peak = 0.0, t2_peak = 0.0, t2_sq = 0.0, t2_re1 = 0.0, t2_im1 = 0.0, t2_re2 = 0.0, t2_im2 = 0.0, t3_peak = 0.0, t3_sq = 0.0;
+    const double m_f0 = TAPS ? f0s[2 * i] : 0.0, m_sr = TAPS ? f0s[2 * i + 1] : 1.0;
     const OwgVoiceInit* vi = inits + i;
     double s[7], c[7], env[7], drift[7];
     double cos_inc[7], sin_inc[7], phase_inc[7], amp[7], decay[7];
@@ -269,6 +282,7 @@ __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restric
             }
         }
         double x = 0.0 + sum;
+        const double reed_x = x;  // T1: the reed alone
         // hammer.rs:150-179 attack noise (additive)
         if (n_left > 0u) {
             const uint32_t played = vi->noise_remaining - n_left;
@@ -294,7 +308,28 @@ __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restric
         const double omy = 1.0 - yy;
         const double alpha = beta * omy;
         q = (q * (1.0 - alpha) + 2.0 * beta) / (1.0 + alpha);
-        o[t] = ((q * omy - 1.0) * 1.8375) * gain;
+        const double t2 = (q * omy - 1.0) * 1.8375;
+        const double t3 = t2 * gain;
+        o[t] = t3;
+        if (TAPS && (int64_t)t >= w_begin && (int64_t)t < w_end) {
+            const double ii = (double)((int64_t)t - w_begin);
+            t1_peak = fmax(t1_peak, fabs(reed_x));
+            t2_peak = fmax(t2_peak, fabs(t2));
+            t2_sq += t2 * t2;
+            const double ph1 = 2.0 * 3.14159265358979323846 * m_f0 * ii / m_sr;
+            const double ph2 = 2.0 * 3.14159265358979323846 * (2.0 * m_f0) * ii / m_sr;
+            t2_re1 += t2 * cos(ph1); t2_im1 -= t2 * sin(ph1);
+            t2_re2 += t2 * cos(ph2); t2_im2 -= t2 * sin(ph2);
+            t3_peak = fmax(t3_peak, fabs(t3));
+            t3_sq += t3 * t3;
+        }
+    }
+    if (TAPS) {
+        double* mj = metrics + (size_t)i * OWG_METRICS;
+        mj[OWG_MET_T1] = t1_peak;
+        mj[OWG_MET_T2 + 0] = t2_peak; mj[OWG_MET_T2 + 1] = t2_sq; mj[OWG_MET_T2 + 2] = t2_re1; mj[OWG_MET_T2 + 3] = t2_im1;
+        mj[OWG_MET_T2 + 4] = t2_re2; mj[OWG_MET_T2 + 5] = t2_im2;
+        mj[OWG_MET_T3 + 0] = t3_peak; mj[OWG_MET_T3 + 1] = t3_sq;
     }
 }
 
@@ -303,7 +338,6 @@ __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restric
 // solve in lane 31 (melange_adapter.rs:72-81: out = main - shadow).  Processes the voice samples in
 // `out` in place.
 struct WarpEntry { int32_t group, first, count; int32_t _pad; int64_t n_max; };
-#define OWG_METRICS 6  // per job: peak |x|, sum x^2, re1, im1, re2, im2 over the analysis window (run_calibrate, main.rs:1139-1223)
 #define OWG_CARRY 40  // doubles of per-lane state carried between chunk launches (12+3+3+1+1 DK, 12+1 oversampler, 5 speaker)
 
 template <bool TREM, bool DIAG>
@@ -516,7 +550,7 @@ __global__ void __launch_bounds__(64) chain_split_kernel(const WarpEntry* __rest
                                                          double* __restrict__ out, int64_t stride,
                                                          int64_t t_begin, int64_t t_end, double* __restrict__ carry /*[warp][OWG_CARRY][32]*/,
                                                          double* __restrict__ metrics /*[job][OWG_METRICS] or null*/, const double* __restrict__ f0s,
-                                                         int64_t w_begin, int64_t w_end, int swap_roles) {
+                                                         int64_t w_begin, int64_t w_end, int swap_roles, int taps) {
     __shared__ __align__(16) double s_rec[TREM ? 2 * OWG_MAT_STRIDE : OWG_MAT_STRIDE];
     __shared__ double s_an[OWG_AN_SPARSE];
     __shared__ OwgChainInit s_ci[32];
@@ -652,9 +686,11 @@ __global__ void __launch_bounds__(64) chain_split_kernel(const WarpEntry* __rest
         spk.thermal = cw[(k++) * 32]; spk.h1 = cw[(k++) * 32]; spk.h2 = cw[(k++) * 32]; spk.l1 = cw[(k++) * 32]; spk.l2 = cw[(k++) * 32];
     }
     double m_peak = 0.0, m_sq = 0.0, m_re1 = 0.0, m_im1 = 0.0, m_re2 = 0.0, m_im2 = 0.0, m_f0 = 0.0, m_sr = 1.0;
+    double q_peak = 0.0, q_sq = 0.0, q_re1 = 0.0, q_im1 = 0.0, q_re2 = 0.0, q_im2 = 0.0;  // T4 (preamp output), calibrate taps only
     if (metrics && is_main) {
         const double* mj = metrics + (size_t)job * OWG_METRICS;
         m_peak = mj[0]; m_sq = mj[1]; m_re1 = mj[2]; m_im1 = mj[3]; m_re2 = mj[4]; m_im2 = mj[5];
+        if (taps) { q_peak = mj[OWG_MET_T4]; q_sq = mj[OWG_MET_T4 + 1]; q_re1 = mj[OWG_MET_T4 + 2]; q_im1 = mj[OWG_MET_T4 + 3]; q_re2 = mj[OWG_MET_T4 + 4]; q_im2 = mj[OWG_MET_T4 + 5]; }
         m_f0 = f0s[2 * job]; m_sr = f0s[2 * job + 1];
     }
     // produce U[t]: the voice sample through the 2x polyphase upsampler (or straight through at native rate)
@@ -701,8 +737,15 @@ __global__ void __launch_bounds__(64) chain_split_kernel(const WarpEntry* __rest
                     m_sq += y_final * y_final;
                     const double ph1 = 2.0 * 3.14159265358979323846 * m_f0 * ii / m_sr;
                     const double ph2 = 2.0 * 3.14159265358979323846 * (2.0 * m_f0) * ii / m_sr;
-                    m_re1 += y_final * cos(ph1); m_im1 -= y_final * sin(ph1);
-                    m_re2 += y_final * cos(ph2); m_im2 -= y_final * sin(ph2);
+                    const double c1 = cos(ph1), s1 = sin(ph1), c2 = cos(ph2), s2 = sin(ph2);
+                    m_re1 += y_final * c1; m_im1 -= y_final * s1;
+                    m_re2 += y_final * c2; m_im2 -= y_final * s2;
+                    if (taps) {
+                        q_peak = fmax(q_peak, fabs(pre_out));
+                        q_sq += pre_out * pre_out;
+                        q_re1 += pre_out * c1; q_im1 -= pre_out * s1;
+                        q_re2 += pre_out * c2; q_im2 -= pre_out * s2;
+                    }
                 }
             } else o[t] = y_final;
         }
@@ -710,6 +753,7 @@ __global__ void __launch_bounds__(64) chain_split_kernel(const WarpEntry* __rest
     if (metrics && is_main) {
         double* mj = metrics + (size_t)job * OWG_METRICS;
         mj[0] = m_peak; mj[1] = m_sq; mj[2] = m_re1; mj[3] = m_im1; mj[4] = m_re2; mj[5] = m_im2;
+        if (taps) { mj[OWG_MET_T4] = q_peak; mj[OWG_MET_T4 + 1] = q_sq; mj[OWG_MET_T4 + 2] = q_re1; mj[OWG_MET_T4 + 3] = q_im1; mj[OWG_MET_T4 + 4] = q_re2; mj[OWG_MET_T4 + 5] = q_im2; }
     }
     if (save) {
         int k = CARRY_B0;

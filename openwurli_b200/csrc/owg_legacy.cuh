@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(32) chain_legacy_kernel(const WarpEntry* __res
                                                           const int32_t* __restrict__ group_rec_index, int64_t g_stride,
                                                           double* __restrict__ out, int64_t stride, DevDiag* diag,
                                                           int64_t t_begin, int64_t t_end, double* __restrict__ carry /*[warp][OWG_CARRY][32]*/,
-                                                          double* __restrict__ metrics, const double* __restrict__ f0s, int64_t w_begin, int64_t w_end) {
+                                                          double* __restrict__ metrics, const double* __restrict__ f0s, int64_t w_begin, int64_t w_end, int taps) {
     __shared__ double s_m[OWG_LG_STRIDE];
     __shared__ OwgChainInit s_ci[32];
     const int lane = threadIdx.x;
@@ -172,9 +172,11 @@ __global__ void __launch_bounds__(32) chain_legacy_kernel(const WarpEntry* __res
         g_prev = cw[(k++) * 32];
     }
     double m_peak = 0.0, m_sq = 0.0, m_re1 = 0.0, m_im1 = 0.0, m_re2 = 0.0, m_im2 = 0.0, m_f0 = 0.0, m_sr = 1.0;
+    double q_peak = 0.0, q_sq = 0.0, q_re1 = 0.0, q_im1 = 0.0, q_re2 = 0.0, q_im2 = 0.0;  // T4 (preamp output), calibrate taps only
     if (metrics && is_main) {
         const double* mj = metrics + (size_t)job * OWG_METRICS;
         m_peak = mj[0]; m_sq = mj[1]; m_re1 = mj[2]; m_im1 = mj[3]; m_re2 = mj[4]; m_im2 = mj[5];
+        if (taps) { q_peak = mj[OWG_MET_T4]; q_sq = mj[OWG_MET_T4 + 1]; q_re1 = mj[OWG_MET_T4 + 2]; q_im1 = mj[OWG_MET_T4 + 3]; q_re2 = mj[OWG_MET_T4 + 4]; q_im2 = mj[OWG_MET_T4 + 5]; }
         m_f0 = f0s[2 * job]; m_sr = f0s[2 * job + 1];
     }
     const int64_t t_stop = t_end < we.n_max ? t_end : we.n_max;
@@ -236,8 +238,15 @@ __global__ void __launch_bounds__(32) chain_legacy_kernel(const WarpEntry* __res
                     m_sq += y_final * y_final;
                     const double ph1 = 2.0 * 3.14159265358979323846 * m_f0 * ii / m_sr;
                     const double ph2 = 2.0 * 3.14159265358979323846 * (2.0 * m_f0) * ii / m_sr;
-                    m_re1 += y_final * cos(ph1); m_im1 -= y_final * sin(ph1);
-                    m_re2 += y_final * cos(ph2); m_im2 -= y_final * sin(ph2);
+                    const double c1 = cos(ph1), s1 = sin(ph1), c2 = cos(ph2), s2 = sin(ph2);
+                    m_re1 += y_final * c1; m_im1 -= y_final * s1;
+                    m_re2 += y_final * c2; m_im2 -= y_final * s2;
+                    if (taps) {
+                        q_peak = fmax(q_peak, fabs(pre_out));
+                        q_sq += pre_out * pre_out;
+                        q_re1 += pre_out * c1; q_im1 -= pre_out * s1;
+                        q_re2 += pre_out * c2; q_im2 -= pre_out * s2;
+                    }
                 }
             } else o[t] = y_final;
         }
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(32) chain_legacy_kernel(const WarpEntry* __res
     if (metrics && is_main) {
         double* mj = metrics + (size_t)job * OWG_METRICS;
         mj[0] = m_peak; mj[1] = m_sq; mj[2] = m_re1; mj[3] = m_im1; mj[4] = m_re2; mj[5] = m_im2;
+        if (taps) { mj[OWG_MET_T4] = q_peak; mj[OWG_MET_T4 + 1] = q_sq; mj[OWG_MET_T4 + 2] = q_re1; mj[OWG_MET_T4 + 3] = q_im1; mj[OWG_MET_T4 + 4] = q_re2; mj[OWG_MET_T4 + 5] = q_im2; }
     }
     if (cw && t_stop < we.n_max) {
         int k = 0;

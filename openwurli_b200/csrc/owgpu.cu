@@ -113,6 +113,7 @@ struct owg_plan {
     bool collect_diag = false;
     bool legacy = false;             // owg_opts.preamp_model == OWG_PREAMP_LEGACY8
     bool use_split = false;          // chain_split_kernel (decided at plan time from the batch size)
+    bool taps = false;               // calibrate taps T1..T4 in addition to T5 (owg_render_calibrate)
     DevBuf<double> d_legacy_recs;    // [group][OWG_LG_STRIDE]
     int64_t n = 0;
     std::vector<unsigned long long> n_samples;
@@ -380,7 +381,8 @@ int owg_plan_voices(const owg_voice_job* jobs, int64_t n, const owg_opts* opts, 
     return OWG_OK;
 }
 
-int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan) {
+// post_gain: optional per-job override of Voice::post_pickup_gain (calibrate's output_scale under a non-default CalibrationConfig)
+static int plan_bench_impl(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan, const double* post_gain) {
     if (!plan || n < 0 || (n > 0 && !jobs)) return fail(OWG_E_BAD_ARG, "owg_plan_bench: bad argument");
     for (int64_t i = 0; i < n; i++) {
         if (bad_voice_job(jobs[i].v)) return fail(OWG_E_BAD_ARG, "owg_plan_bench: job with invalid sample_rate/duration/velocity");
@@ -409,7 +411,10 @@ int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, o
     build_groups_and_warps(pl, specs, &order);
     int rc = launch_tremolo_ctor(pl);  // the device settles the oscillators while the host parameterises the voices
     std::vector<OwgVoiceInit> vi((size_t)n);
-    for (int64_t i = 0; i < n; i++) owg::make_voice_init(jobs[i].v, &vi[i]);
+    for (int64_t i = 0; i < n; i++) {
+        owg::make_voice_init(jobs[i].v, &vi[i]);
+        if (post_gain) vi[i].post_pickup_gain = post_gain[i];
+    }
     std::vector<OwgChainInit> ci((size_t)n);
     for (int64_t i = 0; i < n; i++) ci[i] = specs[i].ci;
     if (!rc) rc = pl->d_vinit.upload(vi, pl->stream);
@@ -418,6 +423,10 @@ int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, o
     pl->h2d_bytes = g_h2d_bytes;
     *plan = pl;
     return OWG_OK;
+}
+
+int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan) {
+    return plan_bench_impl(jobs, n, opts, plan, nullptr);
 }
 
 int64_t owg_plan_samples(const owg_plan* pl, int64_t i) {
@@ -516,7 +525,10 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     } else {  // chain V for every job
         const int threads = 32;
         const int blocks = (int)((pl->n + threads - 1) / threads);
-        voice_kernel<<<blocks, threads, 0, s>>>(pl->d_vinit.p, pl->n, dout, stride);
+        if (pl->taps && pl->metrics_ptr)
+            voice_kernel<true><<<blocks, threads, 0, s>>>(pl->d_vinit.p, pl->n, dout, stride, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
+        else
+            voice_kernel<false><<<blocks, threads, 0, s>>>(pl->d_vinit.p, pl->n, dout, stride, nullptr, nullptr, 0, 0);
         CK(cudaGetLastError());
         launches++;
     }
@@ -566,12 +578,13 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                 if (pl->legacy)
                     chain_legacy_kernel<false><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->d_legacy_recs.p, nullptr,
                                                                  pl->d_group_rec_index.p, 0, dout, stride, pl->collect_diag ? pl->d_diag.p : nullptr, b0, b1,
-                                                                 overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
+                                                                 overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end,
+                                                                 pl->taps ? 1 : 0);
                 else if (!pl->collect_diag && split_chain)
                     chain_split_kernel<false><<<nb, 64, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                 pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride,
                                                                 b0, b1, overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin,
-                                                                pl->w_end, swap_roles);
+                                                                pl->w_end, swap_roles, pl->taps ? 1 : 0);
                 else if (pl->collect_diag)
                     chain_kernel<false, true><<<nb, 32, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                  pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p,
@@ -609,11 +622,12 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                 if (pl->legacy)
                     chain_legacy_kernel<true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->d_legacy_recs.p, pl->d_pot_seq.p,
                                                                 pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride, pl->collect_diag ? pl->d_diag.p : nullptr,
-                                                                b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
+                                                                b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end, pl->taps ? 1 : 0);
                 else if (!pl->collect_diag && split_chain)
                     chain_split_kernel<true><<<nb, 64, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
-                                                               b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end, swap_roles);
+                                                               b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end, swap_roles,
+                                                               pl->taps ? 1 : 0);
                 else if (pl->collect_diag)
                     chain_kernel<true, true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                 pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
@@ -737,6 +751,94 @@ int owg_render_bench_metrics(const owg_bench_job* jobs, int64_t n, double window
             m[1] = mean_sq > 0.0 ? 10.0 * std::log10(mean_sq) : -120.0;
             m[2] = h1 > 1e-15 ? 20.0 * std::log10(h2 / h1) : -120.0;
             m[3] = peak; m[4] = mean_sq; m[5] = h1; m[6] = h2;
+        }
+    }
+    return OWG_OK;
+}
+
+void owg_default_calib_cfg(owg_calib_cfg* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->ds_at_c4 = 0.85; c->ds_exponent = 0.75; c->ds_clamp_lo = 0.02; c->ds_clamp_hi = 0.95; c->target_db = -35.0; c->voicing_slope = -0.04;
+    c->zero_trim = 0;
+}
+
+int owg_render_calibrate(const owg_bench_job* jobs, int64_t n, const owg_calib_cfg* cfg_in, double window_start_s, double window_end_s,
+                         double* rows, const owg_opts* opts) {
+    if (n < 0 || (n > 0 && (!jobs || !rows)) || !(window_end_s > window_start_s) || !(window_start_s >= 0.0))
+        return fail(OWG_E_BAD_ARG, "owg_render_calibrate: bad argument");
+    if (n == 0) return OWG_OK;
+    owg_calib_cfg cfg;
+    if (cfg_in) cfg = *cfg_in; else owg_default_calib_cfg(&cfg);
+    const double sr = jobs[0].v.sample_rate;
+    if (!(sr > 0.0) || !std::isfinite(sr)) return fail(OWG_E_BAD_ARG, "owg_render_calibrate: invalid sample_rate");
+    const int64_t w0 = (int64_t)(window_start_s * sr), w1 = (int64_t)(window_end_s * sr);
+    for (int64_t i = 0; i < n; i++) {
+        if (jobs[i].v.sample_rate != sr) return fail(OWG_E_BAD_ARG, "owg_render_calibrate: all jobs must share one sample_rate");
+        if (!(jobs[i].v.duration_s * sr >= (double)w1)) return fail(OWG_E_BAD_ARG, "owg_render_calibrate: analysis window exceeds a job's duration");
+    }
+    owg_opts o;
+    if (opts) o = *opts; else owg_default_opts(&o);
+    o.out_location = OWG_OUT_DEVICE;
+    o.collect_diag = 0;
+    const int64_t BATCH = 444 * 31;  // one wave of the warp-specialised chain kernel (the taps live in its I/O warp)
+    DevBuf<double> scratch, d_metrics;
+    std::vector<double> raw;
+    const double nwin = (double)(w1 - w0);
+    auto db20 = [](double v) { return v > 1e-15 ? 20.0 * std::log10(v) : -120.0; };                    // to_dbfs, main.rs:2241-2247
+    auto rms_db = [&](double sum_sq) { const double m = sum_sq / nwin; return m > 0.0 ? 10.0 * std::log10(m) : -120.0; };
+    auto h2h1 = [&](const double* r) {  // h2_h1_ratio_db over dft_magnitude, main.rs:893-903, 928-936
+        const double h1 = 2.0 * std::sqrt((r[2] / nwin) * (r[2] / nwin) + (r[3] / nwin) * (r[3] / nwin));
+        const double h2 = 2.0 * std::sqrt((r[4] / nwin) * (r[4] / nwin) + (r[5] / nwin) * (r[5] / nwin));
+        return h1 > 1e-15 ? 20.0 * std::log10(h2 / h1) : -120.0;
+    };
+    for (int64_t b0 = 0; b0 < n; b0 += BATCH) {
+        const int64_t nb = std::min<int64_t>(BATCH, n - b0);
+        // run_calibrate builds pickup and output gain from ITS CalibrationConfig (main.rs:1146, 1191): per-job overrides
+        std::vector<owg_bench_job> jb(jobs + b0, jobs + b0 + nb);
+        std::vector<double> gain((size_t)nb), f0s((size_t)nb * 2);
+        for (int64_t i = 0; i < nb; i++) {
+            jb[i].v.ds_override = owg::calib_displacement_scale(jb[i].v.midi, cfg);
+            gain[i] = owg::calib_output_scale(jb[i].v.midi, jb[i].v.velocity, cfg);
+            f0s[2 * i] = owg::note_frequency(jb[i].v.midi);
+            f0s[2 * i + 1] = sr;
+        }
+        owg_plan* pl = nullptr;
+        if (int rc = plan_bench_impl(jb.data(), nb, &o, &pl, gain.data())) return rc;
+        int rc = pl->d_f0s.upload(f0s, pl->stream);
+        const int64_t stride = (int64_t)pl->max_samples;
+        if (!rc) rc = scratch.alloc((size_t)nb * (size_t)stride);
+        if (!rc) rc = d_metrics.alloc((size_t)nb * OWG_METRICS);
+        if (!rc && cudaMemsetAsync(d_metrics.p, 0, (size_t)nb * OWG_METRICS * sizeof(double), pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "memset failed");
+        if (!rc && !(pl->use_split || pl->legacy)) rc = fail(OWG_E_UNSUPPORTED, "owg_render_calibrate: taps need the warp-specialised or the legacy chain kernel");
+        if (!rc) {
+            pl->metrics_ptr = d_metrics.p;
+            pl->taps = true;
+            pl->w_begin = w0;
+            pl->w_end = w1;
+            rc = owg_plan_execute(pl, scratch.p, stride, OWG_OUT_DEVICE);
+        }
+        if (!rc) {
+            raw.resize((size_t)nb * OWG_METRICS);
+            if (cudaMemcpy(raw.data(), d_metrics.p, raw.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(OWG_E_CUDA, "metrics copy failed");
+        }
+        owg_plan_destroy(pl);
+        if (rc) return rc;
+        for (int64_t i = 0; i < nb; i++) {
+            const double* r = &raw[(size_t)i * OWG_METRICS];
+            double* m = rows + (size_t)(b0 + i) * OWG_CALIBRATE_COLUMNS;
+            const int midi = jb[i].v.midi;
+            m[0] = cfg.ds_at_c4;
+            m[1] = jb[i].v.ds_override;
+            m[2] = r[OWG_MET_T1] * m[1];                                   // y_peak = reed_peak * ds_actual
+            m[3] = db20(r[OWG_MET_T2]); m[4] = rms_db(r[OWG_MET_T2 + 1]); m[5] = h2h1(r + OWG_MET_T2);
+            m[6] = db20(r[OWG_MET_T3]); m[7] = rms_db(r[OWG_MET_T3 + 1]);
+            m[8] = db20(r[OWG_MET_T4]); m[9] = rms_db(r[OWG_MET_T4 + 1]); m[10] = h2h1(r + OWG_MET_T4);
+            m[11] = db20(r[0]); m[12] = rms_db(r[1]); m[13] = h2h1(r);
+            m[14] = 20.0 * std::log10(gain[i]);                            // proxy
+            m[15] = cfg.zero_trim ? 0.0 : owg::register_trim_db(midi);
+            m[16] = m[7] - cfg.target_db;                                  // proxy_error = t3_rms - target
+            m[17] = m[8] - m[11];                                          // tanh_compression = t4_pk - t5_pk
         }
     }
     return OWG_OK;

@@ -262,4 +262,94 @@ static inline void preamp_batch_one(const double* in, size_t n, double fs_base, 
     delete trem;
 }
 
+// ---- `preamp-bench calibrate` (main.rs:1069-1260): one CalibrateRow, restated literally (own reed, own pickup, T1..T5) ----------
+struct CalibrateRow { double v[18]; };
+static inline double dft_magnitude(const double* x, size_t n, double freq, double sr) {  // main.rs:893-903
+    double re = 0.0, im = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        const double phase = 2.0 * PI * freq * (double)i / sr;
+        re += x[i] * std::cos(phase);
+        im -= x[i] * std::sin(phase);
+    }
+    const double nn = (double)n;
+    return 2.0 * std::sqrt((re / nn) * (re / nn) + (im / nn) * (im / nn));
+}
+static inline double peak_abs(const double* x, size_t n) { double p = 0.0; for (size_t i = 0; i < n; i++) p = rmax(p, std::fabs(x[i])); return p; }
+static inline double to_dbfs(double v) { return v > 1e-15 ? 20.0 * std::log10(v) : -120.0; }  // main.rs:2241-2247
+static inline double rms_db(const double* x, size_t n) {
+    double s = 0.0;
+    for (size_t i = 0; i < n; i++) s += x[i] * x[i];
+    const double m = s / (double)n;
+    return m > 0.0 ? 10.0 * std::log10(m) : -120.0;
+}
+static inline double h2_h1_ratio_db(const double* x, size_t n, double f0, double sr) {
+    const double h1 = dft_magnitude(x, n, f0, sr), h2 = dft_magnitude(x, n, 2.0 * f0, sr);
+    return h1 > 1e-15 ? 20.0 * std::log10(h2 / h1) : -120.0;
+}
+static inline CalibrateRow calibrate_row(uint8_t note, uint8_t vel_byte, const CalibrationConfig& cfg, double volume, double speaker_char,
+                                         int preamp_model) {
+    const double BASE_SR = 44100.0, duration = 0.5;
+    const size_t measure_start = (size_t)f64_as_u64(0.100 * BASE_SR), measure_end = (size_t)f64_as_u64(0.400 * BASE_SR);
+    const NoteParams params = note_params(note);
+    const double freq = params.fundamental_hz;
+    const double ds_actual = pickup_displacement_scale_with_config(note, cfg);
+    const double velocity = (double)vel_byte / 127.0;
+    // T1: raw reed (onset_time 0, no MLP, no attack noise)
+    const double detuned = params.fundamental_hz * freq_detune(note);
+    double dwell[NUM_MODES], amp_offsets[NUM_MODES], amplitudes[NUM_MODES];
+    dwell_attenuation(velocity, detuned, params.mode_ratios, dwell);
+    mode_amplitude_offsets(note, amp_offsets);
+    const double vel_scale = std::pow(velocity_scurve(velocity), velocity_exponent(note));
+    for (int i = 0; i < NUM_MODES; i++) amplitudes[i] = params.mode_amplitudes[i] * dwell[i] * amp_offsets[i] * vel_scale;
+    ModalReed reed;
+    reed.init(detuned, params.mode_ratios, amplitudes, params.mode_decay_rates, 0.0, velocity, BASE_SR, (uint32_t)note * 2654435761u);
+    const size_t n = (size_t)f64_as_u64(duration * BASE_SR);
+    std::vector<double> reed_buf(n, 0.0);
+    reed.render(reed_buf.data(), n);
+    const size_t wn = measure_end - measure_start;
+    const double reed_peak = peak_abs(reed_buf.data() + measure_start, wn);
+    // T2: pickup
+    Pickup pickup;
+    pickup.init(BASE_SR, ds_actual);
+    std::vector<double> t2 = reed_buf;
+    pickup.process(t2.data(), n);
+    // T3: output scale
+    const double out_scale = output_scale_with_config(note, velocity, cfg);
+    std::vector<double> t3(n);
+    for (size_t i = 0; i < n; i++) t3[i] = t2[i] * out_scale;
+    // T4: preamp, 2x oversampled, R_ldr = 1 MOhm on a fresh preamp (no reset)
+    AnyPreamp preamp(preamp_model, BASE_SR * 2.0);
+    preamp.set_ldr_resistance(1000000.0);
+    std::vector<double> t4(n);
+    {
+        Oversampler os;
+        for (size_t i = 0; i < n; i++) {
+            double u0, u1;
+            os.up1(t3[i], u0, u1);
+            const double p0 = preamp.process_sample(u0);
+            const double p1 = preamp.process_sample(u1);
+            t4[i] = os.down1(p0, p1);
+        }
+    }
+    // T5: volume^2 -> power amp -> speaker
+    PowerAmp pa;
+    Speaker spk(BASE_SR);
+    spk.set_character(speaker_char);
+    std::vector<double> t5(n);
+    for (size_t i = 0; i < n; i++) t5[i] = spk.process(pa.process(t4[i] * volume * volume)) * POST_SPEAKER_GAIN;
+    CalibrateRow r;
+    const double* w2 = t2.data() + measure_start; const double* w3 = t3.data() + measure_start;
+    const double* w4 = t4.data() + measure_start; const double* w5 = t5.data() + measure_start;
+    r.v[0] = cfg.ds_at_c4; r.v[1] = ds_actual; r.v[2] = reed_peak * ds_actual;
+    r.v[3] = to_dbfs(peak_abs(w2, wn)); r.v[4] = rms_db(w2, wn); r.v[5] = h2_h1_ratio_db(w2, wn, freq, BASE_SR);
+    r.v[6] = to_dbfs(peak_abs(w3, wn)); r.v[7] = rms_db(w3, wn);
+    r.v[8] = to_dbfs(peak_abs(w4, wn)); r.v[9] = rms_db(w4, wn); r.v[10] = h2_h1_ratio_db(w4, wn, freq, BASE_SR);
+    r.v[11] = to_dbfs(peak_abs(w5, wn)); r.v[12] = rms_db(w5, wn); r.v[13] = h2_h1_ratio_db(w5, wn, freq, BASE_SR);
+    r.v[14] = 20.0 * std::log10(out_scale);
+    r.v[15] = cfg.zero_trim ? 0.0 : register_trim_db(note);
+    r.v[16] = r.v[7] - cfg.target_db;
+    r.v[17] = r.v[8] - r.v[11];
+    return r;
+}
+
 }  // namespace ow

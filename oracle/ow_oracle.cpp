@@ -171,6 +171,21 @@ int owo_legacy_idle_pump(double sample_rate, double depth, int64_t n, double* y,
     return OWG_OK;
 }
 
+// `preamp-bench calibrate`: rows[n_notes * n_vels][18] (include/owgpu.h owg_render_calibrate columns), cfg6 = ds_at_c4, ds_exponent,
+// ds_clamp_lo, ds_clamp_hi, target_db, voicing_slope
+int owo_calibrate_rows(const uint8_t* notes, int n_notes, const uint8_t* vels, int n_vels, const double* cfg6, int zero_trim, double volume,
+                       double speaker, int preamp_model, double* rows, int threads) {
+    CalibrationConfig cfg;
+    cfg.ds_at_c4 = cfg6[0]; cfg.ds_exponent = cfg6[1]; cfg.ds_clamp_lo = cfg6[2]; cfg.ds_clamp_hi = cfg6[3]; cfg.target_db = cfg6[4];
+    cfg.voicing_slope = cfg6[5]; cfg.zero_trim = zero_trim != 0;
+    if (preamp_model == 0) pre::settled_state();
+    parallel_for((int64_t)n_notes * n_vels, threads, [&](int64_t k) {
+        const CalibrateRow r = calibrate_row(notes[k / n_vels], vels[k % n_vels], cfg, volume, speaker, preamp_model);
+        std::memcpy(rows + k * 18, r.v, sizeof(r.v));
+    });
+    return OWG_OK;
+}
+
 int owo_last_diag(owg_diag* out) { if (!out) return OWG_E_BAD_ARG; *out = g_diag; return OWG_OK; }
 
 // ---- preamp-only batch (C2) ------------------------------------------------------------------

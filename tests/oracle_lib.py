@@ -110,6 +110,8 @@ def lib():
         L.owo_render_bench_model.argtypes = [C.POINTER(BenchJob), C.c_int64, dp, C.c_int64, C.c_int, C.c_int]
         L.owo_preamp_batch_model.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_double,
                                              C.c_double, dp, C.c_int64, C.c_int, C.c_int]
+        L.owo_calibrate_rows.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int, dp, C.c_int, C.c_double, C.c_double,
+                                         C.c_int, dp, C.c_int]
         L.owo_legacy_dc.argtypes = [C.c_double, dp]
         L.owo_legacy_group.argtypes = [C.c_double, C.c_double, dp]
         L.owo_legacy_run.argtypes = [C.c_double, C.c_double, C.c_int, dp, C.c_int64, dp, dp]
@@ -151,6 +153,17 @@ def render_bench(jobs, threads=1, preamp_model=MELANGE12):
     arr = (BenchJob * n)(*jobs)
     assert lib().owo_render_bench_model(arr, n, dptr(out), stride, threads, preamp_model) == 0
     return out
+
+
+def calibrate_rows(notes, velocities, cfg6=(0.85, 0.75, 0.02, 0.95, -35.0, -0.04), zero_trim=False, volume=0.40, speaker=1.0,
+                   preamp_model=0, threads=4):
+    nn, nv = len(notes), len(velocities)
+    rows = np.zeros((nn * nv, 18))
+    a = (C.c_uint8 * nn)(*notes)
+    b = (C.c_uint8 * nv)(*velocities)
+    c = np.array(cfg6, dtype=np.float64)
+    assert lib().owo_calibrate_rows(a, nn, b, nv, dptr(c), 1 if zero_trim else 0, volume, speaker, preamp_model, dptr(rows), threads) == 0
+    return rows
 
 
 def render_bench_taps(job):

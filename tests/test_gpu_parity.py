@@ -536,3 +536,41 @@ def test_full_c2_preamp_batch_properties():
     ref = _oracle_preamp_batch(x[idx], fs, True, 0.5, 0.0)
     for k, i in enumerate(idx):
         assert_parity(y[i], ref[k], f"full C2 row {i}")
+
+
+def test_calibrate_rows_match_run_calibrate_restatement():
+    """`preamp-bench calibrate`: all 18 numeric CSV columns (taps T1..T5 + derived) reduced on the device, against the oracle's
+    literal restatement of run_calibrate (own reed, own pickup, per-tap windows), with the CLI's non-default CalibrationConfig."""
+    notes, vels = [36, 48, 60, 72, 84, 96], [40, 80, 127]
+    cfg6 = (0.75, 0.75, 0.02, 0.82, -35.0, -0.04)
+    for model, om in ((ow.MELANGE12, O.MELANGE12), (ow.LEGACY8, O.LEGACY8)):
+        got = ow.render_calibrate(notes, vels, ow.calib_cfg(ds_at_c4=0.75, ds_clamp_max=0.82), volume=0.40, speaker=1.0, preamp_model=model)
+        ref = O.calibrate_rows(notes, vels, cfg6, volume=0.40, speaker=1.0, preamp_model=om)
+        assert got.shape == ref.shape == (18, 18)
+        assert np.abs(got[:, :3] - ref[:, :3]).max() < 1e-12                 # ds_at_c4, ds_actual, y_peak
+        # dB columns: a 2e-9 absolute sample difference (the parity budget) on a -62 dBFS tap is 2e-5 dB; legacy: its solver's noise floor
+        tol = 5e-5 if model == ow.MELANGE12 else 2e-3
+        assert np.abs(got[:, 3:] - ref[:, 3:]).max() < tol, (model, np.abs(got[:, 3:] - ref[:, 3:]).max(0))
+    # zero-trim and default-config variants change what they should
+    a = ow.render_calibrate([84], [127], ow.calib_cfg(), volume=0.4)
+    b = ow.render_calibrate([84], [127], ow.calib_cfg(zero_trim=True), volume=0.4)
+    assert a[0, 15] == pytest.approx(3.6) and b[0, 15] == 0.0 and a[0, 14] > b[0, 14]
+    assert a[0, 0] == 0.85
+
+
+def test_calibrate_cli_writes_the_reference_csv_format(tmp_path):
+    from openwurli_b200.cli import preamp_bench
+    out = tmp_path / "cal.csv"
+    assert preamp_bench.main(["calibrate", "--notes", "60,61", "--velocities", "40,127", "--output", str(out)]) == 0
+    lines = out.read_text().strip().split("\n")
+    assert lines[0] == preamp_bench.CALIBRATE_HEADER and len(lines) == 5
+    f = lines[1].split(",")
+    assert f[0] == "60" and f[1] == "C4" and f[2] == "40" and f[3] == "0.7500" and len(f) == 21
+    assert lines[3].split(",")[1] == "C#4"
+    ref = O.calibrate_rows([60, 61], [40, 127], (0.75, 0.75, 0.02, 0.82, -35.0, -0.04), volume=0.40, speaker=1.0)
+    want = preamp_bench.calibrate_csv_lines([60, 61], [40, 127], ref)
+    # identical text except where a value sits within 1e-6 dB of a rounding boundary of the 2-decimal format
+    for g, w in zip(lines[1:], want[1:]):
+        gv, wv = g.split(","), w.split(",")
+        assert gv[:3] == wv[:3]
+        assert all(abs(float(x) - float(y)) <= 0.0101 for x, y in zip(gv[3:], wv[3:]))
