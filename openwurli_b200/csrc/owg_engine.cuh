@@ -70,8 +70,9 @@ __device__ __noinline__ bool voice_render_block(VoiceRT* __restrict__ vp, double
             if (!ramp_done) {
                 if (release_count > ramp) ramp_done = true;
                 else {
+                    const Recip rr = recip_prepare(ramp);  // seven quotients, one divisor: bit-identical to `/` (owg_device.cuh)
 #pragma unroll
-                    for (int m = 0; m < 7; m++) env[m] *= exp(-(vp->damper_rate[m] * release_count / ramp));
+                    for (int m = 0; m < 7; m++) env[m] *= exp(-div_by(vp->damper_rate[m] * release_count, rr));
                 }
             }
             if (ramp_done) {
@@ -598,8 +599,9 @@ __device__ __forceinline__ double voice_sample(VoiceRegs& r, const VoiceRT* __re
         if (!r.ramp_done) {
             if (r.release_count > r.ramp) r.ramp_done = true;
             else {
+                const Recip rr = recip_prepare(r.ramp);  // seven quotients, one divisor: bit-identical to `/` (owg_device.cuh)
 #pragma unroll
-                for (int m = 0; m < 7; m++) r.env[m] *= exp(-(vp->damper_rate[m] * r.release_count / r.ramp));
+                for (int m = 0; m < 7; m++) r.env[m] *= exp(-div_by(vp->damper_rate[m] * r.release_count, rr));
             }
         }
         if (r.ramp_done) {
