@@ -574,3 +574,39 @@ def test_calibrate_cli_writes_the_reference_csv_format(tmp_path):
         gv, wv = g.split(","), w.split(",")
         assert gv[:3] == wv[:3]
         assert all(abs(float(x) - float(y)) <= 0.0101 for x, y in zip(gv[3:], wv[3:]))
+
+
+@pytest.mark.parametrize("note", [72, 84, 91])
+def test_alias_audit_gate_through_the_gpu_engine_path(note):
+    """The reference's only numeric fixture (tests/baselines/alias_audit_v0_5_1.json, one-sided gate of
+    tests/alias_audit_regression.rs:59-114) applied to the GPU render itself: alias_audit::render_stimulus (alias_audit.rs:131-161:
+    engine without warm-up, six 1024-sample settle blocks, note-on at velocity 120, 1.5 s) as one engine job."""
+    import test_oracle_known_answers as K
+    from scipy.signal import lfilter
+    sr, total, settle = 44100.0, int(44100.0 * 1.5), 6 * 1024
+    job = ow.engine_job([(settle, ow.NOTE_ON, note, float(np.float32(120) / np.float32(127.0)))], sample_rate=sr,
+                        duration=(settle + total + 0.5) / sr, volume=0.5, tremolo_depth=0.0, speaker_character=0.0, mlp=True,
+                        block_size=1024, warm_up=False)
+    sig = ow.render_engines([job])[0][settle:settle + total].astype(np.float64)
+    ref = np.zeros(total)
+    O.lib().owo_alias_stimulus(note, 120, sr, 1.5, 0.5, O.dptr(ref))
+    assert np.abs(sig - ref).max() <= 1e-7            # f32 stream parity with the oracle's stimulus
+    tail = sig[-int(sr * 0.5):]
+    nominal = 440.0 * 2.0 ** ((note - 69.0) / 12.0)
+    best_f, best = nominal, K._dft_mag(tail, nominal, sr)
+    f = nominal - 5.0
+    while f <= nominal + 5.0:
+        m = K._dft_mag(tail, f, sr)
+        if m > best:
+            best, best_f = m, f
+        f += 0.1
+    h1 = K._dft_mag(tail, best_f, sr)
+    dbc = np.array([20 * np.log10(K._dft_mag(tail, (k + 1) * best_f, sr) / h1) for k in range(12)])
+    step_up = max(dbc[i + 1] - dbc[i] for i in range(5, 10))
+    y = tail
+    for kind, fc in (("hp", 5000.0), ("hp", 5000.0), ("lp", 18000.0), ("lp", 18000.0)):
+        b, a = K._rbj(kind, fc, np.sqrt(0.5), sr)
+        y = lfilter(b, a, y)
+    hf = 20 * np.log10(np.sqrt(np.mean(y ** 2)) / h1)
+    base_step, base_hf = K.ALIAS_BASELINE[note]
+    assert step_up - base_step <= 1.5 and hf - base_hf <= 2.0, (step_up, base_step, hf, base_hf)
