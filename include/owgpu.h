@@ -148,6 +148,40 @@ int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_
                      int oversample, double tremolo_depth, double r_ldr_static, double* out, int64_t out_stride,
                      const owg_opts* opts);
 
+/* Generic form of the above: rows of `in` (any mono signal at the instance's base rate, e.g. a sum of voices as in `preamp-bench
+ * render-poly`, main.rs:1380-1560) through the full chain B of params[i] (sample_rate, r_ldr, tremolo_depth, volume,
+ * speaker_character, no_preamp, no_poweramp; the voice fields are ignored).  init_order selects how the caller constructs the
+ * static preamp: OWG_INIT_RESET_THEN_SET = `reset(); set_ldr_resistance(r)` (cmd_render, main.rs:438-439), OWG_INIT_SET_THEN_RESET =
+ * `set_ldr_resistance(r); reset()` (render-poly / render-midi, main.rs:1463-1464, 1753-1754: the melange preamp falls back to its
+ * settled 100 kOhm state, the legacy preamp re-solves its DC point at r). */
+#define OWG_INIT_RESET_THEN_SET 0
+#define OWG_INIT_SET_THEN_RESET 1
+int owg_chain_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, const owg_bench_job* params, int32_t init_order,
+                    double* out, int64_t out_stride, const owg_opts* opts);
+
+/* `preamp-bench render-midi` (main.rs:1603-1895): the tool's own voice manager (64 slots, first free slot else the oldest, no
+ * crossfade; note-off to the oldest sounding voice of that key; sustain pedal defers note-offs; silent voices are dropped before each
+ * 64-sample chunk), voices summed in slot order, then chain B with the static preamp in SET_THEN_RESET order, f64 output.
+ * Events carry absolute time in seconds exactly as the tool's SMF walk produces them and must be sorted by time (stable). */
+#define OWG_MIDI_NOTE_ON 0
+#define OWG_MIDI_NOTE_OFF 1
+#define OWG_MIDI_PEDAL 2 /* velocity != 0 -> pedal down */
+typedef struct owg_midi_event {
+    double time_s;
+    uint8_t kind, note, velocity, _pad0;
+    int32_t _pad1;
+} owg_midi_event;
+typedef struct owg_midi_job {
+    const owg_midi_event* ev;
+    int64_t n_ev;
+    int64_t n_samples;       /* total_samples = ((last_event_time + tail) * 44100) as usize */
+    double volume;           /* --volume (0.60) */
+    double speaker_character;/* --speaker (1.0) */
+    int32_t no_poweramp;     /* --no-poweramp */
+    int32_t _pad0;
+} owg_midi_job;
+int owg_render_midi(const owg_midi_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts);
+
 /* Output mode "metrics" (BASELINE config 4): chain B with the `run_calibrate` analysis reduced on the device
  * instead of returning samples (tools/preamp-bench/src/main.rs:1139-1141, 1215-1223, 893-938): over the window
  * [window_start_s, window_end_s) of the final (T5) signal, per job:

@@ -42,6 +42,16 @@ class Opts(C.Structure):
                 ("_reserved", C.c_int32 * 7)]
 
 
+class MidiEvent(C.Structure):
+    _fields_ = [("time_s", C.c_double), ("kind", C.c_uint8), ("note", C.c_uint8), ("velocity", C.c_uint8), ("_pad0", C.c_uint8),
+                ("_pad1", C.c_int32)]
+
+
+class MidiJob(C.Structure):
+    _fields_ = [("ev", C.POINTER(MidiEvent)), ("n_ev", C.c_int64), ("n_samples", C.c_int64), ("volume", C.c_double),
+                ("speaker_character", C.c_double), ("no_poweramp", C.c_int32), ("_pad0", C.c_int32)]
+
+
 class CalibCfg(C.Structure):
     _fields_ = [("ds_at_c4", C.c_double), ("ds_exponent", C.c_double), ("ds_clamp_lo", C.c_double), ("ds_clamp_hi", C.c_double),
                 ("target_db", C.c_double), ("voicing_slope", C.c_double), ("zero_trim", C.c_int32), ("_pad0", C.c_int32)]
@@ -58,7 +68,7 @@ class Diag(C.Structure):
 EXPORTS = ["owg_abi_version", "owg_device_count", "owg_last_error", "owg_default_opts", "owg_render_voices",
            "owg_render_bench", "owg_render_engines", "owg_preamp_batch", "owg_plan_bench", "owg_plan_voices",
            "owg_plan_execute", "owg_plan_samples", "owg_plan_h2d_bytes", "owg_plan_kernel_launches", "owg_plan_last_timing",
-           "owg_plan_destroy", "owg_last_diag", "owg_fp64_peak", "owg_host_voice_init", "owg_host_chain_init", "owg_host_legacy_group", "owg_render_calibrate", "owg_default_calib_cfg", "owg_selftest_division", "owg_render_bench_metrics"]
+           "owg_plan_destroy", "owg_last_diag", "owg_fp64_peak", "owg_host_voice_init", "owg_host_chain_init", "owg_host_legacy_group", "owg_render_calibrate", "owg_default_calib_cfg", "owg_chain_batch", "owg_render_midi", "owg_selftest_division", "owg_render_bench_metrics"]
 
 _lib = None
 
@@ -104,6 +114,9 @@ def lib():
         L.owg_host_voice_init.argtypes = [C.POINTER(VoiceJob), dp]
         L.owg_host_chain_init.argtypes = [C.POINTER(BenchJob), dp]
         L.owg_host_legacy_group.argtypes = [C.c_double, C.c_double, dp]
+        L.owg_chain_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(BenchJob), C.c_int32, C.c_void_p, C.c_int64,
+                                      C.POINTER(Opts)]
+        L.owg_render_midi.argtypes = [C.POINTER(MidiJob), C.c_int64, C.c_void_p, C.c_int64, C.POINTER(Opts)]
         L.owg_default_calib_cfg.argtypes = [C.POINTER(CalibCfg)]
         L.owg_default_calib_cfg.restype = None
         L.owg_render_calibrate.argtypes = [C.POINTER(BenchJob), C.c_int64, C.POINTER(CalibCfg), C.c_double, C.c_double, dp, C.POINTER(Opts)]

@@ -210,6 +210,50 @@ def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000
     return out
 
 
+RESET_THEN_SET, SET_THEN_RESET = 0, 1
+
+
+def chain_batch(x, params, init_order=RESET_THEN_SET, out=None, device=-1, preamp_model=MELANGE12):
+    """Rows of `x` [n_inst, n_samp] (any mono signal, e.g. a sum of voices) through the full chain B of params[i] (bench_job(...): sample
+    rate, ldr, tremolo depth, volume, speaker, bypass flags).  init_order = SET_THEN_RESET is how `render-poly` / `render-midi` construct
+    the static preamp (main.rs:1463-1464)."""
+    if out is None:
+        out = np.zeros_like(x) if isinstance(x, np.ndarray) else x.new_zeros(x.shape)
+    pin, sin, lin = _out_ptr(x)
+    pout, sout, lout = _out_ptr(out)
+    assert lin == lout and len(params) == x.shape[0]
+    arr = (BenchJob * len(params))(*params)
+    o = _opts(device, lout, preamp_model=preamp_model)
+    check(lib().owg_chain_batch(pin, sin, x.shape[0], x.shape[1], arr, int(init_order), pout, sout, C.byref(o)))
+    return out
+
+
+MIDI_ON, MIDI_OFF, MIDI_PEDAL = 0, 1, 2
+
+
+def render_midi(streams, volume=0.60, speaker=1.0, no_poweramp=False, tail=2.0, device=-1, preamp_model=MELANGE12):
+    """`preamp-bench render-midi` for a batch of event lists (smf.timed_events output: [(time_s, kind, note, velocity)]): the tool's own
+    voice manager and chain.  Returns (list of float64 arrays, one per stream)."""
+    from . import smf
+    jobs, keep, ns = [], [], []
+    for ev in streams:
+        arr = (_abi.MidiEvent * max(len(ev), 1))()
+        for k, (t, kind, a, b) in enumerate(ev):
+            code = MIDI_ON if kind == smf.NOTE_ON else (MIDI_OFF if kind == smf.NOTE_OFF else MIDI_PEDAL)
+            arr[k] = _abi.MidiEvent(float(t), code, int(a) if code != MIDI_PEDAL else 0, int(b) if code == MIDI_ON else (int(a) if code == MIDI_PEDAL else 0), 0, 0)
+        n = smf.total_samples(ev, tail, 44100.0)
+        keep.append(arr)
+        ns.append(n)
+        jobs.append(_abi.MidiJob(arr, len(ev), n, float(volume), float(speaker), 1 if no_poweramp else 0, 0))
+    stride = max(ns, default=0)
+    out = np.zeros((len(jobs), max(stride, 1)), dtype=np.float64)
+    if jobs and stride:
+        ja = (_abi.MidiJob * len(jobs))(*jobs)
+        o = _opts(device, OWG_OUT_HOST, preamp_model=preamp_model)
+        check(lib().owg_render_midi(ja, len(jobs), out.ctypes.data, out.shape[1], C.byref(o)))
+    return [out[i, :ns[i]] for i in range(len(jobs))]
+
+
 METRIC_COLUMNS = ("peak_db", "rms_db", "h2_h1_db", "peak", "mean_sq", "h1", "h2")
 
 

@@ -173,10 +173,88 @@ def cmd_calibrate(args):
     return 0
 
 
+def render_poly(notes, velocities, duration=3.0, volume=0.60, speaker_char=1.0, r_ldr=1_000_000.0, no_poweramp=False,
+                preamp_model=api.MELANGE12):
+    """The signal part of cmd_render_poly (main.rs:1396-1507): K voices rendered alone, summed voice by voice, the sum and every voice
+    through its own chain B (static preamp in set-then-reset order).  Returns (final_output, separate_sum, residual)."""
+    n = int(duration * BASE_SR) if duration > 0 else 0
+    jobs = [api.voice_job(midi=nt, velocity=v, sample_rate=BASE_SR, duration=duration, mlp=True, seed=(nt * 2654435761 + i) & 0xFFFFFFFF)
+            for i, (nt, v) in enumerate(zip(notes, velocities))]
+    voices = api.render_voices(jobs)[:, :n]
+    mix = np.zeros(n)
+    for vb in voices:
+        mix += vb                                         # sum_buf[j] += voice_buf[j] (main.rs:1451-1453)
+    rows = np.ascontiguousarray(np.vstack([mix[None, :], voices]))
+    p = api.bench_job(ldr=r_ldr, volume=volume, speaker=speaker_char, no_poweramp=no_poweramp, sample_rate=BASE_SR)
+    out = api.chain_batch(rows, [p] * rows.shape[0], init_order=api.SET_THEN_RESET, preamp_model=preamp_model)
+    final_output = out[0]
+    separate_sum = np.zeros(n)
+    for k in range(1, out.shape[0]):
+        separate_sum += out[k]                            # separate_sum[i] += ... (main.rs:1499-1501)
+    return final_output, separate_sum, final_output - separate_sum
+
+
+def _peak_db(x):
+    return to_dbfs(float(np.max(np.abs(x))) if x.size else 0.0)
+
+
+def _rms_db(x):
+    m = float(np.sum(x * x)) / x.size if x.size else 0.0
+    return 10.0 * math.log10(m) if m > 0.0 else -120.0
+
+
+def cmd_render_poly(args):
+    """`preamp-bench render-poly` (main.rs:1396-1593): same flags, both WAV files and the intermod report."""
+    notes = _csv_u8_list(args, "--notes", "38,59,62,66")
+    vraw = _csv_u8_list(args, "--velocities", "45,40,40,40")
+    duration = parse_flag(args, "--duration", 3.0)
+    volume = parse_flag(args, "--volume", 0.60)
+    speaker_char = parse_flag(args, "--speaker", 1.0)
+    r_ldr = parse_flag(args, "--ldr", 1_000_000.0)
+    no_poweramp = has_flag(args, "--no-poweramp")
+    normalize = has_flag(args, "--normalize")
+    output_path = parse_flag_str(args, "--output", os.path.join(tempfile.gettempdir(), "preamp_render_poly.wav"))
+    model = api.LEGACY8 if parse_flag_str(args, "--preamp-model", "melange12") == "legacy8" else api.MELANGE12
+    velocities = [vraw[i] if i < len(vraw) else (vraw[-1] if vraw else 80) for i in range(len(notes))]
+    sys.stderr.write(f"Rendering {len(notes)} voices, {duration:.1f}s @ {BASE_SR:.0f} Hz...\n")
+    final_output, separate_sum, residual = render_poly(notes, velocities, duration, volume, speaker_char, r_ldr, no_poweramp, model)
+    n = final_output.size
+    ms, me = int(0.2 * BASE_SR), int(min(2.0 * BASE_SR, float(n)))
+    poly_peak, sep_peak, res_peak_db = _peak_db(final_output[ms:me]), _peak_db(separate_sum[ms:me]), _peak_db(residual[ms:me])
+    poly_rms, sep_rms, res_rms = _rms_db(final_output[ms:me]), _rms_db(separate_sum[ms:me]), _rms_db(residual[ms:me])
+    peak = float(np.max(np.abs(final_output))) if n else 0.0
+    wav.write_preamp_bench_wav(output_path, final_output, BASE_SR, wav.normalize_scale(final_output, normalize))
+    residual_path = output_path.replace(".wav", "_residual.wav")
+    res_peak = float(np.max(np.abs(residual))) if n else 0.0
+    wav.write_preamp_bench_wav(residual_path, residual, BASE_SR, 0.5 / res_peak if res_peak > 1e-10 else 1.0)
+    print("Polyphonic render complete")
+    print("  Notes:     [" + ", ".join(f'"{midi_note_name(x)} ({x})"' for x in notes) + "]")
+    print(f"  Velocities: {velocities}")
+    print(f"  Duration:  {duration:.1f}s")
+    print(f"  Volume:    {volume:.3f} (audio taper: {volume * volume:.3f})")
+    print(f"  Speaker:   {speaker_char:.1f}")
+    print(f"  Peak:      {to_dbfs(peak):.1f} dBFS")
+    print()
+    print("  === INTERMOD ANALYSIS (0.2-2.0s window) ===")
+    print(f"  Shared chain (poly):  peak={poly_peak:.1f} dBFS  rms={poly_rms:.1f} dBFS")
+    print(f"  Separate chains (sum): peak={sep_peak:.1f} dBFS  rms={sep_rms:.1f} dBFS")
+    print(f"  Residual (intermod):  peak={res_peak_db:.1f} dBFS  rms={res_rms:.1f} dBFS")
+    print(f"  Intermod ratio:       {poly_rms - res_rms:.1f} dB below signal")
+    print()
+    margin = poly_rms - res_rms
+    verdict = ("CLEAN — intermod negligible" if margin > 60.0 else "OK — intermod present but likely inaudible" if margin > 40.0 else
+               "MARGINAL — intermod may be audible on revealing systems" if margin > 20.0 else "DIRTY — intermod clearly audible")
+    print(f"  Verdict: {verdict}")
+    print()
+    print(f"  Output:    {output_path}")
+    print(f"  Residual:  {residual_path} (normalized for listening)")
+    return 0
+
+
 def cmd_render_midi(args):
-    """`render-midi --midi FILE` (main.rs:1603-1895): the SMF front-end is the reference's (smf.py); the audio path is the plugin's
-    WurliEngine (chain E: 64 slots with stealing crossfade, tremolo, f32) instead of the tool's private voice manager, with the
-    tool's event timing (64-sample blocks).  `--tremolo-depth` defaults to 0 like the tool's static 1 MOhm preamp."""
+    """`render-midi --midi FILE` (main.rs:1603-1895): SMF front-end (smf.py), the tool's own voice manager and chain on the device
+    (owg_render_midi).  `--engine` renders the same schedule through the plugin's WurliEngine instead (chain E: stealing crossfade,
+    tremolo via --tremolo-depth, f32), which is not what the reference tool does."""
     from .. import smf
     midi_path = parse_flag_str(args, "--midi", "")
     if not midi_path:
@@ -188,10 +266,10 @@ def cmd_render_midi(args):
     tail = parse_flag(args, "--tail", 2.0)
     depth = parse_flag(args, "--tremolo-depth", 0.0)
     track = int(parse_flag(args, "--track", 0.0)) if has_flag(args, "--track") else None
-    if has_flag(args, "--no-poweramp"):
+    model = api.LEGACY8 if parse_flag_str(args, "--preamp-model", "melange12") == "legacy8" else api.MELANGE12
+    if has_flag(args, "--engine") and has_flag(args, "--no-poweramp"):
         sys.stderr.write("--no-poweramp is not available on the WurliEngine path\n")
         return 1
-    model = api.LEGACY8 if parse_flag_str(args, "--preamp-model", "melange12") == "legacy8" else api.MELANGE12
     try:
         events = smf.timed_events(open(midi_path, "rb").read(), track)
     except smf.SmfError as e:
@@ -201,6 +279,26 @@ def cmd_render_midi(args):
         sys.stderr.write("No note events found in MIDI file\n")
         return 1
     n = smf.total_samples(events, tail, BASE_SR)
+    if not has_flag(args, "--engine"):
+        out = api.render_midi([events], volume=volume, speaker=speaker_char, no_poweramp=has_flag(args, "--no-poweramp"), tail=tail,
+                              preamp_model=model)[0]
+        peak = float(np.max(np.abs(out))) if out.size else 0.0
+        if peak > 1.0:
+            sys.stderr.write(f"WARNING: Peak exceeds 0 dBFS ({to_dbfs(peak):.1f} dBFS) — consider reducing --volume\n")
+        wav.write_preamp_bench_wav(output_path, out, BASE_SR, 1.0)
+        d = api.last_diag()
+        print("MIDI render complete")
+        print(f"  File:      {midi_path}")
+        print(f"  Notes:     {int(d.nr_iter_hist[0])} note-ons")
+        print(f"  Peak poly: {int(d.nr_iter_hist[3])} voices")
+        print(f"  Duration:  {n / BASE_SR:.1f}s")
+        print(f"  Volume:    {volume:.3f} (audio taper: {volume * volume:.3f})")
+        print(f"  Speaker:   {speaker_char:.1f}")
+        if has_flag(args, "--no-poweramp"):
+            print("  Power amp: BYPASSED")
+        print(f"  Peak:      {to_dbfs(peak):.1f} dBFS")
+        print(f"  Output:    {output_path}")
+        return 0
     job = api.engine_job(smf.engine_events(events, 64, BASE_SR), sample_rate=BASE_SR, duration=n / BASE_SR + 0.5 / BASE_SR, volume=volume,
                          tremolo_depth=depth, speaker_character=speaker_char, block_size=64, warm_up=True)
     out = api.render_engines([job], preamp_model=model)[0][:n].astype(np.float64)
@@ -221,7 +319,8 @@ def cmd_render_midi(args):
     return 0
 
 
-USAGE = """Usage: preamp_bench <render|calibrate|render-midi> [flags]
+USAGE = """Usage: preamp_bench <render|calibrate|render-midi|render-poly> [flags]
+  render-poly --notes a,b,c --velocities x,y,z --duration S --volume X --speaker C --ldr OHM --no-poweramp --normalize --output FILE
   render-midi --midi FILE --output FILE --volume X --speaker C --tail S --track N --tremolo-depth D --preamp-model M
   render     --note N --velocity V --duration S --ldr OHM --volume X --speaker C --tremolo-depth D --sample-rate HZ
              --no-poweramp --no-rail-sag --no-preamp --no-attack-noise --no-mlp --normalize --displacement-scale DS --output FILE
@@ -241,6 +340,8 @@ def main(argv=None):
         return cmd_calibrate(args[1:])
     if args[0] == "render-midi":
         return cmd_render_midi(args[1:])
+    if args[0] == "render-poly":
+        return cmd_render_poly(args[1:])
     sys.stderr.write(f"Unknown subcommand: {args[0]} (only the batched render paths are mirrored)\n{USAGE}")
     return 1
 

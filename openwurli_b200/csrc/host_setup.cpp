@@ -506,7 +506,7 @@ double lg_clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi 
 double lg_ic(double vbe) { return LG_IS * (std::exp(lg_clampd(vbe, -1.0, LG_VBE_MAX) / LG_VT) - 1.0); }  // :668-671
 }  // namespace
 
-void make_legacy_group(double fs, double r_static, double* rec) {
+void make_legacy_group(double fs, double r_static, double* rec, bool dc_at_r) {
     // circuit (dk_preamp_legacy.rs:24-41, stamps :281-310), in the reference's stamping order (the sums into a diagonal
     // entry are order-sensitive in the last bit)
     const LgBranch resistors[] = {
@@ -563,8 +563,13 @@ void make_legacy_group(double fs, double r_static, double* rec) {
     rec[OWG_LG_GCIN] = g_cin;
     rec[OWG_LG_GC1PC] = g_cin * (1.0 + c_cin);
     rec[OWG_LG_CCIN] = c_cin;
-    // DC operating point at R_ldr = 1 MOhm (full_dc_solve, :370-412): Newton on the 2x2 kernel of the resistive network
-    const double r_init = 1000000.0;
+    // DC operating point at R_ldr = 1 MOhm (full_dc_solve, :370-412): Newton on the 2x2 kernel of the resistive network;
+    // with dc_at_r (`set_ldr_resistance(r); reset()`, :620-642) at the resistance set_ldr_resistance left in r_ldr
+    double r_init = 1000000.0;
+    if (dc_at_r && r_static == r_static) {
+        const double nr = r_static > 1000.0 ? r_static : 1000.0;
+        if (std::fabs(nr - r_init) > 0.01) r_init = nr;
+    }
     double g_full[LGN][LGN], s_dc[LGN][LGN], k_dc[4], sv[LGN];
     std::memcpy(g_full, g_dc, sizeof(g_dc));
     g_full[N_FB][N_FB] += 1.0 / r_init;
@@ -599,7 +604,7 @@ void make_legacy_group(double fs, double r_static, double* rec) {
     // `reset(); set_ldr_resistance(r)` (main.rs:438-439; :620-626): f64::max(r, 1000) and the 0.01 Ohm change threshold
     rec[OWG_LG_GINIT] = 1.0 / r_init;
     double g_static = 1.0 / r_init;
-    if (r_static == r_static) {
+    if (!dc_at_r && r_static == r_static) {
         const double nr = r_static > 1000.0 ? r_static : 1000.0;
         if (std::fabs(nr - r_init) > 0.01) g_static = 1.0 / nr;
     }

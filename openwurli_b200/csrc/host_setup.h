@@ -20,7 +20,8 @@ int make_speaker_schedule(double sample_rate, double character_target, int64_t n
 // Legacy 8-node preamp (dk_preamp_legacy.rs:269-412): R_ldr-independent matrices, Sherman-Morrison vectors, Cin-R1 companion
 // constants and the DC operating point at 1 MOhm for `preamp_sr`; rec = OWG_LG_STRIDE doubles (owg_records.h).
 // `r_static`: the static LDR resistance handed to set_ldr_resistance after reset() (NaN = tremolo group).
-void make_legacy_group(double preamp_sr, double r_static, double* rec);
+// dc_at_r: `set_ldr_resistance(r_static); reset()` -- the DC operating point, g_ldr and g_ldr_prev are those of r_static.
+void make_legacy_group(double preamp_sr, double r_static, double* rec, bool dc_at_r = false);
 // CalibrationConfig-parametrised table functions (tables.rs:256-288, 578-616, 465-503) for `preamp-bench calibrate`, whose CLI
 // defaults (ds_at_c4 0.75, upper clamp 0.82) differ from CalibrationConfig::default().
 double calib_displacement_scale(int midi, const owg_calib_cfg& cfg);

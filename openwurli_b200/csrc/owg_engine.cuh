@@ -1072,6 +1072,69 @@ __global__ void __launch_bounds__(32) engine_chain_legacy_kernel(const EngineWar
         for (long long t = ed.n_samples; t < max_samples; t++) o[t] = 0.0f;
 }
 
+// ---- `preamp-bench render-midi` voice manager (main.rs:1735-1850), one thread per MIDI stream, one call per 64-sample chunk --------
+// Reuses EngineState (st_state = active flag, st_note, st_age; pool entry 2*slot) and the render list consumed by
+// engine_voice_mix_kernel.  held[] = the tool's `pedal_held` vector (note-offs deferred while the pedal is down).
+__global__ void midi_events_kernel(const EngineDesc* __restrict__ engines, int n_streams, long long round, const MidiEvent* __restrict__ events,
+                                   const OwgVoiceInit* __restrict__ vinits, const DamperRow* __restrict__ dampers /*[128]*/,
+                                   VoiceRT* __restrict__ pool /*[stream][128]*/, EngineState* __restrict__ states, uint8_t* __restrict__ held,
+                                   int32_t* __restrict__ held_count, const long long* __restrict__ held_offset, double silent_thr) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_streams) return;
+    const EngineDesc ed = engines[e];
+    const long long pos = round * (long long)ed.block_size;
+    if (pos >= ed.n_samples) return;
+    EngineState& S = states[e];
+    VoiceRT* mypool = pool + (size_t)e * 128;
+    uint8_t* myheld = held + held_offset[e];
+    int nheld = held_count[e];
+    long long ev = S.ev;
+    auto note_off_oldest = [&](uint8_t note) {  // the oldest ACTIVE slot of that key (min_by_key(age)); its voice gets note_off()
+        int best = -1;
+        for (int i = 0; i < 64; i++)
+            if (S.st_state[i] && S.st_note[i] == note && (best < 0 || S.st_age[i] < S.st_age[best])) best = i;
+        if (best >= 0) voice_note_off(mypool[2 * best], dampers);
+    };
+    while (ev < ed.ev_end && events[ev].chunk <= round) {
+        const MidiEvent evv = events[ev++];
+        if (evv.kind == OWG_MIDI_NOTE_ON) {
+            S.age_counter += 1;
+            int slot = -1;
+            for (int i = 0; i < 64; i++) if (!S.st_state[i]) { slot = i; break; }       // position(|s| !s.active)
+            if (slot < 0) {                                                              // else min_by_key(age) over all slots
+                slot = 0;
+                for (int i = 1; i < 64; i++) if (S.st_age[i] < S.st_age[slot]) slot = i;
+            }
+            voice_from_init(mypool[2 * slot], vinits[evv.vinit]);
+            S.st_state[slot] = 1; S.st_note[slot] = (uint8_t)evv.note; S.st_age[slot] = S.age_counter;
+            S.d_note_ons++;
+            unsigned long long active = 0;
+            for (int i = 0; i < 64; i++) active += S.st_state[i] ? 1 : 0;
+            if (active > S.d_max_active) S.d_max_active = active;
+        } else if (evv.kind == OWG_MIDI_NOTE_OFF) {
+            if (S.sustain_held) myheld[nheld++] = (uint8_t)evv.note;
+            else note_off_oldest((uint8_t)evv.note);
+        } else {  // pedal
+            S.sustain_held = evv.note != 0 ? 1 : 0;
+            if (!S.sustain_held) {
+                for (int k = 0; k < nheld; k++) note_off_oldest(myheld[k]);
+                nheld = 0;
+            }
+        }
+    }
+    S.ev = ev;
+    held_count[e] = nheld;
+    // clean up silent voices, then the render list in slot order (main.rs:1852-1876)
+    int n_items = 0;
+    for (int i = 0; i < 64; i++) {
+        if (!S.st_state[i]) continue;
+        if (voice_is_silent(mypool[2 * i], ed.sample_rate, silent_thr)) { S.st_state[i] = 0; S.d_freed++; continue; }
+        S.item_pool[n_items] = (uint8_t)(2 * i); S.item_fade[n_items] = -1; S.item_fade_len[n_items] = 1u;
+        n_items++;
+    }
+    S.n_items = n_items;
+}
+
 __global__ void engine_diag_kernel(const EngineState* __restrict__ states, const EngineChainState* __restrict__ chains, int n_engines, EngineDiag* diag) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_engines) return;

@@ -54,7 +54,7 @@ struct OwgPreampGroup {
     double r_static;         // clamped static R (tremolo_depth <= 0)
     double tremolo_depth;    // > 0: Twin-T/LDR trajectory
     int32_t use_defaults;    // 48 kHz and never dirtied: baked *_DEFAULT tables apply (gen_preamp.rs:1941-1955)
-    int32_t _pad;
+    int32_t dc_at_r;         // legacy model, `set_ldr_resistance(r); reset()`: both instances start from the DC point solved at r
     int64_t n_os;            // preamp-rate samples to produce (max over the group's instances)
 };
 
@@ -114,6 +114,12 @@ struct EngineDesc {  // one WurliEngine stream
 
 struct EngineEvent {  // host-prepared: NOTE_ON carries the index of its precomputed OwgVoiceInit
     int64_t sample;
+    int32_t kind, note;
+    int64_t vinit;
+};
+
+struct MidiEvent {  // render-midi: host-prepared; NOTE_ON carries the index of its OwgVoiceInit
+    int64_t chunk;       // first 64-sample chunk whose start time is >= the event's time (main.rs:1790-1795)
     int32_t kind, note;
     int64_t vinit;
 };

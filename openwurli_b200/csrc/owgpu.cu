@@ -109,6 +109,7 @@ struct owg_plan {
     int64_t w_begin = 0, w_end = 0;  // analysis window, base-rate samples
     DevBuf<double> d_f0s;            // per job: nominal fundamental, sample rate
     const double* in_ptr = nullptr;  // kind 2: caller's input [n][in_stride] (host or device, like `out`)
+    int in_location = -1;            // -1 = same as the output's location
     int64_t in_stride = 0;
     bool collect_diag = false;
     bool legacy = false;             // owg_opts.preamp_model == OWG_PREAMP_LEGACY8
@@ -184,6 +185,7 @@ int plan_common(owg_plan* pl, const owg_opts* opts) {
 
 // One instance of the shared mono chain as the planner sees it.
 struct InstSpec {
+    int init_order = 0;   // OWG_INIT_RESET_THEN_SET (cmd_render) | OWG_INIT_SET_THEN_RESET (render-poly / render-midi)
     double fs;            // base sample rate
     int oversample;       // 2x oversampled preamp
     unsigned long long n_samples;
@@ -194,7 +196,7 @@ struct InstSpec {
 // Group instances by (base rate, oversampling, static R | tremolo depth) -- they share DK matrices and the shadow solve --
 // and pack each group into warps of 31 instances + 1 shadow lane, longest renders first.
 void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vector<int32_t>* order_out) {
-    typedef std::tuple<double, int, int, double> Key;  // (fs, oversample, is_trem, r_or_depth)
+    typedef std::tuple<double, int, int, double, int> Key;  // (fs, oversample, is_trem, r_or_depth, legacy DC at r)
     std::map<Key, int> key_to_group;
     std::vector<std::vector<int32_t>> members;
     const double R0 = 9.99999999999999854e4;
@@ -206,17 +208,21 @@ void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vec
         const bool trem = sp.depth > 0.0;
         double r_eff = R0;
         bool dirty = false;
+        int dc_at_r = 0;
         if (pl->legacy) {  // legacy: r = max(r_ldr, 1000) with a 0.01 Ohm change threshold against the constructor's 1 MOhm (dk_preamp_legacy.rs:620-626)
             r_eff = 1.0e6;
             if (!trem) {
                 const double r = sp.r_ldr > 1000.0 ? sp.r_ldr : 1000.0;
                 if (std::fabs(r - 1.0e6) > 0.01) r_eff = r;
+                dc_at_r = sp.init_order == OWG_INIT_SET_THEN_RESET ? 1 : 0;  // reset() after the set: DC point re-solved at r (:628-642)
             }
+        } else if (!trem && sp.init_order == OWG_INIT_SET_THEN_RESET) {
+            // melange: reset() re-clones the settled 100 kOhm state after the set (melange_adapter.rs:22-29): r_eff stays R0
         } else if (!trem && std::isfinite(sp.r_ldr)) {  // reset(); set_ldr_resistance(r_ldr)  (main.rs:438-439, gen_preamp.rs:1973-1984)
             const double r = sp.r_ldr < 1.0e3 ? 1.0e3 : (sp.r_ldr > 1.0e6 ? 1.0e6 : sp.r_ldr);
             if (!(std::fabs(r - R0) < 1e-12)) { r_eff = r; dirty = true; }
         }
-        const Key key(sp.fs, sp.oversample, trem ? 1 : 0, trem ? sp.depth : r_eff);
+        const Key key(sp.fs, sp.oversample, trem ? 1 : 0, trem ? sp.depth : r_eff, dc_at_r);
         auto it = key_to_group.find(key);
         int g;
         if (it == key_to_group.end()) {
@@ -228,6 +234,7 @@ void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vec
             gr.r_static = r_eff;
             gr.tremolo_depth = trem ? sp.depth : 0.0;
             gr.use_defaults = (std::fabs(psr - 48000.0) <= 0.5 && !dirty) ? 1 : 0;
+            gr.dc_at_r = dc_at_r;
             gr.n_os = 0;
             pl->groups.push_back(gr);
             members.emplace_back();
@@ -323,7 +330,8 @@ int upload_chain_plan(owg_plan* pl, const std::vector<OwgChainInit>& ci, const s
     if (pl->legacy) {
         std::vector<double> recs(pl->groups.size() * OWG_LG_STRIDE);
         for (size_t g = 0; g < pl->groups.size(); g++)
-            owg::make_legacy_group(pl->groups[g].preamp_sr, pl->groups[g].tremolo_depth > 0.0 ? NAN : pl->groups[g].r_static, &recs[g * OWG_LG_STRIDE]);
+            owg::make_legacy_group(pl->groups[g].preamp_sr, pl->groups[g].tremolo_depth > 0.0 ? NAN : pl->groups[g].r_static, &recs[g * OWG_LG_STRIDE],
+                                   pl->groups[g].dc_at_r != 0);
         if (!rc) rc = pl->d_legacy_recs.upload(recs, pl->stream);
     } else {
         if (!rc) rc = pl->d_static_recs.alloc(pl->groups.size() * OWG_MAT_STRIDE);
@@ -521,7 +529,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
         // preamp-only batch: the rows start as the caller's input signals
         CK(cudaMemcpy2DAsync(dout, (size_t)stride * sizeof(double), pl->in_ptr, (size_t)pl->in_stride * sizeof(double),
                              (size_t)pl->max_samples * sizeof(double), (size_t)pl->n,
-                             out_location == OWG_OUT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+                             (pl->in_location < 0 ? out_location : pl->in_location) == OWG_OUT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
     } else {  // chain V for every job
         const int threads = 32;
         const int blocks = (int)((pl->n + threads - 1) / threads);
@@ -1234,6 +1242,170 @@ int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_
     }
     owg_plan_destroy(pl);
     return rc;
+}
+
+static int chain_batch_impl(const double* in, int in_location, int64_t in_stride, int64_t n_inst, const unsigned long long* n_samp_each,
+                            int64_t n_samp_max, const owg_bench_job* params, int32_t init_order, double* out, int64_t out_stride,
+                            const owg_opts* opts) {
+    owg_plan* pl = new owg_plan();
+    g_h2d_bytes = 0;
+    pl->kind = 2;
+    pl->n = n_inst;
+    if (int rc = plan_common(pl, opts)) { delete pl; return rc; }
+    std::vector<InstSpec> specs((size_t)n_inst);
+    for (int64_t i = 0; i < n_inst; i++) {
+        InstSpec& sp = specs[i];
+        const owg_bench_job& j = params[i];
+        sp.init_order = init_order;
+        sp.fs = j.v.sample_rate;
+        sp.oversample = j.v.sample_rate < 88200.0 ? 1 : 0;
+        sp.n_samples = n_samp_each ? n_samp_each[i] : (unsigned long long)n_samp_max;
+        sp.depth = j.tremolo_depth;
+        sp.r_ldr = j.r_ldr;
+        owg::make_chain_init(j, 0, &sp.ci);
+    }
+    std::vector<int32_t> order;
+    build_groups_and_warps(pl, specs, &order);
+    std::vector<OwgChainInit> ci((size_t)n_inst);
+    for (int64_t i = 0; i < n_inst; i++) ci[i] = specs[i].ci;
+    int rc = launch_tremolo_ctor(pl);
+    if (!rc) rc = upload_chain_plan(pl, ci, order);
+    if (!rc) {
+        pl->in_ptr = in;
+        pl->in_stride = in_stride;
+        pl->in_location = in_location;
+        rc = owg_plan_execute(pl, out, out_stride, opts ? opts->out_location : OWG_OUT_HOST);
+    }
+    owg_plan_destroy(pl);
+    return rc;
+}
+
+int owg_chain_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, const owg_bench_job* params, int32_t init_order,
+                    double* out, int64_t out_stride, const owg_opts* opts) {
+    if (n_inst < 0 || n_samp < 0 || (init_order != OWG_INIT_RESET_THEN_SET && init_order != OWG_INIT_SET_THEN_RESET))
+        return fail(OWG_E_BAD_ARG, "owg_chain_batch: bad argument");
+    if (n_inst == 0 || n_samp == 0) return OWG_OK;
+    if (!in || !out || !params || in_stride < n_samp || out_stride < n_samp) return fail(OWG_E_BAD_ARG, "owg_chain_batch: null buffer or stride < n_samp");
+    for (int64_t i = 0; i < n_inst; i++) {
+        const owg_bench_job& j = params[i];
+        if (!(j.v.sample_rate > 0.0) || !std::isfinite(j.v.sample_rate) || !std::isfinite(j.volume) || !std::isfinite(j.speaker_character) ||
+            std::isnan(j.tremolo_depth))
+            return fail(OWG_E_BAD_ARG, "owg_chain_batch: invalid chain parameters");
+    }
+    return chain_batch_impl(in, -1, in_stride, n_inst, nullptr, n_samp, params, init_order, out, out_stride, opts);
+}
+
+int owg_render_midi(const owg_midi_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts) {
+    if (n < 0 || (n > 0 && (!jobs || !out))) return fail(OWG_E_BAD_ARG, "owg_render_midi: bad argument");
+    if (n == 0) return OWG_OK;
+    const double SR = 44100.0;  // BASE_SR: the tool renders at 44.1 kHz only
+    const int CHUNK = 64;
+    int64_t max_samples = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const owg_midi_job& j = jobs[i];
+        if (j.n_ev < 0 || (j.n_ev > 0 && !j.ev) || j.n_samples < 0 || !std::isfinite(j.volume) || !std::isfinite(j.speaker_character))
+            return fail(OWG_E_BAD_ARG, "owg_render_midi: invalid job");
+        for (int64_t k = 0; k < j.n_ev; k++) {
+            if (!std::isfinite(j.ev[k].time_s) || (k > 0 && j.ev[k].time_s < j.ev[k - 1].time_s)) return fail(OWG_E_BAD_ARG, "owg_render_midi: events must be finite and sorted by time");
+            if (j.ev[k].kind > OWG_MIDI_PEDAL) return fail(OWG_E_BAD_ARG, "owg_render_midi: unknown event kind");
+        }
+        max_samples = std::max<int64_t>(max_samples, j.n_samples);
+    }
+    if (max_samples == 0) return OWG_OK;
+    if (stride < max_samples) return fail(OWG_E_BAD_ARG, "owg_render_midi: stride smaller than the longest stream");
+    owg_plan pl;  // device / stream / cache plumbing of the voice phase
+    if (int rc = plan_common(&pl, opts)) return rc;
+    cudaStream_t s = pl.stream;
+    std::vector<EngineDesc> eng((size_t)n);
+    std::vector<MidiEvent> events;
+    std::vector<OwgVoiceInit> vinits;
+    std::vector<long long> held_offset((size_t)n);
+    std::vector<owg_bench_job> params((size_t)n);
+    std::vector<unsigned long long> n_each((size_t)n);
+    long long held_total = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const owg_midi_job& j = jobs[i];
+        EngineDesc& e = eng[i];
+        std::memset(&e, 0, sizeof(e));
+        e.sample_rate = SR; e.n_samples = j.n_samples; e.block_size = CHUNK;
+        e.ev_begin = (long long)events.size();
+        held_offset[i] = held_total;
+        uint32_t age = 0;
+        long long chunk = 0;
+        for (int64_t k = 0; k < j.n_ev; k++) {
+            const owg_midi_event& ev = j.ev[k];
+            // the event is applied in the first chunk whose start time `sample_pos as f64 / BASE_SR` is >= time_s (main.rs:1790-1795)
+            while ((double)(chunk * CHUNK) / SR < ev.time_s) chunk++;
+            MidiEvent d;
+            d.chunk = chunk; d.kind = ev.kind; d.vinit = -1;
+            d.note = ev.kind == OWG_MIDI_PEDAL ? (ev.velocity != 0 ? 1 : 0) : (ev.note < 33 ? 33 : (ev.note > 96 ? 96 : ev.note));
+            if (ev.kind == OWG_MIDI_NOTE_ON) {
+                age += 1;
+                owg_voice_job vj;
+                std::memset(&vj, 0, sizeof(vj));
+                vj.midi = (uint8_t)d.note; vj.mlp_enabled = 1; vj.attack_noise = 1;
+                vj.noise_seed = (uint32_t)d.note * 2654435761u + age;
+                vj.velocity = (double)ev.velocity / 127.0;
+                vj.sample_rate = SR; vj.duration_s = 0.0; vj.ds_override = NAN;
+                d.vinit = (long long)vinits.size();
+                vinits.emplace_back();
+                owg::make_voice_init(vj, &vinits.back());
+            } else if (ev.kind == OWG_MIDI_NOTE_OFF) held_total++;
+            events.push_back(d);
+        }
+        e.ev_end = (long long)events.size();
+        std::memset(&params[i], 0, sizeof(owg_bench_job));
+        params[i].v.sample_rate = SR; params[i].r_ldr = 1000000.0; params[i].tremolo_depth = 0.0; params[i].volume = j.volume;
+        params[i].speaker_character = j.speaker_character; params[i].no_poweramp = j.no_poweramp;
+        n_each[i] = (unsigned long long)j.n_samples;
+    }
+    if (events.empty()) events.push_back(MidiEvent{0, OWG_MIDI_PEDAL, 0, -1});
+    if (vinits.empty()) vinits.emplace_back();
+    std::vector<DamperRow> dampers(128);
+    owg::make_damper_rows(SR, dampers.data());
+    DevBuf<EngineDesc> d_eng; DevBuf<MidiEvent> d_events; DevBuf<OwgVoiceInit> d_vinits; DevBuf<DamperRow> d_dampers; DevBuf<long long> d_heldoff;
+    DevBuf<VoiceRT> d_pool; DevBuf<EngineState> d_states; DevBuf<uint8_t> d_held; DevBuf<int32_t> d_heldcount; DevBuf<double> d_rows;
+    int rc = d_eng.upload(eng, s);
+    if (!rc) rc = d_events.upload(events, s);
+    if (!rc) rc = d_vinits.upload(vinits, s);
+    if (!rc) rc = d_dampers.upload(dampers, s);
+    if (!rc) rc = d_heldoff.upload(held_offset, s);
+    if (!rc) rc = d_pool.alloc((size_t)n * 128);
+    if (!rc) rc = d_states.alloc((size_t)n);
+    if (!rc) rc = d_held.alloc((size_t)std::max<long long>(held_total, 1));
+    if (!rc) rc = d_heldcount.alloc((size_t)n);
+    if (!rc) rc = d_rows.alloc((size_t)n * (size_t)max_samples);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(d_pool.p, 0, (size_t)n * 128 * sizeof(VoiceRT), s));
+    CK(cudaMemsetAsync(d_heldcount.p, 0, (size_t)n * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(d_rows.p, 0, (size_t)n * (size_t)max_samples * sizeof(double), s));  // ragged batch: rows end in silence
+    const unsigned eb = (unsigned)((n + 63) / 64);
+    engine_init_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, nullptr, nullptr, d_states.p, nullptr, nullptr, nullptr);
+    CK(cudaGetLastError());
+    const long long n_rounds = (max_samples + CHUNK - 1) / CHUNK;
+    const double silent_thr = owg::silent_threshold();
+    for (long long r = 0; r < n_rounds; r++) {
+        midi_events_kernel<<<eb, 64, 0, s>>>(d_eng.p, (int)n, r, d_events.p, d_vinits.p, d_dampers.p, d_pool.p, d_states.p, d_held.p, d_heldcount.p,
+                                             d_heldoff.p, silent_thr);
+        engine_voice_mix_kernel<<<(unsigned)n, OWG_ENGINE_ITEMS, 0, s>>>(d_eng.p, r, d_pool.p, d_states.p, d_rows.p, max_samples, 0);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    {   // counters: [0] note-ons, [2] voices dropped as silent, [3] peak polyphony
+        std::vector<EngineState> hs((size_t)n);
+        CK(cudaMemcpy(hs.data(), d_states.p, (size_t)n * sizeof(EngineState), cudaMemcpyDeviceToHost));
+        owg_diag& d = g_last_diag;
+        std::memset(&d, 0, sizeof(d));
+        for (auto& st : hs) { d.nr_iter_hist[0] += st.d_note_ons; d.nr_iter_hist[2] += st.d_freed; d.nr_iter_hist[3] = std::max<uint64_t>(d.nr_iter_hist[3], st.d_max_active); }
+        d.kernels_launched = (uint64_t)(2 * n_rounds + 1);
+    }
+    // voices summed: the rest is chain B over the rows (static preamp, `set_ldr_resistance(1e6); reset()` order)
+    owg_opts o;
+    if (opts) o = *opts; else owg_default_opts(&o);
+    o.stream = nullptr;
+    o.collect_diag = 0;
+    return chain_batch_impl(d_rows.p, OWG_OUT_DEVICE, max_samples, n, n_each.data(), max_samples, params.data(), OWG_INIT_SET_THEN_RESET, out,
+                            stride, &o);
 }
 
 int owg_host_voice_init(const owg_voice_job* job, double* o) {

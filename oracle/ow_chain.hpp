@@ -262,6 +262,111 @@ static inline void preamp_batch_one(const double* in, size_t n, double fs_base, 
     delete trem;
 }
 
+// ---- rows through chain B with either construction order of the static preamp (cmd_render vs render-poly / render-midi) ----------
+static inline std::vector<double> chain_rows(const double* in, size_t n, const BenchJob& j, bool set_then_reset) {
+    const double sr = j.sample_rate;
+    const bool do_oversample = sr < 88200.0;
+    const double preamp_sr = do_oversample ? sr * 2.0 : sr;
+    std::vector<double> pout(in, in + n);
+    if (!j.no_preamp) {
+        AnyPreamp preamp(j.preamp_model, preamp_sr);
+        Tremolo* trem = nullptr;
+        if (j.tremolo_depth > 0.0) trem = new Tremolo(j.tremolo_depth, preamp_sr);
+        else if (set_then_reset) { preamp.set_ldr_resistance(j.r_ldr); preamp.reset(); }   // main.rs:1463-1464, 1753-1754
+        else { preamp.reset(); preamp.set_ldr_resistance(j.r_ldr); }                       // main.rs:438-439
+        auto step = [&](double x) {
+            if (trem) preamp.set_ldr_resistance(trem->process());
+            return preamp.process_sample(x);
+        };
+        if (do_oversample) {
+            Oversampler os;
+            for (size_t i = 0; i < n; i++) {
+                double u0, u1;
+                os.up1(in[i], u0, u1);
+                const double p0 = step(u0);
+                const double p1 = step(u1);
+                pout[i] = os.down1(p0, p1);
+            }
+        } else {
+            for (size_t i = 0; i < n; i++) pout[i] = step(in[i]);
+        }
+        delete trem;
+    }
+    PowerAmp pa;
+    Speaker spk(sr);
+    spk.set_character(j.speaker_character);
+    std::vector<double> fin(n, 0.0);
+    for (size_t i = 0; i < n; i++) {
+        const double att = pout[i] * j.volume * j.volume;
+        fin[i] = spk.process(j.no_poweramp ? att : pa.process(att)) * POST_SPEAKER_GAIN;
+    }
+    return fin;
+}
+
+// ---- `preamp-bench render-midi` (main.rs:1726-1880): the tool's own voice manager, 64-sample chunks, chain B ---------------------
+struct MidiEvt { double time_s; int kind; uint8_t note, velocity; };  // kind 0 on, 1 off, 2 pedal (velocity != 0 = down)
+static inline std::vector<double> render_midi(const std::vector<MidiEvt>& events, size_t total_samples, double volume, double speaker_char,
+                                              bool no_poweramp, int preamp_model, uint64_t* note_ons = nullptr, uint64_t* peak_poly = nullptr) {
+    const double BASE_SR = 44100.0;
+    struct Slot { std::unique_ptr<Voice> voice; bool active = false; uint8_t midi_note = 0; uint64_t age = 0; };
+    std::vector<Slot> voices(64);
+    uint64_t age_counter = 0, n_on = 0, peak = 0;
+    std::vector<double> sum(total_samples, 0.0);
+    std::vector<double> voice_buf(64);
+    size_t event_idx = 0, sample_pos = 0;
+    bool pedal_down = false;
+    std::vector<uint8_t> pedal_held;
+    auto note_off_oldest = [&](uint8_t note) {
+        Slot* best = nullptr;
+        for (auto& sl : voices) if (sl.active && sl.midi_note == note && (!best || sl.age < best->age)) best = &sl;
+        if (best && best->voice) best->voice->note_off();
+    };
+    while (sample_pos < total_samples) {
+        const size_t chunk_end = std::min(sample_pos + 64, total_samples);
+        const size_t len = chunk_end - sample_pos;
+        const double chunk_time = (double)sample_pos / BASE_SR;
+        while (event_idx < events.size() && events[event_idx].time_s <= chunk_time) {
+            const MidiEvt& e = events[event_idx];
+            if (e.kind == 0) {
+                const uint8_t note = (uint8_t)rclamp((double)e.note, 33.0, 96.0);
+                const double vel = (double)e.velocity / 127.0;
+                age_counter += 1; n_on += 1;
+                size_t slot = 64;
+                for (size_t i = 0; i < 64; i++) if (!voices[i].active) { slot = i; break; }
+                if (slot == 64) { slot = 0; for (size_t i = 1; i < 64; i++) if (voices[i].age < voices[slot].age) slot = i; }
+                const uint32_t seed = (uint32_t)note * 2654435761u + (uint32_t)age_counter;
+                voices[slot].voice.reset(new Voice());
+                voices[slot].voice->note_on(note, vel, BASE_SR, seed, true);
+                voices[slot].active = true; voices[slot].midi_note = note; voices[slot].age = age_counter;
+                uint64_t act = 0;
+                for (auto& sl : voices) act += sl.active ? 1 : 0;
+                peak = std::max(peak, act);
+            } else if (e.kind == 1) {
+                const uint8_t note = (uint8_t)rclamp((double)e.note, 33.0, 96.0);
+                if (pedal_down) pedal_held.push_back(note); else note_off_oldest(note);
+            } else {
+                pedal_down = e.velocity != 0;
+                if (!pedal_down) { for (uint8_t h : pedal_held) note_off_oldest(h); pedal_held.clear(); }
+            }
+            event_idx++;
+        }
+        for (auto& sl : voices) if (sl.active && sl.voice && sl.voice->is_silent()) { sl.active = false; sl.voice.reset(); }
+        for (auto& sl : voices) {
+            if (!sl.active || !sl.voice) continue;
+            std::fill(voice_buf.begin(), voice_buf.begin() + len, 0.0);
+            sl.voice->render(voice_buf.data(), len);
+            for (size_t i = 0; i < len; i++) sum[sample_pos + i] += voice_buf[i];
+        }
+        sample_pos = chunk_end;
+    }
+    if (note_ons) *note_ons = n_on;
+    if (peak_poly) *peak_poly = peak;
+    BenchJob j;
+    j.sample_rate = BASE_SR; j.r_ldr = 1000000.0; j.tremolo_depth = 0.0; j.volume = volume; j.speaker_character = speaker_char;
+    j.no_poweramp = no_poweramp; j.preamp_model = preamp_model;
+    return chain_rows(sum.data(), total_samples, j, true);
+}
+
 // ---- `preamp-bench calibrate` (main.rs:1069-1260): one CalibrateRow, restated literally (own reed, own pickup, T1..T5) ----------
 struct CalibrateRow { double v[18]; };
 static inline double dft_magnitude(const double* x, size_t n, double freq, double sr) {  // main.rs:893-903

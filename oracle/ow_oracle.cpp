@@ -171,6 +171,33 @@ int owo_legacy_idle_pump(double sample_rate, double depth, int64_t n, double* y,
     return OWG_OK;
 }
 
+// chain B over caller-supplied rows (owg_chain_batch)
+int owo_chain_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, const owg_bench_job* params, int init_order,
+                    double* out, int64_t out_stride, int threads, int preamp_model) {
+    if (!in || !out || !params) return OWG_E_BAD_ARG;
+    if (preamp_model == 0) pre::settled_state();
+    parallel_for(n_inst, threads, [&](int64_t i) {
+        BenchJob b = to_bench(params[i]);
+        b.preamp_model = preamp_model;
+        std::vector<double> r = chain_rows(in + i * in_stride, (size_t)n_samp, b, init_order == 1);
+        std::memcpy(out + i * out_stride, r.data(), r.size() * sizeof(double));
+    });
+    return OWG_OK;
+}
+
+// render-midi (owg_render_midi): one job
+int owo_render_midi(const owg_midi_event* ev, int64_t n_ev, int64_t n_samples, double volume, double speaker, int no_poweramp, int preamp_model,
+                    double* out, uint64_t* counters2) {
+    std::vector<MidiEvt> e((size_t)n_ev);
+    for (int64_t k = 0; k < n_ev; k++) { e[k].time_s = ev[k].time_s; e[k].kind = ev[k].kind; e[k].note = ev[k].note; e[k].velocity = ev[k].velocity; }
+    if (preamp_model == 0) pre::settled_state();
+    uint64_t a = 0, b = 0;
+    std::vector<double> r = render_midi(e, (size_t)n_samples, volume, speaker, no_poweramp != 0, preamp_model, &a, &b);
+    std::memcpy(out, r.data(), r.size() * sizeof(double));
+    if (counters2) { counters2[0] = a; counters2[1] = b; }
+    return OWG_OK;
+}
+
 // `preamp-bench calibrate`: rows[n_notes * n_vels][18] (include/owgpu.h owg_render_calibrate columns), cfg6 = ds_at_c4, ds_exponent,
 // ds_clamp_lo, ds_clamp_hi, target_db, voicing_slope
 int owo_calibrate_rows(const uint8_t* notes, int n_notes, const uint8_t* vels, int n_vels, const double* cfg6, int zero_trim, double volume,

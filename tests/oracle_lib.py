@@ -110,6 +110,8 @@ def lib():
         L.owo_render_bench_model.argtypes = [C.POINTER(BenchJob), C.c_int64, dp, C.c_int64, C.c_int, C.c_int]
         L.owo_preamp_batch_model.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_double,
                                              C.c_double, dp, C.c_int64, C.c_int, C.c_int]
+        L.owo_chain_batch.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.POINTER(BenchJob), C.c_int, dp, C.c_int64, C.c_int, C.c_int]
+        L.owo_render_midi.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, dp, C.POINTER(C.c_uint64)]
         L.owo_calibrate_rows.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int, dp, C.c_int, C.c_double, C.c_double,
                                          C.c_int, dp, C.c_int]
         L.owo_legacy_dc.argtypes = [C.c_double, dp]

@@ -610,3 +610,71 @@ def test_alias_audit_gate_through_the_gpu_engine_path(note):
     hf = 20 * np.log10(np.sqrt(np.mean(y ** 2)) / h1)
     base_step, base_hf = K.ALIAS_BASELINE[note]
     assert step_up - base_step <= 1.5 and hf - base_hf <= 2.0, (step_up, base_step, hf, base_hf)
+
+
+def test_chain_batch_both_preamp_construction_orders():
+    """owg_chain_batch: caller rows (a render-poly style sum of voices) through chain B; cmd_render's reset-then-set order and
+    render-poly's set-then-reset order (melange falls back to the settled 100 kOhm, legacy re-solves its DC point at r)."""
+    fs, n = 44100.0, 6000
+    voices = ow.render_voices([ow.voice_job(midi=m, velocity=90, duration=n / fs + 1e-6, mlp=True, seed=(m * 2654435761 + k) & 0xFFFFFFFF)
+                               for k, m in enumerate((48, 55, 64))])
+    mix = np.zeros(n)
+    for v in voices:
+        mix += v[:n]                                     # `sum_buf[j] += voice_buf[j]`, voice by voice (main.rs:1451-1453)
+    x = np.stack([mix, 0.5 * mix, mix])
+    params = [ow.bench_job(ldr=30000.0, volume=0.6, speaker=1.0), ow.bench_job(ldr=1e6, volume=0.9, speaker=0.3, no_poweramp=True),
+              ow.bench_job(tremolo_depth=0.6, volume=0.5)]
+    oparams = [to_oracle_b(p) for p in params]
+    for model, om in ((ow.MELANGE12, O.MELANGE12), (ow.LEGACY8, O.LEGACY8)):
+        for order in (ow.RESET_THEN_SET, ow.SET_THEN_RESET):
+            got = ow.chain_batch(x, params, init_order=order, preamp_model=model)
+            ref = np.zeros_like(x)
+            arr = (O.BenchJob * 3)(*oparams)
+            assert O.lib().owo_chain_batch(O.dptr(x), n, 3, n, arr, order, O.dptr(ref), n, 3, om) == 0
+            for i in range(3):
+                assert_parity(got[i], ref[i], f"chain_batch model {model} order {order} row {i}",
+                              rel_l2=REL_L2 if model == ow.MELANGE12 else LEGACY_REL_L2)
+        a = ow.chain_batch(x[:1], params[:1], init_order=ow.RESET_THEN_SET, preamp_model=model)
+        b = ow.chain_batch(x[:1], params[:1], init_order=ow.SET_THEN_RESET, preamp_model=model)
+        assert np.abs(a - b).max() > 1e-6                # the two construction orders really are different renders
+
+
+def test_render_midi_voice_manager_and_chain():
+    """owg_render_midi against the oracle's restatement of cmd_render_midi: polyphony beyond 64 (oldest slot replaced, no crossfade),
+    pedal-deferred note-offs, silent-voice clean-up, ragged batch, both preamp models."""
+    from openwurli_b200 import smf
+    import ctypes as C
+    from openwurli_b200 import _abi
+
+    def stream(seed, dur, rate):
+        rng = np.random.default_rng(seed)
+        ev, t = [], 0.0
+        while True:
+            t += rng.exponential(1.0 / rate)
+            if t >= dur:
+                break
+            note = int(rng.integers(30, 100))            # includes keys outside 33..96 (clamped by the tool)
+            ev.append((t, smf.NOTE_ON, note, int(rng.integers(1, 128))))
+            ev.append((t + rng.uniform(0.01, 0.25), smf.NOTE_OFF, note, 0))
+        ev += [(0.05, smf.PEDAL, 1, 0), (0.12, smf.PEDAL, 0, 0), (0.2, smf.PEDAL, 1, 0)]
+        ev.sort(key=lambda e: e[0])
+        return ev
+    streams = [stream(1, 0.3, 40.0), stream(2, 0.25, 900.0), [(0.0, smf.NOTE_ON, 60, 100)]]
+    for model, om in ((ow.MELANGE12, O.MELANGE12), (ow.LEGACY8, O.LEGACY8)):
+        got = ow.render_midi(streams, volume=0.5, speaker=0.8, tail=0.05, preamp_model=model)
+        d = ow.last_diag()
+        tot_on, peak = 0, 0
+        for k, ev in enumerate(streams):
+            n = smf.total_samples(ev, 0.05)
+            arr = (_abi.MidiEvent * len(ev))()
+            for i, (t, kind, a, b) in enumerate(ev):
+                code = 0 if kind == smf.NOTE_ON else (1 if kind == smf.NOTE_OFF else 2)
+                arr[i] = _abi.MidiEvent(t, code, a if code != 2 else 0, b if code == 0 else (a if code == 2 else 0), 0, 0)
+            ref = np.zeros(n)
+            cnt = (C.c_uint64 * 2)()
+            assert O.lib().owo_render_midi(C.cast(arr, C.c_void_p), len(ev), n, 0.5, 0.8, 0, om, O.dptr(ref), cnt) == 0
+            assert got[k].shape == (n,) and np.abs(ref).max() > 1e-3
+            assert_parity(got[k], ref, f"render-midi model {model} stream {k}", rel_l2=REL_L2 if model == ow.MELANGE12 else LEGACY_REL_L2)
+            tot_on += cnt[0]
+            peak = max(peak, cnt[1])
+        assert int(d.nr_iter_hist[0]) == tot_on and int(d.nr_iter_hist[3]) == peak == 64

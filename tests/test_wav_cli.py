@@ -145,8 +145,8 @@ def test_smf_parser_time_map_running_status_and_filters():
 
 
 @pytest.mark.gpu
-def test_render_midi_cli_matches_oracle_engine(tmp_path):
-    """SMF file -> events -> WurliEngine streams -> 24-bit WAV, against the oracle engine fed with the same event schedule."""
+def test_render_midi_cli_matches_oracle(tmp_path):
+    """SMF file -> events -> render-midi voice manager + chain -> 24-bit WAV, against the oracle's restatement of cmd_render_midi."""
     import oracle_lib as ol
     from openwurli_b200 import smf
     eot = b"\x00\xFF\x2F\x00"
@@ -159,7 +159,44 @@ def test_render_midi_cli_matches_oracle_engine(tmp_path):
     ev = smf.timed_events(mid.read_bytes())
     n = smf.total_samples(ev, 0.2)
     assert sr == 44100 and q.size == n
-    ref = ol.render_engines([ol.engine_job(smf.engine_events(ev), sr=44100.0, dur=n / 44100.0 + 0.5 / 44100.0, volume=0.7, depth=0.0, speaker=0.5,
-                                           block=64, warm_up=True)])[0][:n].astype(np.float64)
+    import ctypes as C
+    from openwurli_b200 import _abi
+    arr = (_abi.MidiEvent * len(ev))()
+    for i, (t, kind, a, b) in enumerate(ev):
+        code = 0 if kind == smf.NOTE_ON else (1 if kind == smf.NOTE_OFF else 2)
+        arr[i] = _abi.MidiEvent(t, code, a if code != 2 else 0, b if code == 0 else (a if code == 2 else 0), 0, 0)
+    ref = np.zeros(n)
+    assert ol.lib().owo_render_midi(C.cast(arr, C.c_void_p), len(ev), n, 0.7, 0.5, 0, 0, ol.dptr(ref), None) == 0
     assert np.abs(ref).max() > 1e-3
-    assert np.max(np.abs(q.astype(np.int64) - wav.pcm24_round(ref, 1.0))) <= 2
+    assert np.max(np.abs(q.astype(np.int64) - wav.pcm24_round(ref, 1.0))) <= 1
+    # --engine: the same schedule through the plugin's WurliEngine instead
+    out2 = tmp_path / "b.wav"
+    assert preamp_bench.main(["render-midi", "--midi", str(mid), "--output", str(out2), "--tail", "0.2", "--volume", "0.7", "--speaker", "0.5", "--engine"]) == 0
+    q2, _ = wav.read_wav_pcm24(str(out2))
+    ref2 = ol.render_engines([ol.engine_job(smf.engine_events(ev), sr=44100.0, dur=n / 44100.0 + 0.5 / 44100.0, volume=0.7, depth=0.0, speaker=0.5,
+                                            block=64, warm_up=True)])[0][:n].astype(np.float64)
+    assert np.max(np.abs(q2.astype(np.int64) - wav.pcm24_round(ref2, 1.0))) <= 2
+
+
+@pytest.mark.gpu
+def test_render_poly_signals_match_oracle():
+    """render-poly: shared-chain mix, sum of separately processed voices and the intermod residual against the oracle."""
+    import oracle_lib as ol
+    notes, vels, dur = [38, 59, 62], [45, 40, 40], 0.3
+    fin, sep, res = preamp_bench.render_poly(notes, vels, duration=dur, volume=0.6, speaker_char=1.0, r_ldr=1e6)
+    n = int(dur * 44100.0)
+    voices = ol.render_voices([ol.voice_job(midi=nt, vel=v, dur=dur, mlp=True, seed=(nt * 2654435761 + i) & 0xFFFFFFFF)
+                               for i, (nt, v) in enumerate(zip(notes, vels))])[:, :n]
+    mix = np.zeros(n)
+    for vb in voices:
+        mix += vb
+    rows = np.ascontiguousarray(np.vstack([mix[None, :], voices]))
+    p = ol.bench_job(r_ldr=1e6, volume=0.6, speaker=1.0)
+    arr = (ol.BenchJob * 4)(*[p] * 4)
+    ref = np.zeros_like(rows)
+    assert ol.lib().owo_chain_batch(ol.dptr(rows), n, 4, n, arr, 1, ol.dptr(ref), n, 4, 0) == 0
+    rsep = np.zeros(n)
+    for k in range(1, 4):
+        rsep += ref[k]
+    assert np.abs(fin - ref[0]).max() <= 1e-6 and np.abs(sep - rsep).max() <= 1e-6
+    assert np.abs(res - (ref[0] - rsep)).max() <= 1e-6 and np.abs(res).max() > 1e-7   # shared nonlinearity: the residual is not zero
