@@ -123,6 +123,40 @@ def cmd_render(args):
     return 0
 
 
+def cmd_sensitivity(args):
+    """`preamp-bench sensitivity` (main.rs:1313-1386): calibrate at every DS_AT_C4 of --ds-range; one device batch per DS value."""
+    notes = _csv_u8_list(args, "--notes", "36,48,54,60,66,72,78,84")
+    velocities = _csv_u8_list(args, "--velocities", "40,80,127")
+    ds_values = []
+    for t in parse_flag_str(args, "--ds-range", "0.50,0.55,0.60,0.65,0.70,0.75,0.80,0.85").split(","):
+        try:
+            ds_values.append(float(t.strip()))
+        except ValueError:
+            pass
+    volume = parse_flag(args, "--volume", 0.40)
+    speaker_char = parse_flag(args, "--speaker", 1.0)
+    scale_mode = "zero-trim" if has_flag(args, "--zero-trim") else parse_flag_str(args, "--scale-mode", "track")
+    output_path = parse_flag_str(args, "--output", os.path.join(tempfile.gettempdir(), "sensitivity.csv"))
+    model = api.LEGACY8 if parse_flag_str(args, "--preamp-model", "melange12") == "legacy8" else api.MELANGE12
+    sys.stderr.write(f"Sensitivity: {len(ds_values)} DS × {len(notes)} notes × {len(velocities)} vel = "
+                     f"{len(ds_values) * len(notes) * len(velocities)} renders\n")
+    lines = [CALIBRATE_HEADER]
+    for ds in ds_values:
+        if scale_mode == "freeze":
+            cfg = api.calib_cfg(ds_at_c4=0.85)
+        elif scale_mode == "zero-trim":
+            cfg = api.calib_cfg(ds_at_c4=ds, zero_trim=True)
+        else:
+            cfg = api.calib_cfg(ds_at_c4=ds)
+        rows = api.render_calibrate(notes, velocities, cfg, volume=volume, speaker=speaker_char, preamp_model=model)
+        rows[:, 0] = ds  # the ds_at_c4 column is stamped with the sweep value (main.rs:1371-1374)
+        lines += calibrate_csv_lines(notes, velocities, rows)[1:]
+    with open(output_path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    sys.stderr.write(f"Sensitivity: {len(lines) - 1} total rows → {output_path}\n")
+    return 0
+
+
 def midi_note_name(note):  # main.rs:666-672 (sharps with '#', unlike reed-renderer's file names)
     names = ["C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"]
     return f"{names[note % 12]}{note // 12 - 1}"
@@ -319,7 +353,8 @@ def cmd_render_midi(args):
     return 0
 
 
-USAGE = """Usage: preamp_bench <render|calibrate|render-midi|render-poly> [flags]
+USAGE = """Usage: preamp_bench <render|calibrate|sensitivity|render-midi|render-poly> [flags]
+  sensitivity --notes a,b --velocities x,y --ds-range d1,d2 --scale-mode track|freeze|zero-trim --volume X --speaker C --output FILE
   render-poly --notes a,b,c --velocities x,y,z --duration S --volume X --speaker C --ldr OHM --no-poweramp --normalize --output FILE
   render-midi --midi FILE --output FILE --volume X --speaker C --tail S --track N --tremolo-depth D --preamp-model M
   render     --note N --velocity V --duration S --ldr OHM --volume X --speaker C --tremolo-depth D --sample-rate HZ
@@ -342,6 +377,8 @@ def main(argv=None):
         return cmd_render_midi(args[1:])
     if args[0] == "render-poly":
         return cmd_render_poly(args[1:])
+    if args[0] == "sensitivity":
+        return cmd_sensitivity(args[1:])
     sys.stderr.write(f"Unknown subcommand: {args[0]} (only the batched render paths are mirrored)\n{USAGE}")
     return 1
 

@@ -560,6 +560,10 @@ def test_calibrate_rows_match_run_calibrate_restatement():
 
 def test_calibrate_cli_writes_the_reference_csv_format(tmp_path):
     from openwurli_b200.cli import preamp_bench
+    sens = tmp_path / "sens.csv"
+    assert preamp_bench.main(["sensitivity", "--notes", "60", "--velocities", "80", "--ds-range", "0.5,0.85", "--output", str(sens)]) == 0
+    sl = sens.read_text().strip().split("\n")
+    assert len(sl) == 3 and sl[1].split(",")[3] == "0.5000" and sl[2].split(",")[3] == "0.8500" and sl[1].split(",")[4] != sl[2].split(",")[4]
     out = tmp_path / "cal.csv"
     assert preamp_bench.main(["calibrate", "--notes", "60,61", "--velocities", "40,127", "--output", str(out)]) == 0
     lines = out.read_text().strip().split("\n")
