@@ -293,7 +293,7 @@ void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vec
     }
 }
 
-// Tremolo::new for every tremolo group, launched as early as possible on the oscillator stream (it is ~0.9 s of serial
+// Tremolo::new for every tremolo group, launched as early as possible on the oscillator stream (it is ~0.6 s of serial
 // device work per 88.2 kHz group and nothing else of the plan depends on it).
 int launch_tremolo_ctor(owg_plan* pl) {
     if (pl->trem_group_ids.empty()) return OWG_OK;
