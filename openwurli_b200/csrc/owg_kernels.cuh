@@ -764,6 +764,41 @@ __global__ void __launch_bounds__(64) chain_split_kernel(const WarpEntry* __rest
     }
 }
 
+// ---- output stage alone: volume^2 -> power amp -> speaker -> analysis, one thread per job ---------------------------------------
+// Parameter sweeps (BASELINE config 4: volume x speaker character over the same note / LDR trajectory) share everything up to the
+// preamp output: voice + DK preamp are rendered once per distinct prefix (pre_only rows) and this kernel applies each job's own output
+// stage to its prefix row.  Same arithmetic in the same order as the chain kernels' tail, so the metrics are bit-identical.
+__global__ void __launch_bounds__(128) post_stage_metrics_kernel(const double* __restrict__ pre_rows, int64_t pre_stride, const int32_t* __restrict__ prefix_of,
+                                                                 const OwgChainInit* __restrict__ cinits, const unsigned long long* __restrict__ n_samples,
+                                                                 int64_t n_jobs, double* __restrict__ metrics, const double* __restrict__ f0s,
+                                                                 int64_t w_begin, int64_t w_end) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const OwgChainInit ci = cinits[j];
+    const double* pre = pre_rows + (size_t)prefix_of[j] * pre_stride;
+    const unsigned long long ns = n_samples[j];
+    const double vol = ci.volume, m_f0 = f0s[2 * j], m_sr = f0s[2 * j + 1];
+    SpkState spk = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double m_peak = 0.0, m_sq = 0.0, m_re1 = 0.0, m_im1 = 0.0, m_re2 = 0.0, m_im2 = 0.0;
+    const unsigned long long t_end = ns < (unsigned long long)w_end ? ns : (unsigned long long)w_end;  // nothing after the window is observable
+    for (unsigned long long t = 0; t < t_end; t++) {
+        const double att = pre[t] * vol * vol;
+        const double amped = ci.no_poweramp ? att : poweramp(att, nullptr);
+        const double y_final = speaker(amped, spk, ci) * 7.498942093324558;
+        if ((int64_t)t >= w_begin) {
+            const double ii = (double)((int64_t)t - w_begin);
+            m_peak = fmax(m_peak, fabs(y_final));
+            m_sq += y_final * y_final;
+            const double ph1 = 2.0 * 3.14159265358979323846 * m_f0 * ii / m_sr;
+            const double ph2 = 2.0 * 3.14159265358979323846 * (2.0 * m_f0) * ii / m_sr;
+            m_re1 += y_final * cos(ph1); m_im1 -= y_final * sin(ph1);
+            m_re2 += y_final * cos(ph2); m_im2 -= y_final * sin(ph2);
+        }
+    }
+    double* mj = metrics + (size_t)j * OWG_METRICS;
+    mj[0] = m_peak; mj[1] = m_sq; mj[2] = m_re1; mj[3] = m_im1; mj[4] = m_re2; mj[5] = m_im2;
+}
+
 // ---- FP64 pipe micro-benchmark ------------------------------------------------------------------------
 template <bool FMA>
 __global__ void fp64_peak_kernel(double* sink, int iters, double a, double b) {

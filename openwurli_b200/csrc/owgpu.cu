@@ -390,7 +390,8 @@ int owg_plan_voices(const owg_voice_job* jobs, int64_t n, const owg_opts* opts, 
 }
 
 // post_gain: optional per-job override of Voice::post_pickup_gain (calibrate's output_scale under a non-default CalibrationConfig)
-static int plan_bench_impl(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan, const double* post_gain) {
+static int plan_bench_impl(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan, const double* post_gain,
+                           bool force_pre_only = false) {
     if (!plan || n < 0 || (n > 0 && !jobs)) return fail(OWG_E_BAD_ARG, "owg_plan_bench: bad argument");
     for (int64_t i = 0; i < n; i++) {
         if (bad_voice_job(jobs[i].v)) return fail(OWG_E_BAD_ARG, "owg_plan_bench: job with invalid sample_rate/duration/velocity");
@@ -414,6 +415,7 @@ static int plan_bench_impl(const owg_bench_job* jobs, int64_t n, const owg_opts*
         sp.depth = j.tremolo_depth;
         sp.r_ldr = j.r_ldr;
         owg::make_chain_init(j, 0, &sp.ci);
+        if (force_pre_only) sp.ci.pre_only = 1;
     }
     std::vector<int32_t> order;
     build_groups_and_warps(pl, specs, &order);
@@ -725,6 +727,87 @@ int owg_render_bench_metrics(const owg_bench_job* jobs, int64_t n, double window
     const int64_t BATCH = 65536;  // bounds the device scratch (voice samples) independently of n
     DevBuf<double> scratch, d_metrics;
     std::vector<double> raw;
+    // Shared prefixes: jobs that differ only in the output stage (volume, speaker character, power-amp bypass) have the same voice and
+    // the same preamp output.  When a sweep repeats prefixes, voice + preamp run once per distinct prefix and every job gets its own
+    // output stage from post_stage_metrics_kernel (BASELINE config 4: 32 x 32 output-stage settings per key and tremolo depth).
+    {
+        typedef std::tuple<uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t> PKey;
+        auto bits = [](double x) { uint64_t u; std::memcpy(&u, &x, 8); return u; };
+        std::map<PKey, int32_t> seen;
+        std::vector<int32_t> prefix_of((size_t)n);
+        std::vector<int64_t> first_job;
+        for (int64_t i = 0; i < n; i++) {
+            const owg_bench_job& j = jobs[i];
+            const uint64_t small = (uint64_t)j.v.midi | ((uint64_t)j.v.mlp_enabled << 8) | ((uint64_t)j.v.attack_noise << 16) | ((uint64_t)j.v.flags << 24) |
+                                   ((uint64_t)j.v.noise_seed << 32);
+            const PKey k(small, bits(j.v.velocity), bits(j.v.duration_s), bits(j.v.ds_override), bits(j.r_ldr), bits(j.tremolo_depth),
+                         (uint64_t)(j.no_preamp != 0));
+            auto it = seen.find(k);
+            if (it == seen.end()) { it = seen.emplace(k, (int32_t)first_job.size()).first; first_job.push_back(i); }
+            prefix_of[i] = it->second;
+        }
+        const int64_t np = (int64_t)first_job.size();
+        const char* dedup_env = getenv("OWG_SWEEP_DEDUP");
+        if (np * 2 <= n && !(dedup_env && dedup_env[0] == '0')) {
+            const double nwin = (double)(w1 - w0);
+            for (int64_t p0 = 0; p0 < np; p0 += BATCH) {
+                const int64_t npb = std::min<int64_t>(BATCH, np - p0);
+                std::vector<owg_bench_job> pj((size_t)npb);
+                for (int64_t k = 0; k < npb; k++) pj[k] = jobs[first_job[p0 + k]];
+                owg_plan* pl = nullptr;
+                if (int rc = plan_bench_impl(pj.data(), npb, &o, &pl, nullptr, true)) return rc;
+                const int64_t stride = (int64_t)pl->max_samples;
+                int rc = scratch.alloc((size_t)npb * (size_t)stride);
+                if (!rc) rc = owg_plan_execute(pl, scratch.p, stride, OWG_OUT_DEVICE);
+                cudaStream_t st = pl->stream;
+                // the jobs of these prefixes, in prefix order so that a warp reads one prefix row
+                std::vector<int64_t> members;
+                for (int64_t i = 0; i < n; i++) if (prefix_of[i] >= p0 && prefix_of[i] < p0 + npb) members.push_back(i);
+                std::stable_sort(members.begin(), members.end(), [&](int64_t a, int64_t b) { return prefix_of[a] < prefix_of[b]; });
+                const int64_t nm = (int64_t)members.size();
+                std::vector<OwgChainInit> ci((size_t)nm);
+                std::vector<int32_t> pref((size_t)nm);
+                std::vector<unsigned long long> ns((size_t)nm);
+                std::vector<double> f0s((size_t)nm * 2);
+                for (int64_t k = 0; k < nm; k++) {
+                    const owg_bench_job& j = jobs[members[k]];
+                    owg::make_chain_init(j, 0, &ci[k]);
+                    pref[k] = prefix_of[members[k]] - (int32_t)p0;
+                    const double nsd = j.v.duration_s * j.v.sample_rate;
+                    ns[k] = !(nsd == nsd) || nsd <= 0.0 ? 0ull : (unsigned long long)nsd;
+                    f0s[2 * k] = owg::note_frequency(j.v.midi); f0s[2 * k + 1] = sr;
+                }
+                DevBuf<OwgChainInit> d_ci; DevBuf<int32_t> d_pref; DevBuf<unsigned long long> d_ns; DevBuf<double> d_f0;
+                if (!rc) rc = d_ci.upload(ci, st);
+                if (!rc) rc = d_pref.upload(pref, st);
+                if (!rc) rc = d_ns.upload(ns, st);
+                if (!rc) rc = d_f0.upload(f0s, st);
+                if (!rc) rc = d_metrics.alloc((size_t)nm * OWG_METRICS);
+                if (!rc) {
+                    post_stage_metrics_kernel<<<(unsigned)((nm + 127) / 128), 128, 0, st>>>(scratch.p, stride, d_pref.p, d_ci.p, d_ns.p, nm, d_metrics.p, d_f0.p, w0, w1);
+                    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) rc = fail(OWG_E_CUDA, "post-stage kernel failed");
+                }
+                if (!rc) {
+                    raw.resize((size_t)nm * OWG_METRICS);
+                    if (cudaMemcpy(raw.data(), d_metrics.p, raw.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(OWG_E_CUDA, "metrics copy failed");
+                }
+                owg_plan_destroy(pl);
+                if (rc) return rc;
+                for (int64_t k = 0; k < nm; k++) {
+                    const double* r = &raw[(size_t)k * OWG_METRICS];
+                    double* m = metrics + (size_t)members[k] * OWG_METRIC_COLUMNS;
+                    const double peak = r[0], mean_sq = r[1] / nwin;
+                    const double h1 = 2.0 * std::sqrt((r[2] / nwin) * (r[2] / nwin) + (r[3] / nwin) * (r[3] / nwin));
+                    const double h2 = 2.0 * std::sqrt((r[4] / nwin) * (r[4] / nwin) + (r[5] / nwin) * (r[5] / nwin));
+                    m[0] = peak > 1e-15 ? 20.0 * std::log10(peak) : -120.0;
+                    m[1] = mean_sq > 0.0 ? 10.0 * std::log10(mean_sq) : -120.0;
+                    m[2] = h1 > 1e-15 ? 20.0 * std::log10(h2 / h1) : -120.0;
+                    m[3] = peak; m[4] = mean_sq; m[5] = h1; m[6] = h2;
+                }
+            }
+            return OWG_OK;
+        }
+    }
     for (int64_t b0 = 0; b0 < n; b0 += BATCH) {
         const int64_t nb = std::min<int64_t>(BATCH, n - b0);
         owg_plan* pl = nullptr;

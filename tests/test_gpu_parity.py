@@ -682,3 +682,21 @@ def test_render_midi_voice_manager_and_chain():
             tot_on += cnt[0]
             peak = max(peak, cnt[1])
         assert int(d.nr_iter_hist[0]) == tot_on and int(d.nr_iter_hist[3]) == peak == 64
+
+
+def test_sweep_shared_prefix_path_is_bit_identical():
+    """Config-4 style sweep: jobs that differ only in the output stage share voice + preamp (rendered once per distinct prefix, then
+    post_stage_metrics_kernel per job).  Same metrics, bit for bit, as rendering every job through the full chain."""
+    import os
+    jobs = [ow.calibrate_job(36 + 12 * k, 100, volume=0.2 + 0.2 * a, speaker=c / 3.0, tremolo_depth=0.5 * b)
+            for k in range(3) for b in range(2) for a in range(4) for c in range(4)]
+    jobs += [ow.bench_job(note=70, velocity=60, duration=0.5, no_preamp=True, volume=v) for v in (0.3, 0.6, 0.9)]   # bypass prefix
+    jobs += [ow.bench_job(note=70, velocity=60, duration=0.5, no_poweramp=True, volume=v) for v in (0.3, 0.6)]
+    fast = ow.render_bench_metrics(jobs)
+    os.environ["OWG_SWEEP_DEDUP"] = "0"
+    try:
+        full = ow.render_bench_metrics(jobs)
+    finally:
+        del os.environ["OWG_SWEEP_DEDUP"]
+    assert np.array_equal(fast, full), np.abs(fast - full).max()
+    assert np.all(np.isfinite(fast)) and len({tuple(r) for r in fast}) == len(jobs)

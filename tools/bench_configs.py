@@ -62,6 +62,15 @@ t = timed(lambda: ow.render_bench_metrics(jobs), reps=1)
 res["C4_slice_8x8x8x64keys_0.5s_metrics"] = {"renders": len(jobs), "gpu_s": t, "gpu_audio_s_per_s": len(jobs) * 0.5 / t,
                                               "full_C4_2097152_renders_estimated_s_per_gpu": t * 2097152 / len(jobs)}
 
+# C4 as BASELINE.json states it (volume x tremolo depth x speaker character, 32 x 32 x 32, over 64 keys), a 64-key slice of the depth axis:
+# 4 depths x 32 volumes x 32 speaker settings x 64 keys = 262 144 renders (1/8 of the config); voice + preamp run once per (key, depth)
+jobs = [ow.calibrate_job(33 + k, 100, volume=0.05 + 0.95 * a / 31.0, speaker=c / 31.0, tremolo_depth=b / 3.0)
+        for k in range(64) for b in range(4) for a in range(32) for c in range(32)]
+t = timed(lambda: ow.render_bench_metrics(jobs), reps=1)
+res["C4_eighth_4x32x32x64keys_0.5s_metrics_shared_prefix"] = {"renders": len(jobs), "distinct_prefixes": 64 * 4, "gpu_s": t,
+                                                              "gpu_audio_s_per_s": len(jobs) * 0.5 / t,
+                                                              "full_C4_2097152_renders_estimated_s_per_gpu": t * 2097152 / len(jobs)}
+
 # C5 slice: polyphonic engine streams at 96 kHz with stealing, block 512, warm-up on
 def stream_events(seed, dur, sr):
     s = seed * 2654435761 % (2 ** 32) or 1
