@@ -66,9 +66,33 @@ def test_no_cpu_fallback_without_device():
     assert e.value.code == _abi.OWG_E_NO_DEVICE
 
 
-def test_unimplemented_entry_points_fail_loudly():
+@pytest.mark.skipif(HAS_GPU, reason="checks the behaviour on a machine without a CUDA device")
+def test_every_render_entry_point_refuses_without_device():
+    """No entry point has a CPU path: engines, preamp batch, chain batch, metrics, calibrate and render-midi all return NO_DEVICE."""
+    from openwurli_b200 import smf
+    x = np.zeros((2, 64))
+    calls = [lambda: ow.render_engines([ow.engine_job([(0, ow.NOTE_ON, 60, 0.5)], duration=0.01)]),
+             lambda: ow.preamp_batch(x, 48000.0),
+             lambda: ow.chain_batch(x, [ow.bench_job(), ow.bench_job()]),
+             lambda: ow.render_bench_metrics([ow.calibrate_job(60, 100)]),
+             lambda: ow.render_calibrate([60], [100]),
+             lambda: ow.render_midi([[(0.0, smf.NOTE_ON, 60, 100)]], tail=0.01),
+             lambda: ow.render_voices([ow.voice_job(duration=0.01)])]
+    for f in calls:
+        with pytest.raises(ow.OwgError) as e:
+            f()
+        assert e.value.code == _abi.OWG_E_NO_DEVICE
+
+
+def test_bad_arguments_are_rejected_before_any_device_work():
     L = ow.lib()
-    assert L.owg_render_engines(None, 0, None, 0, None) in (_abi.OWG_E_UNSUPPORTED, _abi.OWG_E_NO_DEVICE, _abi.OWG_E_BAD_ARG, 0)
+    assert L.owg_render_engines(None, 1, None, 0, None) == _abi.OWG_E_BAD_ARG
+    assert L.owg_render_midi(None, 1, None, 0, None) == _abi.OWG_E_BAD_ARG
+    assert L.owg_chain_batch(None, 0, 1, 1, None, 7, None, 0, None) == _abi.OWG_E_BAD_ARG
+    assert L.owg_render_calibrate(None, 1, None, 0.1, 0.4, None, None) == _abi.OWG_E_BAD_ARG
+    assert L.owg_render_calibrate(None, 0, None, 0.4, 0.1, None, None) == _abi.OWG_E_BAD_ARG     # empty window
+    assert L.owg_render_engines(None, 0, None, 0, None) == 0 and L.owg_render_midi(None, 0, None, 0, None) == 0   # empty batches are fine
+    assert b"owg_" in L.owg_last_error() or len(L.owg_last_error()) > 0
 
 
 def _host_init(job):
