@@ -1098,6 +1098,13 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, pl.device);
     int lanes = (int)((n + (long long)sm_count * 4 - 1) / ((long long)sm_count * 4));
     lanes = std::min(31, std::max(1, lanes));
+    // warp-specialised chain (DK warp + I/O warp per CTA) while the batch fits one wave of 3 CTAs per SM; melange model only
+    bool engine_split = false;
+    {
+        const char* env = getenv("OWG_CHAIN_SPLIT");
+        const int lanes_split = (int)((n + (long long)sm_count * 3 - 1) / ((long long)sm_count * 3));
+        if (!legacy && !(env && env[0] == '0') && lanes_split <= 31) { engine_split = true; lanes = std::max(1, lanes_split); }
+    }
     if (const char* env = getenv("OWG_ENGINE_LANES")) lanes = std::min(31, std::max(1, atoi(env)));
     std::vector<int32_t> eorder((size_t)n);
     for (int64_t i = 0; i < n; i++) eorder[i] = (int32_t)i;
@@ -1245,9 +1252,14 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
             launches += 2;
         }
         CK(cudaStreamWaitEvent(sc, ev_voices[sg], 0));
-        engine_chain_kernel<<<(unsigned)ewarps.size(), 32, 0, sc>>>(d_ewarps.p, d_eorder.p, d_eng.p, r0, r1, d_spk.p, d_spkoff.p, d_groups.p, d_post.p,
-                                                                   d_recs.p, pot_stride, d_ans.p, d_chains.p, d_shadow.p, mixbuf, mix_stride, dout, stride,
-                                                                   max_samples, sg + 1 == n_chunks ? 1 : 0);
+        if (engine_split)
+            engine_chain_split_kernel<<<(unsigned)ewarps.size(), 64, 0, sc>>>(d_ewarps.p, d_eorder.p, d_eng.p, r0, r1, d_spk.p, d_spkoff.p, d_groups.p,
+                                                                             d_post.p, d_recs.p, pot_stride, d_ans.p, d_chains.p, d_shadow.p, mixbuf,
+                                                                             mix_stride, dout, stride, max_samples, sg + 1 == n_chunks ? 1 : 0);
+        else
+            engine_chain_kernel<<<(unsigned)ewarps.size(), 32, 0, sc>>>(d_ewarps.p, d_eorder.p, d_eng.p, r0, r1, d_spk.p, d_spkoff.p, d_groups.p, d_post.p,
+                                                                       d_recs.p, pot_stride, d_ans.p, d_chains.p, d_shadow.p, mixbuf, mix_stride, dout, stride,
+                                                                       max_samples, sg + 1 == n_chunks ? 1 : 0);
         CK(cudaGetLastError());
         launches += 1;
         CK(new_event(&ev_chain[sg]));
