@@ -58,6 +58,11 @@ def n_samples(dur, sr):
     return int(dur * sr)
 
 
+class MidiEvent(C.Structure):  # include/owgpu.h owg_midi_event
+    _fields_ = [("time_s", C.c_double), ("kind", C.c_uint8), ("note", C.c_uint8), ("velocity", C.c_uint8), ("_pad0", C.c_uint8),
+                ("_pad1", C.c_int32)]
+
+
 _lib = None
 
 

@@ -700,3 +700,26 @@ def test_sweep_shared_prefix_path_is_bit_identical():
         del os.environ["OWG_SWEEP_DEDUP"]
     assert np.array_equal(fast, full), np.abs(fast - full).max()
     assert np.all(np.isfinite(fast)) and len({tuple(r) for r in fast}) == len(jobs)
+
+
+def test_gpu_against_committed_v2_golden_vectors():
+    """tests/golden/oracle_v2.npz (box-independent target): legacy chain B, engine stream, calibrate rows and render-midi, both models."""
+    from golden.make_golden import CAL_CFG, CAL_NOTES, CAL_VELS, CASES_L, ENGINE_EVENTS, MIDI_EVENTS
+    from openwurli_b200 import smf
+    G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_v2.npz"))
+    for i, kw in enumerate(CASES_L):
+        oj = O.bench_job(**kw)
+        j = ow.bench_job(note=oj.v.midi, velocity=round(oj.v.velocity * 127), duration=oj.v.duration_s, ldr=oj.r_ldr, tremolo_depth=oj.tremolo_depth)
+        j.v.velocity = oj.v.velocity
+        got = ow.render_bench([j], preamp_model=ow.LEGACY8)[0]
+        assert np.abs(got - G2[f"legacy_bench_{i}"]).max() <= 1e-6, i
+    kinds = {0: smf.NOTE_ON, 1: smf.NOTE_OFF, 2: smf.PEDAL}
+    stream = [(t, kinds[k], (a if k != 2 else b), (b if k == 0 else 0)) for t, k, a, b in MIDI_EVENTS]
+    for model in (ow.MELANGE12, ow.LEGACY8):
+        e = ow.render_engines([ow.engine_job(ENGINE_EVENTS, sample_rate=44100.0, duration=0.1, tremolo_depth=0.5, speaker_character=0.5, warm_up=False)],
+                              preamp_model=model)[0]
+        assert np.abs(e.astype(np.float64) - G2[f"engine_{model}"].astype(np.float64)).max() <= 2e-6 if model else 1e-7
+        c = ow.render_calibrate(CAL_NOTES, CAL_VELS, ow.calib_cfg(ds_at_c4=CAL_CFG[0], ds_clamp_max=CAL_CFG[3]), preamp_model=model)
+        assert np.abs(c - G2[f"calibrate_{model}"]).max() <= (5e-5 if model == 0 else 2e-3)
+        y = ow.render_midi([stream], volume=0.6, speaker=1.0, tail=0.05, preamp_model=model)[0]
+        assert np.abs(y - G2[f"midi_{model}"]).max() <= 1e-6
