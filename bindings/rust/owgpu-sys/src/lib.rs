@@ -1,0 +1,225 @@
+//! Raw bindings to `include/owgpu.h` (ABI version 1) plus the thin safe helpers INTEGRATION.md describes.
+//!
+//! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Rust toolchain.  The struct layouts are checked
+//! against the C header by `tests/test_host_logic.py` (sizeof through gcc) on the C side; keep the two in step.
+#![allow(non_camel_case_types)]
+
+use core::ffi::{c_char, c_void};
+
+pub const OWG_OK: i32 = 0;
+pub const OWG_E_BAD_ARG: i32 = -1;
+pub const OWG_E_NO_DEVICE: i32 = -2;
+pub const OWG_E_CUDA: i32 = -3;
+pub const OWG_E_OOM: i32 = -4;
+pub const OWG_E_UNSUPPORTED: i32 = -5;
+
+pub const OWG_OUT_HOST: i32 = 0;
+pub const OWG_OUT_DEVICE: i32 = 1;
+pub const OWG_PREAMP_MELANGE12: i32 = 0; // cfg(feature = "melange-preamp")
+pub const OWG_PREAMP_LEGACY8: i32 = 1; // the reference's default build
+pub const OWG_VOICE_NO_ONSET: u8 = 1;
+pub const OWG_EV_NOTE_ON: u8 = 0;
+pub const OWG_EV_NOTE_OFF: u8 = 1;
+pub const OWG_EV_SUSTAIN: u8 = 2;
+pub const OWG_INIT_RESET_THEN_SET: i32 = 0;
+pub const OWG_INIT_SET_THEN_RESET: i32 = 1;
+pub const OWG_METRIC_COLUMNS: usize = 7;
+pub const OWG_CALIBRATE_COLUMNS: usize = 18;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct owg_voice_job {
+    pub midi: u8,
+    pub mlp_enabled: u8,
+    pub attack_noise: u8,
+    pub flags: u8,
+    pub noise_seed: u32,
+    pub velocity: f64,
+    pub sample_rate: f64,
+    pub duration_s: f64,
+    pub ds_override: f64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct owg_bench_job {
+    pub v: owg_voice_job,
+    pub r_ldr: f64,
+    pub tremolo_depth: f64,
+    pub volume: f64,
+    pub speaker_character: f64,
+    pub no_preamp: i32,
+    pub no_poweramp: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct owg_event {
+    pub sample: i64,
+    pub kind: u8,
+    pub note: u8,
+    pub _pad0: u16,
+    pub velocity: f32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct owg_engine_job {
+    pub sample_rate: f64,
+    pub duration_s: f64,
+    pub volume: f64,
+    pub tremolo_depth: f64,
+    pub speaker_character: f64,
+    pub mlp_enabled: i32,
+    pub block_size: i32,
+    pub warm_up: i32,
+    pub _pad0: i32,
+    pub ev: *const owg_event,
+    pub n_ev: i64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct owg_midi_event {
+    pub time_s: f64,
+    pub kind: u8,
+    pub note: u8,
+    pub velocity: u8,
+    pub _pad0: u8,
+    pub _pad1: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct owg_midi_job {
+    pub ev: *const owg_midi_event,
+    pub n_ev: i64,
+    pub n_samples: i64,
+    pub volume: f64,
+    pub speaker_character: f64,
+    pub no_poweramp: i32,
+    pub _pad0: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct owg_calib_cfg {
+    pub ds_at_c4: f64,
+    pub ds_exponent: f64,
+    pub ds_clamp_lo: f64,
+    pub ds_clamp_hi: f64,
+    pub target_db: f64,
+    pub voicing_slope: f64,
+    pub zero_trim: i32,
+    pub _pad0: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct owg_opts {
+    pub device: i32,
+    pub out_location: i32,
+    pub precision: i32,
+    pub preamp_model: i32,
+    pub stream: *mut c_void,
+    pub collect_diag: i32,
+    pub _reserved: [i32; 7],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct owg_diag {
+    pub nr_iter_hist: [u64; 16],
+    pub nr_max_iter: u64,
+    pub be_fallback: u64,
+    pub voltage_damp: u64,
+    pub nan_reset: u64,
+    pub shadow_nr_iter_hist: [u64; 16],
+    pub shadow_be_fallback: u64,
+    pub shadow_nan_reset: u64,
+    pub poweramp_iter_hist: [u64; 9],
+    pub tremolo_nr_iter_hist: [u64; 16],
+    pub tremolo_be_fallback: u64,
+    pub kernels_launched: u64,
+}
+
+#[repr(C)]
+pub struct owg_plan {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn owg_abi_version() -> i32;
+    pub fn owg_device_count() -> i32;
+    pub fn owg_last_error() -> *const c_char;
+    pub fn owg_default_opts(o: *mut owg_opts);
+    pub fn owg_default_calib_cfg(c: *mut owg_calib_cfg);
+    pub fn owg_render_voices(jobs: *const owg_voice_job, n: i64, out: *mut f64, stride: i64, opts: *const owg_opts) -> i32;
+    pub fn owg_render_bench(jobs: *const owg_bench_job, n: i64, out: *mut f64, stride: i64, opts: *const owg_opts) -> i32;
+    pub fn owg_render_bench_metrics(jobs: *const owg_bench_job, n: i64, window_start_s: f64, window_end_s: f64, metrics: *mut f64,
+                                    opts: *const owg_opts) -> i32;
+    pub fn owg_render_calibrate(jobs: *const owg_bench_job, n: i64, cfg: *const owg_calib_cfg, window_start_s: f64, window_end_s: f64,
+                                rows: *mut f64, opts: *const owg_opts) -> i32;
+    pub fn owg_preamp_batch(input: *const f64, in_stride: i64, n_inst: i64, n_samp: i64, fs_base: f64, oversample: i32, tremolo_depth: f64,
+                            r_ldr_static: f64, out: *mut f64, out_stride: i64, opts: *const owg_opts) -> i32;
+    pub fn owg_chain_batch(input: *const f64, in_stride: i64, n_inst: i64, n_samp: i64, params: *const owg_bench_job, init_order: i32,
+                           out: *mut f64, out_stride: i64, opts: *const owg_opts) -> i32;
+    pub fn owg_render_engines(jobs: *const owg_engine_job, n: i64, out: *mut f32, stride: i64, opts: *const owg_opts) -> i32;
+    pub fn owg_render_midi(jobs: *const owg_midi_job, n: i64, out: *mut f64, stride: i64, opts: *const owg_opts) -> i32;
+    pub fn owg_plan_bench(jobs: *const owg_bench_job, n: i64, opts: *const owg_opts, plan: *mut *mut owg_plan) -> i32;
+    pub fn owg_plan_voices(jobs: *const owg_voice_job, n: i64, opts: *const owg_opts, plan: *mut *mut owg_plan) -> i32;
+    pub fn owg_plan_execute(plan: *mut owg_plan, out: *mut f64, stride: i64, out_location: i32) -> i32;
+    pub fn owg_plan_samples(plan: *const owg_plan, i: i64) -> i64;
+    pub fn owg_plan_h2d_bytes(plan: *const owg_plan) -> i64;
+    pub fn owg_plan_kernel_launches(plan: *const owg_plan) -> i64;
+    pub fn owg_plan_last_timing(plan: *const owg_plan, main_kernel_ms: *mut f32, total_ms: *mut f32) -> i32;
+    pub fn owg_plan_destroy(plan: *mut owg_plan);
+    pub fn owg_last_diag(out: *mut owg_diag) -> i32;
+}
+
+/// The preamp the reference build would have compiled in (`dk_preamp/mod.rs:14-20`).
+pub fn default_opts(melange_preamp: bool) -> owg_opts {
+    let mut o = core::mem::MaybeUninit::<owg_opts>::uninit();
+    // SAFETY: owg_default_opts fully initialises the struct.
+    let mut o = unsafe {
+        owg_default_opts(o.as_mut_ptr());
+        o.assume_init()
+    };
+    o.preamp_model = if melange_preamp { OWG_PREAMP_MELANGE12 } else { OWG_PREAMP_LEGACY8 };
+    o
+}
+
+fn check(rc: i32) -> Result<(), String> {
+    if rc == OWG_OK {
+        return Ok(());
+    }
+    // SAFETY: owg_last_error returns a NUL-terminated thread-local string.
+    let msg = unsafe { std::ffi::CStr::from_ptr(owg_last_error()) }.to_string_lossy().into_owned();
+    Err(format!("libowgpu error {rc}: {msg}"))
+}
+
+/// Batch form of `Voice::render_note` (voice.rs:191-221): MLP off, default seed, attack noise on.
+pub fn render_notes(notes: &[(u8, f64)], duration_secs: f64, sample_rate: f64) -> Result<Vec<Vec<f64>>, String> {
+    let n_samp = (duration_secs * sample_rate) as usize; // voice.rs:214 truncation
+    if notes.is_empty() || n_samp == 0 {
+        return Ok(vec![Vec::new(); notes.len()]);
+    }
+    let jobs: Vec<owg_voice_job> = notes
+        .iter()
+        .map(|&(m, v)| owg_voice_job {
+            midi: m,
+            mlp_enabled: 0,
+            attack_noise: 1,
+            flags: 0,
+            noise_seed: (m as u32).wrapping_mul(2654435761),
+            velocity: v,
+            sample_rate,
+            duration_s: duration_secs,
+            ds_override: f64::NAN,
+        })
+        .collect();
+    let mut out = vec![0.0f64; jobs.len() * n_samp];
+    // SAFETY: pointers and sizes describe the vectors above; opts = NULL selects the defaults.
+    check(unsafe { owg_render_voices(jobs.as_ptr(), jobs.len() as i64, out.as_mut_ptr(), n_samp as i64, core::ptr::null()) })?;
+    Ok(out.chunks(n_samp).map(|c| c.to_vec()).collect())
+}
