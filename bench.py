@@ -311,7 +311,10 @@ def main():
         kernel_s = main_run["main_ms"] * 1e-3 / args.steps
         achieved = flops / kernel_s / 1e12
         line["roofline"] = {"bound": "fp64", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
-                            "traffic": None, "peak_source": "owg_fp64_peak DFMA micro-benchmark measured in this run "
+                            "traffic": (1064522752 if (model == 0 and main_run["n_inst"] == 8128 and args.tremolo_depth > 0) else None),
+                            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 8192-sample chunk launch of chain_split_kernel "
+                                            "(ncu --set full, profiles/r01_v9_chain_split_kernel_full.txt); algorithmic bytes of that launch: 1090 MB",
+                            "peak_source": "owg_fp64_peak DFMA micro-benchmark measured in this run "
                             "(MEASURED_PEAKS.json has no FP64 entry; B200 nominal 37 TFLOP/s)",
                             "peak_unfused_tflops": unfused_peak, "frac_of_unfused": achieved / unfused_peak,
                             "kernel": "owgd::chain_legacy_kernel" if model == 1 else
