@@ -211,9 +211,13 @@ __global__ void tremolo_an_kernel(const OwgPreampGroup* groups, int n_groups, do
 // ---- chain V: reed + attack noise + pickup + gain (voice.rs:162-179), one thread per voice -----------
 // out row i = out + row[i]*stride; writes n_samples[i] doubles.
 // TAPS: also reduce the calibrate taps T1 (reed), T2 (pickup), T3 (x output gain) over [w_begin, w_end) into metrics[i][12..20].
+// [t_begin, t_end): the render can be cut into launches (the first short one lets the chain start early while the rest of the voice
+// runs beside it on another stream); the recurrence state travels through vcarry[OWG_VOICE_CARRY][n].
+#define OWG_VOICE_CARRY 44
 template <bool TAPS>
 __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restrict__ inits, int64_t n, double* __restrict__ out, int64_t stride,
-                                                   double* __restrict__ metrics, const double* __restrict__ f0s, int64_t w_begin, int64_t w_end) {
+                                                   double* __restrict__ metrics, const double* __restrict__ f0s, int64_t w_begin, int64_t w_end,
+                                                   int64_t t_begin, int64_t t_end, double* __restrict__ vcarry) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double t1_peak = 0.0, t2_peak = 0.0, t2_sq = 0.0, t2_re1 = 0.0, t2_im1 = 0.0, t2_re2 = 0.0, t2_im2 = 0.0, t3_peak = 0.0, t3_sq = 0.0;
@@ -243,7 +247,21 @@ __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restric
     const double beta = vi->pickup_beta, ds = vi->pickup_ds, gain = vi->post_pickup_gain;
     const unsigned long long ns = vi->n_samples;
     double* o = out + i * stride;
-    for (unsigned long long t = 0; t < ns; t++) {
+    double* vc = vcarry ? vcarry + i : nullptr;
+    if (vc && t_begin > 0) {  // resume
+        int k = 0;
+#pragma unroll
+        for (int m = 0; m < 7; m++) { s[m] = vc[(k++) * n]; c[m] = vc[(k++) * n]; env[m] = vc[(k++) * n]; drift[m] = vc[(k++) * n]; }
+        jit = (uint32_t)vc[(k++) * n]; n_amp = vc[(k++) * n]; n_left = (uint32_t)vc[(k++) * n]; n_rng = (uint32_t)vc[(k++) * n];
+        z1 = vc[(k++) * n]; z2 = vc[(k++) * n]; q = vc[(k++) * n];
+        if (TAPS) {
+            t1_peak = vc[(k++) * n]; t2_peak = vc[(k++) * n]; t2_sq = vc[(k++) * n]; t2_re1 = vc[(k++) * n]; t2_im1 = vc[(k++) * n];
+            t2_re2 = vc[(k++) * n]; t2_im2 = vc[(k++) * n]; t3_peak = vc[(k++) * n]; t3_sq = vc[(k++) * n];
+        }
+    }
+    const unsigned long long t_lo = (unsigned long long)(t_begin > 0 ? t_begin : 0);
+    const unsigned long long t_hi = (t_end >= 0 && (unsigned long long)t_end < ns) ? (unsigned long long)t_end : ns;
+    for (unsigned long long t = t_lo; t < t_hi; t++) {
         // reed.rs:249-264 onset ramp
         double onset = 1.0;
         if (t < onset_n) {
@@ -323,6 +341,18 @@ __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restric
             t3_peak = fmax(t3_peak, fabs(t3));
             t3_sq += t3 * t3;
         }
+    }
+    if (vc && t_hi < ns) {  // more launches follow
+        int k = 0;
+#pragma unroll
+        for (int m = 0; m < 7; m++) { vc[(k++) * n] = s[m]; vc[(k++) * n] = c[m]; vc[(k++) * n] = env[m]; vc[(k++) * n] = drift[m]; }
+        vc[(k++) * n] = (double)jit; vc[(k++) * n] = n_amp; vc[(k++) * n] = (double)n_left; vc[(k++) * n] = (double)n_rng;
+        vc[(k++) * n] = z1; vc[(k++) * n] = z2; vc[(k++) * n] = q;
+        if (TAPS) {
+            vc[(k++) * n] = t1_peak; vc[(k++) * n] = t2_peak; vc[(k++) * n] = t2_sq; vc[(k++) * n] = t2_re1; vc[(k++) * n] = t2_im1;
+            vc[(k++) * n] = t2_re2; vc[(k++) * n] = t2_im2; vc[(k++) * n] = t3_peak; vc[(k++) * n] = t3_sq;
+        }
+        return;
     }
     if (TAPS) {
         double* mj = metrics + (size_t)i * OWG_METRICS;

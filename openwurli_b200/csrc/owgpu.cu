@@ -138,6 +138,9 @@ struct owg_plan {
     DevBuf<TrmRun> d_trm_run, d_trm_ctor;       // oscillator state: running / as constructed (Tremolo::new, computed at plan time)
     DevBuf<LdrRun> d_ldr_run;                   // LDR envelope + resistance-tracking state between chunks
     cudaStream_t stream_copy = nullptr;          // device->host copy-back of finished chunks
+    cudaStream_t stream_voice = nullptr;         // the tail of the voice render runs here, beside the first chain chunks
+    cudaEvent_t ev_voice1 = nullptr, ev_voice2 = nullptr;
+    DevBuf<double> d_vcarry;                     // voice recurrence state between the two voice launches
     cudaStream_t stream_trem = nullptr;          // the serial Twin-T oscillator runs here, one chunk ahead of its consumers
     std::vector<cudaEvent_t> chunk_events;       // oscillator chunk c finished
     std::vector<cudaEvent_t> chain_ev;           // pairs around every chain launch (device time of the dominant kernel)
@@ -157,6 +160,9 @@ struct owg_plan {
         for (auto e : chain_ev) cudaEventDestroy(e);
         if (stream_trem) cudaStreamDestroy(stream_trem);
         if (stream_copy) cudaStreamDestroy(stream_copy);
+        if (stream_voice) cudaStreamDestroy(stream_voice);
+        if (ev_voice1) cudaEventDestroy(ev_voice1);
+        if (ev_voice2) cudaEventDestroy(ev_voice2);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -503,6 +509,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     // It depends on nothing else in this call, so it is enqueued first (before the voice kernel); the first chunk is short so
     // that the chain can start early.
     const int64_t CH_BASE = 8192, CH_FIRST = 2048;  // base-rate samples per chunk
+    int64_t voice_split_at = -1;                    // > 0: the voice render is cut at this sample into two launches
     auto chunk_lo = [&](int64_t c) -> int64_t { return c <= 0 ? 0 : CH_FIRST + (c - 1) * CH_BASE; };
     int64_t n_chunks = 0;
     const int nt = pl->kind >= 1 ? (int)pl->trem_group_ids.size() : 0;
@@ -535,11 +542,29 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     } else {  // chain V for every job
         const int threads = 32;
         const int blocks = (int)((pl->n + threads - 1) / threads);
-        if (pl->taps && pl->metrics_ptr)
-            voice_kernel<true><<<blocks, threads, 0, s>>>(pl->d_vinit.p, pl->n, dout, stride, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end);
-        else
-            voice_kernel<false><<<blocks, threads, 0, s>>>(pl->d_vinit.p, pl->n, dout, stride, nullptr, nullptr, 0, 0);
-        CK(cudaGetLastError());
+        // Tremolo-only plans consume the voice rows chunk by chunk: render the first two chunks' worth now and the rest on another
+        // stream, beside the first chain chunks (the voice kernel is latency-bound at one warp per 32 renders: ~46 ms for 3 s).
+        voice_split_at = (pl->kind == 1 && nt > 0 && pl->warps_static.empty() && (int64_t)pl->max_samples > 2 * (CH_FIRST + CH_BASE))
+                             ? CH_FIRST + CH_BASE : -1;
+        if (voice_split_at > 0) {
+            if (int rc = pl->d_vcarry.alloc((size_t)OWG_VOICE_CARRY * (size_t)pl->n)) return rc;
+            if (!pl->stream_voice) CK(cudaStreamCreateWithFlags(&pl->stream_voice, cudaStreamNonBlocking));
+            if (!pl->ev_voice1) { CK(cudaEventCreateWithFlags(&pl->ev_voice1, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&pl->ev_voice2, cudaEventDisableTiming)); }
+        }
+        const bool taps = pl->taps && pl->metrics_ptr;
+        for (int part = 0; part < (voice_split_at > 0 ? 2 : 1); part++) {
+            const int64_t tb = part == 0 ? 0 : voice_split_at, te = (voice_split_at > 0 && part == 0) ? voice_split_at : -1;
+            cudaStream_t vs = part == 0 ? s : pl->stream_voice;
+            if (part == 1) { CK(cudaEventRecord(pl->ev_voice1, s)); CK(cudaStreamWaitEvent(vs, pl->ev_voice1, 0)); }
+            double* vc = voice_split_at > 0 ? pl->d_vcarry.p : nullptr;
+            if (taps)
+                voice_kernel<true><<<blocks, threads, 0, vs>>>(pl->d_vinit.p, pl->n, dout, stride, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end, tb, te, vc);
+            else
+                voice_kernel<false><<<blocks, threads, 0, vs>>>(pl->d_vinit.p, pl->n, dout, stride, nullptr, nullptr, 0, 0, tb, te, vc);
+            CK(cudaGetLastError());
+            if (part == 1) CK(cudaEventRecord(pl->ev_voice2, vs));
+            if (part == 1) launches++;
+        }
         launches++;
     }
     bool copied_by_chunks = false;
@@ -616,6 +641,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
             for (int64_t c = 0; c < n_chunks; c++) {
                 const int64_t b0 = chunk_lo(c), b1 = chunk_lo(c + 1);
                 CK(cudaStreamWaitEvent(s, pl->chunk_events[c], 0));
+                if (voice_split_at > 0 && b0 == voice_split_at) CK(cudaStreamWaitEvent(s, pl->ev_voice2, 0));  // the tail of the voice rows
                 // oscillator volts -> LDR law -> the preamp's resistance tracking, in place (off the oscillator's serial thread)
                 tremolo_ldr_kernel<<<nt, 256, 0, s>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max, pl->d_ldr_run.p,
                                                       2 * b0, 2 * b1, pl->legacy ? 1 : 0);
