@@ -718,7 +718,7 @@ def test_gpu_against_committed_v2_golden_vectors():
     for model in (ow.MELANGE12, ow.LEGACY8):
         e = ow.render_engines([ow.engine_job(ENGINE_EVENTS, sample_rate=44100.0, duration=0.1, tremolo_depth=0.5, speaker_character=0.5, warm_up=False)],
                               preamp_model=model)[0]
-        assert np.abs(e.astype(np.float64) - G2[f"engine_{model}"].astype(np.float64)).max() <= 2e-6 if model else 1e-7
+        assert np.abs(e.astype(np.float64) - G2[f"engine_{model}"].astype(np.float64)).max() <= (2e-6 if model else 1e-7)
         c = ow.render_calibrate(CAL_NOTES, CAL_VELS, ow.calib_cfg(ds_at_c4=CAL_CFG[0], ds_clamp_max=CAL_CFG[3]), preamp_model=model)
         assert np.abs(c - G2[f"calibrate_{model}"]).max() <= (5e-5 if model == 0 else 2e-3)
         y = ow.render_midi([stream], volume=0.6, speaker=1.0, tail=0.05, preamp_model=model)[0]
