@@ -258,6 +258,12 @@ int owg_fp64_peak(int32_t device, int32_t fma, float ms_target, double* tera_ins
 
 /* Device self-test: the library's shared-reciprocal division (recip_prepare/div_by, owg_device.cuh) against the
  * compiler's IEEE-754 f64 division on 303104*n_per_thread pseudo-random operand pairs; *mismatches must be 0. */
+/* Diagnostic counters of the lane-tiled chain kernel, accumulated by calls made with collect_diag = 1 on the current device:
+ * [0] DK-warp cycles waiting for input  [1] DK-warp cycles total  [2] I/O-warp cycles waiting for the preamp  [3] I/O-warp cycles
+ * total  [4] Newton loop trips over DK warp-steps  [5] Newton iterations over instance-steps  [6] DK warp-steps  [7] instance-steps.
+ * reset != 0 clears them after reading. */
+int owg_debug_counters(uint64_t* out, int32_t n, int32_t reset);
+
 int owg_selftest_division(int64_t n_per_thread, uint64_t seed, uint64_t* mismatches, uint64_t* tested);
 
 #ifdef __cplusplus

@@ -3,6 +3,7 @@
 #include "../../include/owgpu.h"
 #include "host_setup.h"
 #include "owg_kernels.cuh"
+#include "owg_tile.cuh"
 #include "owg_legacy.cuh"
 #include "owg_engine.cuh"
 
@@ -47,6 +48,7 @@ int usable_devices() {
 struct DeviceCache {
     DkState* d_settled = nullptr;
     bool fade_uploaded = false;
+    bool dkdev_uploaded = false;
     // grow-only device staging buffer for host-output calls (avoids an 8.6 GB cudaMalloc/cudaFree per one-shot render)
     void* stage = nullptr;
     size_t stage_bytes = 0;
@@ -63,6 +65,17 @@ int ensure_device_cache(int device, cudaStream_t stream, DeviceCache** out, int6
         owg::noise_fade_table(fade);
         CK(cudaMemcpyToSymbol(c_noise_fade, fade, sizeof(fade)));
         c.fade_uploaded = true;
+    }
+    if (!c.dkdev_uploaded) {  // junction constants of the tiled kernel's Newton loop, computed on this device (owg_tile.cuh)
+        DkDev* tmp = nullptr;
+        CK(cudaMalloc(&tmp, sizeof(DkDev)));
+        dkdev_init_kernel<<<1, 32, 0, stream>>>(tmp);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaMemcpyToSymbol(c_dkdev, tmp, sizeof(DkDev), 0, cudaMemcpyDeviceToDevice));
+        CK(cudaFree(tmp));
+        c.dkdev_uploaded = true;
+        if (launches) *launches += 1;
     }
     if (!c.d_settled) {
         CK(cudaMalloc(&c.d_settled, sizeof(DkState)));
@@ -114,6 +127,8 @@ struct owg_plan {
     bool collect_diag = false;
     bool legacy = false;             // owg_opts.preamp_model == OWG_PREAMP_LEGACY8
     bool use_split = false;          // chain_split_kernel (decided at plan time from the batch size)
+    bool use_tile = false;           // chain_tile_kernel: 4 lanes per instance (the default for melange chain-B batches)
+    int tile_ipw = 0;                // instance tiles per DK warp (1..7)
     bool taps = false;               // calibrate taps T1..T4 in addition to T5 (owg_render_calibrate)
     DevBuf<double> d_legacy_recs;    // [group][OWG_LG_STRIDE]
     int64_t n = 0;
@@ -278,6 +293,22 @@ void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vec
         if (pl->use_split) lpw = lpw_split < 1 ? 1 : lpw_split;
     }
     if (const char* e = getenv("OWG_LANES_PER_WARP")) { const int v = atoi(e); if (v >= 1 && v <= 31) lpw = v; }
+    // Lane-tiled chain (chain_tile_kernel: 4 lanes per instance, 4 DK warps + 1 I/O warp per CTA, 2 CTAs per SM): the default
+    // while the batch fits two waves of CTAs; beyond that the batch is throughput-bound and the one-thread-per-instance kernels
+    // spend fewer issue slots per instance.  OWG_CHAIN_KERNEL = tile | split | warp forces one of the three.
+    {
+        const char* ck = getenv("OWG_CHAIN_KERNEL");
+        const bool force_tile = ck && ck[0] == 't';
+        const bool forbid_tile = ck && (ck[0] == 's' || ck[0] == 'w');
+        if (ck && ck[0] == 'w') pl->use_split = false;
+        const int64_t cta_slots = 2 * 148;
+        int ipw = (int)((n + cta_slots * OWG_TILE_AW - 1) / (cta_slots * OWG_TILE_AW));
+        ipw = ipw < 1 ? 1 : (ipw > OWG_TILE_IPW ? OWG_TILE_IPW : ipw);
+        if (const char* e = getenv("OWG_TILE_IPW")) { const int v = atoi(e); if (v >= 1 && v <= OWG_TILE_IPW) ipw = v; }
+        const bool fits = (int64_t)n <= 2 * cta_slots * OWG_TILE_AW * OWG_TILE_IPW;
+        pl->use_tile = !pl->legacy && !forbid_tile && (force_tile || fits);
+        if (pl->use_tile) { pl->tile_ipw = ipw; pl->use_split = false; lpw = OWG_TILE_AW * ipw; }
+    }
     std::vector<int32_t>& order = *order_out;
     order.reserve(n);
     for (size_t g = 0; g < pl->groups.size(); g++) {
@@ -615,6 +646,16 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                                                                  pl->d_group_rec_index.p, 0, dout, stride, pl->collect_diag ? pl->d_diag.p : nullptr, b0, b1,
                                                                  overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end,
                                                                  pl->taps ? 1 : 0);
+                else if (pl->use_tile && pl->collect_diag)
+                    chain_tile_kernel<false, true><<<nb, OWG_TILE_THREADS, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                                                  pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, pl->d_diag.p,
+                                                                                  b0, b1, overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin,
+                                                                                  pl->w_end, pl->taps ? 1 : 0, pl->tile_ipw);
+                else if (pl->use_tile)
+                    chain_tile_kernel<false, false><<<nb, OWG_TILE_THREADS, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                                                   pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride, nullptr,
+                                                                                   b0, b1, overlap_d2h ? pl->d_carry.p : nullptr, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin,
+                                                                                   pl->w_end, pl->taps ? 1 : 0, pl->tile_ipw);
                 else if (!pl->collect_diag && split_chain)
                     chain_split_kernel<false><<<nb, 64, 0, s>>>(pl->d_warps_static.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                 pl->d_static_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, 0, dout, stride,
@@ -659,6 +700,16 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
                     chain_legacy_kernel<true><<<nb, 32, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->d_legacy_recs.p, pl->d_pot_seq.p,
                                                                 pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride, pl->collect_diag ? pl->d_diag.p : nullptr,
                                                                 b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end, pl->taps ? 1 : 0);
+                else if (pl->use_tile && pl->collect_diag)
+                    chain_tile_kernel<true, true><<<nb, OWG_TILE_THREADS, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                                                 pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
+                                                                                 pl->d_diag.p, b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end,
+                                                                                 pl->taps ? 1 : 0, pl->tile_ipw);
+                else if (pl->use_tile)
+                    chain_tile_kernel<true, false><<<nb, OWG_TILE_THREADS, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
+                                                                                  pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
+                                                                                  nullptr, b0, b1, pl->d_carry.p, pl->metrics_ptr, pl->d_f0s.p, pl->w_begin, pl->w_end,
+                                                                                  pl->taps ? 1 : 0, pl->tile_ipw);
                 else if (!pl->collect_diag && split_chain)
                     chain_split_kernel<true><<<nb, 64, 0, s>>>(pl->d_warps_trem.p, pl->d_order.p, pl->d_cinit.p, pl->d_nsamp.p, pl->cache->d_settled,
                                                                pl->d_trem_recs.p, pl->d_ans.p, pl->d_group_rec_index.p, pl->trem_n_os_max, dout, stride,
@@ -927,7 +978,7 @@ int owg_render_calibrate(const owg_bench_job* jobs, int64_t n, const owg_calib_c
         if (!rc) rc = scratch.alloc((size_t)nb * (size_t)stride);
         if (!rc) rc = d_metrics.alloc((size_t)nb * OWG_METRICS);
         if (!rc && cudaMemsetAsync(d_metrics.p, 0, (size_t)nb * OWG_METRICS * sizeof(double), pl->stream) != cudaSuccess) rc = fail(OWG_E_CUDA, "memset failed");
-        if (!rc && !(pl->use_split || pl->legacy)) rc = fail(OWG_E_UNSUPPORTED, "owg_render_calibrate: taps need the warp-specialised or the legacy chain kernel");
+        if (!rc && !(pl->use_tile || pl->use_split || pl->legacy)) rc = fail(OWG_E_UNSUPPORTED, "owg_render_calibrate: taps need the lane-tiled, the warp-specialised or the legacy chain kernel");
         if (!rc) {
             pl->metrics_ptr = d_metrics.p;
             pl->taps = true;
@@ -1580,6 +1631,16 @@ int owg_selftest_division(int64_t n_per_thread, uint64_t seed, uint64_t* mismatc
     cudaFree(d);
     *mismatches = h;
     if (tested) *tested = (uint64_t)blocks * threads * (uint64_t)n_per_thread;
+    return OWG_OK;
+}
+
+int owg_debug_counters(uint64_t* out, int32_t n, int32_t reset) {
+    if (!out || n < 0) return fail(OWG_E_BAD_ARG, "owg_debug_counters: bad argument");
+    if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyFromSymbol(h, g_tile_prof, sizeof(h)));
+    for (int i = 0; i < n && i < 8; i++) out[i] = h[i];
+    if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; CK(cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z))); }
     return OWG_OK;
 }
 

@@ -209,3 +209,18 @@ def test_legacy_preamp_plan_constants_match_oracle_bitwise():
     S, An = a[:64].reshape(8, 8), a[64:128].reshape(8, 8)
     assert np.allclose(S, S.T, rtol=1e-9, atol=1e-18)           # reciprocal network
     assert abs(a[186] - 1e-6) < 1e-20 and a[187] == 1.0 / 1e6
+
+
+def test_tile_term_tables_reproduce_build_rhs_bit_for_bit(tmp_path):
+    """owg_tile_tables.h (the lane-tiled kernel's build_rhs slots: 4 lanes x 18 padded terms) against the straightforward rows."""
+    exe = tmp_path / "tile_tables_check"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-o", str(exe), os.path.join(ROOT, "tests", "tile_tables_check.cpp")])
+    assert subprocess.check_output([str(exe)]).decode().strip().endswith("OK")
+
+
+def test_constant_tables_of_product_and_oracle_are_the_same_extraction():
+    """The product and the oracle each carry their own copy of the generated-solver constants (neither tree includes from the
+    other); the two copies must be byte-identical, and identical to a fresh extraction when the reference is present."""
+    a = open(os.path.join(ROOT, "openwurli_b200", "csrc", "ow_consts.inc"), "rb").read()
+    b = open(os.path.join(ROOT, "oracle", "ow_consts.inc"), "rb").read()
+    assert a == b
