@@ -388,9 +388,62 @@ void owo_chain_init(const owg_bench_job* j, double* o) {
     for (int i = 0; i < 18; i++) o[i] = v[i];
 }
 
-// Engine state-machine probe: apply events with block rendering, return counts [active, held, sustained, releasing].
-void owo_engine_counts(const owg_engine_job* job, int32_t* out4) {
-    (void)job; (void)out4;
+// Engine session probe for the restated reference tests (engine.rs:682-1178): runs a script of WurliEngine calls and records the
+// voice-state counts at every QUERY.  ops[i] = {kind, a, b}:
+//   0 note_on(a, b)  1 note_off(a)  2 set_sustain(a != 0)  3 render(a samples; b != 0: append to `out`)  4 QUERY(note a)
+//   5 set_volume(a)  6 set_tremolo_depth(a)  7 set_speaker_character(a)  8 reset()  9 set_sample_rate(a)  10 set_mlp_enabled(a != 0)
+// Each QUERY appends 8 ints to `counts`: active, held, sustained, releasing, has_steal_voice_for(a), voices with note a Held,
+// voices with note a Sustained, sustain flag.  Returns the number of samples written to `out` (or -1 on overflow).
+int64_t owo_engine_script(double sample_rate, int preamp_model, const double* ops, int64_t n_ops, float* out, int64_t out_cap, int32_t* counts, int64_t counts_cap,
+                          double* smoothers /* [3] volume / depth / character .current at the end, may be null */) {
+    WurliEngine e(sample_rate, preamp_model);
+    int64_t n_out = 0, n_q = 0;
+    std::vector<float> buf;
+    for (int64_t i = 0; i < n_ops; i++) {
+        const int kind = (int)ops[3 * i];
+        const double a = ops[3 * i + 1], b = ops[3 * i + 2];
+        switch (kind) {
+            case 0: e.note_on((uint8_t)a, (float)b); break;
+            case 1: e.note_off((uint8_t)a); break;
+            case 2: e.set_sustain(a != 0.0); break;
+            case 3: {
+                const size_t len = (size_t)a;
+                buf.assign(len, 0.0f);
+                e.render(buf.data(), len);
+                if (b != 0.0) {
+                    if (n_out + (int64_t)len > out_cap) return -1;
+                    std::memcpy(out + n_out, buf.data(), len * sizeof(float));
+                    n_out += (int64_t)len;
+                }
+                break;
+            }
+            case 4: {
+                if ((n_q + 1) * 8 > counts_cap) return -1;
+                int32_t* c = counts + n_q * 8;
+                const uint8_t note = (uint8_t)a;  // the reference's test helpers compare the stored (clamped) note with the raw argument
+                c[0] = e.active_voice_count(); c[1] = e.count_state(VState::Held); c[2] = e.count_state(VState::Sustained);
+                c[3] = e.count_state(VState::Releasing);
+                c[4] = c[5] = c[6] = 0;
+                for (auto& sl : e.voices) {
+                    if (sl.midi_note == note && sl.steal_voice) c[4] = 1;  // has_steal_voice_for, engine.rs:631-635
+                    if (sl.midi_note == note && sl.state == VState::Held) c[5]++;
+                    if (sl.midi_note == note && sl.state == VState::Sustained) c[6]++;
+                }
+                c[7] = e.sustain_held ? 1 : 0;
+                n_q++;
+                break;
+            }
+            case 5: e.volume.set_target(a); break;
+            case 6: e.tremolo_depth.set_target(a); break;
+            case 7: e.speaker_character.set_target(a); break;
+            case 8: e.reset(); break;
+            case 9: e.set_sample_rate(a); break;
+            case 10: e.mlp_enabled = a != 0.0; break;
+            default: return -2;
+        }
+    }
+    if (smoothers) { smoothers[0] = e.volume.current; smoothers[1] = e.tremolo_depth.current; smoothers[2] = e.speaker_character.current; }
+    return n_out;
 }
 
 }  // extern "C"

@@ -86,6 +86,8 @@ def lib():
         L.owo_render_engines_model.argtypes = [C.POINTER(EngineJob), C.c_int64, C.POINTER(C.c_float), C.c_int64, C.c_int, C.c_int]
         L.owo_alias_stimulus.argtypes = [C.c_uint8, C.c_uint8, C.c_double, C.c_double, C.c_double, dp]
         L.owo_last_diag.argtypes = [C.POINTER(Diag)]
+        L.owo_engine_script.argtypes = [C.c_double, C.c_int, dp, C.c_int64, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int32), C.c_int64, dp]
+        L.owo_engine_script.restype = C.c_int64
         for name, args in [("owo_midi_to_freq", [C.c_int]), ("owo_tip_mass_ratio", [C.c_int]),
                            ("owo_reed_length_mm", [C.c_int]), ("owo_reed_compliance", [C.c_int]),
                            ("owo_pickup_displacement_scale", [C.c_int]), ("owo_fundamental_decay_rate", [C.c_int]),
@@ -204,3 +206,24 @@ def render_engines(jobs, threads=1, preamp_model=0):
     arr = (EngineJob * n)(*jobs)
     assert lib().owo_render_engines_model(arr, n, out.ctypes.data_as(C.POINTER(C.c_float)), stride, threads, preamp_model) == 0
     return out
+
+
+# ---- engine session scripts (owo_engine_script): the vocabulary of the reference's engine tests (engine.rs:682-1178) ----
+NOTE_ON, NOTE_OFF, SUSTAIN, RENDER, QUERY, SET_VOLUME, SET_DEPTH, SET_CHARACTER, RESET, SET_SAMPLE_RATE, SET_MLP = range(11)
+
+
+def engine_script(ops, sr=44100.0, model=0):
+    """Runs a script of WurliEngine calls on the oracle.  ops: list of (kind, a, b).  Returns (captured float32 samples, list of
+    QUERY results as dicts, final smoother values)."""
+    a = np.array([[float(k), float(x), float(y)] for (k, x, y) in ops], dtype=np.float64)
+    n_cap = int(sum(x for (k, x, y) in ops if k == RENDER and y))
+    n_q = sum(1 for (k, x, y) in ops if k == QUERY)
+    out = np.zeros(max(n_cap, 1), dtype=np.float32)
+    counts = np.zeros(max(n_q, 1) * 8, dtype=np.int32)
+    sm = np.zeros(3)
+    n = lib().owo_engine_script(sr, model, a.ctypes.data_as(C.POINTER(C.c_double)), len(ops), out.ctypes.data_as(C.POINTER(C.c_float)), len(out),
+                                counts.ctypes.data_as(C.POINTER(C.c_int32)), len(counts), sm.ctypes.data_as(C.POINTER(C.c_double)))
+    assert n == n_cap, n
+    keys = ("active", "held", "sustained", "releasing", "has_steal", "note_held", "note_sustained", "sustain_flag")
+    qs = [dict(zip(keys, counts[8 * i:8 * i + 8].tolist())) for i in range(n_q)]
+    return out[:n_cap], qs, sm
