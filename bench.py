@@ -6,8 +6,11 @@
 One "step" = one complete pass of the hot path over the 64-key x 127-velocity grid (8128 `preamp-bench render`
 jobs, chain B, MLP on, 3 s per note, 44.1 kHz).  The default workload has tremolo depth 0.5, i.e. the full
 north_star chain including the Twin-T/LDR coupling; the static-LDR CLI default is measured
-in the same run and reported under "variants".  Under torchrun (N>1) every rank renders its own full grid
-(weak scaling: renders are independent, no data-path collective; seeds are offset per rank).
+in the same run and reported under "variants".  Under torchrun (N>1) two modes are measured in the same run:
+  weak   : every rank renders its own full grid (seeds offset per rank) -- the machine-filling regime; top-level `value`
+  strong : ONE grid, cut over the ranks with openwurli_b200.shard.shard_indices (the north-star split "8128 renders on 8 GPUs"),
+           each rank copying its rows into ONE host buffer in shared memory (host-side gather, no collective) -- `strong_scaling`
+--scaling strong makes the strong-scaled number the top-level `value`.  Renders are independent: no data-path collective.
 
 `value`  : device-timed (CUDA events, max over ranks), init records resident in HBM, output left in HBM.
 `e2e`    : the public API ow.render_bench(jobs, out=pinned_host): host note-on setup + H2D + kernels + D2H of
@@ -154,6 +157,8 @@ def main():
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grid-stride", type=int, default=1, help="debug: take every k-th grid job")
+    ap.add_argument("--scaling", default="both", choices=["weak", "strong", "both"],
+                    help="N>1: weak = a full grid per rank; strong = one grid split over the ranks; both = weak as `value`, strong under `strong_scaling`")
     ap.add_argument("--preamp-model", default="melange12", choices=["melange12", "legacy8"],
                     help="melange12 = the north-star 12-node DK preamp (cargo feature melange-preamp); legacy8 = the reference's default build")
     args = ap.parse_args()
@@ -190,7 +195,8 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "cpu_model": O.cpu_model(),
+                                 "build": "g++ -O3 -march=x86-64-v3 -ffp-contract=off", "stage_ns_single_thread": O.stage_timers(40000)},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0,
                 "note": "CPU oracle = line-by-line C++ restatement of the reference (Rust toolchain absent; see DESIGN.md)"}
@@ -289,6 +295,91 @@ def main():
         # bucket b = last_nr_iterations b -> b+1 iterations ran; bucket 15 (>=15) counted as 16 (lower bound)
         return float((h * (np.arange(16) + 1)).sum() / max(h.sum(), 1.0))
 
+    def strong_passes(depth, steps, warm):
+        """ONE grid split over the ranks (shard.shard_indices): device-timed max over ranks, then the same through the public API with
+        every rank writing its rows into one host buffer in POSIX shared memory (the host-side gather)."""
+        from openwurli_b200 import shard
+        jobs_all = grid_jobs(ow, args.duration, depth, stride=args.grid_stride)     # identical on every rank
+        idx = shard.shard_indices(jobs_all, world, rank)
+        mine = [jobs_all[i] for i in idx]
+        plan = ow.Plan.bench(mine, device=dev, stream=stream, preamp_model=model)
+        out = torch.empty((max(len(mine), 1), plan.max_samples), dtype=torch.float64, device="cuda")
+        for _ in range(warm):
+            plan.execute(out)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(tstream)
+        for _ in range(steps):
+            plan.execute(out)
+        e1.record(tstream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        plan.close()
+        del out
+        # ---- end to end: one result buffer on the host, every rank fills its slab
+        n_samp = int(args.duration * FS)
+        n_all = len(jobs_all)
+        gather = "one POSIX shared-memory buffer, each rank's D2H copy lands in its row range"
+        shm = None
+        host = None
+        contiguous = len(idx) > 0 and idx == list(range(idx[0], idx[0] + len(idx)))
+        try:
+            from multiprocessing import shared_memory
+            if not contiguous:
+                raise RuntimeError("shard is not a contiguous row range")
+            name = "owg_bench_" + os.environ.get("MASTER_PORT", "0")
+            nbytes = n_all * n_samp * 8
+            if rank == 0:
+                free = os.statvfs("/dev/shm").f_bavail * os.statvfs("/dev/shm").f_frsize
+                ok = torch.tensor([1 if free > nbytes + (1 << 28) else 0], device="cuda")
+                if ok.item():
+                    shm = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
+            else:
+                ok = torch.tensor([0], device="cuda")
+            dist.broadcast(ok, 0)
+            if not ok.item():
+                raise RuntimeError("/dev/shm too small")
+            dist.barrier()
+            if rank != 0:
+                shm = shared_memory.SharedMemory(name=name)
+            full = np.ndarray((n_all, n_samp), dtype=np.float64, buffer=shm.buf)
+            host = torch.from_numpy(full[idx[0]:idx[0] + len(idx)])
+            rc = torch.cuda.cudart().cudaHostRegister(host.data_ptr(), host.numel() * 8, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister failed ({rc})")
+        except Exception as ex:  # fall back to private pinned slabs (still one box, no inter-process copy either way)
+            gather = f"per-rank pinned slabs ({ex})"
+            host = torch.empty((max(len(mine), 1), n_samp), dtype=torch.float64).pin_memory()
+        ow.render_bench(mine, out=host, device=dev, preamp_model=model)
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(1, min(steps, 2))
+        for _ in range(e_steps):
+            ow.render_bench(mine, out=host, device=dev, preamp_model=model)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        checksum = torch.tensor([float(host[:, ::997].abs().sum().item())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(checksum, op=dist.ReduceOp.SUM)
+        barrier()
+        if shm is not None:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(host.data_ptr())
+            except Exception:
+                pass
+            del host, full
+            shm.close()
+            if rank == 0:
+                shm.unlink()
+        audio = n_all * args.duration
+        return {"scaling": "strong", "value": audio * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "renders_total": n_all,
+                "renders_per_gpu": [len(idx)], "e2e": {"value": audio * e_steps / t.item(), "unit": UNIT, "d2h_bytes_per_step": n_all * n_samp * 8,
+                                                        "gather": gather, "checksum": checksum.item()},
+                "note": "one C3 grid split over the ranks by instance (shard.shard_indices); a render is a sample-serial recurrence, so a grid "
+                        "that already under-fills one GPU gains little from more GPUs: the per-step latency of a render, not throughput, bounds it"}
+
     main_run = timed_passes(args.tremolo_depth, args.steps, warmup)
     audio_s = main_run["n_inst"] * args.duration * world
     value = audio_s * args.steps / (main_run["ms"] * 1e-3)
@@ -302,6 +393,14 @@ def main():
             "gpu_launches": main_run["launches"], "clocks": main_run["clocks"],
             "checks": {"finite": main_run["finite"], "peak_abs": main_run["peak"], "e2e_checksum": e2e["checksum"]}}
 
+    if world > 1 and args.scaling in ("strong", "both"):
+        st = strong_passes(args.tremolo_depth, args.steps, warmup)
+        if args.scaling == "strong":
+            line.update(value=st["value"], ms_per_step=st["ms_per_step"], scaling="strong", e2e={"value": st["e2e"]["value"], "unit": UNIT,
+                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": st["e2e"]["d2h_bytes_per_step"]})
+            line["weak_scaling"] = {"value": value, "unit": UNIT, "ms_per_step": main_run["ms"] / args.steps, "e2e": e2e_value}
+            line["config"]["renders_per_gpu"] = KEYS * VELS // args.grid_stride // world
+        line["strong_scaling"] = st
     if rank == 0:
         # roofline of the dominant kernel (chain_kernel): algorithmic FLOPs / its CUDA-event duration inside the timed region
         fma_peak = ow.fp64_peak(device=dev, fma=True) * 2.0     # TFLOP/s, DFMA = 2 flop
@@ -364,7 +463,11 @@ def main():
             v1, dt1 = run_cpu(O, args.duration, args.tremolo_depth, 1, 1, model)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n_jobs} evenly spread grid renders x {args.duration:g} s, {threads} threads "
-                                              f"({dt:.1f} s); single-thread: {v1:.2f} audio-s/s"}
+                                              f"({dt:.1f} s); single-thread: {v1:.2f} audio-s/s",
+                                    "single_thread": v1, "cpu_model": O.cpu_model(), "build": "g++ -O3 -march=x86-64-v3 -ffp-contract=off",
+                                    "stage_ns_single_thread": O.stage_timers(40000),
+                                    "reference_published_single_thread": {"melange_tremolo": 4.2, "melange_static": 38.0, "legacy_tremolo": 29.0,
+                                                                          "source": "CHANGELOG.md:105-111, 30 s renders incl. one-time setup, hardware unstated"}}
         print(json.dumps(line))
     elif not args.no_variants and world == 1:
         pass

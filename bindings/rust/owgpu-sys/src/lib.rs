@@ -123,7 +123,9 @@ pub struct owg_opts {
     pub preamp_model: i32,
     pub stream: *mut c_void,
     pub collect_diag: i32,
-    pub _reserved: [i32; 7],
+    /// bit d = use CUDA device d; two or more bits: the call fans out over those GPUs (host output)
+    pub device_mask: u32,
+    pub _reserved: [i32; 6],
 }
 
 #[repr(C)]

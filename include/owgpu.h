@@ -102,7 +102,12 @@ typedef struct owg_opts {
     int32_t preamp_model; /* OWG_PREAMP_* */
     void* stream;         /* cudaStream_t to launch on; NULL = library-owned stream */
     int32_t collect_diag; /* 1 = keep per-call solver counters for owg_last_diag() */
-    int32_t _reserved[7];
+    uint32_t device_mask; /* bit d = use CUDA device d.  0 = single device (`device`).  With two or more bits set, owg_render_voices and
+                           * owg_render_bench (host output) fan the job list out over the selected GPUs inside the call: contiguous job ranges
+                           * balanced by rendered samples, one worker thread, stream and staging buffer per GPU, every GPU copying its rows
+                           * straight into the caller's buffer.  Renders are independent: no collective, each GPU recomputes the (tiny) shared
+                           * sequences of the preamp groups it touches.  Order the jobs by preamp group to keep groups on one GPU. */
+    int32_t _reserved[6];
 } owg_opts;
 
 /* Solver counters of the last call on this thread that had collect_diag=1 (sums over all jobs).
@@ -260,7 +265,8 @@ int owg_fp64_peak(int32_t device, int32_t fma, float ms_target, double* tera_ins
  * compiler's IEEE-754 f64 division on 303104*n_per_thread pseudo-random operand pairs; *mismatches must be 0. */
 /* Diagnostic counters of the lane-tiled chain kernel, accumulated by calls made with collect_diag = 1 on the current device:
  * [0] DK-warp cycles waiting for input  [1] DK-warp cycles total  [2] I/O-warp cycles waiting for the preamp  [3] I/O-warp cycles
- * total  [4] Newton loop trips over DK warp-steps  [5] Newton iterations over instance-steps  [6] DK warp-steps  [7] instance-steps.
+ * total  [4] Newton loop trips over DK warp-steps  [5] Newton iterations over instance-steps  [6] DK warp-steps  [7] instance-steps
+ * [8] Newton iterations repeated by the generic (reference-order) code, counted per lane.
  * reset != 0 clears them after reading. */
 int owg_debug_counters(uint64_t* out, int32_t n, int32_t reset);
 

@@ -39,7 +39,7 @@ class EngineJob(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("out_location", C.c_int32), ("precision", C.c_int32),
                 ("preamp_model", C.c_int32), ("stream", C.c_void_p), ("collect_diag", C.c_int32),
-                ("_reserved", C.c_int32 * 7)]
+                ("device_mask", C.c_uint32), ("_reserved", C.c_int32 * 6)]
 
 
 class MidiEvent(C.Structure):

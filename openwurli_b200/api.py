@@ -46,7 +46,7 @@ def _samples(duration, sample_rate):
 MELANGE12, LEGACY8 = 0, 1  # owg_opts.preamp_model: gen_preamp.rs 12-node (north star) | dk_preamp_legacy.rs 8-node (reference default build)
 
 
-def _opts(device=-1, out_location=OWG_OUT_HOST, stream=None, collect_diag=False, preamp_model=MELANGE12):
+def _opts(device=-1, out_location=OWG_OUT_HOST, stream=None, collect_diag=False, preamp_model=MELANGE12, devices=None):
     o = Opts()
     lib().owg_default_opts(C.byref(o))
     o.preamp_model = int(preamp_model)
@@ -54,6 +54,11 @@ def _opts(device=-1, out_location=OWG_OUT_HOST, stream=None, collect_diag=False,
     o.out_location = out_location
     o.stream = stream
     o.collect_diag = 1 if collect_diag else 0
+    if devices is not None:  # in-call multi-GPU fan-out (owg_opts.device_mask)
+        mask = 0
+        for d in devices:
+            mask |= 1 << int(d)
+        o.device_mask = mask
     return o
 
 
@@ -168,21 +173,23 @@ def _alloc_out(n, stride, out):
     return np.zeros((n, stride), dtype=np.float64)
 
 
-def render_voices(jobs, out=None, device=-1, collect_diag=False):
-    """Batch of Voice::note_on + render (chain V). Returns [n, max_samples] float64."""
+def render_voices(jobs, out=None, device=-1, collect_diag=False, devices=None):
+    """Batch of Voice::note_on + render (chain V). Returns [n, max_samples] float64.  devices=[0, 1, ...]: one call fans the job
+    list out over those GPUs (host output only)."""
     stride = max([_samples(j.duration_s, j.sample_rate) for j in jobs], default=0)
     out = _alloc_out(len(jobs), stride, out)
     if len(jobs) == 0 or stride == 0:
         return out
     ptr, st, loc = _out_ptr(out)
     arr = (VoiceJob * len(jobs))(*jobs)
-    o = _opts(device, loc, None, collect_diag)
+    o = _opts(device, loc, None, collect_diag, devices=devices)
     check(lib().owg_render_voices(arr, len(jobs), ptr, st, C.byref(o)))
     return out
 
 
-def render_bench(jobs, out=None, device=-1, collect_diag=False, preamp_model=MELANGE12):
-    """Batch of `preamp-bench render` (chain B). Returns [n, max_samples] float64 (pre-WAV samples).
+def render_bench(jobs, out=None, device=-1, collect_diag=False, preamp_model=MELANGE12, devices=None):
+    """Batch of `preamp-bench render` (chain B). Returns [n, max_samples] float64 (pre-WAV samples).  devices=[0, 1, ...]: one call
+    fans the job list out over those GPUs (contiguous ranges balanced by rendered samples; host output only).
     preamp_model: MELANGE12 (`--features melange-preamp`, the north-star path) or LEGACY8 (the reference's default build)."""
     stride = max([_samples(j.v.duration_s, j.v.sample_rate) for j in jobs], default=0)
     out = _alloc_out(len(jobs), stride, out)
@@ -190,7 +197,7 @@ def render_bench(jobs, out=None, device=-1, collect_diag=False, preamp_model=MEL
         return out
     ptr, st, loc = _out_ptr(out)
     arr = (BenchJob * len(jobs))(*jobs)
-    o = _opts(device, loc, None, collect_diag, preamp_model)
+    o = _opts(device, loc, None, collect_diag, preamp_model, devices=devices)
     check(lib().owg_render_bench(arr, len(jobs), ptr, st, C.byref(o)))
     return out
 

@@ -17,6 +17,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -38,6 +39,8 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
         }                                                                                          \
     } while (0)
 
+inline int popcount32(uint32_t x) { int c = 0; while (x) { c += (int)(x & 1u); x >>= 1; } return c; }
+
 int usable_devices() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -53,6 +56,11 @@ struct DeviceCache {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     bool stage_in_use = false;
+    // Tremolo::new per preamp rate: the oscillator state after the 50 warm-up + 2*sr settle samples (tremolo.rs:92-102).  It depends on
+    // the rate only (depth enters shunt_impedance, tremolo.rs:152-167), so it is computed once per device and rate -- like the
+    // reference would if it cached its constructor the way it caches the preamp's settled state.
+    struct TrmCtor { TrmRun* state = nullptr; cudaEvent_t ready = nullptr; };
+    std::map<uint64_t, TrmCtor> trm_ctor;
 };
 std::mutex g_cache_mu;
 std::map<int, DeviceCache> g_cache;
@@ -192,6 +200,7 @@ int plan_common(owg_plan* pl, const owg_opts* opts) {
     if (o.preamp_model != OWG_PREAMP_MELANGE12 && o.preamp_model != OWG_PREAMP_LEGACY8) return fail(OWG_E_UNSUPPORTED, "unknown preamp_model");
     pl->legacy = o.preamp_model == OWG_PREAMP_LEGACY8;
     int dev = o.device;
+    if (popcount32(o.device_mask) == 1) { dev = 0; while (!(o.device_mask & (1u << dev))) dev++; }  // a one-bit mask names the device
     if (dev < 0) CK(cudaGetDevice(&dev));
     CK(cudaSetDevice(dev));
     pl->device = dev;
@@ -346,12 +355,35 @@ int launch_tremolo_ctor(owg_plan* pl) {
         rc = fail(OWG_E_CUDA, "stream creation failed");
     if (!rc) {
         // Constructors run at plan time, per-sample processing at execute time: Tremolo::new (50 warm-up + 2*sr settle
-        // samples of the Twin-T oscillator, tremolo.rs:84-115) is evaluated once per tremolo group, like Voice::note_on on
-        // the host and DkPreamp::new's cached settled state.  Asynchronous: every later oscillator launch goes to the same
-        // in-order stream, so nothing has to wait here.
-        tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                             pl->d_trm_ctor.p, -1, -1, nullptr);
-        if (cudaGetLastError() != cudaSuccess) rc = fail(OWG_E_CUDA, "tremolo constructor kernel launch failed");
+        // samples of the Twin-T oscillator, tremolo.rs:84-115) is evaluated once per device and preamp rate (it does not depend on
+        // the depth) and cached, like Voice::note_on on the host and DkPreamp::new's cached settled state.  Asynchronous: every
+        // later oscillator launch goes to the same in-order stream, so nothing has to wait here.
+        auto bits = [](double x) { uint64_t u; std::memcpy(&u, &x, 8); return u; };
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        DeviceCache& c = *pl->cache;
+        bool all_cached = getenv("OWG_TREM_CTOR_CACHE") == nullptr || getenv("OWG_TREM_CTOR_CACHE")[0] != '0';
+        for (int gi = 0; gi < nt && all_cached; gi++) all_cached = c.trm_ctor.count(bits(pl->groups[pl->trem_group_ids[gi]].preamp_sr)) != 0;
+        if (all_cached) {
+            for (int gi = 0; gi < nt && !rc; gi++) {
+                const DeviceCache::TrmCtor& tc = c.trm_ctor[bits(pl->groups[pl->trem_group_ids[gi]].preamp_sr)];
+                if (cudaStreamWaitEvent(pl->stream_trem, tc.ready, 0) != cudaSuccess ||
+                    cudaMemcpyAsync(pl->d_trm_ctor.p + gi, tc.state, sizeof(TrmRun), cudaMemcpyDeviceToDevice, pl->stream_trem) != cudaSuccess)
+                    rc = fail(OWG_E_CUDA, "tremolo constructor cache copy failed");
+            }
+        } else {
+            tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                                 pl->d_trm_ctor.p, -1, -1, nullptr);
+            if (cudaGetLastError() != cudaSuccess) rc = fail(OWG_E_CUDA, "tremolo constructor kernel launch failed");
+            for (int gi = 0; gi < nt && !rc; gi++) {
+                const uint64_t key = bits(pl->groups[pl->trem_group_ids[gi]].preamp_sr);
+                if (c.trm_ctor.count(key)) continue;
+                DeviceCache::TrmCtor tc;
+                if (cudaMalloc(&tc.state, sizeof(TrmRun)) != cudaSuccess || cudaEventCreateWithFlags(&tc.ready, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaMemcpyAsync(tc.state, pl->d_trm_ctor.p + gi, sizeof(TrmRun), cudaMemcpyDeviceToDevice, pl->stream_trem) != cudaSuccess ||
+                    cudaEventRecord(tc.ready, pl->stream_trem) != cudaSuccess) { rc = fail(OWG_E_CUDA, "tremolo constructor cache fill failed"); break; }
+                c.trm_ctor[key] = tc;
+            }
+        }
     }
     return rc;
 }
@@ -770,7 +802,68 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     return OWG_OK;
 }
 
+extern "C++" {
+namespace {
+// In-call multi-GPU fan-out (owg_opts.device_mask): contiguous job ranges balanced by rendered samples, one worker thread per
+// selected GPU, each rendering its range through the single-device entry point straight into the caller's host rows.
+template <class Job, class SampleCount, class RenderOne>
+int fan_out_devices(const Job* jobs, int64_t n, double* out, int64_t stride, const owg_opts& o, SampleCount n_samples_of, RenderOne render_one) {
+    const int ndev_avail = usable_devices();
+    std::vector<int> devs;
+    for (int d = 0; d < 32 && d < ndev_avail; d++) if (o.device_mask & (1u << d)) devs.push_back(d);
+    if (devs.empty()) return fail(OWG_E_BAD_ARG, "device_mask selects no usable CUDA device");
+    if (o.out_location != OWG_OUT_HOST) return fail(OWG_E_BAD_ARG, "device_mask fan-out needs host output (OWG_OUT_HOST)");
+    if (o.stream) return fail(OWG_E_BAD_ARG, "device_mask fan-out uses library-owned streams (opts->stream must be NULL)");
+    const int nd = (int)devs.size();
+    double total = 0.0;
+    for (int64_t i = 0; i < n; i++) total += (double)n_samples_of(jobs[i]);
+    std::vector<int64_t> bounds(nd + 1, n);
+    bounds[0] = 0;
+    if (total <= 0.0) { for (int k = 1; k < nd; k++) bounds[k] = n * k / nd; }
+    else {
+        double acc = 0.0;
+        int cut = 1;
+        for (int64_t i = 0; i < n && cut < nd; i++) {
+            acc += (double)n_samples_of(jobs[i]);
+            while (cut < nd && acc >= total * cut / nd) bounds[cut++] = i + 1;
+        }
+    }
+    std::vector<int> rcs(nd, OWG_OK);
+    std::vector<std::string> errs(nd);
+    std::vector<owg_diag> diags(nd);
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; k++) {
+        th.emplace_back([&, k] {
+            const int64_t b0 = bounds[k], b1 = bounds[k + 1];
+            if (b1 <= b0) return;
+            owg_opts ok = o;
+            ok.device = devs[k];
+            ok.device_mask = 0;
+            rcs[k] = render_one(jobs + b0, b1 - b0, out + (size_t)b0 * (size_t)stride, stride, &ok);
+            if (rcs[k] != OWG_OK) errs[k] = g_err;
+            else if (o.collect_diag) diags[k] = g_last_diag;
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int k = 0; k < nd; k++) if (rcs[k] != OWG_OK) return fail(rcs[k], "device " + std::to_string(devs[k]) + ": " + errs[k]);
+    if (o.collect_diag) {  // counters of a fanned-out call = sums over the GPUs
+        owg_diag& d = g_last_diag;
+        std::memset(&d, 0, sizeof(d));
+        for (int k = 0; k < nd; k++) {
+            const uint64_t* src = reinterpret_cast<const uint64_t*>(&diags[k]);
+            uint64_t* dst = reinterpret_cast<uint64_t*>(&d);
+            for (size_t w = 0; w < sizeof(owg_diag) / sizeof(uint64_t); w++) dst[w] += src[w];
+        }
+    }
+    return OWG_OK;
+}
+}  // namespace
+}  // extern "C++"
+
 int owg_render_voices(const owg_voice_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts) {
+    if (opts && popcount32(opts->device_mask) >= 2 && n > 0 && jobs && out)
+        return fan_out_devices(jobs, n, out, stride, *opts, [](const owg_voice_job& j) { const double x = j.duration_s * j.sample_rate; return x > 0.0 ? x : 0.0; },
+                               [](const owg_voice_job* j, int64_t m, double* o, int64_t st, const owg_opts* op) { return owg_render_voices(j, m, o, st, op); });
     owg_plan* pl = nullptr;
     if (int rc = owg_plan_voices(jobs, n, opts, &pl)) return rc;
     const int rc = owg_plan_execute(pl, out, stride, opts ? opts->out_location : OWG_OUT_HOST);
@@ -779,6 +872,9 @@ int owg_render_voices(const owg_voice_job* jobs, int64_t n, double* out, int64_t
 }
 
 int owg_render_bench(const owg_bench_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts) {
+    if (opts && popcount32(opts->device_mask) >= 2 && n > 0 && jobs && out)
+        return fan_out_devices(jobs, n, out, stride, *opts, [](const owg_bench_job& j) { const double x = j.v.duration_s * j.v.sample_rate; return x > 0.0 ? x : 0.0; },
+                               [](const owg_bench_job* j, int64_t m, double* o, int64_t st, const owg_opts* op) { return owg_render_bench(j, m, o, st, op); });
     owg_plan* pl = nullptr;
     if (int rc = owg_plan_bench(jobs, n, opts, &pl)) return rc;
     const int rc = owg_plan_execute(pl, out, stride, opts ? opts->out_location : OWG_OUT_HOST);
@@ -1637,10 +1733,15 @@ int owg_selftest_division(int64_t n_per_thread, uint64_t seed, uint64_t* mismatc
 int owg_debug_counters(uint64_t* out, int32_t n, int32_t reset) {
     if (!out || n < 0) return fail(OWG_E_BAD_ARG, "owg_debug_counters: bad argument");
     if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
-    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CK(cudaMemcpyFromSymbol(h, g_tile_prof, sizeof(h)));
-    for (int i = 0; i < n && i < 8; i++) out[i] = h[i];
-    if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; CK(cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z))); }
+    unsigned long long h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyFromSymbol(h, g_tile_prof, 8 * sizeof(unsigned long long)));
+    CK(cudaMemcpyFromSymbol(&h[8], g_tile_rare, sizeof(unsigned long long)));
+    for (int i = 0; i < n && i < 9; i++) out[i] = h[i];
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        CK(cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z)));
+        CK(cudaMemcpyToSymbol(g_tile_rare, z, sizeof(unsigned long long)));
+    }
     return OWG_OK;
 }
 

@@ -12,6 +12,7 @@
 #include <thread>
 #include <atomic>
 #include <cstdio>
+#include <chrono>
 
 using namespace ow;
 
@@ -386,6 +387,33 @@ void owo_chain_init(const owg_bench_job* j, double* o) {
     const double v[18] = {j->volume, s.a2, s.a3, 1.0 + s.a2 + s.a3, s.thermal_coeff, s.thermal_alpha, s.hpf.b0, s.hpf.b1, s.hpf.b2, s.hpf.a1, s.hpf.a2,
                           s.lpf.b0, s.lpf.b1, s.lpf.b2, s.lpf.a1, s.lpf.a2, s.character < 0.001 ? 0.0 : 1.0, j->v.sample_rate < 88200.0 ? 1.0 : 0.0};
     for (int i = 0; i < 18; i++) o[i] = v[i];
+}
+
+// Per-stage single-thread timers of the restatement (ns per preamp-rate sample), for the CPU-baseline sanity gate:
+// out[0] gen_preamp step with the per-sample matrix rebuild (the tremolo case: set_runtime_R + process_sample), out[1] the same with
+// a static R_ldr, out[2] one Twin-T oscillator step (gen_tremolo process_sample), all at 88.2 kHz.
+int owo_stage_timers(int n, double* out3) {
+    if (!out3 || n <= 0) return OWG_E_BAD_ARG;
+    using clk = std::chrono::steady_clock;
+    volatile double sink = 0.0;
+    pre::CircuitState a;
+    a.set_default();
+    a.set_sample_rate(88200.0);
+    auto t0 = clk::now();
+    for (int i = 0; i < n; i++) { a.set_runtime_R_r_ldr(50000.0 + (i % 1000)); sink = sink + pre::process_sample(1e-3 * std::sin(i * 0.03), a); }
+    auto t1 = clk::now();
+    for (int i = 0; i < n; i++) sink = sink + pre::process_sample(1e-3 * std::sin(i * 0.03), a);
+    auto t2 = clk::now();
+    trm::CircuitState t;
+    t.set_default();
+    t.set_sample_rate(88200.0);
+    auto t3 = clk::now();
+    for (int i = 0; i < n; i++) sink = sink + trm::process_sample(0.0, t);
+    auto t4 = clk::now();
+    out3[0] = std::chrono::duration<double, std::nano>(t1 - t0).count() / n;
+    out3[1] = std::chrono::duration<double, std::nano>(t2 - t1).count() / n;
+    out3[2] = std::chrono::duration<double, std::nano>(t4 - t3).count() / n;
+    return OWG_OK;
 }
 
 // Engine session probe for the restated reference tests (engine.rs:682-1178): runs a script of WurliEngine calls and records the

@@ -88,6 +88,7 @@ def lib():
         L.owo_last_diag.argtypes = [C.POINTER(Diag)]
         L.owo_engine_script.argtypes = [C.c_double, C.c_int, dp, C.c_int64, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int32), C.c_int64, dp]
         L.owo_engine_script.restype = C.c_int64
+        L.owo_stage_timers.argtypes = [C.c_int, dp]
         for name, args in [("owo_midi_to_freq", [C.c_int]), ("owo_tip_mass_ratio", [C.c_int]),
                            ("owo_reed_length_mm", [C.c_int]), ("owo_reed_compliance", [C.c_int]),
                            ("owo_pickup_displacement_scale", [C.c_int]), ("owo_fundamental_decay_rate", [C.c_int]),
@@ -227,3 +228,20 @@ def engine_script(ops, sr=44100.0, model=0):
     keys = ("active", "held", "sustained", "releasing", "has_steal", "note_held", "note_sustained", "sustain_flag")
     qs = [dict(zip(keys, counts[8 * i:8 * i + 8].tolist())) for i in range(n_q)]
     return out[:n_cap], qs, sm
+
+
+def stage_timers(n=100000):
+    """ns per preamp-rate sample of the restatement, single thread: (preamp step with matrix rebuild, preamp step static, oscillator step)."""
+    out = (C.c_double * 3)()
+    lib().owo_stage_timers(int(n), out)
+    return {"preamp_step_with_rebuild_ns": out[0], "preamp_step_static_ns": out[1], "tremolo_oscillator_step_ns": out[2]}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"

@@ -8,8 +8,8 @@ import openwurli_b200 as ow
 
 
 def counters(reset=True):
-    a = (C.c_uint64 * 8)()
-    ow.lib().owg_debug_counters(a, 8, 1 if reset else 0)
+    a = (C.c_uint64 * 9)()
+    ow.lib().owg_debug_counters(a, 9, 1 if reset else 0)
     return list(a)
 
 
@@ -29,7 +29,7 @@ def run(stride, depth, dur, env, diag, no_pa=False):
     res = {"n": len(jobs), "depth": depth, "dur": dur, "env": env, "diag": diag, "no_pa": no_pa, "chain_ms": round(t[0], 2), "us_per_base_sample": round(t[0] * 1e3 / n_samp, 3)}
     if diag and c[6]:
         res.update({"dk_wait_frac": round(c[0] / max(c[1], 1), 4), "io_wait_frac": round(c[2] / max(c[3], 1), 4), "trips_per_warp_step": round(c[4] / c[6], 3),
-                    "iters_per_inst_step": round(c[5] / max(c[7], 1), 3), "dk_cycles_per_step": round((c[1] - c[0]) / c[6], 1)})
+                    "iters_per_inst_step": round(c[5] / max(c[7], 1), 3), "dk_cycles_per_step": round((c[1] - c[0]) / c[6], 1), "rare_lane_iters": c[8]})
     pl.close()
     print(json.dumps(res), flush=True)
 

@@ -8,8 +8,8 @@ import openwurli_b200 as ow
 
 
 def counters():
-    a = (C.c_uint64 * 8)()
-    ow.lib().owg_debug_counters(a, 8, 1)
+    a = (C.c_uint64 * 9)()
+    ow.lib().owg_debug_counters(a, 9, 1)
     return list(a)
 
 
@@ -27,7 +27,7 @@ def run(stride, depth, dur, env, diag=False):
     c = counters()
     res = {"n": len(jobs), "depth": depth, "dur": dur, "env": env, "chain_ms": round(t[0], 2), "us_per_base_sample": round(t[0] * 1e3 / int(dur * 44100), 3)}
     if diag and c[6]:
-        res.update({"dk_wait_frac": round(c[0] / max(c[1], 1), 4), "trips_per_warp_step": round(c[4] / c[6], 3), "dk_cycles_per_step": round((c[1] - c[0]) / c[6], 1)})
+        res.update({"dk_wait_frac": round(c[0] / max(c[1], 1), 4), "trips_per_warp_step": round(c[4] / c[6], 3), "dk_cycles_per_step": round((c[1] - c[0]) / c[6], 1), "rare_lane_iters": c[8]})
     pl.close()
     print(json.dumps(res), flush=True)
     return out
