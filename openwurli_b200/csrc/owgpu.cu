@@ -1733,14 +1733,16 @@ int owg_selftest_division(int64_t n_per_thread, uint64_t seed, uint64_t* mismatc
 int owg_debug_counters(uint64_t* out, int32_t n, int32_t reset) {
     if (!out || n < 0) return fail(OWG_E_BAD_ARG, "owg_debug_counters: bad argument");
     if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
-    unsigned long long h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long h[17] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     CK(cudaMemcpyFromSymbol(h, g_tile_prof, 8 * sizeof(unsigned long long)));
     CK(cudaMemcpyFromSymbol(&h[8], g_tile_rare, sizeof(unsigned long long)));
-    for (int i = 0; i < n && i < 9; i++) out[i] = h[i];
+    CK(cudaMemcpyFromSymbol(&h[9], g_tile_sec, 8 * sizeof(unsigned long long)));
+    for (int i = 0; i < n && i < 17; i++) out[i] = h[i];
     if (reset) {
         unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         CK(cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z)));
         CK(cudaMemcpyToSymbol(g_tile_rare, z, sizeof(unsigned long long)));
+        CK(cudaMemcpyToSymbol(g_tile_sec, z, sizeof(z)));
     }
     return OWG_OK;
 }

@@ -1,4 +1,4 @@
-// Host check of openwurli_b200/csrc/owg_tile_tables.h: the lane-tiled evaluation of build_rhs (4 lanes x 18 padded term slots)
+// Host check of openwurli_b200/csrc/owg_tile_tables.h: the lane-tiled evaluation of build_rhs (4 lanes x 14 padded term slots)
 // must reproduce the straightforward rows (gen_preamp.rs:3041-3095, as restated in owg_device.cuh / oracle) bit for bit,
 // including the -0.0 x 1.0 padding and the per-row summation order.  Built and run by tests/test_host_logic.py.
 #include <cstdint>
@@ -50,9 +50,11 @@ int main() {
         ref[7] += ni[5] * il[2];
         ref[8] += ni[6] * il[2];
         ref[0] += (input + xin_prev) / 1.0;
-        // tiled evaluation
+        // tiled evaluation: position-major gather buffer, exactly as the kernel fills and reads it
+        static const int TROWS[4][3] = OWG_TILE_ROWS_INIT;
+        static const int LOC[16] = OWG_TILE_LOC_INIT;
         double xs[16];
-        for (int i = 0; i < 12; i++) xs[i] = vp[i];
+        for (int q = 0; q < 4; q++) for (int p = 0; p < 3; p++) xs[p * 4 + q] = vp[TROWS[q][p]];
         for (int i = 0; i < 3; i++) xs[12 + i] = il[i];
         xs[15] = 1.0;
         auto coef_of = [&](int c) -> double {
@@ -65,16 +67,19 @@ int main() {
         for (int q = 0; q < 4; q++) {
             double r[3];
             for (int s = 0; s < OWG_TILE_SLOTS; s++) {
-                const int row = OWG_TILE_SLOT_ROW(q, s), k = OWG_TILE_SLOT_K(s);
+                const int pos = OWG_TILE_SLOT_POS(s), k = OWG_TILE_SLOT_K(s);
+                const int row = TROWS[q][pos];
                 const OwgRhsTerm tm = ROWS[row][k];
                 double c = coef_of(tm.c);
-                if (q == 2 && s == 8) c = an66;  // the kernel's per-sample a_neg[6][6]
-                const double term = c * xs[tm.x];
-                const int ri = s < 7 ? 0 : (s < 14 ? 1 : 2);
-                if (k == 0) r[ri] = term; else r[ri] += term;
+                if (q == OWG_TILE_AN66_LANE && s == OWG_TILE_AN66_SLOT) {  // the kernel's per-sample a_neg[6][6]
+                    if (tm.c != 24) { std::printf("an66 slot does not hold a_neg entry 24\n"); bad++; }
+                    c = an66;
+                } else if (tm.c == 24) { std::printf("a_neg entry 24 outside the an66 slot\n"); bad++; }
+                const double term = c * xs[LOC[tm.x]];
+                if (k == 0) r[pos] = term; else r[pos] += term;
             }
-            r[0] += q == 0 ? (input + xin_prev) / 1.0 : -0.0;
-            got[q] = r[0]; got[q + 4] = r[1]; got[q + 8] = r[2];
+            r[2] += q == 0 ? (input + xin_prev) / 1.0 : -0.0;  // row 0 = lane 0, position 2
+            for (int p = 0; p < 3; p++) got[TROWS[q][p]] = r[p];
         }
         for (int i = 0; i < 12; i++) {
             uint64_t a, b;
@@ -82,13 +87,27 @@ int main() {
             if (a != b) { if (bad < 5) std::printf("row %d trial %d: %.17g vs %.17g\n", i, trial, ref[i], got[i]); bad++; }
         }
     }
-    // structural checks: rows 8..11 fit 4 slots; every a_neg entry used exactly once
-    int used[38] = {0};
-    for (int r = 0; r < 12; r++)
-        for (int k = 0; k < OWG_TILE_ROW_TERMS; k++) {
-            if (ROWS[r][k].c < 38) used[ROWS[r][k].c]++;
-            if (r >= 8 && k >= 4 && ROWS[r][k].c != OWG_TC_PAD) { std::printf("row %d has more than 4 terms\n", r); bad++; }
+    // structural checks: every row fits the slot count of its position; rows and LOC are inverse maps; every a_neg entry used once
+    static const int TROWS2[4][3] = OWG_TILE_ROWS_INIT;
+    static const int LOC2[16] = OWG_TILE_LOC_INIT;
+    static const int CAP[3] = {7, 4, 3};
+    int used[38] = {0}, seen[12] = {0};
+    for (int q = 0; q < 4; q++)
+        for (int p = 0; p < 3; p++) {
+            const int r = TROWS2[q][p];
+            seen[r]++;
+            if (LOC2[r] != p * 4 + q) { std::printf("LOC[%d] is not the inverse of ROWS\n", r); bad++; }
+            for (int k = CAP[p]; k < OWG_TILE_ROW_TERMS; k++)
+                if (ROWS[r][k].c != OWG_TC_PAD) { std::printf("row %d has more than %d terms\n", r, CAP[p]); bad++; }
         }
+    for (int r = 0; r < 12; r++) if (seen[r] != 1) { std::printf("row %d owned %d times\n", r, seen[r]); bad++; }
+    for (int i = 12; i < 16; i++) if (LOC2[i] != i) { std::printf("LOC[%d] must be the identity\n", i); bad++; }
+    if (TROWS2[0][2] != 0 || TROWS2[1][0] != 2 || TROWS2[1][1] != 5 || TROWS2[2][0] != 4 || TROWS2[2][1] != 8 || TROWS2[2][2] != 10 || TROWS2[3][2] != 11) {
+        std::printf("the kernel's fixed roles (input row, p rows, output row, V-source row) moved\n"); bad++;
+    }
+    for (int r = 0; r < 12; r++)
+        for (int k = 0; k < OWG_TILE_ROW_TERMS; k++)
+            if (ROWS[r][k].c < 38) used[ROWS[r][k].c]++;
     for (int e = 0; e < 38; e++) if (used[e] != 1) { std::printf("a_neg entry %d used %d times\n", e, used[e]); bad++; }
     std::printf("%s\n", bad ? "FAIL" : "OK");
     return bad ? 1 : 0;
