@@ -267,6 +267,8 @@ int owg_fp64_peak(int32_t device, int32_t fma, float ms_target, double* tera_ins
  * [0] DK-warp cycles waiting for input  [1] DK-warp cycles total  [2] I/O-warp cycles waiting for the preamp  [3] I/O-warp cycles
  * total  [4] Newton loop trips over DK warp-steps  [5] Newton iterations over instance-steps  [6] DK warp-steps  [7] instance-steps
  * [8] Newton iterations repeated by the generic (reference-order) code, counted per lane.
+ * [9..16] DK-warp cycles by section (head, build_rhs, S*rhs, Newton junction row, Newton elimination, Newton step/votes, S_NI + guard
+ * vote, adapter + state shift)  [17] Newton iterations of the 8-lane Twin-T oscillator that took the generic code.
  * reset != 0 clears them after reading. */
 int owg_debug_counters(uint64_t* out, int32_t n, int32_t reset);
 

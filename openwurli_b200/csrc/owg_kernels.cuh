@@ -1,7 +1,7 @@
 // CUDA kernels of libowgpu (sm_100a).  See DESIGN.md for the launch geometry and data layout.
 #pragma once
 #include "owg_device.cuh"
-#include "owg_tremolo.cuh"
+#include "owg_tremolo_tile.cuh"
 
 namespace owgd {
 
@@ -107,6 +107,72 @@ __global__ void tremolo_group_kernel(const OwgPreampGroup* groups, const int* tr
     if (diag) {
         for (int i = 0; i < 16; i++) atomicAdd(&diag->trm_hist[i], (unsigned long long)td.hist[i]);
         atomicAdd(&diag->trm_be, (unsigned long long)td.be_fallback);
+    }
+}
+
+// The same sequence on 8 lanes per oscillator (owg_tremolo_tile.cuh): bit-identical to tremolo_group_kernel, ~3x shorter step.
+__global__ void __launch_bounds__(32) tremolo_group_tile_kernel(const OwgPreampGroup* groups, const int* trem_group_ids, int n_trem, double* pot_seq,
+                                                                int64_t pot_stride, TrmRun* run, long long live_begin, long long live_end, DevDiag* diag) {
+    const int gi = blockIdx.x, lane = threadIdx.x;
+    if (gi >= n_trem || lane >= 8) return;
+    const OwgPreampGroup gr = groups[trem_group_ids[gi]];
+    const double sr = gr.preamp_sr;
+    __shared__ TrmMats m;
+    __shared__ TrmK kq;
+    __shared__ double trm_sc[OWG_TRM_SCRATCH];
+    __shared__ TrmTileSm sm;
+    __shared__ TrmState st;
+    __shared__ TrmTileDiag td;
+    const double tot = sr * 2.0;
+    const long long n_settle = !(tot == tot) || tot <= 0.0 ? 0ll : (long long)tot;
+    const long long n_pre = 50 + n_settle;
+    const bool ctor = live_begin < 0;
+    const long long n_begin = ctor ? 0 : n_pre + live_begin;
+    const long long n_end = ctor ? n_pre : n_pre + (live_end < gr.n_os ? live_end : gr.n_os);
+    if (n_begin >= n_end) return;
+    const bool rate_differs = fabs(sr - 48000.0) > 0.5;
+    if (lane == 0) {
+        kq = trm_consts();
+        trm_defaults(m);
+        if (ctor) {
+            for (int i = 0; i < TN; i++) st.v[i] = TRM_DC_OP[i];
+            for (int i = 0; i < TM; i++) { st.il[i] = TRM_DC_NL_I[i]; st.ilpp[i] = TRM_DC_NL_I[i]; }
+            st.xin_prev = 0.0;
+        } else {
+            st = run[gi].st;
+            if (rate_differs) trm_rebuild(m, sr * 1.0);  // same deterministic rebuild as at step 50
+        }
+        for (int i = 0; i < 16; i++) td.hist[i] = 0;
+        td.be_fallback = 0; td.nan_reset = 0;
+    }
+    __syncwarp(OWG_TT_MASK);
+    const int r = lane < TN ? lane : TN - 1, jq = lane & 3;
+    TrmLaneK c;
+    trm_lane_consts(c, m, sm.xs, r, jq);
+    double pi[TM], raw_v, raw_il[TM];
+    trm_tile_load(sm, st, pi, raw_v, raw_il, lane);
+    double* o = pot_seq + (size_t)gi * pot_stride;
+    uint32_t generic_count = 0;
+    for (long long n = n_begin; n < n_end; n++) {
+        if (n == 50 && rate_differs) {  // set_sample_rate after the 50 warm-up samples at the baked 48 kHz matrices (tremolo.rs:92-102)
+            __syncwarp(OWG_TT_MASK);
+            if (lane == 0) trm_rebuild(m, sr * 1.0);
+            __syncwarp(OWG_TT_MASK);
+            trm_lane_consts(c, m, sm.xs, r, jq);
+        }
+        const bool live = n >= n_pre;
+        const double v_out = trm_step_tile(sm, c, m, kq, trm_sc, pi, raw_v, raw_il, lane, (diag && live) ? &td : nullptr, generic_count);
+        if (live && lane == 0) o[n - n_pre] = v_out;
+    }
+    trm_tile_store(sm, st, raw_v, raw_il, lane);
+    __syncwarp(OWG_TT_MASK);
+    if (lane == 0) {
+        run[gi].st = st;
+        if (generic_count) atomicAdd(&g_trm_generic, (unsigned long long)generic_count);
+        if (diag) {
+            for (int i = 0; i < 16; i++) atomicAdd(&diag->trm_hist[i], (unsigned long long)td.hist[i]);
+            atomicAdd(&diag->trm_be, (unsigned long long)td.be_fallback);
+        }
     }
 }
 

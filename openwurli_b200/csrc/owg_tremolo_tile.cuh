@@ -19,6 +19,12 @@
 
 namespace owgd {
 
+__device__ __forceinline__ double owg_lds64(uint32_t addr) {  // shared-memory load from a 32-bit shared-window address
+    double x;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr));
+    return x;
+}
+
 #define OWG_TT_MASK 0xFFu
 #define OWG_TT_TERMS 6
 // home buffer (doubles): [0..6] flushed v_prev, [7] 1.0, [8..11] flushed i_nl_prev, [12..15] i_nl_prev_prev (cold path only)
@@ -78,13 +84,14 @@ __device__ __forceinline__ void trm_lane_consts(TrmLaneK& c, const TrmMats& m, c
     c.nvb = jq == 0 ? TRM_N_V[0][4] : (jq == 1 ? TRM_N_V[1][2] : TRM_N_V[3][4]);
 }
 
-struct TrmTileDiag { uint32_t hist[16]; uint32_t be_fallback, nan_reset, generic_iters; };
+struct TrmTileDiag { uint32_t hist[16]; uint32_t be_fallback, nan_reset; };
+__device__ unsigned long long g_trm_generic;  // Newton iterations of the tiled oscillator that took the generic code (debug counter)
 
 // One process_sample(0.0) of the oscillator on 8 lanes.  State: home buffer `sm.xs` (flushed v_prev, i_nl_prev, i_nl_prev_prev) plus
 // the registers (pi: Newton predictor of this step; raw_v / raw_il: the unflushed state the step leaves, kept for the launch's
 // final TrmRun record).  Returns v[0] (identical in every lane).
 __device__ __forceinline__ double trm_step_tile(TrmTileSm& sm, const TrmLaneK& c, const TrmMats& m, const TrmK& kq, double* sc, double (&pi)[TM],
-                                                double& raw_v, double (&raw_il)[TM], const int lane, TrmTileDiag* dg) {
+                                                double& raw_v, double (&raw_il)[TM], const int lane, TrmTileDiag* dg, uint32_t& generic_count) {
     const int r = lane < TN ? lane : TN - 1, jq = lane & 3;
     const bool even = (jq & 1) == 0;
     // ---- build_rhs row r (gen_tremolo.rs:2371-2410); input = input_prev = 0, so rhs[0] += (0 + 0) * g_in = +0.0 ----
@@ -106,47 +113,112 @@ __device__ __forceinline__ double trm_step_tile(TrmTileSm& sm, const TrmLaneK& c
     double il0 = pi[0], il1 = pi[1], il2 = pi[2], il3 = pi[3];
     const BjtK& bk = (jq & 2) ? kq.q1 : kq.q0;
     const Recip rc = even ? bk.r_nf : bk.r_nr;
+    const double cja = even ? bk.is_nfvt : bk.is_bf_nfvt;
+    const bool lane2 = jq == 2, lane03 = (jq == 0) | (jq == 3), lane1 = jq == 1;
     uint32_t last = T_MAX_ITER;
+#pragma unroll 1
     for (int iter = 0; iter < T_MAX_ITER; iter++) {
-        DivPolicy<false> D;
-        const double x2 = jq == 2 ? il3 : il2;
-        const double x3 = (jq == 0 || jq == 3) ? il3 : 1.0;
+        unsigned bad = 0;
+        const double x2 = lane2 ? il3 : il2;
+        const double x3 = lane03 ? il3 : 1.0;
         const double v_d = p + c.kr[0] * il0 + c.kr[1] * il1 + c.kd2 * x2 + c.kd3 * x3;
-        const double e_own = fast_exp(D.div(v_d, rc));
+        const double e_own = fast_exp_sl(div_sl(v_d, rc, bad, true));
         const double e_par = __shfl_xor_sync(OWG_TT_MASK, e_own, 1, 8);
         const double exp_be = even ? e_own : e_par, exp_bc = even ? e_par : e_own;
         // bjt_evaluate, Ebers-Moll branch (gen_tremolo.rs:1566-1636): even lanes need (ic, j0, j1), odd lanes (ib, j2, j3)
         const double ib_rev = bk.is_br * (exp_bc - 1.0);
         const double ic = bk.is * (exp_be - exp_bc) - ib_rev;
         const double ib = bk.is_bf * (exp_be - 1.0) + ib_rev;
-        const double ja = even ? bk.is_nfvt * exp_be : bk.is_bf_nfvt * exp_be;
-        const double jb = even ? -bk.is_nrvt * exp_bc - bk.is_br_nrvt * exp_bc : bk.is_br_nrvt * exp_bc;
-        const double il_own = jq == 0 ? il0 : (jq == 1 ? il1 : (jq == 2 ? il2 : il3));
+        const double ja = cja * exp_be;                 // j0 = is/(nf vt) exp_be | j2 = is/(bf nf vt) exp_be
+        const double j3 = bk.is_br_nrvt * exp_bc;
+        const double j1 = -bk.is_nrvt * exp_bc - j3;    // the reference's second product is j3's, bit for bit
+        const double jb = even ? j1 : j3;
+        const double il_own = lane2 ? il2 : (lane1 ? il1 : (jq == 0 ? il0 : il3));
         const double f = il_own - (even ? ic : ib);
-        // row jq of J = I - J_dev K (gen_tremolo.rs:2497-2512)
+        // row jq of J = I - J_dev K (gen_tremolo.rs:2497-2512), its right-hand side, and -- speculatively, while the other rows are still
+        // being written -- the reciprocal of its first element: whichever row wins the first pivot search brings its reciprocal along
+        const double a_own0 = c.jd[0] - ja * c.ka[0] - jb * c.kb[0];
+        const Recip r_own = recip_prepare(a_own0);
+        // (lanes 4..7 mirror lanes 0..3 bit for bit and store the same values to the same slots: no branch around the stores)
         double2* e0 = &sm.ex[iter & 1][0][0];
-        if (lane < 4) {
-            e0[jq] = make_double2(c.jd[0] - ja * c.ka[0] - jb * c.kb[0], c.jd[1] - ja * c.ka[1] - jb * c.kb[1]);
-            e0[4 + jq] = make_double2(c.jd[2] - ja * c.ka[2] - jb * c.kb[2], c.jd[3] - ja * c.ka[3] - jb * c.kb[3]);
-            e0[8 + jq] = make_double2(f, 0.0);
-        }
+        e0[jq] = make_double2(a_own0, c.jd[1] - ja * c.ka[1] - jb * c.kb[1]);
+        e0[4 + jq] = make_double2(c.jd[2] - ja * c.ka[2] - jb * c.kb[2], c.jd[3] - ja * c.ka[3] - jb * c.kb[3]);
+        e0[8 + jq] = make_double2(f, r_own.r);
         __syncwarp(OWG_TT_MASK);
-        double a[4][4], b[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const double2 t0 = e0[q], t1 = e0[4 + q], t2 = e0[8 + q];
-            a[q][0] = t0.x; a[q][1] = t0.y; a[q][2] = t1.x; a[q][3] = t1.y; b[q] = t2.x;
-        }
+        // ---- 4x4 elimination with partial pivoting (gen_tremolo.rs:2515-2561), straight-line, identically in every lane ----
+        // column 0: the sequential "first strict maximum" search is a set of pairwise comparisons; swap(0, max_row) by ADDRESS
         bool singular;
-        trm_solve4(a, b, singular, D);
-        const double d0 = b[0], d1 = b[1], d2 = b[2], d3 = b[3];
+        double d0, d1, d2, d3;
+        {
+            const double m0 = fabs(e0[0].x), m1 = fabs(e0[1].x), m2 = fabs(e0[2].x), m3 = fabs(e0[3].x);
+            // (bitwise & | on purpose: no short-circuit branches in the loop body)
+            const bool w3 = (m3 > m0) & (m3 > m1) & (m3 > m2);
+            const bool w2 = !w3 & (m2 > m0) & (m2 > m1);
+            const bool w1 = !w3 & !w2 & (m1 > m0);
+            const int mr = (w3 ? 3 : 0) | (w2 ? 2 : 0) | (w1 ? 1 : 0);
+            const int i1 = w1 ? 0 : 1, i2 = w2 ? 0 : 2, i3 = w3 ? 0 : 3;
+            const double2 Pa = e0[mr], Pb = e0[4 + mr], Pc = e0[8 + mr];
+            const double2 Aa = e0[i1], Ab = e0[4 + i1], Ac = e0[8 + i1];
+            const double2 Ba = e0[i2], Bb = e0[4 + i2], Bc = e0[8 + i2];
+            const double2 Ca = e0[i3], Cb = e0[4 + i3], Cc = e0[8 + i3];
+            const double P0 = Pa.x, P1 = Pa.y, P2 = Pb.x, P3 = Pb.y, PB = Pc.x;
+            singular = fabs(P0) < KC(14);
+            Recip rp; rp.r = Pc.y; rp.nb = -P0; rp.b = P0;
+            double A1 = Aa.y, A2 = Ab.x, A3 = Ab.y, AB = Ac.x;
+            double B1 = Ba.y, B2 = Bb.x, B3 = Bb.y, BB = Bc.x;
+            double C1 = Ca.y, C2 = Cb.x, C3 = Cb.y, CB = Cc.x;
+            const double fa = div_sl(Aa.x, rp, bad, true), fb = div_sl(Ba.x, rp, bad, true), fc = div_sl(Ca.x, rp, bad, true);
+            A1 -= fa * P1; A2 -= fa * P2; A3 -= fa * P3; AB -= fa * PB;
+            B1 -= fb * P1; B2 -= fb * P2; B3 -= fb * P3; BB -= fb * PB;
+            C1 -= fc * P1; C2 -= fc * P2; C3 -= fc * P3; CB -= fc * PB;
+            // column 1 among rows A, B, C
+            const double n1 = fabs(A1), n2 = fabs(B1), n3 = fabs(C1);
+            const bool y3 = (n3 > n1) & (n3 > n2);
+            const bool y2 = !y3 & (n2 > n1);
+            const double S1 = y3 ? C1 : (y2 ? B1 : A1), S2 = y3 ? C2 : (y2 ? B2 : A2), S3 = y3 ? C3 : (y2 ? B3 : A3), SB = y3 ? CB : (y2 ? BB : AB);
+            const double T1 = y2 ? A1 : B1, TB0 = y2 ? AB : BB;
+            double T2 = y2 ? A2 : B2, T3 = y2 ? A3 : B3;
+            const double U1 = y3 ? A1 : C1, UB0 = y3 ? AB : CB;
+            double U2 = y3 ? A2 : C2, U3 = y3 ? A3 : C3;
+            singular = singular | (fabs(S1) < KC(14));
+            const Recip rs = recip_prepare(S1);
+            const double ft = div_sl(T1, rs, bad, true), fu = div_sl(U1, rs, bad, true);
+            T2 -= ft * S2; T3 -= ft * S3;
+            const double TB = TB0 - ft * SB;
+            U2 -= fu * S2; U3 -= fu * S3;
+            const double UB = UB0 - fu * SB;
+            // column 2 among rows T, U
+            const bool z = fabs(U2) > fabs(T2);
+            const double V2 = z ? U2 : T2, V3 = z ? U3 : T3, VB = z ? UB : TB;
+            const double W2 = z ? T2 : U2, WB0 = z ? TB : UB;
+            double W3 = z ? T3 : U3;
+            singular = singular | (fabs(V2) < KC(14));
+            const Recip rv = recip_prepare(V2);
+            const double fw = div_sl(W2, rv, bad, true);
+            W3 -= fw * V3;
+            const double WB = WB0 - fw * VB;
+            // column 3: pivot test only; back substitution, sums in ascending column order
+            singular = singular | (fabs(W3) < KC(14));
+            const Recip rw = recip_prepare(W3);
+            d3 = div_sl(WB, rw, bad, true);
+            d2 = div_sl(VB - V3 * d3, rv, bad, true);
+            double s1 = SB - S2 * d2;
+            s1 -= S3 * d3;
+            d1 = div_sl(s1, rs, bad, true);
+            double s0 = PB - P1 * d1;
+            s0 -= P2 * d2;
+            s0 -= P3 * d3;
+            d0 = div_sl(s0, rp, bad, true);
+        }
         const double it0 = il0 - d0, it1 = il1 - d1, it2 = il2 - d2, it3 = il3 - d3;
         const double vt = p + c.kr[0] * it0 + c.kr[1] * it1 + c.kr[2] * it2 + c.kr[3] * it3;
         const double dvt = vt - v_d;
-        // fast path <=> no junction moves by more than 0.1 mV: then pnjlim returns its argument, every ratio is exactly 1, gamma = 1,
-        // the 3.5 V cap is out of reach and il -= 1.0 * d is the trial point itself.  `wild` keeps everything below finite.
-        const bool wild = !(fabs(d0) <= KC(38)) || !(fabs(d1) <= KC(38)) || !(fabs(d2) <= KC(38)) || !(fabs(d3) <= KC(38));
-        const bool generic = singular || D.bad != 0u || wild || !(fabs(dvt) <= KC(13));
+        // fast path <=> pnjlim returns its argument at every junction (it limits only when vtrial > vcrit AND |vtrial - v_d| > 2 vt,
+        // gen_tremolo.rs:1181-1196) and no junction moves by more than 3.5 V: then every ratio is exactly 1, gamma = 1, the cap does
+        // not act and il -= 1.0 * d is the trial point itself (gen_tremolo.rs:2640-2700).  `wild` keeps everything below finite.
+        const bool wild = !(fabs(d0) <= KC(38)) | !(fabs(d1) <= KC(38)) | !(fabs(d2) <= KC(38)) | !(fabs(d3) <= KC(38));
+        const double jvt = (jq & 2) ? TRM_DEVICE_1_VT : TRM_DEVICE_0_VT, jvcrit = (jq & 2) ? TRM_DEVICE_1_VCRIT : TRM_DEVICE_0_VCRIT;
+        const bool generic = singular | (bad != 0u) | wild | !(fabs(dvt) <= 3.5) | ((vt > jvcrit) & (fabs(dvt) > jvt + jvt));
         const double thr = KC(9) * fmax(fabs(v_d), fabs(v_d + dvt)) + KC(10);
         const bool fail = fabs(dvt) > thr;
         const unsigned gbal = __ballot_sync(OWG_TT_MASK, generic);
@@ -155,7 +227,7 @@ __device__ __forceinline__ double trm_step_tile(TrmTileSm& sm, const TrmLaneK& c
             if (lane < 4) sc[30 + jq] = p;
             if (lane == 0) { sc[26] = il0; sc[27] = il1; sc[28] = il2; sc[29] = il3; }
             __syncwarp(OWG_TT_MASK);
-            if (lane == 0) { sc[25] = trm_nr_iter_exact(sc, m, kq) ? 1.0 : 0.0; if (dg) dg->generic_iters++; }
+            if (lane == 0) { sc[25] = trm_nr_iter_exact(sc, m, kq) ? 1.0 : 0.0; generic_count++; }
             __syncwarp(OWG_TT_MASK);
             il0 = sc[26]; il1 = sc[27]; il2 = sc[28]; il3 = sc[29];
             conv = sc[25] != 0.0;

@@ -339,6 +339,13 @@ void build_groups_and_warps(owg_plan* pl, std::vector<InstSpec>& specs, std::vec
     }
 }
 
+// The Twin-T oscillator runs on 8 lanes per group (tremolo_group_tile_kernel) unless OWG_TREM_KERNEL=thread asks for the one-thread
+// kernel (kept for A/B checks: the two produce bit-identical sequences).
+bool trem_tile_enabled() {
+    const char* e = getenv("OWG_TREM_KERNEL");
+    return !(e && e[0] == 't' && e[1] == 'h');
+}
+
 // Tremolo::new for every tremolo group, launched as early as possible on the oscillator stream (it is ~0.6 s of serial
 // device work per 88.2 kHz group and nothing else of the plan depends on it).
 int launch_tremolo_ctor(owg_plan* pl) {
@@ -371,8 +378,12 @@ int launch_tremolo_ctor(owg_plan* pl) {
                     rc = fail(OWG_E_CUDA, "tremolo constructor cache copy failed");
             }
         } else {
-            tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                                 pl->d_trm_ctor.p, -1, -1, nullptr);
+            if (trem_tile_enabled())
+                tremolo_group_tile_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                                          pl->d_trm_ctor.p, -1, -1, nullptr);
+            else
+                tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                                     pl->d_trm_ctor.p, -1, -1, nullptr);
             if (cudaGetLastError() != cudaSuccess) rc = fail(OWG_E_CUDA, "tremolo constructor kernel launch failed");
             for (int gi = 0; gi < nt && !rc; gi++) {
                 const uint64_t key = bits(pl->groups[pl->trem_group_ids[gi]].preamp_sr);
@@ -590,8 +601,12 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
         CK(cudaMemcpyAsync(pl->d_trm_run.p, pl->d_trm_ctor.p, (size_t)nt * sizeof(TrmRun), cudaMemcpyDeviceToDevice, pl->stream_trem));
         for (int64_t c = 0; c < n_chunks; c++) {
             const int64_t os0 = chunk_lo(c) * 2, os1 = chunk_lo(c + 1) * 2;  // covers 2x-oversampled groups; native-rate groups use half
-            tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
-                                                                 pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr);
+            if (trem_tile_enabled())
+                tremolo_group_tile_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                                          pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr);
+            else
+                tremolo_group_kernel<<<nt, 32, 0, pl->stream_trem>>>(pl->d_groups.p, pl->d_trem_ids.p, nt, pl->d_pot_seq.p, pl->trem_n_os_max,
+                                                                     pl->d_trm_run.p, os0, os1, pl->collect_diag ? pl->d_diag.p : nullptr);
             CK(cudaGetLastError());
             CK(cudaEventRecord(pl->chunk_events[c], pl->stream_trem));
             launches++;
@@ -1733,16 +1748,18 @@ int owg_selftest_division(int64_t n_per_thread, uint64_t seed, uint64_t* mismatc
 int owg_debug_counters(uint64_t* out, int32_t n, int32_t reset) {
     if (!out || n < 0) return fail(OWG_E_BAD_ARG, "owg_debug_counters: bad argument");
     if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
-    unsigned long long h[17] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long h[18] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     CK(cudaMemcpyFromSymbol(h, g_tile_prof, 8 * sizeof(unsigned long long)));
     CK(cudaMemcpyFromSymbol(&h[8], g_tile_rare, sizeof(unsigned long long)));
     CK(cudaMemcpyFromSymbol(&h[9], g_tile_sec, 8 * sizeof(unsigned long long)));
-    for (int i = 0; i < n && i < 17; i++) out[i] = h[i];
+    CK(cudaMemcpyFromSymbol(&h[17], g_trm_generic, sizeof(unsigned long long)));
+    for (int i = 0; i < n && i < 18; i++) out[i] = h[i];
     if (reset) {
         unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         CK(cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z)));
         CK(cudaMemcpyToSymbol(g_tile_rare, z, sizeof(unsigned long long)));
         CK(cudaMemcpyToSymbol(g_tile_sec, z, sizeof(z)));
+        CK(cudaMemcpyToSymbol(g_trm_generic, z, sizeof(unsigned long long)));
     }
     return OWG_OK;
 }
