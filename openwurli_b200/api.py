@@ -202,7 +202,8 @@ def render_bench(jobs, out=None, device=-1, collect_diag=False, preamp_model=MEL
     return out
 
 
-def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000.0, out=None, device=-1, preamp_model=MELANGE12):
+def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000.0, out=None, device=-1, preamp_model=MELANGE12,
+                 collect_diag=False):
     """Preamp-only batch (BASELINE config 2): rows of `x` [n_inst, n_samp] (numpy float64, or a torch CUDA tensor)
     through upsample_2x -> DkPreamp::process_sample x2 -> downsample_2x (`process_oversampled`, preamp-bench main.rs:961-974),
     LDR driven by Tremolo::new(tremolo_depth, fs_preamp) when tremolo_depth > 0 (main.rs:432-461), else static r_ldr."""
@@ -211,7 +212,7 @@ def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000
     pin, sin, lin = _out_ptr(x)
     pout, sout, lout = _out_ptr(out)
     assert lin == lout, "input and output must both be host or both be device buffers"
-    o = _opts(device, lout, preamp_model=preamp_model)
+    o = _opts(device, lout, preamp_model=preamp_model, collect_diag=collect_diag)
     check(lib().owg_preamp_batch(pin, sin, x.shape[0], x.shape[1], float(fs_base), 1 if oversample else 0,
                                  float(tremolo_depth), float(r_ldr), pout, sout, C.byref(o)))
     return out

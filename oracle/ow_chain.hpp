@@ -237,7 +237,7 @@ static inline std::vector<double> render_bench(const BenchJob& j, Taps* taps = n
 
 // ---- preamp-only harness (C2): process_oversampled pattern, main.rs:961-974 + tremolo as in cmd_render :432-461
 static inline void preamp_batch_one(const double* in, size_t n, double fs_base, bool oversample,
-                                    double tremolo_depth_or_neg, double r_ldr_static, double* out, int preamp_model = 0) {
+                                    double tremolo_depth_or_neg, double r_ldr_static, double* out, int preamp_model = 0, ChainDiag* dg = nullptr) {
     const double preamp_sr = oversample ? fs_base * 2.0 : fs_base;
     AnyPreamp preamp(preamp_model, preamp_sr);
     Tremolo* trem = nullptr;
@@ -259,6 +259,7 @@ static inline void preamp_batch_one(const double* in, size_t n, double fs_base, 
     } else {
         for (size_t i = 0; i < n; i++) out[i] = step(in[i]);
     }
+    if (dg && preamp.mel) { dg->main = preamp.mel->diag_main; dg->shadow = preamp.mel->diag_shadow; }
     delete trem;
 }
 

@@ -227,6 +227,25 @@ int owo_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_
     return OWG_OK;
 }
 
+// Preamp-only batch that also gathers the melange preamp's guard counters (Newton histogram, max-iteration exits, BE fallbacks,
+// voltage damping, NaN resets) into owo_last_diag: the parity tests drive those guards with out-of-range inputs.
+int owo_preamp_batch_diag(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double fs_base, int oversample,
+                          double tremolo_depth, double r_ldr_static, double* out, int64_t out_stride, int threads) {
+    if (!in || !out || n_inst < 0 || n_samp < 0) return OWG_E_BAD_ARG;
+    pre::settled_state();
+    std::vector<ChainDiag> dgs((size_t)n_inst);
+    parallel_for(n_inst, threads, [&](int64_t i) {
+        preamp_batch_one(in + i * in_stride, (size_t)n_samp, fs_base, oversample != 0, tremolo_depth, r_ldr_static, out + i * out_stride, 0, &dgs[i]);
+    });
+    std::memset(&g_diag, 0, sizeof(g_diag));
+    for (auto& d : dgs) {
+        for (int b = 0; b < 16; b++) { g_diag.nr_iter_hist[b] += d.main.nr_iter_hist[b]; g_diag.shadow_nr_iter_hist[b] += d.shadow.nr_iter_hist[b]; }
+        g_diag.nr_max_iter += d.main.nr_max_iter; g_diag.be_fallback += d.main.be_fallback; g_diag.voltage_damp += d.main.voltage_damp;
+        g_diag.nan_reset += d.main.nan_reset; g_diag.shadow_be_fallback += d.shadow.be_fallback; g_diag.shadow_nan_reset += d.shadow.nan_reset;
+    }
+    return OWG_OK;
+}
+
 // ---- chain E ----------------------------------------------------------------------------------
 static void run_engine(const owg_engine_job& j, float* out, int preamp_model = 0) {
     WurliEngine eng(j.sample_rate, preamp_model);

@@ -260,6 +260,49 @@ def test_preamp_batch_parity(depth, r, fs, oversample):
     assert np.abs(z).max() < 1e-9
 
 
+def _guard_inputs(fs, n):
+    """Inputs far outside the instrument's range (the pickup delivers millivolts): every guard of process_sample fires -- Newton
+    runs into its iteration cap, the backward-Euler fallback and its 64-sample cooldown, voltage damping, pnjlim's logarithmic branch,
+    the input clamp and the non-finite input filter (gen_preamp.rs:3399-3420, 3478-3635)."""
+    t = np.arange(n) / fs
+    x = np.zeros((8, n))
+    x[0] = 5 * np.sin(2 * np.pi * 1000 * t)
+    x[1] = 30 * np.sin(2 * np.pi * 200 * t)
+    x[2] = 60 * np.sin(2 * np.pi * 3000 * t)
+    x[3] = 80 * np.sign(np.sin(2 * np.pi * 500 * t))
+    x[4] = 0.01 * np.sin(2 * np.pi * 440 * t)
+    x[4, 700], x[4, 900], x[4, 1100] = np.nan, np.inf, -np.inf
+    x[5] = 100 * np.random.default_rng(5).standard_normal(n)
+    x[6] = 1e3 * np.sin(2 * np.pi * 50 * t)
+    x[7] = np.where((np.arange(n) // 200) % 2 == 0, 99.0, -99.0)
+    return x
+
+
+@pytest.mark.parametrize("depth,r", [(0.0, 1e6), (0.5, 0.0)])
+def test_preamp_guards_fire_and_match_the_oracle(depth, r, monkeypatch):
+    """the guard paths must be compared with counters that are NOT zero.  The same batch goes through the
+    lane-tiled kernel (fast path + its generic slow path), the one-thread kernel and the oracle."""
+    fs, n = 44100.0, 2000
+    x = _guard_inputs(fs, n)
+    ref = np.zeros_like(x)
+    O.lib().owo_preamp_batch_diag(O.dptr(x), n, x.shape[0], n, fs, 1, depth, r, O.dptr(ref), n, 4)
+    dc = O.last_diag()
+    assert dc.be_fallback > 1000 and dc.voltage_damp > 1000 and dc.nr_max_iter > 1000 and dc.nr_iter_hist[15] > 1000
+    assert np.isfinite(ref).all()
+    outs = {}
+    for kern in ("tile", "warp"):
+        monkeypatch.setenv("OWG_CHAIN_KERNEL", kern)
+        outs[kern] = ow.preamp_batch(x, fs, oversample=True, tremolo_depth=depth, r_ldr=r)
+        outs[kern + "_diag"] = ow.preamp_batch(x, fs, oversample=True, tremolo_depth=depth, r_ldr=r, collect_diag=True)
+        dg = ow.last_diag()
+        assert np.array_equal(outs[kern], outs[kern + "_diag"]), kern
+        assert list(dg.nr_iter_hist) == list(dc.nr_iter_hist), (kern, list(dg.nr_iter_hist), list(dc.nr_iter_hist))
+        assert (dg.nr_max_iter, dg.be_fallback, dg.voltage_damp, dg.nan_reset) == (dc.nr_max_iter, dc.be_fallback, dc.voltage_damp, dc.nan_reset), kern
+    assert np.array_equal(outs["tile"], outs["warp"]), np.abs(outs["tile"] - outs["warp"]).max()
+    for i in range(x.shape[0]):
+        assert_parity(outs["tile"][i], ref[i], f"guards[{i}] depth={depth}", 1e-6, 1e-7)
+
+
 def test_preamp_batch_device_buffers_and_linearity_in_small_signal():
     import torch
     x = _c2_inputs(64, 2000, 48000.0) * 1e-3  # microvolt inputs: linear up to the solver's own RELTOL (1e-3) exit slack
