@@ -33,6 +33,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 KEYS, VELS, FS = 64, 127, 44100.0
 METRIC = "audio_seconds_rendered_per_second"
+# ncu --set full summary of one chunk launch of the dominant kernel (tools/ncu_summary.py): roofline.traffic is read from it
+TRAFFIC_ARTEFACT = "profiles/chain_kernel_traffic.json"
 UNIT = "audio-s/s"
 
 
@@ -408,16 +410,23 @@ def main():
         iters = mean_nr_iterations(args.tremolo_depth)
         flops = algorithmic_flops(main_run["n_inst"], main_run["n_samp"], iters, args.tremolo_depth, model)
         kernel_s = main_run["main_ms"] * 1e-3 / args.steps
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, TRAFFIC_ARTEFACT)))
+        except (OSError, ValueError):
+            pass
+        traffic_applies = bool(traffic.get("dram_bytes")) and model == 0 and main_run["n_inst"] == 8128 and args.tremolo_depth > 0
         achieved = flops / kernel_s / 1e12
         line["roofline"] = {"bound": "fp64", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
-                            "traffic": (1064522752 if (model == 0 and main_run["n_inst"] == 8128 and args.tremolo_depth > 0) else None),
-                            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 8192-sample chunk launch of chain_split_kernel "
-                                            "(ncu --set full, profiles/r01_v9_chain_split_kernel_full.txt); algorithmic bytes of that launch: 1090 MB",
+                            "traffic": traffic["dram_bytes"] if traffic_applies else None,
+                            "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum of one chunk launch of the dominant kernel, read from "
+                                             f"{TRAFFIC_ARTEFACT} (ncu --set full capture: {traffic.get('note', '')}); algorithmic bytes of that launch: "
+                                             f"{traffic.get('algorithmic_bytes')}") if traffic_applies else "no ncu capture for this configuration",
                             "peak_source": "owg_fp64_peak DFMA micro-benchmark measured in this run "
                             "(MEASURED_PEAKS.json has no FP64 entry; B200 nominal 37 TFLOP/s)",
                             "peak_unfused_tflops": unfused_peak, "frac_of_unfused": achieved / unfused_peak,
                             "kernel": "owgd::chain_legacy_kernel" if model == 1 else
-                            ("owgd::chain_split_kernel" if main_run["n_inst"] <= 444 * 31 else "owgd::chain_kernel"), "kernel_ms_per_step": kernel_s * 1e3, "mean_nr_iterations": iters,
+                            ("owgd::chain_tile_kernel" if main_run["n_inst"] <= 2 * 2 * 148 * 4 * 7 else "owgd::chain_kernel"), "kernel_ms_per_step": kernel_s * 1e3, "mean_nr_iterations": iters,
                             "algorithmic_gflop_per_step": flops / 1e9}
         if not args.no_variants:
             other = 0.0 if args.tremolo_depth > 0 else 0.5
