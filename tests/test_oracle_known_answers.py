@@ -417,3 +417,68 @@ def test_alias_audit_one_sided_gate(note):
     assert np.all(np.isfinite(sig)) and h1 > 0
     assert step_up - base_step <= 1.5, (step_up, base_step)
     assert hf - base_hf <= 2.0, (hf, base_hf)
+
+
+# ---- legacy preamp, layers 1 and 2 of the reference's own test pyramid (dk_preamp_legacy.rs:1108-1491) ---------------------------
+def _legacy_netlist():
+    """G, C and the DC source vector exactly as the reference's L1 tests spell them out, stamp by stamp (component values :21-40)."""
+    R2, R3, RE1, RC1, RE2A, RE2B, RC2, R9, R10, VCC = 2e6, 470e3, 33e3, 150e3, 270.0, 820.0, 1800.0, 6800.0, 56e3, 15.0
+    C3, C4, CE1, CE2 = 100e-12, 100e-12, 4.7e-6, 22e-6
+    B1, E1, C1, E2, E2B, C2, OUT, FB = range(8)
+    g = np.zeros((8, 8))
+    g[B1, B1] = 1 / R2 + 1 / R3          # :1114
+    g[E1, E1] = 1 / RE1                  # :1122
+    g[C1, C1] = 1 / RC1                  # :1130
+    g[E2, E2] = 1 / RE2A                 # :1138
+    g[E2B, E2B] = 1 / RE2A + 1 / RE2B    # :1146
+    g[C2, C2] = 1 / RC2 + 1 / R9         # :1154
+    g[OUT, OUT] = 1 / R9 + 1 / R10       # :1162
+    g[FB, FB] = 1 / R10                  # :1170 (no R_ldr)
+    g[E2, E2B] = g[E2B, E2] = -1 / RE2A  # :1183
+    g[C2, OUT] = g[OUT, C2] = -1 / R9    # :1187
+    g[OUT, FB] = g[FB, OUT] = -1 / R10   # :1191
+    c = np.zeros((8, 8))
+    c[B1, B1], c[E1, E1], c[C1, C1], c[E2, E2], c[E2B, E2B], c[C2, C2], c[FB, FB] = C3, CE1, C3 + C4, CE2, CE2, C4, CE1   # :1227-1238
+    c[B1, C1] = c[C1, B1] = -C3          # :1241
+    c[C2, C1] = c[C1, C2] = -C4          # :1243
+    c[E1, FB] = c[FB, E1] = -CE1         # :1245
+    c[E2, E2B] = c[E2B, E2] = -CE2       # :1247
+    w = np.zeros(8)
+    w[B1], w[C1], w[C2] = VCC / R2, VCC / RC1, VCC / RC2   # :1278-1280
+    return g, c, w
+
+
+@pytest.mark.parametrize("sr", [88200.0, 96000.0, 176400.0])
+def test_legacy_preamp_l1_stamps_and_l2_identities(sr):
+    """test_l1_* (:1108-1293): every G / C / w stamp; test_l2_s_base_inverse_identity (:1296), test_l2_k_matches_full_product (:1380),
+    test_l2_sm_gives_correct_s_eff (:1331) and test_l2_a_neg_base_is_rldr_independent (:1455), against the oracle's plan constants
+    (the record the product's host code reproduces bit for bit, tests/test_host_logic.py)."""
+    R1, CIN = 22e3, 0.022e-6
+    B1, E1, C1, E2, E2B, C2, OUT, FB = range(8)
+    g, c, w = _legacy_netlist()
+    rec = np.zeros(188)
+    assert O.lib().owo_legacy_group(sr, 1e6, O.dptr(rec)) == 0
+    S, An, two_w = rec[0:64].reshape(8, 8), rec[64:128].reshape(8, 8), rec[128:136]
+    g_cin = (2 * CIN * sr) / (1 + 2 * R1 * CIN * sr)          # :1305-1306
+    assert abs(rec[169] - g_cin) <= 1e-15
+    assert np.abs(two_w / 2 - w).max() < 1e-12                 # test_l1_dc_source_vector
+    assert np.abs(c - c.T).max() < 1e-20                       # test_l1_c_matrix_symmetry
+    ge = g.copy()
+    ge[B1, B1] += g_cin
+    A = 2 * sr * c + ge
+    # A_neg_base = 2C/T - G: with S_base it pins every stamp of G and C at once (a wrong stamp moves an entry by >= 1e-6 S)
+    assert np.abs(An - (2 * sr * c - ge)).max() < 1e-9, np.abs(An - (2 * sr * c - ge)).max()
+    assert np.abs(S @ A - np.eye(8)).max() < 1e-8              # test_l2_s_base_inverse_identity
+    D0, D1 = rec[144:152], rec[152:160]
+    assert np.abs(D0 - (S[:, E1] - S[:, C1])).max() < 1e-15 and np.abs(D1 - (S[:, E2] - S[:, C2])).max() < 1e-15
+    k_full = np.array([[D0[B1] - D0[E1], D1[B1] - D1[E1]], [D0[C1] - D0[E2], D1[C1] - D1[E2]]])   # N_v S N_i, compute_k :795-811
+    assert np.abs(rec[160:164].reshape(2, 2) - k_full).max() < 1e-10   # test_l2_k_matches_full_product
+    for r_ldr in (19000.0, 100e3, 1e6):                        # test_l2_sm_gives_correct_s_eff: Sherman-Morrison vs brute force
+        gl = 1.0 / r_ldr
+        s_eff = S - gl * np.outer(S[:, FB], S[FB, :]) / (1 + gl * S[FB, FB])
+        Ar = A.copy()
+        Ar[FB, FB] += gl
+        assert np.abs(s_eff @ Ar - np.eye(8)).max() < 1e-8
+    rec2 = np.zeros(188)
+    O.lib().owo_legacy_group(sr, 19000.0, O.dptr(rec2))
+    assert np.array_equal(rec2[64:128], rec[64:128]) and np.array_equal(rec2[0:64], rec[0:64])   # test_l2_a_neg_base_is_rldr_independent
