@@ -272,6 +272,24 @@ int owg_fp64_peak(int32_t device, int32_t fma, float ms_target, double* tera_ins
  * reset != 0 clears them after reading. */
 int owg_debug_counters(uint64_t* out, int32_t n, int32_t reset);
 
+/* ---- alias_audit::analyze on the device (crates/openwurli-dsp/src/alias_audit.rs:163-282) ------------------------------------------
+ * The click-band metrics of `preamp-bench alias-audit` / tests/alias_audit_regression.rs reduced where the stream was rendered:
+ * steady-state tail of analyze_seconds, f0 refined on the reference's 0.1 Hz grid (+-5 Hz around nominal_f0), 12 harmonic single-bin
+ * DFTs, plateau metric over H6..H11, 5-18 kHz band RMS through four RBJ biquads.  results is host memory [n_rows][OWG_ALIAS_COLUMNS]:
+ *   0 f0_hz  1 h1_dbfs  2..13 harmonic_db  14..25 harmonic_dbc  26 max_step_up_db  27 max_step_up_from_harmonic  28 hf_band_dbc */
+#define OWG_ALIAS_COLUMNS 29
+#define OWG_ROWS_F64 0
+#define OWG_ROWS_F32 1
+/* rows: [n_rows][stride] samples of type row_dtype, in host or device memory as opts->out_location says; the last
+ * floor(sample_rate * analyze_seconds) samples of the first n_samples of every row are analysed. */
+int owg_alias_analyze(const void* rows, int32_t row_dtype, int64_t stride, int64_t n_rows, int64_t n_samples, double sample_rate,
+                      double analyze_seconds, const double* nominal_f0, double* results, const owg_opts* opts);
+/* owg_render_engines into a device buffer of the library, then owg_alias_analyze on samples [0, n_samples_i) of every stream, where
+ * n_samples_i = floor(duration_s * sample_rate) (alias_audit::render_stimulus + analyze, alias_audit.rs:131-204, batched; the streams
+ * never leave the GPU).  All jobs must share sample_rate and duration. */
+int owg_render_engines_alias(const owg_engine_job* jobs, int64_t n, double analyze_seconds, const double* nominal_f0, double* results,
+                             const owg_opts* opts);
+
 int owg_selftest_division(int64_t n_per_thread, uint64_t seed, uint64_t* mismatches, uint64_t* tested);
 
 #ifdef __cplusplus

@@ -360,6 +360,59 @@ def render_engines(jobs, out=None, device=-1, preamp_model=MELANGE12):
     return out
 
 
+ALIAS_COLUMNS = 29  # f0_hz, h1_dbfs, harmonic_db[12], harmonic_dbc[12], max_step_up_db, max_step_up_from_harmonic, hf_band_dbc
+
+
+class AliasAuditResult:
+    """alias_audit::AliasAuditResult (alias_audit.rs:60-80) from one row of owg_alias_analyze."""
+
+    def __init__(self, row):
+        self.f0_hz, self.h1_dbfs = float(row[0]), float(row[1])
+        self.harmonic_db, self.harmonic_dbc = np.array(row[2:14]), np.array(row[14:26])
+        self.max_step_up_db, self.max_step_up_from_harmonic, self.hf_band_dbc = float(row[26]), int(row[27]), float(row[28])
+
+
+def note_hz(note):
+    """alias_audit::midi_note_hz (alias_audit.rs:279-282)."""
+    return 440.0 * 2.0 ** ((note - 69.0) / 12.0)
+
+
+def alias_analyze(rows, sample_rate, nominal_f0, analyze_seconds=0.5, device=-1):
+    """alias_audit::analyze (alias_audit.rs:163-204) for every row of `rows` ([n, samples] float32 / float64, numpy or torch CUDA):
+    the reduction runs on the device; returns [n, ALIAS_COLUMNS] float64."""
+    n = rows.shape[0]
+    res = np.zeros((n, ALIAS_COLUMNS))
+    f0 = np.ascontiguousarray(np.asarray(nominal_f0, dtype=np.float64))
+    assert f0.shape == (n,)
+    if isinstance(rows, np.ndarray):
+        assert rows.flags.c_contiguous and rows.dtype in (np.float32, np.float64)
+        ptr, st, loc, f32 = rows.ctypes.data, rows.shape[1], OWG_OUT_HOST, rows.dtype == np.float32
+    else:
+        import torch
+        assert rows.is_contiguous() and rows.dtype in (torch.float32, torch.float64)
+        if rows.is_cuda:
+            torch.cuda.current_stream(rows.device).synchronize()
+        ptr, st, loc, f32 = rows.data_ptr(), rows.shape[1], (OWG_OUT_DEVICE if rows.is_cuda else OWG_OUT_HOST), rows.dtype == torch.float32
+    o = _opts(device, loc)
+    dp = C.POINTER(C.c_double)
+    check(lib().owg_alias_analyze(ptr, 1 if f32 else 0, st, n, rows.shape[1], float(sample_rate), float(analyze_seconds),
+                                  f0.ctypes.data_as(dp), res.ctypes.data_as(dp), C.byref(o)))
+    return res
+
+
+def render_engines_alias(jobs, nominal_f0, analyze_seconds=0.5, device=-1, preamp_model=MELANGE12):
+    """Engine streams rendered AND analysed on the device (alias_audit::run_with_note batched): only [n, ALIAS_COLUMNS] numbers come back."""
+    n = len(jobs)
+    res = np.zeros((n, ALIAS_COLUMNS))
+    f0 = np.ascontiguousarray(np.asarray(nominal_f0, dtype=np.float64))
+    assert f0.shape == (n,)
+    arr = (_abi.EngineJob * max(n, 1))(*jobs)
+    o = _opts(device, OWG_OUT_HOST, preamp_model=preamp_model)
+    dp = C.POINTER(C.c_double)
+    check(lib().owg_render_engines_alias(arr, n, float(analyze_seconds), f0.ctypes.data_as(dp), res.ctypes.data_as(dp), C.byref(o)))
+    return res
+
+
 class Voice:
     """Mirror of openwurli_dsp::voice::Voice's one-shot constructor (voice.rs:191-221)."""
 

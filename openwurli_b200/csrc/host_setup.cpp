@@ -643,4 +643,9 @@ void noise_fade_table(double* t16) {  // hammer.rs:161-168: 0.5*(1-cos(pi*pos/16
     for (int pos = 0; pos < 16; pos++) t16[pos] = 0.5 * (1.0 - std::cos(kPi * ((double)pos / 16.0)));
 }
 
+void rbj_coefficients(int kind, double fc, double q, double fs, double* out5) {
+    const Rbj r = rbj(kind, fc, q, fs);
+    out5[0] = r.b0; out5[1] = r.b1; out5[2] = r.b2; out5[3] = r.a1; out5[4] = r.a2;
+}
+
 }  // namespace owg

@@ -31,4 +31,6 @@ double register_trim_db(int midi);
 double silent_threshold();
 // tables::midi_to_freq (tables.rs:34-36)
 double note_frequency(int midi);
+// melange-primitives Biquad::lowpass / highpass (RBJ cookbook, normalised by a0): out5 = b0, b1, b2, a1, a2.  kind 0 = LP, 1 = HP.
+void rbj_coefficients(int kind, double fc, double q, double fs, double* out5);
 }  // namespace owg

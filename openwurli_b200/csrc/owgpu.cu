@@ -6,6 +6,7 @@
 #include "owg_tile.cuh"
 #include "owg_legacy.cuh"
 #include "owg_engine.cuh"
+#include "owg_alias.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -1762,6 +1763,72 @@ int owg_debug_counters(uint64_t* out, int32_t n, int32_t reset) {
         CK(cudaMemcpyToSymbol(g_trm_generic, z, sizeof(unsigned long long)));
     }
     return OWG_OK;
+}
+
+static int alias_analyze_device(const void* d_rows, int32_t row_dtype, int64_t stride, int64_t n_rows, int64_t n_samples, double sample_rate,
+                                double analyze_seconds, const double* nominal_f0, double* results, cudaStream_t s) {
+    const double an = sample_rate * analyze_seconds;
+    const int64_t analyze_n = !(an == an) || an <= 0.0 ? 0 : (int64_t)an;
+    if (analyze_n <= 0 || n_samples < analyze_n) return fail(OWG_E_BAD_ARG, "owg_alias_analyze: the streams are shorter than the analysis window");
+    DevBuf<double> d_f0, d_out;
+    std::vector<double> f0v(nominal_f0, nominal_f0 + n_rows);
+    int rc = d_f0.upload(f0v, s);
+    if (!rc) rc = d_out.alloc((size_t)n_rows * OWG_ALIAS_OUT);
+    if (rc) return rc;
+    AliasBq hp, lp;
+    double c5[5];
+    owg::rbj_coefficients(1, 5000.0, 0.70710678118654752440, sample_rate, c5);
+    hp = AliasBq{c5[0], c5[1], c5[2], c5[3], c5[4]};
+    owg::rbj_coefficients(0, 18000.0, 0.70710678118654752440, sample_rate, c5);
+    lp = AliasBq{c5[0], c5[1], c5[2], c5[3], c5[4]};
+    if (row_dtype == OWG_ROWS_F32)
+        alias_analyze_kernel<float><<<(unsigned)n_rows, 128, 0, s>>>((const float*)d_rows, stride, n_samples, analyze_n, sample_rate, d_f0.p, hp, lp, d_out.p);
+    else
+        alias_analyze_kernel<double><<<(unsigned)n_rows, 128, 0, s>>>((const double*)d_rows, stride, n_samples, analyze_n, sample_rate, d_f0.p, hp, lp, d_out.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(results, d_out.p, (size_t)n_rows * OWG_ALIAS_OUT * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return OWG_OK;
+}
+
+int owg_alias_analyze(const void* rows, int32_t row_dtype, int64_t stride, int64_t n_rows, int64_t n_samples, double sample_rate,
+                      double analyze_seconds, const double* nominal_f0, double* results, const owg_opts* opts) {
+    if (!rows || !nominal_f0 || !results || n_rows < 0 || n_samples < 0 || stride < n_samples || (row_dtype != OWG_ROWS_F64 && row_dtype != OWG_ROWS_F32) ||
+        !(sample_rate > 0.0) || !std::isfinite(sample_rate) || !(analyze_seconds > 0.0))
+        return fail(OWG_E_BAD_ARG, "owg_alias_analyze: bad argument");
+    if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
+    if (n_rows == 0) return OWG_OK;
+    owg_opts o;
+    if (opts) o = *opts; else owg_default_opts(&o);
+    if (o.device >= 0) CK(cudaSetDevice(o.device));
+    cudaStream_t s = (cudaStream_t)o.stream;
+    const size_t esz = row_dtype == OWG_ROWS_F32 ? 4 : 8;
+    if (o.out_location == OWG_OUT_DEVICE) return alias_analyze_device(rows, row_dtype, stride, n_rows, n_samples, sample_rate, analyze_seconds, nominal_f0, results, s);
+    DevBuf<unsigned char> d_rows;
+    if (int rc = d_rows.alloc((size_t)n_rows * (size_t)stride * esz)) return rc;
+    CK(cudaMemcpyAsync(d_rows.p, rows, (size_t)n_rows * (size_t)stride * esz, cudaMemcpyHostToDevice, s));
+    return alias_analyze_device(d_rows.p, row_dtype, stride, n_rows, n_samples, sample_rate, analyze_seconds, nominal_f0, results, s);
+}
+
+int owg_render_engines_alias(const owg_engine_job* jobs, int64_t n, double analyze_seconds, const double* nominal_f0, double* results,
+                             const owg_opts* opts) {
+    if (!jobs || !nominal_f0 || !results || n < 0) return fail(OWG_E_BAD_ARG, "owg_render_engines_alias: bad argument");
+    if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
+    if (n == 0) return OWG_OK;
+    for (int64_t i = 1; i < n; i++)
+        if (jobs[i].sample_rate != jobs[0].sample_rate || jobs[i].duration_s != jobs[0].duration_s)
+            return fail(OWG_E_BAD_ARG, "owg_render_engines_alias: all streams must share sample_rate and duration");
+    const double ns = jobs[0].sample_rate * jobs[0].duration_s;
+    const int64_t n_samples = !(ns == ns) || ns <= 0.0 ? 0 : (int64_t)ns;
+    owg_opts o;
+    if (opts) o = *opts; else owg_default_opts(&o);
+    if (o.device >= 0) CK(cudaSetDevice(o.device));
+    DevBuf<float> d_sig;
+    if (int rc = d_sig.alloc((size_t)n * (size_t)n_samples)) return rc;
+    o.out_location = OWG_OUT_DEVICE;
+    if (int rc = owg_render_engines(jobs, n, d_sig.p, n_samples, &o)) return rc;
+    return alias_analyze_device(d_sig.p, OWG_ROWS_F32, n_samples, n, n_samples, jobs[0].sample_rate, analyze_seconds, nominal_f0, results,
+                                (cudaStream_t)o.stream);
 }
 
 int owg_fp64_peak(int32_t device, int32_t fma_mode, float ms_target, double* tera_instr_per_s) {

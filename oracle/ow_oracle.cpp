@@ -303,6 +303,61 @@ int owo_alias_stimulus(uint8_t note, uint8_t velocity, double sr, double seconds
     return OWG_OK;
 }
 
+// alias_audit::analyze (alias_audit.rs:163-282) on a rendered signal: steady-state tail of `analyze_seconds`, f0 refinement on a
+// 0.1 Hz grid, 12 harmonic single-bin DFTs, plateau metric over H6..H11, 5-18 kHz band RMS through four RBJ biquads.
+// out[29] = f0_hz, h1_dbfs, harmonic_db[12], harmonic_dbc[12], max_step_up_db, max_step_up_from_harmonic, hf_band_dbc
+int owo_alias_analyze(const double* signal, int64_t n, double sr, double analyze_seconds, double nominal_f0, double* out) {
+    const int64_t analyze_n = (int64_t)f64_as_u64(sr * analyze_seconds);
+    if (!signal || !out || n < analyze_n || analyze_n <= 0) return OWG_E_BAD_ARG;
+    const double* tail = signal + (n - analyze_n);
+    auto dft_magnitude = [&](double freq) {  // :225-236
+        const double nn = (double)analyze_n;
+        double re = 0.0, im = 0.0;
+        const double omega = 2.0 * PI * freq / sr;
+        for (int64_t i = 0; i < analyze_n; i++) {
+            const double phase = omega * (double)i;
+            re += tail[i] * std::cos(phase);
+            im -= tail[i] * std::sin(phase);
+        }
+        return 2.0 * std::sqrt((re / nn) * (re / nn) + (im / nn) * (im / nn));
+    };
+    auto mag_to_db = [](double mag) { return mag > 0.0 ? 20.0 * std::log10(mag) : -200.0; };
+    double best_f = nominal_f0, best_mag = dft_magnitude(nominal_f0);  // refine_f0 :248-261
+    for (double f = nominal_f0 - 5.0; f <= nominal_f0 + 5.0; f += 0.1) {
+        const double mag = dft_magnitude(f);
+        if (mag > best_mag) { best_mag = mag; best_f = f; }
+    }
+    const double f0 = best_f;
+    const double h1 = dft_magnitude(f0);
+    double* hdb = out + 2;
+    double* hdbc = out + 14;
+    for (int k = 0; k < 12; k++) {
+        const double mag = dft_magnitude((double)(k + 1) * f0);
+        hdb[k] = mag_to_db(mag);
+        hdbc[k] = h1 > 0.0 ? 20.0 * std::log10(mag / h1) : -200.0;
+    }
+    hdbc[0] = 0.0;
+    double worst = -INFINITY;
+    int worst_from = 6;
+    for (int i = 5; i < 10; i++) {  // plateau_metric :206-222
+        const double delta = hdbc[i + 1] - hdbc[i];
+        if (delta > worst) { worst = delta; worst_from = i + 1; }
+    }
+    Biquad hp1, hp2, lp1, lp2;  // bandpass_rms :266-277
+    hp1.set(Biquad::HP, 5000.0, 0.70710678118654752440, sr); hp2 = hp1;
+    lp1.set(Biquad::LP, 18000.0, 0.70710678118654752440, sr); lp2 = lp1;
+    double sum_sq = 0.0;
+    for (int64_t i = 0; i < analyze_n; i++) {
+        const double y = lp2.process(lp1.process(hp2.process(hp1.process(tail[i]))));
+        sum_sq += y * y;
+    }
+    const double hf_rms = std::sqrt(sum_sq / (double)analyze_n);
+    out[0] = f0; out[1] = mag_to_db(h1);
+    out[26] = worst; out[27] = (double)worst_from;
+    out[28] = h1 > 0.0 ? 20.0 * std::log10(hf_rms / h1) : -200.0;
+    return OWG_OK;
+}
+
 // ---- known-answer probes (host-side setup functions) --------------------------------------------
 double owo_midi_to_freq(int midi) { return midi_to_freq((uint8_t)midi); }
 double owo_tip_mass_ratio(int midi) { return tip_mass_ratio((uint8_t)midi); }

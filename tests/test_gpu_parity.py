@@ -659,6 +659,43 @@ def test_alias_audit_gate_through_the_gpu_engine_path(note):
     assert step_up - base_step <= 1.5 and hf - base_hf <= 2.0, (step_up, base_step, hf, base_hf)
 
 
+def _alias_job(note):
+    """alias_audit::render_stimulus (alias_audit.rs:131-161) as one engine job: no warm-up, six 1024-sample settle blocks, note-on at
+    velocity 120, 1.5 s; the analysed stream is the part after the settle blocks."""
+    sr, total, settle = 44100.0, int(44100.0 * 1.5), 6 * 1024
+    return ow.engine_job([(settle, ow.NOTE_ON, note, float(np.float32(120) / np.float32(127.0)))], sample_rate=sr, duration=(settle + total + 0.5) / sr,
+                         volume=0.5, tremolo_depth=0.0, speaker_character=0.0, mlp=True, block_size=1024, warm_up=False)
+
+
+def test_alias_analyze_on_the_device_matches_the_oracle_and_the_fixture():
+    """(f2) alias_audit::analyze as a device-side reduction: same numbers as the oracle's restatement on the same stream, through the
+    row API (host f64 / f32 rows, device rows) and through owg_render_engines_alias (render + analyse without the samples leaving the
+    GPU), then the reference's JSON gate on the device numbers."""
+    import json
+    import torch
+    notes = [72, 84, 91]
+    sr, total, settle = 44100.0, int(44100.0 * 1.5), 6 * 1024
+    jobs = [_alias_job(n) for n in notes]
+    sig32 = ow.render_engines(jobs)[:, : settle + total]
+    f0 = [ow.note_hz(n) for n in notes]
+    ref = np.zeros((3, 29))
+    for i in range(3):
+        assert O.lib().owo_alias_analyze(O.dptr(sig32[i].astype(np.float64)), settle + total, sr, 0.5, f0[i], O.dptr(ref[i])) == 0
+    rows32 = np.ascontiguousarray(sig32)
+    for got in (ow.alias_analyze(rows32, sr, f0), ow.alias_analyze(rows32.astype(np.float64), sr, f0), ow.alias_analyze(torch.from_numpy(rows32).cuda(), sr, f0),
+                ow.render_engines_alias(jobs, f0)):
+        assert np.array_equal(got[:, 0], ref[:, 0]) and np.array_equal(got[:, 27], ref[:, 27])   # refined f0 and plateau index: same decisions
+        assert np.abs(got[:, 1:14] - ref[:, 1:14]).max() < 1e-7 and np.abs(got[:, 26] - ref[:, 26]).max() < 1e-6     # dB of clean bins
+        assert np.abs(got[:, 14:26] - ref[:, 14:26]).max() < 1e-6 and np.abs(got[:, 28] - ref[:, 28]).max() < 1e-8
+    base = {e["note"]: e for e in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_alias_audit_v0_5_1.json")))["entries"]}
+    got = ow.render_engines_alias(jobs, f0)
+    for i, n in enumerate(notes):
+        r = ow.AliasAuditResult(got[i])
+        assert abs(r.f0_hz - base[n]["f0_hz"]) <= 5.1e-5
+        assert r.max_step_up_db - base[n]["max_step_up_db"] <= 1.5 and r.hf_band_dbc - base[n]["hf_band_dbc"] <= 2.0   # alias_audit_regression.rs:59-114
+        assert r.max_step_up_from_harmonic == base[n]["max_step_up_from_harmonic"]
+
+
 def test_chain_batch_both_preamp_construction_orders():
     """owg_chain_batch: caller rows (a render-poly style sum of voices) through chain B; cmd_render's reset-then-set order and
     render-poly's set-then-reset order (melange falls back to the settled 100 kOhm, legacy re-solves its DC point at r)."""

@@ -7,11 +7,15 @@ solver constants, the gain / tremolo figures quoted in its CHANGELOG, and the on
 has (tests/baselines/alias_audit_v0_5_1.json, one-sided gate).
 """
 import ctypes as C
+import json
+import os
 
 import numpy as np
 import pytest
 
 import oracle_lib as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 L = O.lib()
 
@@ -482,3 +486,58 @@ def test_legacy_preamp_l1_stamps_and_l2_identities(sr):
     rec2 = np.zeros(188)
     O.lib().owo_legacy_group(sr, 19000.0, O.dptr(rec2))
     assert np.array_equal(rec2[64:128], rec[64:128]) and np.array_equal(rec2[0:64], rec[0:64])   # test_l2_a_neg_base_is_rldr_independent
+
+
+# ---- alias_audit::analyze against the reference's JSON fixture, two-sided (h1_dbfs / harmonic_dbc / f0 were ignored) -------
+def _alias_oracle(note):
+    sr, total = 44100.0, int(44100.0 * 1.5)
+    sig = np.zeros(total)
+    O.lib().owo_alias_stimulus(note, 120, sr, 1.5, 0.5, O.dptr(sig))
+    out = np.zeros(29)
+    assert O.lib().owo_alias_analyze(O.dptr(sig), total, sr, 0.5, 440.0 * 2.0 ** ((note - 69.0) / 12.0), O.dptr(out)) == 0
+    return sig, out
+
+
+def test_alias_audit_analyze_two_sided_against_the_reference_fixture():
+    """tests/golden/ref_alias_audit_v0_5_1.json is a verbatim copy of the reference's crates/openwurli-dsp/tests/baselines/alias_audit_v0_5_1.json
+    (a data fixture, captured by the reference at v0.5.1).  Two-sided checks of the oracle's render + analyze (alias_audit.rs:131-282):
+      * f0_hz: the refined fundamental reproduces all three fixture values to their 4 printed decimals -- pins per-key detuning, the MLP
+        frequency correction and the 0.1 Hz search grid;
+      * h1_dbfs: v0.6.0 differs from the v0.5.1 capture by ONE gain offset common to all notes (CHANGELOG.md:66-70: the corrected LDR
+        divider raised the no-vibrato preamp gain from ~6 to ~14 dB and POST_SPEAKER_GAIN dropped 4.5 dB: +8 - 4.5 = +3.5 dB); a
+        gain-staging slip in any per-note path (output_scale, register trim, pickup) would break the "common" part;
+      * the even low harmonics H2 / H4 (set by the pickup's 1/(1-y) asymmetry, upstream of the changed gain) stay within 0.5 dB;
+      * the one-sided gate of alias_audit_regression.rs:59-114 and the plateau harmonic index."""
+    base = {e["note"]: e for e in json.load(open(os.path.join(HERE, "golden", "ref_alias_audit_v0_5_1.json")))["entries"]}
+    offs = []
+    for note in (72, 84, 91):
+        _, out = _alias_oracle(note)
+        b = base[note]
+        assert abs(out[0] - b["f0_hz"]) <= 5.1e-5, (note, out[0], b["f0_hz"])
+        offs.append(out[1] - b["h1_dbfs"])
+        dbc = out[14:26]
+        assert dbc[0] == 0.0 and abs(dbc[1] - b["harmonic_dbc"][1]) <= 0.5 and abs(dbc[3] - b["harmonic_dbc"][3]) <= 0.5, (note, dbc[:4])
+        assert out[26] - b["max_step_up_db"] <= 1.5 and out[28] - b["hf_band_dbc"] <= 2.0
+        assert abs(out[28] - b["hf_band_dbc"]) <= 0.5          # the 5-18 kHz band relative to H1 barely moved between the versions
+        assert int(out[27]) == b["max_step_up_from_harmonic"]
+        # harmonic_db and harmonic_dbc are consistent with h1_dbfs
+        assert np.abs((out[2:14] - out[1]) - dbc)[1:].max() < 1e-9
+    assert max(offs) - min(offs) <= 0.1, offs
+    assert 3.0 <= np.mean(offs) <= 4.0, offs
+
+
+def test_alias_analyze_matches_a_numpy_restatement():
+    from scipy.signal import lfilter
+    sig, out = _alias_oracle(84)
+    sr = 44100.0
+    tail = sig[-int(sr * 0.5):]
+    f0 = out[0]
+    h1 = _dft_mag(tail, f0, sr)
+    assert abs(20 * np.log10(h1) - out[1]) < 1e-8
+    for k in range(12):
+        assert abs(20 * np.log10(_dft_mag(tail, (k + 1) * f0, sr)) - out[2 + k]) < 1e-6
+    y = tail
+    for kind, fc in (("hp", 5000.0), ("hp", 5000.0), ("lp", 18000.0), ("lp", 18000.0)):
+        b, a = _rbj(kind, fc, np.sqrt(0.5), sr)
+        y = lfilter(b, a, y)
+    assert abs(20 * np.log10(np.sqrt(np.mean(y ** 2)) / h1) - out[28]) < 1e-6
