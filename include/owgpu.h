@@ -64,6 +64,11 @@ typedef struct owg_bench_job {
 #define OWG_EV_NOTE_ON 0
 #define OWG_EV_NOTE_OFF 1
 #define OWG_EV_SUSTAIN 2 /* note != 0 -> pedal down */
+/* Parameter automation (engine.rs:378-388; the plugin calls these at the top of every process() block, openwurli-plugin/src/lib.rs):
+ * the new target is `velocity` (f32 like the plugin's parameter values), the smoothers ramp to it over 5 ms. */
+#define OWG_EV_SET_VOLUME 3
+#define OWG_EV_SET_TREMOLO_DEPTH 4
+#define OWG_EV_SET_SPEAKER_CHARACTER 5
 typedef struct owg_event {
     int64_t sample;  /* base-rate sample index at which the event applies (block-quantised like the plugin host) */
     uint8_t kind;

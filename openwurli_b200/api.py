@@ -320,12 +320,15 @@ def render_calibrate(notes, velocities, cfg=None, volume=0.40, speaker=1.0, wind
 
 
 NOTE_ON, NOTE_OFF, SUSTAIN = 0, 1, 2
+# parameter automation events (engine.rs:378-388): the value travels in the event's velocity field, `note` is ignored
+SET_VOLUME, SET_TREMOLO_DEPTH, SET_SPEAKER_CHARACTER = 3, 4, 5
 
 
 def engine_job(events, sample_rate=44100.0, duration=1.0, volume=0.5, tremolo_depth=0.5, speaker_character=0.0,
                mlp=True, block_size=512, warm_up=True):
     """One WurliEngine stream (engine.rs:194-462).  `events` = [(sample, kind, note, velocity)], sorted by sample;
-    kind in NOTE_ON / NOTE_OFF / SUSTAIN (note != 0 = pedal down); velocity is rounded to f32 like note_on(u8, f32).
+    kind in NOTE_ON / NOTE_OFF / SUSTAIN (note != 0 = pedal down); velocity is rounded to f32 like note_on(u8, f32);
+    SET_VOLUME / SET_TREMOLO_DEPTH / SET_SPEAKER_CHARACTER carry the new smoother target in `velocity` (applied at the start of their block).
     Defaults are the engine's own (volume 0.5, depth 0.5, character 0.0, MLP on; engine.rs:224-226); warm_up=True
     constructs through set_sample_rate() as the plugin does (0.6 s warm-up)."""
     arr = (_abi.Event * max(len(events), 1))()

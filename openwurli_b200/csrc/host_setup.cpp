@@ -459,6 +459,52 @@ int make_speaker_schedule(double fs, double target, int64_t n_warm, int64_t n_to
     return n;
 }
 
+int make_engine_schedule(double fs, const AutoEvent* chr, int n_chr, const AutoEvent* vol, int n_vol, int64_t n_total, uint32_t ramp, SpkUpdate* out,
+                         int max_out) {
+    int n = 0;
+    double character = 1.0;  // Speaker::new (speaker.rs:63-78)
+    if (n < max_out) fill_spk(&out[n++], -1, character, fs);
+    double cur = 0.0, tgt = 0.0, step = 0.0;  // LinearSmoother::new(0.0, ramp) (engine.rs:226)
+    uint32_t remaining = 0;
+    int ci = 0, vi = 0;
+    int64_t t = 0;
+    while (t < n_total) {
+        while (vi < n_vol && vol[vi].at <= t) {  // set_volume at the start of the block: its own schedule entry
+            if (n >= max_out) return -1;
+            std::memset(&out[n], 0, sizeof(SpkUpdate));
+            out[n].at = vol[vi].at; out[n].a2 = vol[vi].target; out[n]._pad = 1;
+            n++; vi++;
+        }
+        while (ci < n_chr && chr[ci].at <= t) {  // set_speaker_character -> LinearSmoother::set_target (engine.rs:85-98)
+            const double target = chr[ci++].target;
+            if (!(std::fabs(target - tgt) < 1e-9)) {
+                tgt = target;
+                const double delta = tgt - cur;
+                if (ramp == 0) { cur = tgt; remaining = 0; }
+                else { step = delta / (double)ramp; remaining = ramp; }
+            }
+        }
+        if (remaining > 0) {
+            cur += step;
+            remaining -= 1;
+            if (remaining == 0) cur = tgt;
+        }
+        const double c = clampd(cur, 0.0, 1.0);  // Speaker::set_character (speaker.rs:81-87)
+        if (std::fabs(c - character) > 0.002) {
+            character = c;
+            if (n < max_out) fill_spk(&out[n++], t, character, fs);
+            else return -1;
+        }
+        if (remaining == 0) {  // flat until the next event: jump there
+            int64_t nxt = n_total;
+            if (ci < n_chr) nxt = std::min<int64_t>(nxt, chr[ci].at);
+            if (vi < n_vol) nxt = std::min<int64_t>(nxt, vol[vi].at);
+            t = std::max<int64_t>(t + 1, nxt);
+        } else t++;
+    }
+    return n;
+}
+
 // ---- legacy 8-node preamp: plan-time constants ----------------------------------------------------------------------
 namespace {
 enum LgNode { N_BASE1 = 0, N_EMIT1, N_COLL1, N_EMIT2, N_EMIT2B, N_COLL2, N_OUT, N_FB, LGN };

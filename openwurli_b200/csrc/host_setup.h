@@ -17,6 +17,11 @@ void make_damper_rows(double sample_rate, DamperRow* rows128);
 // effect at (entry 0 = the constructor state, at = -1).  The target is applied after `n_warm` samples.
 int make_speaker_schedule(double sample_rate, double character_target, int64_t n_warm, int64_t n_total, uint32_t ramp_samples,
                           SpkUpdate* out, int max_out);
+// The same with automation: chr_at / chr_target = set_speaker_character calls (render() sample index incl. warm-up, sorted; the first
+// is the construction-time target at n_warm), vol_at / vol_target = set_volume calls, merged into one schedule in time order.
+struct AutoEvent { int64_t at; double target; };
+int make_engine_schedule(double sample_rate, const AutoEvent* chr, int n_chr, const AutoEvent* vol, int n_vol, int64_t n_total, uint32_t ramp_samples,
+                         SpkUpdate* out, int max_out);
 // Legacy 8-node preamp (dk_preamp_legacy.rs:269-412): R_ldr-independent matrices, Sherman-Morrison vectors, Cin-R1 companion
 // constants and the DC operating point at 1 MOhm for `preamp_sr`; rec = OWG_LG_STRIDE doubles (owg_records.h).
 // `r_static`: the static LDR resistance handed to set_ldr_resistance after reset() (NaN = tremolo group).

@@ -169,6 +169,26 @@ __device__ __forceinline__ void voice_note_off(VoiceRT& v, const DamperRow* __re
 
 // ---- shared per-group sequences for engines -------------------------------------------------------------------------
 // Tremolo::new(0.5, os_sr) [2 s settle] then one process() per preamp-rate sample with the depth trajectory of the engine's
+// One entry of an engine's schedule (host-prepared, owg_records.h): kind 0 = Speaker::update_coefficients (the host simulated the
+// character smoother and set_character's 0.002 dead-band), kind 1 = WurliEngine::set_volume -> LinearSmoother::set_target
+// (engine.rs:85-98, 378-380) at the start of the block the event falls in.
+__device__ __forceinline__ void sched_apply(const SpkUpdate& u, OwgChainInit& sc, double& vol_current, double& vol_target, double& vol_step,
+                                            uint32_t& vol_remaining, const int ramp_samples) {
+    if (u._pad == 1) {
+        const double target = u.a2;
+        if (!(fabs(target - vol_target) < 1e-9)) {
+            vol_target = target;
+            const double delta = target - vol_current;
+            if (ramp_samples == 0) { vol_current = target; vol_remaining = 0; }
+            else { vol_step = delta / (double)ramp_samples; vol_remaining = (uint32_t)ramp_samples; }
+        }
+        return;
+    }
+    sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
+    sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
+    sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+}
+
 // LinearSmoother (engine.rs:67-130, 532-547): 0.5 during the warm-up, then a ramp_samples-long linear ramp to the target.
 // Output: pot_0_resistance in effect per preamp-rate sample (warm-up first).
 struct EngTrmRun {  // oscillator state between chunk launches
@@ -224,8 +244,9 @@ __global__ void engine_tremolo_kernel(const EngineGroup* groups, int n_groups, d
 // Tremolo::process after the oscillator + the engine's depth smoother (engine.rs:67-130, 532-547: 0.5 during the warm-up, then a
 // ramp_samples-long linear ramp to the target) + the preamp's resistance tracking; in place on seq (volts in, pot_0_resistance
 // out), `dseq` is scratch for the depth trajectory.  One CTA per group; serial recurrences on thread 0, maps on all threads.
+struct DepthEv { long long at_os; double target; };  // WurliEngine::set_tremolo_depth at the start of a block (preamp-rate index incl. warm-up)
 __global__ void __launch_bounds__(256) engine_ldr_kernel(const EngineGroup* groups, int n_groups, double* seq, double* dseq, long long seq_stride,
-                                                         EngLdrRun* run, long long live_end_base, int legacy) {
+                                                         EngLdrRun* run, long long live_end_base, int legacy, const DepthEv* __restrict__ dep_ev) {
     // legacy != 0: the consumer is the 8-node legacy preamp (set_ldr_resistance: max(R, 1000), 0.01 Ohm threshold); output = g_ldr
     const int gi = blockIdx.x;
     if (gi >= n_groups) return;
@@ -254,15 +275,21 @@ __global__ void __launch_bounds__(256) engine_ldr_kernel(const EngineGroup* grou
         }
         double env = R.env, sm_current = R.sm_current, sm_target = R.sm_target, sm_step = R.sm_step, depth = R.depth;
         uint32_t sm_remaining = R.sm_remaining;
+        int dep_next = gr.dep_ev_begin;
+        while (dep_next < gr.dep_ev_end && dep_ev[dep_next].at_os < t0) dep_next++;  // events of earlier chunks are already applied
         for (long long tl = t0; tl < t1; tl++) {
-            if (tl == gr.n_warm_os) {  // set_tremolo_depth(target): LinearSmoother::set_target (engine.rs:85-98)
-                if (!(fabs(gr.depth_target - sm_target) < 1e-9)) {
-                    sm_target = gr.depth_target;
+            // set_tremolo_depth(target): LinearSmoother::set_target (engine.rs:85-98, 382-384) -- the construction-time target right after
+            // the warm-up, then the stream's automation events at the start of their blocks
+            auto set_target = [&](const double target) {
+                if (!(fabs(target - sm_target) < 1e-9)) {
+                    sm_target = target;
                     const double delta = sm_target - sm_current;
                     if (gr.ramp_samples == 0) { sm_current = sm_target; sm_remaining = 0; }
                     else { sm_step = delta / (double)gr.ramp_samples; sm_remaining = (uint32_t)gr.ramp_samples; }
                 }
-            }
+            };
+            if (tl == gr.n_warm_os) set_target(gr.depth_target);
+            while (dep_next < gr.dep_ev_end && dep_ev[dep_next].at_os == tl) set_target(dep_ev[dep_next++].target);
             if ((tl % sub) == 0) {  // once per base-rate sample: depth = smoother.next(); tremolo.set_depth(depth)
                 if (sm_remaining > 0) {
                     sm_current += sm_step;
@@ -817,15 +844,12 @@ __global__ void __launch_bounds__(32) engine_chain_kernel(const EngineWarp* __re
         int spk_next = C.spk_next;
         long long spk_clock = C.spk_clock;
         double vol_current = C.vol_current;
-        const double vol_target = C.vol_target, vol_step = C.vol_step;
+        double vol_target = C.vol_target, vol_step = C.vol_step;
         uint32_t vol_remaining = C.vol_remaining;
         unsigned long long d_out_nan = 0;
         if (T0 == 0 && is_main) {
             while (spk_next < ed.n_spk_updates && sched[spk_next].at < spk_clock) {  // updates that happened during the warm-up
-                const SpkUpdate& u = sched[spk_next++];
-                sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
-                sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
-                sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+                sched_apply(sched[spk_next++], sc, vol_current, vol_target, vol_step, vol_remaining, ed.ramp_samples);
             }
         }
         const int n_sub = gr.oversample ? 2 : 1;
@@ -882,10 +906,7 @@ __global__ void __launch_bounds__(32) engine_chain_kernel(const EngineWarp* __re
             } else stage_out = pp0;
             if (live) {
                 while (spk_next < ed.n_spk_updates && sched[spk_next].at <= spk_clock) {  // set_character() -> update_coefficients()
-                    const SpkUpdate& u = sched[spk_next++];
-                    sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
-                    sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
-                    sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+                    sched_apply(sched[spk_next++], sc, vol_current, vol_target, vol_step, vol_remaining, ed.ramp_samples);
                 }
                 spk_clock += 1;
                 const double shaped = speaker(stage_out, spk, sc);
@@ -911,7 +932,7 @@ __global__ void __launch_bounds__(32) engine_chain_kernel(const EngineWarp* __re
             C.dk = dk;
             for (int k = 0; k < 3; k++) { C.ua[k] = ua[k]; C.ub[k] = ub[k]; C.da[k] = da[k]; C.db[k] = db[k]; }
             C.down_delay = down_delay; C.spk = spk; C.sc = sc; C.spk_next = spk_next; C.spk_clock = spk_clock;
-            C.vol_current = vol_current; C.vol_remaining = vol_remaining; C.d_out_nan += d_out_nan;
+            C.vol_current = vol_current; C.vol_remaining = vol_remaining; C.vol_target = vol_target; C.vol_step = vol_step; C.d_out_nan += d_out_nan;
         }
     }
     if (last_segment && is_main)
@@ -1028,15 +1049,12 @@ __global__ void __launch_bounds__(64) engine_chain_split_kernel(const EngineWarp
             int spk_next = C.spk_next;
             long long spk_clock = C.spk_clock;
             double vol_current = C.vol_current;
-            const double vol_target = C.vol_target, vol_step = C.vol_step;
+            double vol_target = C.vol_target, vol_step = C.vol_step;
             uint32_t vol_remaining = C.vol_remaining;
             unsigned long long d_out_nan = 0;
             if (T0 == 0 && is_main) {
                 while (spk_next < ed.n_spk_updates && sched[spk_next].at < spk_clock) {  // updates that happened during the warm-up
-                    const SpkUpdate& u = sched[spk_next++];
-                    sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
-                    sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
-                    sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+                    sched_apply(sched[spk_next++], sc, vol_current, vol_target, vol_step, vol_remaining, ed.ramp_samples);
                 }
             }
             auto produce = [&](long long t) {
@@ -1070,10 +1088,7 @@ __global__ void __launch_bounds__(64) engine_chain_split_kernel(const EngineWarp
                 } else stage_out = pp0;
                 if (live) {
                     while (spk_next < ed.n_spk_updates && sched[spk_next].at <= spk_clock) {  // set_character() -> update_coefficients()
-                        const SpkUpdate& u = sched[spk_next++];
-                        sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
-                        sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
-                        sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+                        sched_apply(sched[spk_next++], sc, vol_current, vol_target, vol_step, vol_remaining, ed.ramp_samples);
                     }
                     spk_clock += 1;
                     const double shaped = speaker(stage_out, spk, sc);
@@ -1097,7 +1112,7 @@ __global__ void __launch_bounds__(64) engine_chain_split_kernel(const EngineWarp
             if (is_main) {
                 for (int k = 0; k < 3; k++) { C.ua[k] = ua[k]; C.ub[k] = ub[k]; C.da[k] = da[k]; C.db[k] = db[k]; }
                 C.down_delay = down_delay; C.spk = spk; C.sc = sc; C.spk_next = spk_next; C.spk_clock = spk_clock;
-                C.vol_current = vol_current; C.vol_remaining = vol_remaining; C.d_out_nan += d_out_nan;
+                C.vol_current = vol_current; C.vol_remaining = vol_remaining; C.vol_target = vol_target; C.vol_step = vol_step; C.d_out_nan += d_out_nan;
             }
         }
     }
@@ -1174,15 +1189,12 @@ __global__ void __launch_bounds__(32) engine_chain_legacy_kernel(const EngineWar
         int spk_next = C.spk_next;
         long long spk_clock = C.spk_clock;
         double vol_current = C.vol_current;
-        const double vol_target = C.vol_target, vol_step = C.vol_step;
+        double vol_target = C.vol_target, vol_step = C.vol_step;
         uint32_t vol_remaining = C.vol_remaining;
         unsigned long long d_out_nan = 0;
         if (T0 == 0 && is_main) {
             while (spk_next < ed.n_spk_updates && sched[spk_next].at < spk_clock) {  // updates that happened during the warm-up
-                const SpkUpdate& u = sched[spk_next++];
-                sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
-                sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
-                sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+                sched_apply(sched[spk_next++], sc, vol_current, vol_target, vol_step, vol_remaining, ed.ramp_samples);
             }
         }
         const int n_sub = gr.oversample ? 2 : 1;
@@ -1223,10 +1235,7 @@ __global__ void __launch_bounds__(32) engine_chain_legacy_kernel(const EngineWar
             } else stage_out = pp0;
             if (live) {
                 while (spk_next < ed.n_spk_updates && sched[spk_next].at <= spk_clock) {
-                    const SpkUpdate& u = sched[spk_next++];
-                    sc.spk_a2 = u.a2; sc.spk_a3 = u.a3; sc.spk_norm = u.norm; sc.spk_thermal_coeff = u.thermal_coeff; sc.spk_tanh = u.tanh_on;
-                    sc.hpf_b0 = u.hpf_b0; sc.hpf_b1 = u.hpf_b1; sc.hpf_b2 = u.hpf_b2; sc.hpf_a1 = u.hpf_a1; sc.hpf_a2 = u.hpf_a2;
-                    sc.lpf_b0 = u.lpf_b0; sc.lpf_b1 = u.lpf_b1; sc.lpf_b2 = u.lpf_b2; sc.lpf_a1 = u.lpf_a1; sc.lpf_a2 = u.lpf_a2;
+                    sched_apply(sched[spk_next++], sc, vol_current, vol_target, vol_step, vol_remaining, ed.ramp_samples);
                 }
                 spk_clock += 1;
                 const double shaped = speaker(stage_out, spk, sc);
@@ -1252,7 +1261,7 @@ __global__ void __launch_bounds__(32) engine_chain_legacy_kernel(const EngineWar
             C.lg = st; C.g_prev = g_prev;
             for (int k = 0; k < 3; k++) { C.ua[k] = ua[k]; C.ub[k] = ub[k]; C.da[k] = da[k]; C.db[k] = db[k]; }
             C.down_delay = down_delay; C.spk = spk; C.sc = sc; C.spk_next = spk_next; C.spk_clock = spk_clock;
-            C.vol_current = vol_current; C.vol_remaining = vol_remaining; C.d_out_nan += d_out_nan;
+            C.vol_current = vol_current; C.vol_remaining = vol_remaining; C.vol_target = vol_target; C.vol_step = vol_step; C.d_out_nan += d_out_nan;
         }
     }
     if (last_segment && is_main)

@@ -97,7 +97,9 @@ struct DamperRow {  // ModalReed::start_damper (reed.rs:191-216) per MIDI key, c
     int32_t enabled, _pad;
 };
 
-struct SpkUpdate {  // one Speaker::update_coefficients (speaker.rs:89-101) on the host-simulated character ramp
+struct SpkUpdate {  // one entry of an engine's schedule
+    // _pad == 0: one Speaker::update_coefficients (speaker.rs:89-101) on the host-simulated character ramp
+    // _pad == 1: WurliEngine::set_volume(a2) (engine.rs:378-380) at the start of a block
     int64_t at;   // base-rate sample index (counted from the first render() sample incl. warm-up) at which it takes effect
     double a2, a3, norm, thermal_coeff;
     double hpf_b0, hpf_b1, hpf_b2, hpf_a1, hpf_a2, lpf_b0, lpf_b1, lpf_b2, lpf_a1, lpf_a2;
@@ -130,5 +132,6 @@ struct EngineGroup {
     double depth_target;      // set_tremolo_depth() target applied right after the warm-up
     int64_t n_warm_os, n_os; // preamp-rate samples: warm-up, then rendered
     int32_t oversample, ramp_samples, use_defaults, _pad;
+    int32_t dep_ev_begin, dep_ev_end;  // this group's set_tremolo_depth events in the launch's DepthEv array
 };
 

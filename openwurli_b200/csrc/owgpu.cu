@@ -1155,9 +1155,11 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     std::vector<int32_t> damper_sched((size_t)n);
     std::vector<SpkUpdate> spk_updates;
     std::vector<long long> spk_offsets;
-    std::map<std::tuple<double, double, int>, int> group_key;
+    std::map<std::tuple<double, double, int, std::vector<std::pair<long long, double>>>, int> group_key;
     std::map<double, int> damper_key;
-    std::map<std::tuple<double, double, long long>, std::pair<int, int>> spk_key;  // -> (schedule id, n updates)
+    // schedule = (rate, warm-up length, stream length class, character events, volume events) -> (schedule id, n updates)
+    std::map<std::tuple<double, long long, std::vector<std::pair<long long, double>>, std::vector<std::pair<long long, double>>>, std::pair<int, int>> spk_key;
+    std::vector<DepthEv> depth_events;
     long long max_samples = 0, max_block = 1, pot_stride = 0;
     for (int64_t i = 0; i < n; i++) {
         const owg_engine_job& j = jobs[i];
@@ -1173,8 +1175,18 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
         max_samples = std::max(max_samples, (long long)e.n_samples);
         max_block = std::max<long long>(max_block, e.block_size);
         const int sub = e.oversample ? 2 : 1;
-        // shared sequences: (rate, depth target, warm-up)
-        const auto gk = std::make_tuple(sr, j.tremolo_depth, j.warm_up ? 1 : 0);
+        // parameter automation: set_volume / set_tremolo_depth / set_speaker_character events act at the start of their block
+        std::vector<std::pair<long long, double>> ev_vol, ev_dep, ev_chr;
+        ev_chr.emplace_back((long long)e.n_warm, j.speaker_character);  // the construction-time target, right after the warm-up
+        for (int64_t k = 0; k < j.n_ev; k++) {
+            const owg_event& ev = j.ev[k];
+            if (ev.kind != OWG_EV_SET_VOLUME && ev.kind != OWG_EV_SET_TREMOLO_DEPTH && ev.kind != OWG_EV_SET_SPEAKER_CHARACTER) continue;
+            if (ev.sample < 0 || ev.sample >= e.n_samples) continue;
+            const long long at = (long long)e.n_warm + (ev.sample / e.block_size) * (long long)e.block_size;
+            (ev.kind == OWG_EV_SET_VOLUME ? ev_vol : (ev.kind == OWG_EV_SET_TREMOLO_DEPTH ? ev_dep : ev_chr)).emplace_back(at, (double)ev.velocity);
+        }
+        // shared sequences: (rate, depth target, warm-up, depth automation)
+        const auto gk = std::make_tuple(sr, j.tremolo_depth, j.warm_up ? 1 : 0, ev_dep);
         auto git = group_key.find(gk);
         if (git == group_key.end()) {
             EngineGroup g;
@@ -1187,6 +1199,9 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
             g.oversample = e.oversample;
             g.ramp_samples = e.ramp_samples;
             g.use_defaults = std::fabs(g.preamp_sr - 48000.0) <= 0.5 ? 1 : 0;
+            g.dep_ev_begin = (int32_t)depth_events.size();
+            for (auto& de : ev_dep) depth_events.push_back(DepthEv{de.first * sub, de.second});
+            g.dep_ev_end = (int32_t)depth_events.size();
             group_key[gk] = (int)groups.size();
             e.group = (int)groups.size();
             groups.push_back(g);
@@ -1200,14 +1215,17 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
             dampers.resize(dampers.size() + 128);
             owg::make_damper_rows(sr, &dampers[dampers.size() - 128]);
         } else damper_sched[i] = dit->second;
-        // speaker coefficient schedule per (rate, character target, warm-up length)
-        const auto sk = std::make_tuple(sr, j.speaker_character, (long long)e.n_warm);
+        // speaker coefficient / volume schedule per (rate, warm-up length, character events, volume events)
+        const auto sk = std::make_tuple(sr, (long long)e.n_warm, ev_chr, ev_vol);
         auto sit = spk_key.find(sk);
         if (sit == spk_key.end()) {
-            const int cap = e.ramp_samples + 8;
+            const int cap = (int)((e.ramp_samples + 8) * ev_chr.size() + ev_vol.size() + 8);
             std::vector<SpkUpdate> tmp((size_t)cap);
-            const int nu = owg::make_speaker_schedule(sr, j.speaker_character, e.n_warm, e.n_warm + e.n_samples + e.ramp_samples + 2,
-                                                      (uint32_t)e.ramp_samples, tmp.data(), cap);
+            std::vector<owg::AutoEvent> ac, av;
+            for (auto& x : ev_chr) ac.push_back(owg::AutoEvent{x.first, x.second});
+            for (auto& x : ev_vol) av.push_back(owg::AutoEvent{x.first, x.second});
+            const int nu = owg::make_engine_schedule(sr, ac.data(), (int)ac.size(), av.data(), (int)av.size(), e.n_warm + e.n_samples + e.ramp_samples + 2,
+                                                     (uint32_t)e.ramp_samples, tmp.data(), cap);
             if (nu < 0) return fail(OWG_E_CUDA, "speaker schedule overflow");
             spk_key[sk] = std::make_pair((int)spk_offsets.size(), nu);
             e.spk_sched = (int)spk_offsets.size();
@@ -1264,6 +1282,9 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
                 d.vinit = (long long)vinits.size();
                 vinits.emplace_back();
                 owg::make_voice_init(vj, &vinits.back());
+            } else if (ev.kind == OWG_EV_SET_VOLUME || ev.kind == OWG_EV_SET_TREMOLO_DEPTH || ev.kind == OWG_EV_SET_SPEAKER_CHARACTER) {
+                if (!std::isfinite(ev.velocity)) return fail(OWG_E_BAD_ARG, "owg_render_engines: non-finite parameter value");
+                continue;  // handled through the schedules above, not by the voice state machine
             } else if (ev.kind != OWG_EV_NOTE_OFF && ev.kind != OWG_EV_SUSTAIN) return fail(OWG_E_BAD_ARG, "owg_render_engines: unknown event kind");
             events.push_back(d);
         }
@@ -1316,7 +1337,7 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
     DevBuf<EngineDesc> d_eng; DevBuf<EngineEvent> d_events; DevBuf<OwgVoiceInit> d_vinits;
     DevBuf<DamperRow> d_dampers; DevBuf<int32_t> d_dsched, d_eorder; DevBuf<SpkUpdate> d_spk; DevBuf<long long> d_spkoff;
     DevBuf<double> d_recs, d_ans, d_mix; DevBuf<DkState> d_post, d_shadow; DevBuf<VoiceRT> d_pool; DevBuf<float> d_out;
-    DevBuf<EngineState> d_states; DevBuf<EngineChainState> d_chains; DevBuf<EngineWarp> d_ewarps; DevBuf<EngLdrRun> d_ldrrun; DevBuf<double> d_depth, d_lgrecs, d_glast;
+    DevBuf<EngineState> d_states; DevBuf<EngineChainState> d_chains; DevBuf<EngineWarp> d_ewarps; DevBuf<EngLdrRun> d_ldrrun; DevBuf<DepthEv> d_depev; DevBuf<double> d_depth, d_lgrecs, d_glast;
     DevBuf<LgState> d_post_lg, d_shadow_lg;
     DevBuf<EngineDiag> d_diag;
     int rc = d_eng.upload(eng, s);
@@ -1342,6 +1363,8 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
         if (!rc) rc = d_shadow.alloc(ewarps.size());
     }
     if (!rc) rc = d_ldrrun.alloc((size_t)ng);
+    if (depth_events.empty()) depth_events.push_back(DepthEv{-1, 0.0});
+    if (!rc) rc = d_depev.upload(depth_events, s);
     if (!rc) rc = d_depth.alloc((size_t)ng * (size_t)pot_stride);
     if (!rc) rc = d_pool.alloc((size_t)n * 128);
     if (!rc) rc = d_states.alloc((size_t)n);
@@ -1404,7 +1427,7 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
         CK(cudaEventRecord(ev_voices[sg], s));
         // matrices of this chunk, then (first chunk) the warm-up solve and the chain states
         CK(cudaStreamWaitEvent(sc, ev_osc[sg], 0));
-        engine_ldr_kernel<<<ng, 256, 0, sc>>>(d_groups.p, ng, d_pot.p, d_depth.p, pot_stride, d_ldrrun.p, r1 * max_block, legacy ? 1 : 0);
+        engine_ldr_kernel<<<ng, 256, 0, sc>>>(d_groups.p, ng, d_pot.p, d_depth.p, pot_stride, d_ldrrun.p, r1 * max_block, legacy ? 1 : 0, d_depev.p);
         CK(cudaGetLastError());
         launches += 1;
         if (legacy) {

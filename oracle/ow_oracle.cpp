@@ -265,6 +265,9 @@ static void run_engine(const owg_engine_job& j, float* out, int preamp_model = 0
             if (ev.kind == OWG_EV_NOTE_ON) eng.note_on(ev.note, ev.velocity);
             else if (ev.kind == OWG_EV_NOTE_OFF) eng.note_off(ev.note);
             else if (ev.kind == OWG_EV_SUSTAIN) eng.set_sustain(ev.note != 0);
+            else if (ev.kind == OWG_EV_SET_VOLUME) eng.volume.set_target((double)ev.velocity);                        // engine.rs:378-380
+            else if (ev.kind == OWG_EV_SET_TREMOLO_DEPTH) eng.tremolo_depth.set_target((double)ev.velocity);          // :382-384
+            else if (ev.kind == OWG_EV_SET_SPEAKER_CHARACTER) eng.speaker_character.set_target((double)ev.velocity);  // :386-388
         }
         eng.render(out + pos, (size_t)len);
     }

@@ -339,6 +339,31 @@ def test_engine_single_notes_warm_and_cold():
     _engine_parity(pairs, "engine single")
 
 
+def test_engine_parameter_automation_events():
+    """engine.rs:378-388: set_volume / set_tremolo_depth / set_speaker_character at the top of arbitrary blocks (the plugin calls them every
+    block): the smoothers ramp mid-stream, ramps get re-targeted while still in flight, several setters hit the same block, a setter to the
+    current target is a no-op, and the speaker's 0.002 dead-band sees a slow character sweep."""
+    notes = [(0, ow.NOTE_ON, 57, 0.9), (300, ow.NOTE_ON, 64, 0.7), (20000, ow.NOTE_OFF, 57, 0.0)]
+    auto1 = [(2000, ow.SET_VOLUME, 0, 0.9), (2100, ow.SET_VOLUME, 0, 0.2),          # re-targeted 100 samples into a 220-sample ramp
+             (6000, ow.SET_TREMOLO_DEPTH, 0, 1.0), (6000, ow.SET_SPEAKER_CHARACTER, 0, 1.0), (6000, ow.SET_VOLUME, 0, 0.2),   # same block; no-op volume
+             (12000, ow.SET_TREMOLO_DEPTH, 0, 0.0), (12100, ow.SET_SPEAKER_CHARACTER, 0, 0.35), (16000, ow.SET_VOLUME, 0, 1.0),
+             (16050, ow.SET_TREMOLO_DEPTH, 0, 0.6)]
+    auto2 = [(k * 512, ow.SET_SPEAKER_CHARACTER, 0, float(np.float32(k / 40.0))) for k in range(1, 41)]   # a sweep, one step per block
+    ev1 = sorted(notes + auto1, key=lambda e: e[0])
+    ev2 = sorted(notes + auto2, key=lambda e: e[0])
+    pairs = [_engine_pair(ev1, duration=0.55, warm_up=True, block_size=512), _engine_pair(ev1, duration=0.55, warm_up=False, block_size=64, tremolo_depth=0.3),
+             _engine_pair(ev2, duration=0.55, warm_up=True, block_size=512, speaker_character=0.0),
+             _engine_pair(ev1, duration=0.3, warm_up=True, block_size=256, sample_rate=96000.0)]
+    got, _ = _engine_parity(pairs, "engine automation")
+    plain = ow.render_engines([_engine_pair(sorted(notes, key=lambda e: e[0]), duration=0.55, warm_up=True, block_size=512)[0]])
+    assert np.abs(got[0][:plain.shape[1]] - plain[0]).max() > 1e-3       # the automation really changes the stream
+    for model, om in ((ow.LEGACY8, O.LEGACY8),):
+        g = ow.render_engines([p[0] for p in pairs[:2]], preamp_model=model)
+        r = O.render_engines([p[1] for p in pairs[:2]], threads=2, preamp_model=om)
+        for i in range(2):
+            assert_parity(g[i].astype(np.float64), r[i].astype(np.float64), f"legacy automation[{i}]", MAX_ABS, LEGACY_REL_L2)
+
+
 def test_engine_polyphony_sustain_restrike_and_stealing():
     rng = np.random.RandomState(7)
     ev = []
