@@ -21,6 +21,14 @@ pub const OWG_VOICE_NO_ONSET: u8 = 1;
 pub const OWG_EV_NOTE_ON: u8 = 0;
 pub const OWG_EV_NOTE_OFF: u8 = 1;
 pub const OWG_EV_SUSTAIN: u8 = 2;
+/// Parameter automation (engine.rs:378-388): the new smoother target travels in `owg_event::velocity`.
+pub const OWG_EV_SET_VOLUME: u8 = 3;
+pub const OWG_EV_SET_TREMOLO_DEPTH: u8 = 4;
+pub const OWG_EV_SET_SPEAKER_CHARACTER: u8 = 5;
+/// Columns of one `owg_alias_analyze` result row (alias_audit::AliasAuditResult).
+pub const OWG_ALIAS_COLUMNS: usize = 29;
+pub const OWG_ROWS_F64: i32 = 0;
+pub const OWG_ROWS_F32: i32 = 1;
 pub const OWG_INIT_RESET_THEN_SET: i32 = 0;
 pub const OWG_INIT_SET_THEN_RESET: i32 = 1;
 pub const OWG_METRIC_COLUMNS: usize = 7;
@@ -168,6 +176,12 @@ extern "C" {
                            out: *mut f64, out_stride: i64, opts: *const owg_opts) -> i32;
     pub fn owg_render_engines(jobs: *const owg_engine_job, n: i64, out: *mut f32, stride: i64, opts: *const owg_opts) -> i32;
     pub fn owg_render_midi(jobs: *const owg_midi_job, n: i64, out: *mut f64, stride: i64, opts: *const owg_opts) -> i32;
+    /// alias_audit::analyze (alias_audit.rs:163-282) on the device; `results` is host memory `[n_rows][OWG_ALIAS_COLUMNS]`.
+    pub fn owg_alias_analyze(rows: *const core::ffi::c_void, row_dtype: i32, stride: i64, n_rows: i64, n_samples: i64, sample_rate: f64,
+                             analyze_seconds: f64, nominal_f0: *const f64, results: *mut f64, opts: *const owg_opts) -> i32;
+    /// Engine streams rendered and analysed on the device; all jobs share sample_rate and duration.
+    pub fn owg_render_engines_alias(jobs: *const owg_engine_job, n: i64, analyze_seconds: f64, nominal_f0: *const f64, results: *mut f64,
+                                    opts: *const owg_opts) -> i32;
     pub fn owg_plan_bench(jobs: *const owg_bench_job, n: i64, opts: *const owg_opts, plan: *mut *mut owg_plan) -> i32;
     pub fn owg_plan_voices(jobs: *const owg_voice_job, n: i64, opts: *const owg_opts, plan: *mut *mut owg_plan) -> i32;
     pub fn owg_plan_execute(plan: *mut owg_plan, out: *mut f64, stride: i64, out_location: i32) -> i32;

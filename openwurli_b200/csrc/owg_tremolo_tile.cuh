@@ -48,7 +48,7 @@ __constant__ TrmRhsTerm c_trm_rows[8][OWG_TT_TERMS] = {
 struct TrmTileSm {
     double xs[16];
     double rs[8];
-    __align__(16) double2 ex[2][3][4];  // Newton rows: [iteration parity][(a0,a1) | (a2,a3) | (f, -)][junction]
+    __align__(16) double2 ex[2][3][8];  // Newton rows: [iteration parity][(a0,a1) | (a2,a3) | (f, 1/a0)][lane]; lanes 4..7 are mirror copies
 };
 
 // per-lane constants, reloaded whenever the matrices change (set_sample_rate at step 50)
@@ -139,11 +139,11 @@ __device__ __forceinline__ double trm_step_tile(TrmTileSm& sm, const TrmLaneK& c
         // being written -- the reciprocal of its first element: whichever row wins the first pivot search brings its reciprocal along
         const double a_own0 = c.jd[0] - ja * c.ka[0] - jb * c.kb[0];
         const Recip r_own = recip_prepare(a_own0);
-        // (lanes 4..7 mirror lanes 0..3 bit for bit and store the same values to the same slots: no branch around the stores)
+        // (lanes 4..7 mirror lanes 0..3 bit for bit and store into their own slots, which nobody reads: no branch around the stores)
         double2* e0 = &sm.ex[iter & 1][0][0];
-        e0[jq] = make_double2(a_own0, c.jd[1] - ja * c.ka[1] - jb * c.kb[1]);
-        e0[4 + jq] = make_double2(c.jd[2] - ja * c.ka[2] - jb * c.kb[2], c.jd[3] - ja * c.ka[3] - jb * c.kb[3]);
-        e0[8 + jq] = make_double2(f, r_own.r);
+        e0[lane] = make_double2(a_own0, c.jd[1] - ja * c.ka[1] - jb * c.kb[1]);
+        e0[8 + lane] = make_double2(c.jd[2] - ja * c.ka[2] - jb * c.kb[2], c.jd[3] - ja * c.ka[3] - jb * c.kb[3]);
+        e0[16 + lane] = make_double2(f, r_own.r);
         __syncwarp(OWG_TT_MASK);
         // ---- 4x4 elimination with partial pivoting (gen_tremolo.rs:2515-2561), straight-line, identically in every lane ----
         // column 0: the sequential "first strict maximum" search is a set of pairwise comparisons; swap(0, max_row) by ADDRESS
@@ -157,10 +157,10 @@ __device__ __forceinline__ double trm_step_tile(TrmTileSm& sm, const TrmLaneK& c
             const bool w1 = !w3 & !w2 & (m1 > m0);
             const int mr = (w3 ? 3 : 0) | (w2 ? 2 : 0) | (w1 ? 1 : 0);
             const int i1 = w1 ? 0 : 1, i2 = w2 ? 0 : 2, i3 = w3 ? 0 : 3;
-            const double2 Pa = e0[mr], Pb = e0[4 + mr], Pc = e0[8 + mr];
-            const double2 Aa = e0[i1], Ab = e0[4 + i1], Ac = e0[8 + i1];
-            const double2 Ba = e0[i2], Bb = e0[4 + i2], Bc = e0[8 + i2];
-            const double2 Ca = e0[i3], Cb = e0[4 + i3], Cc = e0[8 + i3];
+            const double2 Pa = e0[mr], Pb = e0[8 + mr], Pc = e0[16 + mr];
+            const double2 Aa = e0[i1], Ab = e0[8 + i1], Ac = e0[16 + i1];
+            const double2 Ba = e0[i2], Bb = e0[8 + i2], Bc = e0[16 + i2];
+            const double2 Ca = e0[i3], Cb = e0[8 + i3], Cc = e0[16 + i3];
             const double P0 = Pa.x, P1 = Pa.y, P2 = Pb.x, P3 = Pb.y, PB = Pc.x;
             singular = fabs(P0) < KC(14);
             Recip rp; rp.r = Pc.y; rp.nb = -P0; rp.b = P0;
