@@ -8,6 +8,7 @@
 // PARITY PINNING: the reference (Rust) cannot be compiled here; this oracle is pinned by the
 // reference's own known-answer tests and baked-constant identities only (tests/test_oracle_*.py).
 #include "ow_engine.hpp"
+#include "ow_power_amp_melange.hpp"
 #include "../include/owgpu.h"
 #include <thread>
 #include <atomic>
@@ -359,6 +360,38 @@ int owo_alias_analyze(const double* signal, int64_t n, double sr, double analyze
     out[26] = worst; out[27] = (double)worst_from;
     out[28] = h1 > 0.0 ? 20.0 * std::log10(hf_rms / h1) : -200.0;
     return OWG_OK;
+}
+
+// ---- melange power amplifier + rail sag (power_amp.rs; SURVEY 8(f) #4: oracle side only) --------------------------------------------
+int owo_have_melange_power_amp() {
+#ifdef OW_HAVE_MELANGE_POWER_AMP
+    return 1;
+#else
+    return 0;
+#endif
+}
+// RailDynamics alone: v_out[n] -> (v_rail_pos, v_rail_neg) after each step; rails[2n]
+int owo_rail_dynamics(double sample_rate, const double* v_out, int64_t n, double* rails) {
+    ow::pam::RailDynamics r(sample_rate);
+    for (int64_t i = 0; i < n; i++) { r.step(v_out[i]); rails[2 * i] = r.v_rail_pos; rails[2 * i + 1] = r.v_rail_neg; }
+    return OWG_OK;
+}
+// PowerAmp::new_at_sample_rate(sr); set_rail_sag(rail_sag); y[i] = process(x[i]); rails (optional) = rail_voltages() after each sample;
+// toggle_off_at >= 0: set_rail_sag(false) before that sample.  Returns the number of divergence-guard resets, or < 0.
+int64_t owo_power_amp_melange(double sample_rate, int rail_sag, const double* x, int64_t n, double* y, double* rails, int64_t toggle_off_at) {
+#ifdef OW_HAVE_MELANGE_POWER_AMP
+    ow::pam::PowerAmp pa(sample_rate);
+    pa.set_rail_sag(rail_sag != 0);
+    for (int64_t i = 0; i < n; i++) {
+        if (i == toggle_off_at) pa.set_rail_sag(false);
+        y[i] = pa.process(x[i]);
+        if (rails) pa.rail_voltages(rails[2 * i], rails[2 * i + 1]);
+    }
+    return (int64_t)pa.resets;
+#else
+    (void)sample_rate; (void)rail_sag; (void)x; (void)n; (void)y; (void)rails; (void)toggle_off_at;
+    return -1;
+#endif
 }
 
 // ---- known-answer probes (host-side setup functions) --------------------------------------------

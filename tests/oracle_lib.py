@@ -116,6 +116,9 @@ def lib():
         L.owo_speaker_run.argtypes = [C.c_double, C.c_double, dp, C.c_int64, dp]
         L.owo_oversampler_roundtrip.argtypes = [dp, C.c_int64, dp]
         L.owo_render_bench_model.argtypes = [C.POINTER(BenchJob), C.c_int64, dp, C.c_int64, C.c_int, C.c_int]
+        L.owo_rail_dynamics.argtypes = [C.c_double, dp, C.c_int64, dp]
+        L.owo_power_amp_melange.argtypes = [C.c_double, C.c_int, dp, C.c_int64, dp, dp, C.c_int64]
+        L.owo_power_amp_melange.restype = C.c_int64
         L.owo_alias_analyze.argtypes = [dp, C.c_int64, C.c_double, C.c_double, C.c_double, dp]
         L.owo_preamp_batch_diag.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double, dp, C.c_int64, C.c_int]
         L.owo_preamp_batch_model.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_double,
