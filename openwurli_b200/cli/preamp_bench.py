@@ -353,7 +353,8 @@ def cmd_render_midi(args):
     return 0
 
 
-USAGE = """Usage: preamp_bench <render|calibrate|sensitivity|render-midi|render-poly> [flags]
+USAGE = """Usage: preamp_bench <render|calibrate|sensitivity|render-midi|render-poly|alias-audit> [flags]
+  alias-audit --note N | --notes a,b,c  --velocity V  --json
   sensitivity --notes a,b --velocities x,y --ds-range d1,d2 --scale-mode track|freeze|zero-trim --volume X --speaker C --output FILE
   render-poly --notes a,b,c --velocities x,y,z --duration S --volume X --speaker C --ldr OHM --no-poweramp --normalize --output FILE
   render-midi --midi FILE --output FILE --volume X --speaker C --tail S --track N --tremolo-depth D --preamp-model M
@@ -362,6 +363,47 @@ USAGE = """Usage: preamp_bench <render|calibrate|sensitivity|render-midi|render-
              --preamp-model melange12|legacy8   (compile-time cargo feature in the reference)
   calibrate  --notes a,b,c --velocities x,y,z --ds-at-c4 D --ds-clamp-max M --volume X --speaker C --zero-trim --output FILE
 """
+
+
+def alias_audit_results(notes, velocity=120):
+    """alias_audit::run_with_note for several notes in ONE device batch (alias_audit.rs:106-204): render_stimulus as engine jobs
+    (no warm-up, six 1024-sample settle blocks, note-on, 1.5 s at 44.1 kHz, volume 0.5, depth 0, character 0, MLP on), analysed on the device."""
+    sr, total, settle = 44100.0, int(44100.0 * 1.5), 6 * 1024
+    vel = float(np.float32(velocity) / np.float32(127.0))   # `velocity as f32 / 127.0`
+    jobs = [api.engine_job([(settle, api.NOTE_ON, int(n), vel)], sample_rate=sr, duration=(settle + total + 0.5) / sr, volume=0.5, tremolo_depth=0.0,
+                          speaker_character=0.0, mlp=True, block_size=1024, warm_up=False) for n in notes]
+    rows = api.render_engines_alias(jobs, [api.note_hz(int(n)) for n in notes], analyze_seconds=0.5)
+    return [api.AliasAuditResult(r) for r in rows]
+
+
+def alias_audit_text(note, velocity, r, want_json):
+    """The two output formats of cmd_alias_audit (main.rs:985-1066)."""
+    if want_json:
+        return ("{\n" + f'  "f0_hz": {r.f0_hz:.4f},\n  "h1_dbfs": {r.h1_dbfs:.3f},\n  "harmonic_dbc": [' + ", ".join(f"{v:.3f}" for v in r.harmonic_dbc) + "],\n"
+                + f'  "max_step_up_db": {r.max_step_up_db:.3f},\n  "max_step_up_from_harmonic": {r.max_step_up_from_harmonic},\n  "hf_band_dbc": {r.hf_band_dbc:.3f}\n' + "}")
+    lines = ["Click-band alias audit", f"  Stimulus:   note={note} vel={velocity} vol={0.5:.2f}",
+             f"  Render:     {1.5:.2f}s @ {44100.0:.0f} Hz, analyzing last {0.5:.2f}s", "",
+             f"  Detected f0:  {r.f0_hz:.3f} Hz  (nominal {api.note_hz(note):.3f} Hz)", f"  H1:           {r.h1_dbfs:.2f} dBFS", "",
+             "  Harmonic envelope (dBc relative to H1):"]
+    for i, dbc in enumerate(r.harmonic_dbc):
+        marker = " *" if 6 <= i + 1 and i < 11 else "  "
+        lines.append(f"    H{i + 1:<2} {marker} {dbc:>8.2f} dBc")
+    lines += ["                  (* = harmonics in plateau-detection band)", "",
+              f"  max_step_up_db:  {r.max_step_up_db:+.2f} dB  (worst rise: H{r.max_step_up_from_harmonic} \u2192 H{r.max_step_up_from_harmonic + 1})",
+              "                   target: \u2264 0 dB (monotonic descent); gate: \u2264 +1.0",
+              f"  hf_band_dbc:     {r.hf_band_dbc:.2f} dBc  (5\u201318 kHz RMS rel. to H1)",
+              "                   target: track baseline; gate: \u2264 baseline + 2.0 dB"]
+    return "\n".join(lines)
+
+
+def cmd_alias_audit(args):
+    """`preamp-bench alias-audit [--note N] [--velocity V] [--json]` (main.rs:985-1066); `--notes a,b,c` audits several notes in one batch."""
+    want_json = has_flag(args, "--json")
+    velocity = _as_u8(parse_flag(args, "--velocity", 120.0))
+    notes = _csv_u8_list(args, "--notes", []) or [_as_u8(parse_flag(args, "--note", 84.0))]
+    for n, r in zip(notes, alias_audit_results(notes, velocity)):
+        print(alias_audit_text(n, velocity, r, want_json))
+    return 0
 
 
 def main(argv=None):
@@ -379,6 +421,8 @@ def main(argv=None):
         return cmd_render_poly(args[1:])
     if args[0] == "sensitivity":
         return cmd_sensitivity(args[1:])
+    if args[0] == "alias-audit":
+        return cmd_alias_audit(args[1:])
     sys.stderr.write(f"Unknown subcommand: {args[0]} (only the batched render paths are mirrored)\n{USAGE}")
     return 1
 

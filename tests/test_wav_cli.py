@@ -200,3 +200,24 @@ def test_render_poly_signals_match_oracle():
         rsep += ref[k]
     assert np.abs(fin - ref[0]).max() <= 1e-6 and np.abs(sep - rsep).max() <= 1e-6
     assert np.abs(res - (ref[0] - rsep)).max() <= 1e-6 and np.abs(res).max() > 1e-7   # shared nonlinearity: the residual is not zero
+
+
+@pytest.mark.gpu
+def test_alias_audit_cli_json_matches_the_reference_fixture(capsys):
+    """`preamp-bench alias-audit --json` (main.rs:985-1017) for the three fixture notes in one device batch: same keys and number formats as the
+    reference's hand-rolled JSON; f0 equal to the fixture's value, the regression gate of alias_audit_regression.rs on the printed numbers."""
+    import json
+    from openwurli_b200.cli import preamp_bench
+    base = {e["note"]: e for e in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_alias_audit_v0_5_1.json")))["entries"]}
+    assert preamp_bench.main(["alias-audit", "--notes", "72,84,91", "--velocity", "120", "--json"]) == 0
+    out = capsys.readouterr().out
+    docs = [json.loads(d + "}") for d in out.strip()[:-1].split("}\n")]   # three JSON documents, one after the other
+    assert len(docs) == 3
+    for note, d in zip((72, 84, 91), docs):
+        assert list(d.keys()) == ["f0_hz", "h1_dbfs", "harmonic_dbc", "max_step_up_db", "max_step_up_from_harmonic", "hf_band_dbc"]
+        assert d["f0_hz"] == base[note]["f0_hz"] and len(d["harmonic_dbc"]) == 12 and d["harmonic_dbc"][0] == 0.0
+        assert d["max_step_up_db"] - base[note]["max_step_up_db"] <= 1.5 and d["hf_band_dbc"] - base[note]["hf_band_dbc"] <= 2.0
+        assert d["max_step_up_from_harmonic"] == base[note]["max_step_up_from_harmonic"]
+    assert preamp_bench.main(["alias-audit", "--note", "84"]) == 0
+    text = capsys.readouterr().out
+    assert text.startswith("Click-band alias audit\n  Stimulus:   note=84 vel=120 vol=0.50") and "(* = harmonics in plateau-detection band)" in text

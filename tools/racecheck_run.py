@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Tiny chain-B batch for `compute-sanitizer --tool racecheck --kernel-name regex:chain_tile`: 0.01 s notes, static LDR and tremolo,
+"""Tiny chain-B batch for `compute-sanitizer --tool racecheck --kernel-name kns=chain_tile`: 0.01 s notes, static LDR and tremolo,
 checked against the oracle like smoke() (racecheck slows the instrumented kernel by orders of magnitude)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
