@@ -400,7 +400,7 @@ def cmd_alias_audit(args):
     """`preamp-bench alias-audit [--note N] [--velocity V] [--json]` (main.rs:985-1066); `--notes a,b,c` audits several notes in one batch."""
     want_json = has_flag(args, "--json")
     velocity = _as_u8(parse_flag(args, "--velocity", 120.0))
-    notes = _csv_u8_list(args, "--notes", []) or [_as_u8(parse_flag(args, "--note", 84.0))]
+    notes = _csv_u8_list(args, "--notes", "") or [_as_u8(parse_flag(args, "--note", 84.0))]
     for n, r in zip(notes, alias_audit_results(notes, velocity)):
         print(alias_audit_text(n, velocity, r, want_json))
     return 0
