@@ -3,7 +3,12 @@
 #include "../../include/owgpu.h"
 #include "owg_records.h"
 
+struct PaModel;  // owg_pa_core.h
+
 namespace owg {
+// Melange power amplifier (gen_power_amp.rs) at `sample_rate`: baked 88.2 kHz tables or set_sample_rate's rebuilt ones, device constants,
+// rail-sag coefficients (host_pa_setup.cpp).
+void pa_build_model(double sample_rate, PaModel* m);
 // Voice::note_on(+overrides) -> flat init record (voice.rs:28-142).
 void make_voice_init(const owg_voice_job& job, OwgVoiceInit* out);
 // Speaker / volume parameters of one `preamp-bench render` job (main.rs:478-496).

@@ -1,0 +1,130 @@
+// TEST HARNESS: runs the PRODUCT's tile-collective power-amplifier code (openwurli_b200/csrc/owg_pa_core.h, the source the CUDA kernel is
+// built from) on the CPU, one coroutine per lane in lock-step, so that the lane-tiled algorithm can be compared with the oracle without a
+// GPU.  Collectives: a lane that reaches a collective publishes its operand and yields round-robin until all 16 lanes have arrived.
+// Not part of the product (the product path is the CUDA kernel in owg_poweramp.cuh); built by tests/test_power_amp_melange.py.
+#include <ucontext.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../openwurli_b200/csrc/host_setup.h"
+#include "../openwurli_b200/csrc/owg_pa_core.h"
+
+namespace {
+constexpr int L = 16;
+struct Emu {
+    ucontext_t main_ctx, ctx[L];
+    std::vector<char> stacks[L];
+    bool done[L];
+    int cur = 0, arrived = 0;
+    unsigned long gen = 0;
+    double slot_d[L];
+    int slot_i[L];
+    void yield_next() {
+        const int from = cur;
+        int nxt = (cur + 1) % L;
+        while (done[nxt] && nxt != from) nxt = (nxt + 1) % L;
+        if (nxt == from) return;
+        cur = nxt;
+        swapcontext(&ctx[from], &ctx[nxt]);
+    }
+    void barrier() {
+        const unsigned long g = gen;
+        if (++arrived == L) { arrived = 0; gen++; return; }
+        while (gen == g) yield_next();
+    }
+};
+Emu* g_emu;
+struct EmuTile {
+    int lane;
+    void sync() const { g_emu->barrier(); }
+    double shfl(double x, int src) const { g_emu->slot_d[lane] = x; g_emu->barrier(); const double r = g_emu->slot_d[src]; g_emu->barrier(); return r; }
+    double shfl_xor(double x, int m) const { return shfl(x, lane ^ m); }
+    int shfl_i(int x, int src) const { g_emu->slot_i[lane] = x; g_emu->barrier(); const int r = g_emu->slot_i[src]; g_emu->barrier(); return r; }
+    int shfl_xor_i(int x, int m) const { return shfl_i(x, lane ^ m); }
+    bool any(bool p) const {
+        g_emu->slot_i[lane] = p ? 1 : 0; g_emu->barrier();
+        int r = 0; for (int i = 0; i < L; i++) r |= g_emu->slot_i[i];
+        g_emu->barrier(); return r != 0;
+    }
+};
+struct Job {
+    const PaModel* m; const PaShared* sh; PaScratch* sc; const PaSettled* settled; const double* x; double* y; int64_t n; double pre_gain;
+    bool rail_sag; PaSettled* settle; double* rails; uint32_t* counters;
+};
+Job g_job;
+void lane_main(int lane) {
+    EmuTile t{lane};
+    pa_tile_render(t, *g_job.m, *g_job.sh, *g_job.sc, g_job.settled, g_job.x, g_job.y, g_job.n, g_job.pre_gain, g_job.rail_sag, g_job.settle,
+                   g_job.rails, g_job.counters);
+    g_emu->done[lane] = true;
+    // hand over to a lane that is still running, or back to main when this was the last one
+    for (int i = 1; i <= L; i++) {
+        const int nxt = (lane + i) % L;
+        if (!g_emu->done[nxt]) { g_emu->cur = nxt; setcontext(&g_emu->ctx[nxt]); }
+    }
+    setcontext(&g_emu->main_ctx);
+}
+void run_tile(const Job& job) {
+    Emu emu;
+    g_emu = &emu;
+    g_job = job;
+    for (int i = 0; i < L; i++) {
+        emu.done[i] = false;
+        emu.stacks[i].resize(1 << 20);
+        getcontext(&emu.ctx[i]);
+        emu.ctx[i].uc_stack.ss_sp = emu.stacks[i].data();
+        emu.ctx[i].uc_stack.ss_size = emu.stacks[i].size();
+        emu.ctx[i].uc_link = nullptr;
+        makecontext(&emu.ctx[i], (void (*)())lane_main, 1, i);
+    }
+    emu.cur = 0;
+    swapcontext(&emu.main_ctx, &emu.ctx[0]);
+}
+PaSettled g_settled;
+bool g_have_settled = false;
+}  // namespace
+
+extern "C" {
+// PowerAmp::new_at_sample_rate(sample_rate), set_rail_sag(rail_sag), y[i] = process(x[i] * pre_gain); rails2 = rail_voltages() at the end;
+// counters4 = {divergence-guard resets, backward-Euler retries, NaN resets, last_nr_iterations}
+int paemu_render(double sample_rate, int rail_sag, const double* x, int64_t n, double pre_gain, double* y, double* rails2, uint32_t* counters4) {
+    static PaModel m0, m;
+    static PaShared sh;
+    static PaScratch sc;
+    if (!g_have_settled) {
+        if (const char* cache = getenv("PAEMU_SETTLED_CACHE")) {  // debugging aid: reuse a settled state computed by an earlier run
+            if (FILE* f = fopen(cache, "rb")) { g_have_settled = fread(&g_settled, sizeof(g_settled), 1, f) == 1; fclose(f); }
+        }
+    }
+    if (!g_have_settled) {
+        owg::pa_build_model(88200.0, &m0);
+        pa_stage_shared(m0, sh, 0, 1);
+        run_tile(Job{&m0, &sh, &sc, nullptr, nullptr, nullptr, PA_SETTLE_SAMPLES, 1.0, false, &g_settled, nullptr, nullptr});
+        g_have_settled = true;
+        if (const char* cache = getenv("PAEMU_SETTLED_CACHE")) {
+            if (FILE* f = fopen(cache, "wb")) { fwrite(&g_settled, sizeof(g_settled), 1, f); fclose(f); }
+        }
+    }
+    owg::pa_build_model(sample_rate, &m);
+    pa_stage_shared(m, sh, 0, 1);
+    run_tile(Job{&m, &sh, &sc, &g_settled, x, y, n, pre_gain, rail_sag != 0, nullptr, rails2, counters4});
+    return 0;
+}
+// the model's matrices for the host-setup test: out = s[400] k[256] s_ni[320] s_be[400] k_be[256] s_ni_be[320] a_neg_be[400] dc_block_r
+int paemu_model(double sample_rate, double* out) {
+    static PaModel m;
+    owg::pa_build_model(sample_rate, &m);
+    double* o = out;
+    memcpy(o, m.s, sizeof(m.s)); o += 400;
+    memcpy(o, m.k, sizeof(m.k)); o += 256;
+    memcpy(o, m.s_ni, sizeof(m.s_ni)); o += 320;
+    memcpy(o, m.s_be, sizeof(m.s_be)); o += 400;
+    memcpy(o, m.k_be, sizeof(m.k_be)); o += 256;
+    memcpy(o, m.s_ni_be, sizeof(m.s_ni_be)); o += 320;
+    memcpy(o, m.a_neg_be, sizeof(m.a_neg_be)); o += 400;
+    *o = m.dc_block_r;
+    return 0;
+}
+}

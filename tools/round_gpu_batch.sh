@@ -21,4 +21,5 @@ print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "fr
 for k,v in d.get("variants",{}).items(): print(k[:70], v["value"], v["ms_per_step"])
 r=json.loads(open("$O/${TAG}_bench_ref.json").read().strip().splitlines()[-1]); print("ref", r["value"])
 PY
-grep -c "Race reported" $O/${TAG}_racecheck_chain_tile.log; tail -1 $O/${TAG}_racecheck_chain_tile.log
+OWG_CHAIN_KERNEL=split timeout 600 compute-sanitizer --tool racecheck --kernel-name kns=chain_split --log-file $O/${TAG}_racecheck_chain_split.log python tools/racecheck_run.py > $O/${TAG}_racecheck_chain_split.out 2>&1
+grep -c "Race reported" $O/${TAG}_racecheck_chain_tile.log; tail -1 $O/${TAG}_racecheck_chain_tile.log; tail -1 $O/${TAG}_racecheck_chain_split.log
