@@ -100,6 +100,11 @@ typedef struct owg_engine_job {
 #define OWG_PREAMP_LEGACY8 1   /* dk_preamp_legacy.rs hand-written 8-node solver: the reference's DEFAULT build
                                 * (openwurli-dsp/Cargo.toml:10-19); chain B, preamp batch and metrics entry points */
 
+#define OWG_POWER_AMP_BEHAVIORAL 0          /* power_amp.rs:167-275 (`legacy-power-amp`, the DEFAULT build): closed-loop NR approximation */
+#define OWG_POWER_AMP_MELANGE 1             /* power_amp.rs:279-465 + gen_power_amp.rs (`--no-default-features`): melange 7-BJT class-AB
+                                             * nodal solver with rail sag and the divergence guard */
+#define OWG_POWER_AMP_MELANGE_IDEAL_RAILS 2 /* the same with set_rail_sag(false) (`preamp-bench render --no-rail-sag`, main.rs:481-483) */
+
 typedef struct owg_opts {
     int32_t device;       /* CUDA device ordinal; -1 = current device */
     int32_t out_location; /* OWG_OUT_HOST | OWG_OUT_DEVICE */
@@ -112,7 +117,9 @@ typedef struct owg_opts {
                            * balanced by rendered samples, one worker thread, stream and staging buffer per GPU, every GPU copying its rows
                            * straight into the caller's buffer.  Renders are independent: no collective, each GPU recomputes the (tiny) shared
                            * sequences of the preamp groups it touches.  Order the jobs by preamp group to keep groups on one GPU. */
-    int32_t _reserved[6];
+    int32_t power_amp_model; /* OWG_POWER_AMP_*; the melange models are served by owg_render_bench, owg_chain_batch and
+                              * owg_power_amp_batch, every other entry point answers OWG_E_UNSUPPORTED for them */
+    int32_t _reserved[5];
 } owg_opts;
 
 /* Solver counters of the last call on this thread that had collect_diag=1 (sums over all jobs).
@@ -157,6 +164,14 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
 int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double fs_base,
                      int oversample, double tremolo_depth, double r_ldr_static, double* out, int64_t out_stride,
                      const owg_opts* opts);
+
+/* The melange power amplifier alone: row i = PowerAmp::new_at_sample_rate(sample_rate) (power_amp.rs:326-349: the settled
+ * CircuitState of gen_power_amp.rs re-rated with set_sample_rate), set_rail_sag(rail_sag != 0), y[t] = process(x[t]) (power_amp.rs:373-436:
+ * gen_power_amp::process_sample (gen_power_amp.rs:8838) / HEADROOM, divergence guard with last-good hold, clamp to +-1, RailDynamics::step).
+ * One 16-lane tile per row.  rails (optional) [n_inst][2] = rail_voltages() after the last sample; counters (optional) [n_inst][4] =
+ * {divergence-guard resets, backward-Euler retries, NaN resets, last_nr_iterations}.  in / out follow opts->out_location. */
+int owg_power_amp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double sample_rate, int32_t rail_sag, double* out,
+                        int64_t out_stride, double* rails, uint32_t* counters, const owg_opts* opts);
 
 /* Generic form of the above: rows of `in` (any mono signal at the instance's base rate, e.g. a sum of voices as in `preamp-bench
  * render-poly`, main.rs:1380-1560) through the full chain B of params[i] (sample_rate, r_ldr, tremolo_depth, volume,

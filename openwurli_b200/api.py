@@ -46,10 +46,14 @@ def _samples(duration, sample_rate):
 MELANGE12, LEGACY8 = 0, 1  # owg_opts.preamp_model: gen_preamp.rs 12-node (north star) | dk_preamp_legacy.rs 8-node (reference default build)
 
 
-def _opts(device=-1, out_location=OWG_OUT_HOST, stream=None, collect_diag=False, preamp_model=MELANGE12, devices=None):
+PA_BEHAVIORAL, PA_MELANGE, PA_MELANGE_IDEAL_RAILS = 0, 1, 2   # owg_opts.power_amp_model
+
+
+def _opts(device=-1, out_location=OWG_OUT_HOST, stream=None, collect_diag=False, preamp_model=MELANGE12, devices=None, power_amp_model=PA_BEHAVIORAL):
     o = Opts()
     lib().owg_default_opts(C.byref(o))
     o.preamp_model = int(preamp_model)
+    o.power_amp_model = int(power_amp_model)
     o.device = device
     o.out_location = out_location
     o.stream = stream
@@ -187,17 +191,19 @@ def render_voices(jobs, out=None, device=-1, collect_diag=False, devices=None):
     return out
 
 
-def render_bench(jobs, out=None, device=-1, collect_diag=False, preamp_model=MELANGE12, devices=None):
+def render_bench(jobs, out=None, device=-1, collect_diag=False, preamp_model=MELANGE12, devices=None, power_amp_model=PA_BEHAVIORAL):
     """Batch of `preamp-bench render` (chain B). Returns [n, max_samples] float64 (pre-WAV samples).  devices=[0, 1, ...]: one call
     fans the job list out over those GPUs (contiguous ranges balanced by rendered samples; host output only).
-    preamp_model: MELANGE12 (`--features melange-preamp`, the north-star path) or LEGACY8 (the reference's default build)."""
+    preamp_model: MELANGE12 (`--features melange-preamp`, the north-star path) or LEGACY8 (the reference's default build).
+    power_amp_model: PA_BEHAVIORAL (`legacy-power-amp`, the default build), PA_MELANGE (the melange 7-BJT solver with rail sag,
+    `--no-default-features`) or PA_MELANGE_IDEAL_RAILS (`--no-rail-sag`)."""
     stride = max([_samples(j.v.duration_s, j.v.sample_rate) for j in jobs], default=0)
     out = _alloc_out(len(jobs), stride, out)
     if len(jobs) == 0 or stride == 0:
         return out
     ptr, st, loc = _out_ptr(out)
     arr = (BenchJob * len(jobs))(*jobs)
-    o = _opts(device, loc, None, collect_diag, preamp_model, devices=devices)
+    o = _opts(device, loc, None, collect_diag, preamp_model, devices=devices, power_amp_model=power_amp_model)
     check(lib().owg_render_bench(arr, len(jobs), ptr, st, C.byref(o)))
     return out
 
@@ -216,6 +222,25 @@ def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000
     check(lib().owg_preamp_batch(pin, sin, x.shape[0], x.shape[1], float(fs_base), 1 if oversample else 0,
                                  float(tremolo_depth), float(r_ldr), pout, sout, C.byref(o)))
     return out
+
+
+def power_amp_batch(x, sample_rate=44100.0, rail_sag=True, out=None, device=-1, want_state=False):
+    """The melange 7-BJT power amplifier alone (power_amp.rs melange_adapter + gen_power_amp.rs): row i of `x` [n_inst, n_samp] through
+    PowerAmp::new_at_sample_rate(sample_rate), set_rail_sag(rail_sag), process().  want_state: also return (rails [n, 2] = rail_voltages()
+    after the last sample, counters [n, 4] = divergence-guard resets, backward-Euler retries, NaN resets, last_nr_iterations)."""
+    if out is None:
+        out = np.zeros_like(x) if isinstance(x, np.ndarray) else x.new_zeros(x.shape)
+    pin, sin, lin = _out_ptr(x)
+    pout, sout, lout = _out_ptr(out)
+    assert lin == lout, "input and output must both be host or both be device buffers"
+    assert tuple(out.shape) == tuple(x.shape)
+    o = _opts(device, lout)
+    rails = np.zeros((x.shape[0], 2), dtype=np.float64)
+    counters = np.zeros((x.shape[0], 4), dtype=np.uint32)
+    check(lib().owg_power_amp_batch(pin, sin, x.shape[0], x.shape[1], float(sample_rate), 1 if rail_sag else 0, pout, sout,
+                                    rails.ctypes.data_as(C.POINTER(C.c_double)) if want_state else None,
+                                    counters.ctypes.data_as(C.POINTER(C.c_uint32)) if want_state else None, C.byref(o)))
+    return (out, rails, counters) if want_state else out
 
 
 RESET_THEN_SET, SET_THEN_RESET = 0, 1

@@ -508,9 +508,13 @@ PA_HD void pa_lane_load_settled(const PaModel& m, const PaSettled& st, int l, Pa
 // PowerAmp::process (power_amp.rs:373-436) over a row, 16 samples per block (lane l loads x[t0 + l] and stores y[t0 + l]: coalesced).
 // settle != nullptr: the raw solver on silence from CircuitState::default()'s initial state for n samples, final state -> *settle
 // (compute_settled_state); no adapter.
-template <class T>
+struct PaNoPost { PA_HD double operator()(double v) { return v; } };
+// vol: the row is attenuated as (x * vol) * vol before the amplifier (chain B's audio-taper volume, main.rs:489; 1.0 = plain process()).
+// bypass: `--no-poweramp` (the attenuated sample goes straight to `post`).  post: per-sample output stage after the amplifier (chain B: the
+// speaker), run redundantly by every lane on the replicated amplifier output.
+template <class T, class Post>
 PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaScratch& sc, const PaSettled* settled, const double* x, double* y,
-                          int64_t n, double pre_gain, bool rail_sag, PaSettled* settle, double* rails_out, uint32_t* counters_out) {
+                          int64_t n, double vol, bool rail_sag, bool bypass, PaSettled* settle, double* rails_out, uint32_t* counters_out, Post& post) {
     const int l = t.lane;
     PaLane s;
     s.rail_pos = PA_RAIL_DC_BIAS; s.rail_neg = PA_RAIL_DC_BIAS; s.iavg_pos = 0.0; s.iavg_neg = 0.0; s.last_good = 0.0;
@@ -527,8 +531,10 @@ PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaSc
             double out;
             if (settle) {
                 out = pa_tile_process_sample(t, m, sh, sc, s, 0.0, 0.0, 0.0);
+            } else if (bypass) {
+                out = (t.shfl(xin, k) * vol) * vol;
             } else {
-                const double input = t.shfl(xin, k) * pre_gain;
+                const double input = (t.shfl(xin, k) * vol) * vol;
                 const double off_pos = rail_sag ? s.rail_pos - PA_RAIL_DC_BIAS : 0.0;
                 const double off_neg = rail_sag ? s.rail_neg - PA_RAIL_DC_BIAS : 0.0;
                 const double raw = pa_tile_process_sample(t, m, sh, sc, s, input, off_pos, off_neg);
@@ -556,6 +562,7 @@ PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaSc
                     }
                 }
             }
+            if (!settle) out = post(out);
             if (l == k) yout = out;
         }
         if (!settle && y && l < nb) y[t0 + l] = yout;

@@ -1,0 +1,81 @@
+// CUDA side of the melange power amplifier: the tile collectives of owg_pa_core.h on sub-warp shuffles, the batch kernel
+// (one 16-lane tile per instance, two instances per warp, 8 per CTA) and the settled-state kernel.
+//   reference: crates/openwurli-dsp/src/gen_power_amp.rs:8838 (process_sample), power_amp.rs:279-465 (adapter), :65-165 (rail sag);
+//   chain B's output stage: tools/preamp-bench/src/main.rs:478-496 (volume^2 -> PowerAmp::new() -> Speaker -> POST_SPEAKER_GAIN).
+#pragma once
+#include "owg_device.cuh"
+#include "owg_pa_core.h"
+
+namespace owgd {
+
+// 16 lanes of a warp; the two tiles of a warp may diverge (different Newton trip counts): every collective names its own half-warp mask
+struct PaCudaTile {
+    int lane;
+    unsigned mask;
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ double shfl(double x, int src) const { return __shfl_sync(mask, x, src, 16); }
+    __device__ __forceinline__ double shfl_xor(double x, int m) const { return __shfl_xor_sync(mask, x, m, 16); }
+    __device__ __forceinline__ int shfl_i(int x, int src) const { return __shfl_sync(mask, x, src, 16); }
+    __device__ __forceinline__ int shfl_xor_i(int x, int m) const { return __shfl_xor_sync(mask, x, m, 16); }
+    __device__ __forceinline__ bool any(bool p) const { return (__ballot_sync(mask, p) & mask) != 0u; }
+};
+
+#define OWG_PA_TILES_PER_CTA 8
+#define OWG_PA_THREADS (OWG_PA_TILES_PER_CTA * 16)
+
+struct PaSpeakerPost {  // chain B's tail behind the amplifier: Speaker::process * POST_SPEAKER_GAIN (main.rs:495)
+    SpkState spk;
+    const OwgChainInit* ci;
+    __device__ __forceinline__ double operator()(double v) { return speaker(v, spk, *ci) * 7.498942093324558; }
+};
+
+// rows: [n_inst][stride] in place (input -> output).  index: optional list of the instances this launch covers (one sample-rate model).
+// cinits != nullptr: chain B output stage (volume^2, --no-poweramp, speaker); otherwise the plain adapter (owg_power_amp_batch).
+__global__ void __launch_bounds__(OWG_PA_THREADS) pa_melange_kernel(const PaModel* __restrict__ model, const PaSettled* __restrict__ settled, double* __restrict__ rows,
+                                                                    int64_t stride, const int32_t* __restrict__ index, int64_t n_tiles,
+                                                                    const unsigned long long* __restrict__ n_samples, int64_t n_samp_all, int rail_sag,
+                                                                    const OwgChainInit* __restrict__ cinits, double* __restrict__ rails,
+                                                                    uint32_t* __restrict__ counters) {
+    __shared__ PaShared sh;
+    __shared__ PaScratch sc[OWG_PA_TILES_PER_CTA];
+    pa_stage_shared(*model, sh, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int tile_in_cta = threadIdx.x >> 4;
+    const int64_t tile = (int64_t)blockIdx.x * OWG_PA_TILES_PER_CTA + tile_in_cta;
+    if (tile >= n_tiles) return;  // whole tiles leave together; no CTA-wide barrier below
+    const int64_t inst = index ? index[tile] : tile;
+    PaCudaTile t;
+    t.lane = threadIdx.x & 15;
+    t.mask = 0xffffu << (threadIdx.x & 16);
+    double* row = rows + (size_t)inst * stride;
+    const int64_t n = n_samples ? (int64_t)n_samples[inst] : n_samp_all;
+    double* r_out = rails ? rails + 2 * inst : nullptr;
+    uint32_t* c_out = counters ? counters + 4 * inst : nullptr;
+    if (cinits) {
+        PaSpeakerPost post;
+        post.spk = SpkState{0.0, 0.0, 0.0, 0.0, 0.0};
+        post.ci = &cinits[inst];
+        pa_tile_render(t, *model, sh, sc[tile_in_cta], settled, row, row, n, cinits[inst].volume, rail_sag != 0, cinits[inst].no_poweramp != 0, nullptr, r_out,
+                       c_out, post);
+    } else {
+        PaNoPost post;
+        pa_tile_render(t, *model, sh, sc[tile_in_cta], settled, row, row, n, 1.0, rail_sag != 0, false, nullptr, r_out, c_out, post);
+    }
+}
+
+// compute_settled_state (power_amp.rs:291-296) behind CircuitState::default() (gen_power_amp.rs:8421-8490): one tile, 50 + 44 100 silent
+// samples of the raw solver with the baked 88.2 kHz tables; once per device and process (the reference's OnceLock)
+__global__ void __launch_bounds__(32) pa_settle_kernel(const PaModel* __restrict__ model, PaSettled* __restrict__ out) {
+    __shared__ PaShared sh;
+    __shared__ PaScratch sc;
+    pa_stage_shared(*model, sh, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (threadIdx.x >= 16) return;
+    PaCudaTile t;
+    t.lane = threadIdx.x;
+    t.mask = 0xffffu;
+    PaNoPost post;
+    pa_tile_render(t, *model, sh, sc, nullptr, nullptr, nullptr, PA_SETTLE_SAMPLES, 1.0, false, false, out, nullptr, nullptr, post);
+}
+
+}  // namespace owgd

@@ -7,6 +7,7 @@
 #include "owg_legacy.cuh"
 #include "owg_engine.cuh"
 #include "owg_alias.cuh"
+#include "owg_poweramp.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -62,6 +63,9 @@ struct DeviceCache {
     // reference would if it cached its constructor the way it caches the preamp's settled state.
     struct TrmCtor { TrmRun* state = nullptr; cudaEvent_t ready = nullptr; };
     std::map<uint64_t, TrmCtor> trm_ctor;
+    // melange power amplifier: the settled CircuitState (power_amp.rs:289-297, the reference's OnceLock) and one model per sample rate
+    PaSettled* d_pa_settled = nullptr;
+    std::map<uint64_t, PaModel*> d_pa_models;
 };
 std::mutex g_cache_mu;
 std::map<int, DeviceCache> g_cache;
@@ -199,6 +203,8 @@ int plan_common(owg_plan* pl, const owg_opts* opts) {
     if (opts) o = *opts; else owg_default_opts(&o);
     if (o.precision != OWG_PRECISION_F64_EXACT) return fail(OWG_E_UNSUPPORTED, "only OWG_PRECISION_F64_EXACT is implemented");
     if (o.preamp_model != OWG_PREAMP_MELANGE12 && o.preamp_model != OWG_PREAMP_LEGACY8) return fail(OWG_E_UNSUPPORTED, "unknown preamp_model");
+    if (o.power_amp_model != OWG_POWER_AMP_BEHAVIORAL)
+        return fail(OWG_E_UNSUPPORTED, "power_amp_model: the melange power amplifier is served by owg_render_bench, owg_chain_batch and owg_power_amp_batch");
     pl->legacy = o.preamp_model == OWG_PREAMP_LEGACY8;
     int dev = o.device;
     if (popcount32(o.device_mask) == 1) { dev = 0; while (!(o.device_mask & (1u << dev))) dev++; }  // a one-bit mask names the device
@@ -887,10 +893,155 @@ int owg_render_voices(const owg_voice_job* jobs, int64_t n, double* out, int64_t
     return rc;
 }
 
+// ---- melange power amplifier (gen_power_amp.rs + power_amp.rs melange_adapter) ----------------------------------------
+namespace {
+// model of `sample_rate` and the settled state on `device` (cached for the life of the process)
+int ensure_pa(int device, cudaStream_t stream, double sample_rate, const PaModel** d_model, const PaSettled** d_settled, int64_t* launches) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    DeviceCache& c = g_cache[device];
+    auto model_for = [&](double sr, PaModel** out) -> int {
+        uint64_t key; std::memcpy(&key, &sr, 8);
+        auto it = c.d_pa_models.find(key);
+        if (it == c.d_pa_models.end()) {
+            std::vector<PaModel> h(1);
+            owg::pa_build_model(sr, &h[0]);
+            PaModel* d = nullptr;
+            CK(cudaMalloc(&d, sizeof(PaModel)));
+            CK(cudaMemcpy(d, h.data(), sizeof(PaModel), cudaMemcpyHostToDevice));
+            g_h2d_bytes += sizeof(PaModel);
+            it = c.d_pa_models.emplace(key, d).first;
+        }
+        *out = it->second;
+        return OWG_OK;
+    };
+    if (!c.d_pa_settled) {
+        PaModel* d_default = nullptr;
+        if (int rc = model_for(88200.0, &d_default)) return rc;
+        PaSettled* d = nullptr;
+        CK(cudaMalloc(&d, sizeof(PaSettled)));
+        pa_settle_kernel<<<1, 32, 0, stream>>>(d_default, d);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        c.d_pa_settled = d;
+        if (launches) *launches += 1;
+    }
+    PaModel* dm = nullptr;
+    if (int rc = model_for(sample_rate, &dm)) return rc;
+    *d_model = dm;
+    *d_settled = c.d_pa_settled;
+    return OWG_OK;
+}
+
+// the amplifier over device rows, in place; d_index / n_tiles select the instances of this launch
+int launch_pa_rows(int device, cudaStream_t st, double sample_rate, double* d_rows, int64_t stride, const int32_t* d_index, int64_t n_tiles,
+                   const unsigned long long* d_ns, int64_t n_samp_all, int rail_sag, const OwgChainInit* d_ci, double* d_rails, uint32_t* d_counters,
+                   int64_t* launches) {
+    if (n_tiles <= 0) return OWG_OK;
+    const PaModel* dm = nullptr;
+    const PaSettled* ds = nullptr;
+    if (int rc = ensure_pa(device, st, sample_rate, &dm, &ds, launches)) return rc;
+    const unsigned grid = (unsigned)((n_tiles + OWG_PA_TILES_PER_CTA - 1) / OWG_PA_TILES_PER_CTA);
+    pa_melange_kernel<<<grid, OWG_PA_THREADS, 0, st>>>(dm, ds, d_rows, stride, d_index, n_tiles, d_ns, n_samp_all, rail_sag, d_ci, d_rails, d_counters);
+    CK(cudaGetLastError());
+    if (launches) *launches += 1;
+    return OWG_OK;
+}
+
+int resolve_device(const owg_opts& o, int* dev_out) {
+    if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device (libowgpu has no CPU fallback)");
+    int dev = o.device;
+    if (popcount32(o.device_mask) == 1) { dev = 0; while (!(o.device_mask & (1u << dev))) dev++; }
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    CK(cudaSetDevice(dev));
+    *dev_out = dev;
+    return OWG_OK;
+}
+
+// chain B with the melange amplifier: voice + preamp through the usual plan (pre-amplifier rows on the device), then volume^2 -> melange
+// PowerAmp::new() (44.1 kHz, main.rs:480) -> speaker in pa_melange_kernel
+int render_bench_melange_pa(const owg_bench_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts& opts) {
+    if (n < 0 || (n > 0 && (!jobs || !out))) return fail(OWG_E_BAD_ARG, "owg_render_bench: bad argument");
+    if (n == 0) return OWG_OK;
+    owg_opts o = opts;
+    const int rail_sag = opts.power_amp_model == OWG_POWER_AMP_MELANGE ? 1 : 0;
+    o.power_amp_model = OWG_POWER_AMP_BEHAVIORAL;
+    o.out_location = OWG_OUT_DEVICE;
+    owg_plan* pl = nullptr;
+    if (int rc = plan_bench_impl(jobs, n, &o, &pl, nullptr, true)) return rc;
+    const int64_t dstride = std::max<int64_t>((int64_t)pl->max_samples, 1);
+    int rc = stride < (int64_t)pl->max_samples ? fail(OWG_E_BAD_ARG, "stride smaller than the longest render") : OWG_OK;
+    DevBuf<double> rows;
+    DevBuf<OwgChainInit> d_ci;
+    DevBuf<unsigned long long> d_ns;
+    if (!rc) rc = rows.alloc((size_t)n * (size_t)dstride);
+    if (!rc) rc = owg_plan_execute(pl, rows.p, dstride, OWG_OUT_DEVICE);
+    cudaStream_t st = pl->stream;
+    std::vector<OwgChainInit> ci((size_t)n);
+    std::vector<unsigned long long> ns((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        owg::make_chain_init(jobs[i], 0, &ci[i]);
+        const double nsd = jobs[i].v.duration_s * jobs[i].v.sample_rate;
+        ns[i] = !(nsd == nsd) || nsd <= 0.0 ? 0ull : (unsigned long long)nsd;
+    }
+    if (!rc) rc = d_ci.upload(ci, st);
+    if (!rc) rc = d_ns.upload(ns, st);
+    int64_t launches = 0;
+    if (!rc) rc = launch_pa_rows(pl->device, st, 44100.0, rows.p, dstride, nullptr, n, d_ns.p, 0, rail_sag, d_ci.p, nullptr, nullptr, &launches);
+    if (!rc) {
+        const cudaMemcpyKind kind = opts.out_location == OWG_OUT_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (cudaMemcpy2DAsync(out, (size_t)stride * sizeof(double), rows.p, (size_t)dstride * sizeof(double), (size_t)pl->max_samples * sizeof(double), (size_t)n,
+                              kind, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            rc = fail(OWG_E_CUDA, std::string("melange power amplifier stage failed: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+    g_last_diag.kernels_launched += (uint64_t)launches;
+    owg_plan_destroy(pl);
+    return rc;
+}
+}  // namespace
+
+int owg_power_amp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double sample_rate, int32_t rail_sag, double* out,
+                        int64_t out_stride, double* rails, uint32_t* counters, const owg_opts* opts) {
+    if (n_inst < 0 || n_samp < 0 || !(sample_rate > 0.0) || !std::isfinite(sample_rate)) return fail(OWG_E_BAD_ARG, "owg_power_amp_batch: bad argument");
+    if (n_inst == 0 || n_samp == 0) return OWG_OK;
+    if (!in || !out || in_stride < n_samp || out_stride < n_samp) return fail(OWG_E_BAD_ARG, "owg_power_amp_batch: null buffer or stride < n_samp");
+    owg_opts o;
+    if (opts) o = *opts; else owg_default_opts(&o);
+    int dev = 0;
+    if (int rc = resolve_device(o, &dev)) return rc;
+    cudaStream_t st = (cudaStream_t)o.stream;
+    bool own = false;
+    if (!st) { CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); own = true; }
+    const bool on_device = o.out_location == OWG_OUT_DEVICE;
+    DevBuf<double> rows, d_rails;
+    DevBuf<uint32_t> d_cnt;
+    int rc = rows.alloc((size_t)n_inst * (size_t)n_samp);
+    if (!rc && rails) rc = d_rails.alloc((size_t)n_inst * 2);
+    if (!rc && counters) rc = d_cnt.alloc((size_t)n_inst * 4);
+    auto cuda_ok = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && !rc) rc = fail(OWG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); };
+    const size_t w = (size_t)n_samp * sizeof(double);
+    if (!rc) cuda_ok(cudaMemcpy2DAsync(rows.p, w, in, (size_t)in_stride * sizeof(double), w, (size_t)n_inst, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st), "input copy");
+    if (!on_device) g_h2d_bytes += (int64_t)(w * (size_t)n_inst);
+    int64_t launches = 0;
+    if (!rc) rc = launch_pa_rows(dev, st, sample_rate, rows.p, n_samp, nullptr, n_inst, nullptr, n_samp, rail_sag ? 1 : 0, nullptr, rails ? d_rails.p : nullptr,
+                                 counters ? d_cnt.p : nullptr, &launches);
+    if (!rc) cuda_ok(cudaMemcpy2DAsync(out, (size_t)out_stride * sizeof(double), rows.p, w, w, (size_t)n_inst, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st), "output copy");
+    if (!rc) cuda_ok(cudaStreamSynchronize(st), "melange power amplifier kernel");
+    if (!rc && rails) cuda_ok(cudaMemcpy(rails, d_rails.p, (size_t)n_inst * 2 * sizeof(double), cudaMemcpyDeviceToHost), "rails copy");
+    if (!rc && counters) cuda_ok(cudaMemcpy(counters, d_cnt.p, (size_t)n_inst * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost), "counters copy");
+    if (own) cudaStreamDestroy(st);
+    g_last_diag.kernels_launched = (uint64_t)launches;
+    return rc;
+}
+
 int owg_render_bench(const owg_bench_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts) {
     if (opts && popcount32(opts->device_mask) >= 2 && n > 0 && jobs && out)
         return fan_out_devices(jobs, n, out, stride, *opts, [](const owg_bench_job& j) { const double x = j.v.duration_s * j.v.sample_rate; return x > 0.0 ? x : 0.0; },
                                [](const owg_bench_job* j, int64_t m, double* o, int64_t st, const owg_opts* op) { return owg_render_bench(j, m, o, st, op); });
+    if (opts && opts->power_amp_model != OWG_POWER_AMP_BEHAVIORAL) {
+        if (opts->power_amp_model != OWG_POWER_AMP_MELANGE && opts->power_amp_model != OWG_POWER_AMP_MELANGE_IDEAL_RAILS)
+            return fail(OWG_E_UNSUPPORTED, "unknown power_amp_model");
+        return render_bench_melange_pa(jobs, n, out, stride, *opts);
+    }
     owg_plan* pl = nullptr;
     if (int rc = owg_plan_bench(jobs, n, opts, &pl)) return rc;
     const int rc = owg_plan_execute(pl, out, stride, opts ? opts->out_location : OWG_OUT_HOST);

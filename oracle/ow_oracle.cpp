@@ -394,6 +394,63 @@ int64_t owo_power_amp_melange(double sample_rate, int rail_sag, const double* x,
 #endif
 }
 
+// chain B's output stage with the melange amplifier (tools/preamp-bench/src/main.rs:478-496 built with --no-default-features):
+// attenuated = pre * volume * volume; PowerAmp::new() (44.1 kHz) with set_rail_sag(!no_rail_sag); Speaker::new(sr), set_character; * POST_SPEAKER_GAIN
+int owo_output_stage_melange(const double* pre, int64_t n, double sample_rate, double volume, double speaker_character, int no_poweramp, int rail_sag,
+                             double* out) {
+#ifdef OW_HAVE_MELANGE_POWER_AMP
+    ow::pam::PowerAmp pa;
+    pa.set_rail_sag(rail_sag != 0);
+    Speaker spk(sample_rate);
+    spk.set_character(speaker_character);
+    for (int64_t i = 0; i < n; i++) {
+        const double att = pre[i] * volume * volume;
+        const double amp = no_poweramp ? att : pa.process(att);
+        out[i] = spk.process(amp) * POST_SPEAKER_GAIN;
+    }
+    return OWG_OK;
+#else
+    (void)pre; (void)n; (void)sample_rate; (void)volume; (void)speaker_character; (void)no_poweramp; (void)rail_sag; (void)out;
+    return -1;
+#endif
+}
+// CircuitState::default() + n_extra x process_sample(0.0) (n_extra = 44100: compute_settled_state, power_amp.rs:291-296):
+// out54 = v_prev[20] i_nl_prev[16] i_nl_prev_prev[16] dc_block_x_prev dc_block_y_prev
+int owo_power_amp_settled(int64_t n_extra, double* out54) {
+#ifdef OW_HAVE_MELANGE_POWER_AMP
+    gen_power_amp::CircuitState st = gen_power_amp::CircuitState::default_();
+    for (int64_t i = 0; i < n_extra; i++) gen_power_amp::process_sample(0.0, st);
+    double* o = out54;
+    for (double v : st.v_prev) *o++ = v;
+    for (double v : st.i_nl_prev) *o++ = v;
+    for (double v : st.i_nl_prev_prev) *o++ = v;
+    *o++ = st.dc_block_x_prev[0]; *o++ = st.dc_block_y_prev[0];
+    return OWG_OK;
+#else
+    (void)n_extra; (void)out54;
+    return -1;
+#endif
+}
+// CircuitState matrices after PowerAmp::new_at_sample_rate(sr): out = s[400] k[256] s_ni[320] s_be[400] k_be[256] s_ni_be[320] a_neg_be[400] dc_block_r
+int owo_power_amp_matrices(double sample_rate, double* out) {
+#ifdef OW_HAVE_MELANGE_POWER_AMP
+    ow::pam::PowerAmp pa(sample_rate);
+    double* o = out;
+    for (auto& r : pa.state.s) for (double v : r) *o++ = v;
+    for (auto& r : pa.state.k) for (double v : r) *o++ = v;
+    for (auto& r : pa.state.s_ni) for (double v : r) *o++ = v;
+    for (auto& r : pa.state.s_be) for (double v : r) *o++ = v;
+    for (auto& r : pa.state.k_be) for (double v : r) *o++ = v;
+    for (auto& r : pa.state.s_ni_be) for (double v : r) *o++ = v;
+    for (auto& r : pa.state.a_neg_be) for (double v : r) *o++ = v;
+    *o = pa.state.dc_block_r;
+    return OWG_OK;
+#else
+    (void)sample_rate; (void)out;
+    return -1;
+#endif
+}
+
 // ---- known-answer probes (host-side setup functions) --------------------------------------------
 double owo_midi_to_freq(int midi) { return midi_to_freq((uint8_t)midi); }
 double owo_tip_mass_ratio(int midi) { return tip_mass_ratio((uint8_t)midi); }

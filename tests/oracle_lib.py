@@ -119,6 +119,9 @@ def lib():
         L.owo_rail_dynamics.argtypes = [C.c_double, dp, C.c_int64, dp]
         L.owo_power_amp_melange.argtypes = [C.c_double, C.c_int, dp, C.c_int64, dp, dp, C.c_int64]
         L.owo_power_amp_melange.restype = C.c_int64
+        L.owo_output_stage_melange.argtypes = [dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp]
+        L.owo_power_amp_matrices.argtypes = [C.c_double, dp]
+        L.owo_power_amp_settled.argtypes = [C.c_int64, dp]
         L.owo_alias_analyze.argtypes = [dp, C.c_int64, C.c_double, C.c_double, C.c_double, dp]
         L.owo_preamp_batch_diag.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double, dp, C.c_int64, C.c_int]
         L.owo_preamp_batch_model.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_double,

@@ -56,8 +56,9 @@ struct Job {
 Job g_job;
 void lane_main(int lane) {
     EmuTile t{lane};
-    pa_tile_render(t, *g_job.m, *g_job.sh, *g_job.sc, g_job.settled, g_job.x, g_job.y, g_job.n, g_job.pre_gain, g_job.rail_sag, g_job.settle,
-                   g_job.rails, g_job.counters);
+    PaNoPost post;
+    pa_tile_render(t, *g_job.m, *g_job.sh, *g_job.sc, g_job.settled, g_job.x, g_job.y, g_job.n, g_job.pre_gain, g_job.rail_sag, false, g_job.settle,
+                   g_job.rails, g_job.counters, post);
     g_emu->done[lane] = true;
     // hand over to a lane that is still running, or back to main when this was the last one
     for (int i = 1; i <= L; i++) {
@@ -110,6 +111,25 @@ int paemu_render(double sample_rate, int rail_sag, const double* x, int64_t n, d
     owg::pa_build_model(sample_rate, &m);
     pa_stage_shared(m, sh, 0, 1);
     run_tile(Job{&m, &sh, &sc, &g_settled, x, y, n, pre_gain, rail_sag != 0, nullptr, rails2, counters4});
+    return 0;
+}
+// CircuitState::default() followed by n_extra silent samples of the raw solver (n_extra = 44100: compute_settled_state):
+// out54 = v_prev[20] i_nl_prev[16] i_nl_prev_prev[16] dc_block_x_prev dc_block_y_prev
+int paemu_settle(int64_t n_extra, double* out54) {
+    static PaModel m0;
+    static PaShared sh;
+    static PaScratch sc;
+    PaSettled st;
+    owg::pa_build_model(88200.0, &m0);
+    pa_stage_shared(m0, sh, 0, 1);
+    run_tile(Job{&m0, &sh, &sc, nullptr, nullptr, nullptr, 50 + n_extra, 1.0, false, &st, nullptr, nullptr});
+    memcpy(out54, &st, sizeof(st));
+    return 0;
+}
+// use this settled state (e.g. the oracle's) instead of computing it on the emulator (44 150 emulated samples take minutes)
+int paemu_set_settled(const double* in54) {
+    memcpy(&g_settled, in54, sizeof(g_settled));
+    g_have_settled = true;
     return 0;
 }
 // the model's matrices for the host-setup test: out = s[400] k[256] s_ni[320] s_be[400] k_be[256] s_ni_be[320] a_neg_be[400] dc_block_r
