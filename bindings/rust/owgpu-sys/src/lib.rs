@@ -133,8 +133,14 @@ pub struct owg_opts {
     pub collect_diag: i32,
     /// bit d = use CUDA device d; two or more bits: the call fans out over those GPUs (host output)
     pub device_mask: u32,
-    pub _reserved: [i32; 6],
+    /// OWG_POWER_AMP_*: 0 behavioural (`legacy-power-amp`, default build), 1 melange 7-BJT solver with rail sag, 2 the same with ideal rails
+    pub power_amp_model: i32,
+    pub _reserved: [i32; 5],
 }
+
+pub const OWG_POWER_AMP_BEHAVIORAL: i32 = 0;
+pub const OWG_POWER_AMP_MELANGE: i32 = 1;
+pub const OWG_POWER_AMP_MELANGE_IDEAL_RAILS: i32 = 2;
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]
@@ -172,6 +178,10 @@ extern "C" {
                                 rows: *mut f64, opts: *const owg_opts) -> i32;
     pub fn owg_preamp_batch(input: *const f64, in_stride: i64, n_inst: i64, n_samp: i64, fs_base: f64, oversample: i32, tremolo_depth: f64,
                             r_ldr_static: f64, out: *mut f64, out_stride: i64, opts: *const owg_opts) -> i32;
+    /// PowerAmp::new_at_sample_rate + set_rail_sag + process per row (power_amp.rs:279-465 over gen_power_amp.rs); `rails` `[n][2]` and
+    /// `counters` `[n][4]` (resets, backward-Euler retries, NaN resets, last_nr_iterations) may be null.
+    pub fn owg_power_amp_batch(input: *const f64, in_stride: i64, n_inst: i64, n_samp: i64, sample_rate: f64, rail_sag: i32, out: *mut f64,
+                               out_stride: i64, rails: *mut f64, counters: *mut u32, opts: *const owg_opts) -> i32;
     pub fn owg_chain_batch(input: *const f64, in_stride: i64, n_inst: i64, n_samp: i64, params: *const owg_bench_job, init_order: i32,
                            out: *mut f64, out_stride: i64, opts: *const owg_opts) -> i32;
     pub fn owg_render_engines(jobs: *const owg_engine_job, n: i64, out: *mut f32, stride: i64, opts: *const owg_opts) -> i32;

@@ -117,8 +117,9 @@ typedef struct owg_opts {
                            * balanced by rendered samples, one worker thread, stream and staging buffer per GPU, every GPU copying its rows
                            * straight into the caller's buffer.  Renders are independent: no collective, each GPU recomputes the (tiny) shared
                            * sequences of the preamp groups it touches.  Order the jobs by preamp group to keep groups on one GPU. */
-    int32_t power_amp_model; /* OWG_POWER_AMP_*; the melange models are served by owg_render_bench, owg_chain_batch and
-                              * owg_power_amp_batch, every other entry point answers OWG_E_UNSUPPORTED for them */
+    int32_t power_amp_model; /* OWG_POWER_AMP_*; the melange models are served by owg_render_bench, owg_chain_batch, owg_render_midi and
+                              * owg_power_amp_batch (chain B's output stage: PowerAmp::new() at 44.1 kHz, main.rs:480); every other entry
+                              * point answers OWG_E_UNSUPPORTED for them */
     int32_t _reserved[5];
 } owg_opts;
 

@@ -246,7 +246,7 @@ def power_amp_batch(x, sample_rate=44100.0, rail_sag=True, out=None, device=-1, 
 RESET_THEN_SET, SET_THEN_RESET = 0, 1
 
 
-def chain_batch(x, params, init_order=RESET_THEN_SET, out=None, device=-1, preamp_model=MELANGE12):
+def chain_batch(x, params, init_order=RESET_THEN_SET, out=None, device=-1, preamp_model=MELANGE12, power_amp_model=PA_BEHAVIORAL):
     """Rows of `x` [n_inst, n_samp] (any mono signal, e.g. a sum of voices) through the full chain B of params[i] (bench_job(...): sample
     rate, ldr, tremolo depth, volume, speaker, bypass flags).  init_order = SET_THEN_RESET is how `render-poly` / `render-midi` construct
     the static preamp (main.rs:1463-1464)."""
@@ -256,7 +256,7 @@ def chain_batch(x, params, init_order=RESET_THEN_SET, out=None, device=-1, pream
     pout, sout, lout = _out_ptr(out)
     assert lin == lout and len(params) == x.shape[0]
     arr = (BenchJob * len(params))(*params)
-    o = _opts(device, lout, preamp_model=preamp_model)
+    o = _opts(device, lout, preamp_model=preamp_model, power_amp_model=power_amp_model)
     check(lib().owg_chain_batch(pin, sin, x.shape[0], x.shape[1], arr, int(init_order), pout, sout, C.byref(o)))
     return out
 
@@ -264,7 +264,7 @@ def chain_batch(x, params, init_order=RESET_THEN_SET, out=None, device=-1, pream
 MIDI_ON, MIDI_OFF, MIDI_PEDAL = 0, 1, 2
 
 
-def render_midi(streams, volume=0.60, speaker=1.0, no_poweramp=False, tail=2.0, device=-1, preamp_model=MELANGE12):
+def render_midi(streams, volume=0.60, speaker=1.0, no_poweramp=False, tail=2.0, device=-1, preamp_model=MELANGE12, power_amp_model=PA_BEHAVIORAL):
     """`preamp-bench render-midi` for a batch of event lists (smf.timed_events output: [(time_s, kind, note, velocity)]): the tool's own
     voice manager and chain.  Returns (list of float64 arrays, one per stream)."""
     from . import smf
@@ -282,7 +282,7 @@ def render_midi(streams, volume=0.60, speaker=1.0, no_poweramp=False, tail=2.0, 
     out = np.zeros((len(jobs), max(stride, 1)), dtype=np.float64)
     if jobs and stride:
         ja = (_abi.MidiJob * len(jobs))(*jobs)
-        o = _opts(device, OWG_OUT_HOST, preamp_model=preamp_model)
+        o = _opts(device, OWG_OUT_HOST, preamp_model=preamp_model, power_amp_model=power_amp_model)
         check(lib().owg_render_midi(ja, len(jobs), out.ctypes.data, out.shape[1], C.byref(o)))
     return [out[i, :ns[i]] for i in range(len(jobs))]
 

@@ -204,7 +204,7 @@ int plan_common(owg_plan* pl, const owg_opts* opts) {
     if (o.precision != OWG_PRECISION_F64_EXACT) return fail(OWG_E_UNSUPPORTED, "only OWG_PRECISION_F64_EXACT is implemented");
     if (o.preamp_model != OWG_PREAMP_MELANGE12 && o.preamp_model != OWG_PREAMP_LEGACY8) return fail(OWG_E_UNSUPPORTED, "unknown preamp_model");
     if (o.power_amp_model != OWG_POWER_AMP_BEHAVIORAL)
-        return fail(OWG_E_UNSUPPORTED, "power_amp_model: the melange power amplifier is served by owg_render_bench, owg_chain_batch and owg_power_amp_batch");
+        return fail(OWG_E_UNSUPPORTED, "power_amp_model: the melange power amplifier is served by owg_render_bench, owg_chain_batch, owg_render_midi and owg_power_amp_batch");
     pl->legacy = o.preamp_model == OWG_PREAMP_LEGACY8;
     int dev = o.device;
     if (popcount32(o.device_mask) == 1) { dev = 0; while (!(o.device_mask & (1u << dev))) dev++; }  // a one-bit mask names the device
@@ -1704,7 +1704,48 @@ int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_
 
 static int chain_batch_impl(const double* in, int in_location, int64_t in_stride, int64_t n_inst, const unsigned long long* n_samp_each,
                             int64_t n_samp_max, const owg_bench_job* params, int32_t init_order, double* out, int64_t out_stride,
-                            const owg_opts* opts) {
+                            const owg_opts* opts, bool force_pre_only = false) {
+    if (!force_pre_only && opts && opts->power_amp_model != OWG_POWER_AMP_BEHAVIORAL) {
+        // the melange amplifier (render-poly / render-midi built with --no-default-features, main.rs:1470-1481, 1756-1889): the chain up to
+        // the preamp output into device rows, then volume^2 -> PowerAmp::new() -> speaker in pa_melange_kernel
+        if (opts->power_amp_model != OWG_POWER_AMP_MELANGE && opts->power_amp_model != OWG_POWER_AMP_MELANGE_IDEAL_RAILS)
+            return fail(OWG_E_UNSUPPORTED, "unknown power_amp_model");
+        owg_opts o = *opts;
+        o.power_amp_model = OWG_POWER_AMP_BEHAVIORAL;
+        o.out_location = OWG_OUT_DEVICE;
+        int dev = 0;
+        if (int rc = resolve_device(o, &dev)) return rc;
+        o.device = dev; o.device_mask = 0;
+        cudaStream_t st = (cudaStream_t)o.stream;
+        bool own = false;
+        if (!st) { CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); own = true; o.stream = st; }
+        DevBuf<double> rows;
+        DevBuf<OwgChainInit> d_ci;
+        DevBuf<unsigned long long> d_ns;
+        int rc = rows.alloc((size_t)n_inst * (size_t)n_samp_max);
+        const int in_loc = in_location >= 0 ? in_location : opts->out_location;
+        if (!rc) rc = chain_batch_impl(in, in_loc, in_stride, n_inst, n_samp_each, n_samp_max, params, init_order, rows.p, n_samp_max, &o, true);
+        std::vector<OwgChainInit> ci((size_t)n_inst);
+        std::vector<unsigned long long> ns((size_t)n_inst);
+        for (int64_t i = 0; i < n_inst; i++) {
+            owg::make_chain_init(params[i], 0, &ci[i]);
+            ns[i] = n_samp_each ? n_samp_each[i] : (unsigned long long)n_samp_max;
+        }
+        if (!rc) rc = d_ci.upload(ci, st);
+        if (!rc) rc = d_ns.upload(ns, st);
+        int64_t launches = 0;
+        if (!rc) rc = launch_pa_rows(dev, st, 44100.0, rows.p, n_samp_max, nullptr, n_inst, d_ns.p, 0, opts->power_amp_model == OWG_POWER_AMP_MELANGE ? 1 : 0,
+                                     d_ci.p, nullptr, nullptr, &launches);
+        if (!rc) {
+            const cudaMemcpyKind kind = opts->out_location == OWG_OUT_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            if (cudaMemcpy2DAsync(out, (size_t)out_stride * sizeof(double), rows.p, (size_t)n_samp_max * sizeof(double), (size_t)n_samp_max * sizeof(double),
+                                  (size_t)n_inst, kind, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+                rc = fail(OWG_E_CUDA, std::string("melange power amplifier stage failed: ") + cudaGetErrorString(cudaGetLastError()));
+        }
+        if (own) cudaStreamDestroy(st);
+        g_last_diag.kernels_launched += (uint64_t)launches;
+        return rc;
+    }
     owg_plan* pl = new owg_plan();
     g_h2d_bytes = 0;
     pl->kind = 2;
@@ -1721,6 +1762,7 @@ static int chain_batch_impl(const double* in, int in_location, int64_t in_stride
         sp.depth = j.tremolo_depth;
         sp.r_ldr = j.r_ldr;
         owg::make_chain_init(j, 0, &sp.ci);
+        if (force_pre_only) sp.ci.pre_only = 1;
     }
     std::vector<int32_t> order;
     build_groups_and_warps(pl, specs, &order);
@@ -1772,7 +1814,10 @@ int owg_render_midi(const owg_midi_job* jobs, int64_t n, double* out, int64_t st
     if (max_samples == 0) return OWG_OK;
     if (stride < max_samples) return fail(OWG_E_BAD_ARG, "owg_render_midi: stride smaller than the longest stream");
     owg_plan pl;  // device / stream / cache plumbing of the voice phase
-    if (int rc = plan_common(&pl, opts)) return rc;
+    owg_opts o_plan;
+    if (opts) o_plan = *opts; else owg_default_opts(&o_plan);
+    o_plan.power_amp_model = OWG_POWER_AMP_BEHAVIORAL;  // the amplifier model concerns the chain stage only (chain_batch_impl below)
+    if (int rc = plan_common(&pl, &o_plan)) return rc;
     cudaStream_t s = pl.stream;
     std::vector<EngineDesc> eng((size_t)n);
     std::vector<MidiEvent> events;

@@ -189,3 +189,22 @@ def test_gpu_chain_b_with_the_melange_power_amp_matches_the_oracle():
     o = ow.api._opts(power_amp_model=ow.PA_MELANGE)
     x = np.zeros((1, 64))
     assert ow.lib().owg_preamp_batch(x.ctypes.data_as(C.c_void_p), 64, 1, 64, 44100.0, 1, 0.0, 1e6, x.ctypes.data_as(C.c_void_p), 64, C.byref(o)) == -5
+
+
+@pytest.mark.gpu
+@needs_solver
+def test_gpu_chain_batch_routes_caller_rows_through_the_melange_power_amp():
+    """owg_chain_batch (render-poly's mix / per-voice chains, main.rs:1470-1481) with power_amp_model = PA_MELANGE: caller rows, preamp
+    bypassed so that the rows are the amplifier's input -> volume^2 -> melange amplifier -> speaker, against owo_output_stage_melange."""
+    import openwurli_b200 as ow
+    sr, n = 44100.0, 1500
+    sig = _signals(sr, n)
+    x = np.ascontiguousarray(np.stack([sig[1], sig[2] * 4.0, sig[5] * 3.0, sig[7]]))
+    vols, chars = (0.6, 0.9, 0.5, 1.0), (1.0, 0.0, 0.4, 0.7)
+    params = [ow.bench_job(volume=v, speaker=c, no_preamp=True, duration=n / sr) for v, c in zip(vols, chars)]
+    g = ow.chain_batch(x, params, power_amp_model=ow.PA_MELANGE)
+    for i in range(len(params)):
+        ref = np.zeros(n)
+        assert L.owo_output_stage_melange(O.dptr(np.ascontiguousarray(x[i])), n, sr, vols[i], chars[i], 0, 1, O.dptr(ref)) == 0
+        err, rel = _close(g[i], ref)
+        assert err <= 1e-6 and rel <= 1e-7, (i, err, rel)
