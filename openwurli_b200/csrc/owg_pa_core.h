@@ -72,7 +72,9 @@ struct PaScratch {  // per tile
     double w[PA_N];        // rhs, then v_pred
     double ci[PA_M];       // i_nl / i_trial gather
     double ip[PA_M];       // flushed i_nl_prev
-    double prow[2][PA_M + 2];  // pivot row + right-hand side, double-buffered by column parity
+    double a[PA_M][PA_M + 1];  // the Newton system, one row per lane (column 16 = right-hand side); odd stride: conflict-free rows
+    double x[PA_M];            // its solution
+    int32_t sing, _pad;        // back substitution met a zero pivot
 };
 struct PaLane {  // per-lane registers carried from sample to sample
     double v0, v1;          // v_prev[l], v_prev[16 + l] (l < 4)
@@ -178,21 +180,25 @@ PA_HD void pa_bjt_evaluate(double vbe, double vbc, const double* d, double& ic, 
     jac[2] = dib_fwd_dvbe + dib_leak_dvbe; jac[3] = dib_rev_dvbc + dib_leak_dvbc;
 }
 
-// bjt_with_parasitics (gen_power_amp.rs:8062-8150): inner 2x2 Newton on the internal junction voltages behind RB / RC / RE, then the
-// terminal-voltage Jacobian through the inverse of the inner Jacobian
+// bjt_with_parasitics (gen_power_amp.rs:8062-8150): inner 2x2 Newton on the internal junction voltages behind RB / RC / RE (<= 15 updates),
+// then the terminal-voltage Jacobian through the inverse of the inner Jacobian.  The reference re-evaluates the device after leaving the
+// loop; when it left by convergence or a vanishing determinant that evaluation repeats the last one bit for bit, so one call site serves
+// both (the 16th pass is the evaluation after 15 updates).
 PA_HD void pa_bjt_with_parasitics(double vbe_ext, double vbc_ext, const double* d, double& ic, double& ib, double* jac) {
     const double rb = d[PD_RB], rc = d[PD_RC], re = d[PD_RE], max_step = d[PD_MAX_STEP];
     double vbe_int = vbe_ext, vbc_int = vbc_ext;
-    for (int it = 0; it < 15; it++) {
+    double j11, j12, j21, j22, det;
+    for (int it = 0;; it++) {
         pa_bjt_evaluate(vbe_int, vbc_int, d, ic, ib, jac);
+        j11 = (1.0 + jac[2] * rb) + (jac[0] + jac[2]) * re;
+        j12 = jac[3] * rb + (jac[1] + jac[3]) * re;
+        j21 = jac[2] * rb - jac[0] * rc;
+        j22 = (1.0 + jac[3] * rb) - jac[1] * rc;
+        det = j11 * j22 - j12 * j21;
+        if (it == 15) break;
         const double f1 = ((vbe_int - vbe_ext) + ib * rb) + (ic + ib) * re;
         const double f2 = ((vbc_int - vbc_ext) + ib * rb) - ic * rc;
         if (fabs(f1) < 1e-10 && fabs(f2) < 1e-10) break;
-        const double j11 = (1.0 + jac[2] * rb) + (jac[0] + jac[2]) * re;
-        const double j12 = jac[3] * rb + (jac[1] + jac[3]) * re;
-        const double j21 = jac[2] * rb - jac[0] * rc;
-        const double j22 = (1.0 + jac[3] * rb) - jac[1] * rc;
-        const double det = j11 * j22 - j12 * j21;
         if (fabs(det) < 1e-30) break;
         const double inv_det = 1.0 / det;
         const double dvbe = (j22 * f1 - j12 * f2) * inv_det;
@@ -200,12 +206,6 @@ PA_HD void pa_bjt_with_parasitics(double vbe_ext, double vbc_ext, const double* 
         vbe_int -= pa_clamp(dvbe, -max_step, max_step);
         vbc_int -= pa_clamp(dvbc, -max_step, max_step);
     }
-    pa_bjt_evaluate(vbe_int, vbc_int, d, ic, ib, jac);
-    const double j11 = (1.0 + jac[2] * rb) + (jac[0] + jac[2]) * re;
-    const double j12 = jac[3] * rb + (jac[1] + jac[3]) * re;
-    const double j21 = jac[2] * rb - jac[0] * rc;
-    const double j22 = (1.0 + jac[3] * rb) - jac[1] * rc;
-    const double det = j11 * j22 - j12 * j21;
     if (fabs(det) < 1e-30) return;
     const double inv_det = 1.0 / det;
     const double fi11 = j22 * inv_det, fi12 = (-j12) * inv_det, fi21 = (-j21) * inv_det, fi22 = j11 * inv_det;
@@ -232,16 +232,22 @@ PA_HD void pa_stage_shared(const PaModel& m, PaShared& sh, int tid, int nthreads
 }
 
 // ---- the 16x16 Newton linear solve, row per lane (gen_power_amp.rs:9300-9345 / :10870-10915) -------------------------------------------
-// a[0..15], b: this lane's row and right-hand side.  Returns false when the reference's elimination or back substitution reports a
-// singular system; otherwise xs[0..15] holds the full solution in every lane.
+// sc.a[l][0..15 | 16]: lane l's row and right-hand side, written by the caller.  Returns false when the reference's elimination or back
+// substitution reports a singular system; otherwise sc.x[0..15] holds the solution.  Rolled loops over rows in shared memory (a register
+// copy of the row needs every index static, i.e. the whole elimination unrolled: 50 k instructions, instruction-fetch bound).  A row swap
+// exchanges the two lanes' row indices, not the rows.  The two tiles of a warp run this in lock-step: there is no early exit (a tile that
+// has found its system singular keeps executing the collectives on values nobody reads).
 template <class T>
-PA_HD bool pa_tile_solve16(const T& t, double* a, double b, double* xs, PaScratch& sc) {
+PA_HD bool pa_tile_solve16(const T& t, PaScratch& sc) {
     const int l = t.lane;
-#pragma unroll
+    int myrow = l;  // the storage row that currently holds logical row l
+    bool singular = false;
+    if (l == 0) sc.sing = 0;
+#pragma unroll 1
     for (int col = 0; col < PA_M; col++) {
         // pivot: largest |a[row][col]| over rows >= col, the lowest row on ties (the reference scans upwards with a strict `>`;
         // a NaN in a lower row is never selected, a NaN on the diagonal stays the pivot: it is entered as +inf and recognised below)
-        const double mine = fabs(a[col]);
+        const double mine = fabs(sc.a[myrow][col]);
         double mv = l < col ? -1.0 : (mine == mine ? mine : (l == col ? INFINITY : -1.0));
         int mi = l;
 #pragma unroll
@@ -252,136 +258,138 @@ PA_HD bool pa_tile_solve16(const T& t, double* a, double b, double* xs, PaScratc
         }
         const double diag_abs = t.shfl(mine, col);
         const double max_val = mi == col ? diag_abs : mv;  // the reference's max_val (NaN when the diagonal is NaN and nothing beats it)
-        if (max_val < 1e-15) return false;
-        if (mi != col) {  // swap rows col and mi: the two lanes exchange what is still live of their rows
-            const int src = l == col ? mi : (l == mi ? col : l);
-#pragma unroll
-            for (int j = col; j < PA_M; j++) a[j] = t.shfl(a[j], src);
-            b = t.shfl(b, src);
-        }
-        double* pr = sc.prow[col & 1];
-        if (l == col) {
-#pragma unroll
-            for (int j = col; j < PA_M; j++) pr[j] = a[j];
-            pr[PA_M] = b;
-        }
-        t.sync();
+        singular = singular || max_val < 1e-15;
+        const bool sw = !singular && mi != col;
+        const int other = t.shfl_i(myrow, l == col ? mi : (l == mi ? col : l));
+        if (sw) myrow = other;  // rows col and mi change hands
+        const int prow = t.shfl_i(myrow, col);
+        t.sync();  // every row is up to date (the caller's assembly, the previous column's updates)
         if (l > col) {
-            const double factor = a[col] / pr[col];
-#pragma unroll
-            for (int j = col + 1; j < PA_M; j++) a[j] -= factor * pr[j];
-            b -= factor * pr[PA_M];
+            const double* pr = sc.a[prow];
+            double* ar = sc.a[myrow];
+            const double factor = ar[col] / pr[col];
+#pragma unroll 4
+            for (int j = col + 1; j <= PA_M; j++) ar[j] -= factor * pr[j];
         }
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = PA_M - 1; i >= 0; i--) {
-        double sum = b;
-#pragma unroll
-        for (int j = i + 1; j < PA_M; j++) sum -= a[j] * xs[j];
-        const bool bad = fabs(a[i]) < 1e-15;
-        if (t.shfl_i(bad ? 1 : 0, i)) return false;
-        xs[i] = t.shfl(sum / a[i], i);
+        t.sync();  // x[i + 1 ..] (and, the first time, the last column's updates) are visible
+        if (l == i) {
+            const double* ar = sc.a[myrow];
+            double sum = ar[PA_M];
+#pragma unroll 4
+            for (int j = i + 1; j < PA_M; j++) sum -= ar[j] * sc.x[j];
+            if (fabs(ar[i]) < 1e-15) sc.sing = 1;
+            sc.x[i] = sum / ar[i];
+        }
     }
-    return true;
+    t.sync();
+    return !(singular || sc.sing != 0);
 }
 
-// One Newton loop of process_sample on the tile.  BE = false: the trapezoidal-slot loop (:8930-10560, global step scaling);
-// BE = true: the backward-Euler retry (:10600-12260, per-device damping).  p = this lane's p[l]; i_nl = this lane's iterate (in/out);
-// kmat = K or K_be in the padded shared layout.  Returns the iteration index at which the loop converged, or PA_MAX_ITER.
-template <bool BE, class T>
-PA_HD uint32_t pa_tile_newton(const T& t, const PaShared& sh, const double* kmat, PaScratch& sc, const double p, double& i_nl) {
+// One Newton loop of process_sample on the tile.  be = false: the first loop (:8930-10560, one global step scale); be = true: the
+// backward-Euler retry (:10600-12260, one scale per device).  p = this lane's p[l]; i_nl = this lane's iterate (in/out).  Returns the
+// iteration index at which the loop converged, or PA_MAX_ITER.  One body serves both loops and both tiles of a warp: every collective is
+// executed by every lane in every iteration (a tile that is done, or not concerned, is `active == false` and commits nothing), so the
+// CUDA build uses full-warp shuffles / votes and the kernel holds a single copy of the junction model and the elimination.
+template <class T>
+PA_HD uint32_t pa_tile_newton(const T& t, const PaShared& sh, PaScratch& sc, const bool be, bool active, const double p, double& i_nl) {
     const int l = t.lane;
     const double* dv = sh.dev[l >> 1];
+    const double* kmat = be ? sh.k_be : sh.k;
     const double* krow = kmat + l * PA_KS;
     const double* kA = kmat + (l & ~1) * PA_KS;  // K rows 2d and 2d + 1 of this lane's device
     const double* kB = kA + PA_KS;
     const bool odd = (l & 1) != 0;
+    uint32_t result = PA_MAX_ITER;
+#pragma unroll 1
     for (uint32_t iter = 0; iter < PA_MAX_ITER; iter++) {
-        t.sync();  // the previous iteration's readers of ci are done
+        if (!t.warp_any(active)) break;
+        t.sync();  // the previous iteration's readers of ci / x are done
         sc.ci[l] = i_nl;
         t.sync();
         double v_d = p;
-#pragma unroll
+#pragma unroll 4
         for (int j = 0; j < PA_M; j++) v_d += krow[j] * sc.ci[j];
         const double vbe = t.shfl(v_d, l & ~1), vbc = t.shfl(v_d, l | 1);
         double ic, ib, jac[4];
         pa_bjt_with_parasitics(vbe, vbc, dv, ic, ib, jac);
         const double i_dev = odd ? ib : ic, jA = odd ? jac[2] : jac[0], jB = odd ? jac[3] : jac[1];
         const double f = i_nl - i_dev;
-        double a[PA_M], xs[PA_M];
+        {
+            double* ar = sc.a[l];
+#pragma unroll 4
+            for (int c = 0; c < PA_M; c++) ar[c] = ((c == l ? 1.0 : 0.0) - jA * kA[c]) - jB * kB[c];
+            ar[PA_M] = f;
+        }
+        const bool ok = pa_tile_solve16(t, sc);
+        const double delta = sc.x[l];
+        sc.ci[l] = i_nl - delta;  // i_trial (first loop); the readers of ci above are past the solve's barriers
+        t.sync();
+        // the junction-voltage step this lane limits and tests, and its limiter ratio
+        double dvj, r = INFINITY, alpha = 1.0;
+        bool limited = false;
+        if (!be) {
+            double v_trial = p;
+#pragma unroll 4
+            for (int j = 0; j < PA_M; j++) v_trial += krow[j] * sc.ci[j];
+            dvj = v_trial - v_d;
+            const double v_lim = fabs(dvj) > 1e-4 ? pa_pnjlim(v_trial, v_d, dv[PD_VT], dv[PD_VCRIT]) : v_trial;
+            const double dv_lim = v_lim - v_d;
+            if (fabs(dvj) > 1e-15) r = dvj * dv_lim < 0.0 ? 0.0 : pa_clamp(dv_lim / dvj, 0.0, 1.0);
+            if (!(r == r)) r = INFINITY;  // a NaN ratio never lowers global_alpha (`r < global_alpha` is false)
+        } else {
+            double acc = krow[0] * sc.x[0];  // dv = -(K_be[l][0] delta0 + ... + K_be[l][15] delta15)
+#pragma unroll 4
+            for (int j = 1; j < PA_M; j++) acc += krow[j] * sc.x[j];
+            dvj = -acc;
+            if (fabs(dvj) > 1e-4) {
+                const double v_lim = pa_pnjlim(v_d + dvj, v_d, dv[PD_VT], dv[PD_VCRIT]);
+                const double ratio = fmax((v_lim - v_d) / dvj, 0.01);
+                if (ratio < alpha) { alpha = ratio; limited = ratio < 1.0; }
+            }
+        }
+        double rmin = r;
 #pragma unroll
-        for (int c = 0; c < PA_M; c++) a[c] = ((c == l ? 1.0 : 0.0) - jA * kA[c]) - jB * kB[c];
-        const bool ok = pa_tile_solve16(t, a, f, xs, sc);
-        if (!ok) {  // singular Jacobian: damped fixed-point step on the residual
-            if (BE) i_nl -= pa_clamp(f * 0.5, -0.01, 0.01);
-            else {
+        for (int off = 8; off >= 1; off >>= 1) {
+            const double o = t.shfl_xor(rmin, off);
+            rmin = o < rmin ? o : rmin;
+        }
+        const bool any_lim_be = t.any(limited);
+        const double pair = t.shfl_xor(alpha, 1);
+        bool any_limited;
+        double scale;  // what multiplies this lane's delta
+        if (!be) {
+            any_limited = rmin < 1.0;
+            scale = any_limited ? rmin : 1.0;  // global_alpha
+        } else {
+            any_limited = any_lim_be;
+            scale = fmin(alpha, pair);  // one factor per device: alpha[2d] = alpha[2d + 1] = min of the pair
+        }
+        double mx = fabs(dvj * scale);  // the largest junction step AFTER the limiter's scaling
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) mx = fmax(mx, t.shfl_xor(mx, off));
+        if (mx > 3.5) {
+            scale *= fmax(3.5 / mx, 0.1);
+            if (!be) any_limited = true;
+        }
+        const double step = dvj * scale;
+        const double thr = 1e-3 * fmax(fabs(v_d), fabs(v_d + step)) + 1e-6;
+        const bool not_conv = t.any(fabs(step) > thr);
+        if (active) {
+            if (ok) {
+                i_nl -= scale * delta;
+                if (!any_limited && !not_conv) { result = iter; active = false; }
+            } else if (be) {  // singular Jacobian: damped fixed-point step on the residual
+                i_nl -= pa_clamp(f * 0.5, -0.01, 0.01);
+            } else {
                 const double cl = fmax(fabs(i_nl) * 0.1, 0.01);
                 i_nl -= pa_clamp(f * 0.5, -cl, cl);
             }
-            continue;
-        }
-        double delta = 0.0;
-#pragma unroll
-        for (int j = 0; j < PA_M; j++) if (j == l) delta = xs[j];
-        if (!BE) {
-            const double i_trial = i_nl - delta;
-            t.sync();
-            sc.ci[l] = i_trial;
-            t.sync();
-            double v_trial = p;
-#pragma unroll
-            for (int j = 0; j < PA_M; j++) v_trial += krow[j] * sc.ci[j];
-            const double dv_trial = v_trial - v_d;
-            const double v_lim = fabs(dv_trial) > 1e-4 ? pa_pnjlim(v_trial, v_d, dv[PD_VT], dv[PD_VCRIT]) : v_trial;
-            const double dv_lim = v_lim - v_d;
-            double r = INFINITY;  // no constraint from this junction
-            if (fabs(dv_trial) > 1e-15) r = dv_trial * dv_lim < 0.0 ? 0.0 : pa_clamp(dv_lim / dv_trial, 0.0, 1.0);
-            if (!(r == r)) r = INFINITY;  // a NaN ratio never lowers global_alpha (`r < global_alpha` is false)
-            double rmin = r;
-#pragma unroll
-            for (int off = 8; off >= 1; off >>= 1) {
-                const double o = t.shfl_xor(rmin, off);
-                rmin = o < rmin ? o : rmin;
-            }
-            bool any_limited = rmin < 1.0;
-            double global_alpha = any_limited ? rmin : 1.0;
-            double mx = fabs(dv_trial * global_alpha);  // the largest junction step AFTER the limiter's scaling
-#pragma unroll
-            for (int off = 8; off >= 1; off >>= 1) mx = fmax(mx, t.shfl_xor(mx, off));
-            if (mx > 3.5) { global_alpha *= fmax(3.5 / mx, 0.1); any_limited = true; }
-            i_nl -= global_alpha * delta;
-            if (!any_limited) {
-                const double step = dv_trial * global_alpha;
-                const double thr = 1e-3 * fmax(fabs(v_d), fabs(v_d + step)) + 1e-6;
-                if (!t.any(fabs(step) > thr)) return iter;
-            }
-        } else {
-            double dvv = 0.0;  // dv = -(K_be[l][0] delta0 + ... + K_be[l][15] delta15)
-#pragma unroll
-            for (int j = 0; j < PA_M; j++) dvv = j == 0 ? krow[0] * xs[0] : dvv + krow[j] * xs[j];
-            dvv = -dvv;
-            double alpha = 1.0;
-            bool limited = false;
-            if (fabs(dvv) > 1e-4) {
-                const double v_lim = pa_pnjlim(v_d + dvv, v_d, dv[PD_VT], dv[PD_VCRIT]);
-                const double ratio = fmax((v_lim - v_d) / dvv, 0.01);
-                if (ratio < alpha) { alpha = ratio; limited = ratio < 1.0; }
-            }
-            const bool any_limited = t.any(limited);
-            alpha = fmin(alpha, t.shfl_xor(alpha, 1));  // one factor per device: alpha[2d] = alpha[2d + 1] = min of the pair (even, odd order)
-            double mx = fabs(dvv * alpha);
-#pragma unroll
-            for (int off = 8; off >= 1; off >>= 1) mx = fmax(mx, t.shfl_xor(mx, off));
-            if (mx > 3.5) alpha *= fmax(3.5 / mx, 0.1);
-            i_nl -= alpha * delta;
-            if (!any_limited) {
-                const double step = dvv * alpha;
-                const double thr = 1e-3 * fmax(fabs(v_d), fabs(v_d + step)) + 1e-6;
-                if (!t.any(fabs(step) > thr)) return iter;
-            }
         }
     }
-    return PA_MAX_ITER;
+    return result;
 }
 
 PA_HD double pa_rhs_row(const PaShared& sh, const PaScratch& sc, int i) {
@@ -430,44 +438,64 @@ PA_HD double pa_tile_process_sample(const T& t, const PaModel& m, const PaShared
     sc.w[l] = vp0;
     if (two) sc.w[16 + l] = vp1;
     t.sync();
-    const double p = sh.nv_val[l][0] * sc.w[sh.nv_col[l][0]] + sh.nv_val[l][1] * sc.w[sh.nv_col[l][1]];
+    double p = sh.nv_val[l][0] * sc.w[sh.nv_col[l][0]] + sh.nv_val[l][1] * sc.w[sh.nv_col[l][1]];
     double i_nl = 2.0 * s.ip - s.ipp;
-    uint32_t iters = pa_tile_newton<false>(t, sh, sh.k, sc, p, i_nl);
-    const double* sni = sh.s_ni;
-    if (iters >= PA_MAX_ITER) {
-        // ---- backward-Euler retry (:10565-12275): dense products in the reference's order; cold tables come from global memory ----
-        s.be_fallbacks++;
-        double rb0 = m.rhs_const_be[l], rb1 = two ? m.rhs_const_be[16 + l] : 0.0;
-        for (int j = 0; j < PA_N; j++) rb0 += m.a_neg_be[l][j] * sc.vp[j];
-        for (int j = 0; j < PA_M; j++) rb0 += m.n_i[l][j] * sc.ip[j];
-        if (l == 0) rb0 += in * m.input_conductance;
-        if (two) {
-            for (int j = 0; j < PA_N; j++) rb1 += m.a_neg_be[16 + l][j] * sc.vp[j];
-            for (int j = 0; j < PA_M; j++) rb1 += m.n_i[16 + l][j] * sc.ip[j];
+    uint32_t iters = PA_MAX_ITER;
+    bool be = false, act = true;  // this tile's loop flavour and whether it takes part
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {  // one call site: the kernel holds one copy of the Newton body
+        const uint32_t it = pa_tile_newton(t, sh, sc, be, act, p, i_nl);
+        if (act) iters = it;
+        if (phase == 1) break;
+        const bool need_be = iters >= PA_MAX_ITER;
+        if (!t.warp_any(need_be)) break;
+        // ---- backward-Euler retry (:10565-12275): dense products in the reference's order; cold tables come from global memory.
+        // The warp walks through it together; only a tile that needs it computes and commits ----
+        double rb0 = 0.0, rb1 = 0.0;
+        if (need_be) {
+            s.be_fallbacks++;
+            rb0 = m.rhs_const_be[l];
+            for (int j = 0; j < PA_N; j++) rb0 += m.a_neg_be[l][j] * sc.vp[j];
+            for (int j = 0; j < PA_M; j++) rb0 += m.n_i[l][j] * sc.ip[j];
+            if (l == 0) rb0 += in * m.input_conductance;
+            if (two) {
+                rb1 = m.rhs_const_be[16 + l];
+                for (int j = 0; j < PA_N; j++) rb1 += m.a_neg_be[16 + l][j] * sc.vp[j];
+                for (int j = 0; j < PA_M; j++) rb1 += m.n_i[16 + l][j] * sc.ip[j];
+            }
         }
         t.sync();
-        sc.w[l] = rb0;
-        if (two) sc.w[16 + l] = rb1;
+        if (need_be) {
+            sc.w[l] = rb0;
+            if (two) sc.w[16 + l] = rb1;
+        }
         t.sync();
-        vp0 = 0.0; vp1 = 0.0;
-        for (int j = 0; j < PA_N; j++) vp0 += m.s_be[l][j] * sc.w[j];
-        if (two) for (int j = 0; j < PA_N; j++) vp1 += m.s_be[16 + l][j] * sc.w[j];
+        if (need_be) {
+            vp0 = 0.0; vp1 = 0.0;
+            for (int j = 0; j < PA_N; j++) vp0 += m.s_be[l][j] * sc.w[j];
+            if (two) for (int j = 0; j < PA_N; j++) vp1 += m.s_be[16 + l][j] * sc.w[j];
+        }
         t.sync();
-        sc.w[l] = vp0;
-        if (two) sc.w[16 + l] = vp1;
+        if (need_be) {
+            sc.w[l] = vp0;
+            if (two) sc.w[16 + l] = vp1;
+        }
         t.sync();
-        double p_be = 0.0;
-        for (int j = 0; j < PA_N; j++) p_be += m.n_v[l][j] * sc.w[j];
-        i_nl = 2.0 * s.ip - s.ipp;
-        iters = pa_tile_newton<true>(t, sh, sh.k_be, sc, p_be, i_nl);
-        sni = nullptr;
+        if (need_be) {
+            p = 0.0;
+            for (int j = 0; j < PA_N; j++) p += m.n_v[l][j] * sc.w[j];
+            i_nl = 2.0 * s.ip - s.ipp;
+        }
+        be = need_be; act = need_be;
     }
+    const bool need_be = be;
     s.last_iters = iters;
     t.sync();
     sc.ci[l] = i_nl;
     t.sync();
     double v0 = vp0, v1 = vp1;
-    if (sni) {
+    if (!need_be) {
+        const double* sni = sh.s_ni;
 #pragma unroll
         for (int j = 0; j < PA_M; j++) v0 += sni[l * PA_KS + j] * sc.ci[j];
         if (two) {
@@ -478,7 +506,9 @@ PA_HD double pa_tile_process_sample(const T& t, const PaModel& m, const PaShared
         for (int j = 0; j < PA_M; j++) v0 += m.s_ni_be[l][j] * sc.ci[j];
         if (two) for (int j = 0; j < PA_M; j++) v1 += m.s_ni_be[16 + l][j] * sc.ci[j];
     }
-    if (t.any(!pa_finite(v0) || (two && !pa_finite(v1)))) {  // :12296-12310
+    const bool bad = t.any(!pa_finite(v0) || (two && !pa_finite(v1)));  // :12296-12310
+    const double raw_out = t.shfl(v0, 8);  // OUTPUT_NODES = [8], OUTPUT_SCALES = [1.0]
+    if (bad) {
         s.v0 = m.dc_op[l];
         if (two) s.v1 = m.dc_op[16 + l];
         s.ip = m.dc_nl_i[l]; s.ipp = m.dc_nl_i[l];
@@ -490,7 +520,6 @@ PA_HD double pa_tile_process_sample(const T& t, const PaModel& m, const PaShared
     if (two) s.v1 = v1;
     s.ipp = s.ip;
     s.ip = i_nl;
-    const double raw_out = t.shfl(v0, 8);  // OUTPUT_NODES = [8], OUTPUT_SCALES = [1.0]
     const double dc_blocked = (raw_out - s.dc_x) + m.dc_block_r * s.dc_y;
     s.dc_x = raw_out;
     s.dc_y = dc_blocked;
@@ -505,16 +534,19 @@ PA_HD void pa_lane_load_settled(const PaModel& m, const PaSettled& st, int l, Pa
     s.dc_x = m.rerated ? 0.0 : st.dc_x; s.dc_y = m.rerated ? 0.0 : st.dc_y;
 }
 
-// PowerAmp::process (power_amp.rs:373-436) over a row, 16 samples per block (lane l loads x[t0 + l] and stores y[t0 + l]: coalesced).
-// settle != nullptr: the raw solver on silence from CircuitState::default()'s initial state for n samples, final state -> *settle
-// (compute_settled_state); no adapter.
 struct PaNoPost { PA_HD double operator()(double v) { return v; } };
+// PowerAmp::process (power_amp.rs:373-436) over a row, 16 samples per block (lane l loads x[t0 + l] and stores y[t0 + l]: coalesced).
 // vol: the row is attenuated as (x * vol) * vol before the amplifier (chain B's audio-taper volume, main.rs:489; 1.0 = plain process()).
 // bypass: `--no-poweramp` (the attenuated sample goes straight to `post`).  post: per-sample output stage after the amplifier (chain B: the
 // speaker), run redundantly by every lane on the replicated amplifier output.
+// settle != nullptr: the raw solver on silence from CircuitState::default()'s initial state for n samples, final state -> *settle
+// (compute_settled_state); no adapter.
+// The two tiles of a warp walk through the samples together (n_steps = the longer of their rows; `valid` = false for a tile that only keeps
+// its warp company): one call site of process_sample, every collective executed by every lane.
 template <class T, class Post>
 PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaScratch& sc, const PaSettled* settled, const double* x, double* y,
-                          int64_t n, double vol, bool rail_sag, bool bypass, PaSettled* settle, double* rails_out, uint32_t* counters_out, Post& post) {
+                          int64_t n, int64_t n_steps, bool valid, double vol, bool rail_sag, bool bypass, PaSettled* settle, double* rails_out,
+                          uint32_t* counters_out, Post& post) {
     const int l = t.lane;
     PaLane s;
     s.rail_pos = PA_RAIL_DC_BIAS; s.rail_neg = PA_RAIL_DC_BIAS; s.iavg_pos = 0.0; s.iavg_neg = 0.0; s.last_good = 0.0;
@@ -524,23 +556,21 @@ PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaSc
         s.ip = m.dc_nl_i[l]; s.ipp = m.dc_nl_i[l];
         s.dc_x = m.nan_out; s.dc_y = 0.0;
     } else pa_lane_load_settled(m, *settled, l, s);
-    for (int64_t t0 = 0; t0 < n; t0 += 16) {
-        const int nb = n - t0 < 16 ? (int)(n - t0) : 16;
-        double xin = (!settle && l < nb) ? x[t0 + l] : 0.0, yout = 0.0;
+    const bool adapter = settle == nullptr;
+    for (int64_t t0 = 0; t0 < n_steps; t0 += 16) {
+        const int nb = n_steps - t0 < 16 ? (int)(n_steps - t0) : 16;
+        const bool mine = valid && t0 + l < n;
+        double xin = (adapter && mine) ? x[t0 + l] : 0.0, yout = 0.0;
         for (int k = 0; k < nb; k++) {
-            double out;
-            if (settle) {
-                out = pa_tile_process_sample(t, m, sh, sc, s, 0.0, 0.0, 0.0);
-            } else if (bypass) {
-                out = (t.shfl(xin, k) * vol) * vol;
-            } else {
-                const double input = (t.shfl(xin, k) * vol) * vol;
-                const double off_pos = rail_sag ? s.rail_pos - PA_RAIL_DC_BIAS : 0.0;
-                const double off_neg = rail_sag ? s.rail_neg - PA_RAIL_DC_BIAS : 0.0;
-                const double raw = pa_tile_process_sample(t, m, sh, sc, s, input, off_pos, off_neg);
+            const double input = adapter ? (t.shfl(xin, k) * vol) * vol : 0.0;
+            const double off_pos = (adapter && rail_sag) ? s.rail_pos - PA_RAIL_DC_BIAS : 0.0;
+            const double off_neg = (adapter && rail_sag) ? s.rail_neg - PA_RAIL_DC_BIAS : 0.0;
+            const double raw = pa_tile_process_sample(t, m, sh, sc, s, input, off_pos, off_neg);
+            const bool insane = t.any(!pa_finite(s.v0) || fabs(s.v0) > 100.0 || (l < 4 && (!pa_finite(s.v1) || fabs(s.v1) > 100.0)));
+            double out = raw;
+            if (adapter) {
                 const double result = raw / PA_HEADROOM;
                 const bool nr_failed = s.last_iters >= PA_MAX_ITER - 1;
-                const bool insane = t.any(!pa_finite(s.v0) || fabs(s.v0) > 100.0 || (l < 4 && (!pa_finite(s.v1) || fabs(s.v1) > 100.0)));
                 if (!pa_finite(result) || nr_failed || insane) {  // divergence guard: re-clone the settled state, hold the last good output
                     pa_lane_load_settled(m, *settled, l, s);
                     s.rail_pos = PA_RAIL_DC_BIAS; s.rail_neg = PA_RAIL_DC_BIAS; s.iavg_pos = 0.0; s.iavg_neg = 0.0;
@@ -561,11 +591,12 @@ PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaSc
                         s.rail_neg += an * (target_neg - s.rail_neg);
                     }
                 }
+                if (bypass) out = input;
+                out = post(out);
             }
-            if (!settle) out = post(out);
             if (l == k) yout = out;
         }
-        if (!settle && y && l < nb) y[t0 + l] = yout;
+        if (adapter && y && mine) y[t0 + l] = yout;
     }
     if (settle) {
         settle->v_prev[l] = s.v0;
@@ -573,7 +604,7 @@ PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaSc
         settle->i_nl_prev[l] = s.ip; settle->i_nl_pp[l] = s.ipp;
         if (l == 0) { settle->dc_x = s.dc_x; settle->dc_y = s.dc_y; }
     }
-    if (l == 0) {
+    if (l == 0 && valid) {
         if (rails_out) { rails_out[0] = rail_sag ? s.rail_pos : PA_RAIL_DC_BIAS; rails_out[1] = rail_sag ? s.rail_neg : PA_RAIL_DC_BIAS; }
         if (counters_out) { counters_out[0] = s.resets; counters_out[1] = s.be_fallbacks; counters_out[2] = s.nan_resets; counters_out[3] = s.last_iters; }
     }

@@ -918,8 +918,8 @@ int ensure_pa(int device, cudaStream_t stream, double sample_rate, const PaModel
         PaModel* d_default = nullptr;
         if (int rc = model_for(88200.0, &d_default)) return rc;
         PaSettled* d = nullptr;
-        CK(cudaMalloc(&d, sizeof(PaSettled)));
-        pa_settle_kernel<<<1, 32, 0, stream>>>(d_default, d);
+        CK(cudaMalloc(&d, 2 * sizeof(PaSettled)));  // [1]: the redundant second half-warp's copy
+        pa_settle_kernel<<<1, 32, 0, stream>>>(d_default, d, d + 1);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(stream));
         c.d_pa_settled = d;

@@ -48,6 +48,7 @@ struct EmuTile {
         int r = 0; for (int i = 0; i < L; i++) r |= g_emu->slot_i[i];
         g_emu->barrier(); return r != 0;
     }
+    bool warp_any(bool p) const { return any(p); }  // one tile per emulated warp
 };
 struct Job {
     const PaModel* m; const PaShared* sh; PaScratch* sc; const PaSettled* settled; const double* x; double* y; int64_t n; double pre_gain;
@@ -57,8 +58,8 @@ Job g_job;
 void lane_main(int lane) {
     EmuTile t{lane};
     PaNoPost post;
-    pa_tile_render(t, *g_job.m, *g_job.sh, *g_job.sc, g_job.settled, g_job.x, g_job.y, g_job.n, g_job.pre_gain, g_job.rail_sag, false, g_job.settle,
-                   g_job.rails, g_job.counters, post);
+    pa_tile_render(t, *g_job.m, *g_job.sh, *g_job.sc, g_job.settled, g_job.x, g_job.y, g_job.n, g_job.n, true, g_job.pre_gain, g_job.rail_sag, false,
+                   g_job.settle, g_job.rails, g_job.counters, post);
     g_emu->done[lane] = true;
     // hand over to a lane that is still running, or back to main when this was the last one
     for (int i = 1; i <= L; i++) {
