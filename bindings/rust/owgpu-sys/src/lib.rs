@@ -182,6 +182,8 @@ extern "C" {
     /// `counters` `[n][4]` (resets, backward-Euler retries, NaN resets, last_nr_iterations) may be null.
     pub fn owg_power_amp_batch(input: *const f64, in_stride: i64, n_inst: i64, n_samp: i64, sample_rate: f64, rail_sag: i32, out: *mut f64,
                                out_stride: i64, rails: *mut f64, counters: *mut u32, opts: *const owg_opts) -> i32;
+    /// frees the grow-only device staging buffers no call is using (device = -1: every device); returns the bytes released
+    pub fn owg_release_caches(device: i32) -> i64;
     pub fn owg_chain_batch(input: *const f64, in_stride: i64, n_inst: i64, n_samp: i64, params: *const owg_bench_job, init_order: i32,
                            out: *mut f64, out_stride: i64, opts: *const owg_opts) -> i32;
     pub fn owg_render_engines(jobs: *const owg_engine_job, n: i64, out: *mut f32, stride: i64, opts: *const owg_opts) -> i32;

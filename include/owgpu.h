@@ -258,6 +258,13 @@ void owg_plan_destroy(owg_plan* plan);
 
 int owg_last_diag(owg_diag* out);
 
+/* The library keeps, per device and for the life of the process, the settled solver states (the reference's OnceLock caches:
+ * melange_adapter.rs:12, power_amp.rs:289) and a grow-only device staging buffer for host-output renders (as large as the largest
+ * one-shot render so far: 8.6 GB for the C3 grid).  This call frees the staging buffers that no call is using (device = -1: on every
+ * device) and returns the bytes released, so a co-resident framework gets the memory back; the next host-output render re-allocates.
+ * The current CUDA device of the calling thread is left as it was. */
+int64_t owg_release_caches(int32_t device);
+
 /* ---- host-logic probes (no device needed) -------------------------------------------------- */
 /* Flattened per-voice init record the kernels start from (what Voice::note_on leaves behind,
  * voice.rs:28-142 / reed.rs:108-182): out[0..41] = 7x{cos_inc, sin_inc, phase_inc, amplitude,

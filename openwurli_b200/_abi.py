@@ -68,7 +68,7 @@ class Diag(C.Structure):
 EXPORTS = ["owg_abi_version", "owg_device_count", "owg_last_error", "owg_default_opts", "owg_render_voices",
            "owg_render_bench", "owg_render_engines", "owg_preamp_batch", "owg_plan_bench", "owg_plan_voices",
            "owg_plan_execute", "owg_plan_samples", "owg_plan_h2d_bytes", "owg_plan_kernel_launches", "owg_plan_last_timing",
-           "owg_plan_destroy", "owg_last_diag", "owg_fp64_peak", "owg_host_voice_init", "owg_host_chain_init", "owg_host_legacy_group", "owg_render_calibrate", "owg_default_calib_cfg", "owg_chain_batch", "owg_render_midi", "owg_selftest_division", "owg_render_bench_metrics", "owg_debug_counters", "owg_alias_analyze", "owg_render_engines_alias", "owg_power_amp_batch"]
+           "owg_plan_destroy", "owg_last_diag", "owg_fp64_peak", "owg_host_voice_init", "owg_host_chain_init", "owg_host_legacy_group", "owg_render_calibrate", "owg_default_calib_cfg", "owg_chain_batch", "owg_render_midi", "owg_selftest_division", "owg_render_bench_metrics", "owg_debug_counters", "owg_alias_analyze", "owg_render_engines_alias", "owg_power_amp_batch", "owg_release_caches"]
 
 _lib = None
 
@@ -114,6 +114,8 @@ def lib():
         L.owg_host_voice_init.argtypes = [C.POINTER(VoiceJob), dp]
         L.owg_host_chain_init.argtypes = [C.POINTER(BenchJob), dp]
         L.owg_host_legacy_group.argtypes = [C.c_double, C.c_double, dp]
+        L.owg_release_caches.argtypes = [C.c_int32]
+        L.owg_release_caches.restype = C.c_int64
         L.owg_power_amp_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_void_p, C.c_int64,
                                           C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(Opts)]
         L.owg_chain_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(BenchJob), C.c_int32, C.c_void_p, C.c_int64,

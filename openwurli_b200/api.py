@@ -66,6 +66,12 @@ def _opts(device=-1, out_location=OWG_OUT_HOST, stream=None, collect_diag=False,
     return o
 
 
+def release_caches(device=-1):
+    """Free the library's grow-only device staging buffers (host-output renders keep one as large as the largest render so far);
+    returns the bytes released."""
+    return int(lib().owg_release_caches(int(device)))
+
+
 def device_count():
     return lib().owg_device_count()
 
@@ -172,9 +178,22 @@ class Plan:
 
 
 def _alloc_out(n, stride, out):
+    """The caller's buffer (checked: at least n rows of at least `stride` samples; the C side can only check the stride) or a fresh one."""
     if out is not None:
+        if tuple(out.shape)[0] < n or (n > 0 and tuple(out.shape)[1] < stride):
+            raise ValueError(f"out has shape {tuple(out.shape)}, need at least ({n}, {stride})")
         return out
     return np.zeros((n, stride), dtype=np.float64)
+
+
+def _device_for(out, device):
+    """A CUDA tensor is rendered on ITS device: opts.device = -1 would mean the current device, which need not be the tensor's."""
+    if not isinstance(out, np.ndarray) and getattr(out, "is_cuda", False):
+        idx = out.device.index
+        if device not in (-1, idx):
+            raise ValueError(f"out lives on cuda:{idx} but device={device} was requested")
+        return idx
+    return device
 
 
 def render_voices(jobs, out=None, device=-1, collect_diag=False, devices=None):
@@ -186,7 +205,7 @@ def render_voices(jobs, out=None, device=-1, collect_diag=False, devices=None):
         return out
     ptr, st, loc = _out_ptr(out)
     arr = (VoiceJob * len(jobs))(*jobs)
-    o = _opts(device, loc, None, collect_diag, devices=devices)
+    o = _opts(_device_for(out, device), loc, None, collect_diag, devices=devices)
     check(lib().owg_render_voices(arr, len(jobs), ptr, st, C.byref(o)))
     return out
 
@@ -203,7 +222,7 @@ def render_bench(jobs, out=None, device=-1, collect_diag=False, preamp_model=MEL
         return out
     ptr, st, loc = _out_ptr(out)
     arr = (BenchJob * len(jobs))(*jobs)
-    o = _opts(device, loc, None, collect_diag, preamp_model, devices=devices, power_amp_model=power_amp_model)
+    o = _opts(_device_for(out, device), loc, None, collect_diag, preamp_model, devices=devices, power_amp_model=power_amp_model)
     check(lib().owg_render_bench(arr, len(jobs), ptr, st, C.byref(o)))
     return out
 
@@ -218,7 +237,9 @@ def preamp_batch(x, fs_base, oversample=True, tremolo_depth=0.0, r_ldr=1_000_000
     pin, sin, lin = _out_ptr(x)
     pout, sout, lout = _out_ptr(out)
     assert lin == lout, "input and output must both be host or both be device buffers"
-    o = _opts(device, lout, preamp_model=preamp_model, collect_diag=collect_diag)
+    if tuple(out.shape) != tuple(x.shape):
+        raise ValueError(f"out has shape {tuple(out.shape)}, x has {tuple(x.shape)}")
+    o = _opts(_device_for(out, device), lout, preamp_model=preamp_model, collect_diag=collect_diag)
     check(lib().owg_preamp_batch(pin, sin, x.shape[0], x.shape[1], float(fs_base), 1 if oversample else 0,
                                  float(tremolo_depth), float(r_ldr), pout, sout, C.byref(o)))
     return out
@@ -233,8 +254,9 @@ def power_amp_batch(x, sample_rate=44100.0, rail_sag=True, out=None, device=-1, 
     pin, sin, lin = _out_ptr(x)
     pout, sout, lout = _out_ptr(out)
     assert lin == lout, "input and output must both be host or both be device buffers"
-    assert tuple(out.shape) == tuple(x.shape)
-    o = _opts(device, lout)
+    if tuple(out.shape) != tuple(x.shape):
+        raise ValueError(f"out has shape {tuple(out.shape)}, x has {tuple(x.shape)}")
+    o = _opts(_device_for(out, device), lout)
     rails = np.zeros((x.shape[0], 2), dtype=np.float64)
     counters = np.zeros((x.shape[0], 4), dtype=np.uint32)
     check(lib().owg_power_amp_batch(pin, sin, x.shape[0], x.shape[1], float(sample_rate), 1 if rail_sag else 0, pout, sout,
@@ -255,8 +277,10 @@ def chain_batch(x, params, init_order=RESET_THEN_SET, out=None, device=-1, pream
     pin, sin, lin = _out_ptr(x)
     pout, sout, lout = _out_ptr(out)
     assert lin == lout and len(params) == x.shape[0]
+    if tuple(out.shape) != tuple(x.shape):
+        raise ValueError(f"out has shape {tuple(out.shape)}, x has {tuple(x.shape)}")
     arr = (BenchJob * len(params))(*params)
-    o = _opts(device, lout, preamp_model=preamp_model, power_amp_model=power_amp_model)
+    o = _opts(_device_for(out, device), lout, preamp_model=preamp_model, power_amp_model=power_amp_model)
     check(lib().owg_chain_batch(pin, sin, x.shape[0], x.shape[1], arr, int(init_order), pout, sout, C.byref(o)))
     return out
 

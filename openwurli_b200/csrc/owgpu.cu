@@ -999,6 +999,23 @@ int render_bench_melange_pa(const owg_bench_job* jobs, int64_t n, double* out, i
 }
 }  // namespace
 
+int64_t owg_release_caches(int32_t device) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    int64_t freed = 0;
+    int prev = -1;
+    const bool have_prev = cudaGetDevice(&prev) == cudaSuccess;
+    for (auto& kv : g_cache) {
+        if (device >= 0 && kv.first != device) continue;
+        DeviceCache& c = kv.second;
+        if (c.stage && !c.stage_in_use && cudaSetDevice(kv.first) == cudaSuccess) {
+            if (cudaFree(c.stage) == cudaSuccess) freed += (int64_t)c.stage_bytes; else cudaGetLastError();
+            c.stage = nullptr; c.stage_bytes = 0;
+        }
+    }
+    if (have_prev) cudaSetDevice(prev);
+    return freed;
+}
+
 int owg_power_amp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double sample_rate, int32_t rail_sag, double* out,
                         int64_t out_stride, double* rails, uint32_t* counters, const owg_opts* opts) {
     if (n_inst < 0 || n_samp < 0 || !(sample_rate > 0.0) || !std::isfinite(sample_rate)) return fail(OWG_E_BAD_ARG, "owg_power_amp_batch: bad argument");

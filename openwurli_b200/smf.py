@@ -48,45 +48,63 @@ def parse_tracks(data):
         if tag != b"MTrk":
             continue  # alien chunk: skipped
         ev, p, status = [], 0, None
-        while p < len(body):
-            delta, p = _vlq(body, p)
-            b0 = body[p]
-            if b0 == 0xFF:  # meta
-                mtype = body[p + 1]
-                mlen, q = _vlq(body, p + 2)
-                payload = body[q:q + mlen]
-                p = q + mlen
-                if mtype == 0x51 and mlen == 3:
-                    ev.append((delta, "tempo", int.from_bytes(payload, "big"), 0))
+        # midly 0.5 without its `strict` feature (the reference's Cargo.toml enables none): a malformed event -- truncated data, a
+        # data byte with no running status, a system common / realtime status (F1-F6, F8-FE), which an SMF cannot contain -- silently
+        # ends the track, keeping what was read; meta and sysex events cancel running status
+        try:
+            while p < len(body):
+                delta, p = _vlq(body, p)
+                if p >= len(body):
+                    break
+                b0 = body[p]
+                if b0 == 0xFF:  # meta
+                    if p + 1 >= len(body):
+                        break
+                    mtype = body[p + 1]
+                    mlen, q = _vlq(body, p + 2)
+                    if q + mlen > len(body):
+                        break
+                    payload = body[q:q + mlen]
+                    p = q + mlen
+                    status = None
+                    if mtype == 0x51 and mlen == 3:
+                        ev.append((delta, "tempo", int.from_bytes(payload, "big"), 0))
+                    else:
+                        ev.append((delta, None, 0, 0))
+                    if mtype == 0x2F:
+                        break
+                    continue
+                if b0 in (0xF0, 0xF7):  # sysex / escape
+                    slen, q = _vlq(body, p + 1)
+                    if q + slen > len(body):
+                        break
+                    p = q + slen
+                    status = None
+                    ev.append((delta, None, 0, 0))
+                    continue
+                if b0 >= 0xF1:  # F1-F6, F8-FE: not allowed in a Standard MIDI File
+                    break
+                if b0 & 0x80:
+                    status = b0
+                    p += 1
+                elif status is None:
+                    break
+                hi = status & 0xF0
+                n_data = 1 if hi in (0xC0, 0xD0) else 2
+                d = body[p:p + n_data]
+                if len(d) < n_data:
+                    break
+                p += n_data
+                if hi == 0x90:
+                    ev.append((delta, "on", d[0] & 0x7F, d[1] & 0x7F))
+                elif hi == 0x80:
+                    ev.append((delta, "off", d[0] & 0x7F, d[1] & 0x7F))
+                elif hi == 0xB0:
+                    ev.append((delta, "cc", d[0] & 0x7F, d[1] & 0x7F))
                 else:
                     ev.append((delta, None, 0, 0))
-                if mtype == 0x2F:
-                    break
-                continue
-            if b0 in (0xF0, 0xF7):  # sysex / escape
-                slen, q = _vlq(body, p + 1)
-                p = q + slen
-                ev.append((delta, None, 0, 0))
-                continue
-            if b0 & 0x80:
-                status = b0
-                p += 1
-            elif status is None:
-                raise SmfError("running status without a status byte")
-            hi = status & 0xF0
-            n_data = 1 if hi in (0xC0, 0xD0) else 2
-            d = body[p:p + n_data]
-            if len(d) < n_data:
-                raise SmfError("truncated channel message")
-            p += n_data
-            if hi == 0x90:
-                ev.append((delta, "on", d[0] & 0x7F, d[1] & 0x7F))
-            elif hi == 0x80:
-                ev.append((delta, "off", d[0] & 0x7F, d[1] & 0x7F))
-            elif hi == 0xB0:
-                ev.append((delta, "cc", d[0] & 0x7F, d[1] & 0x7F))
-            else:
-                ev.append((delta, None, 0, 0))
+        except SmfError:
+            pass  # a truncated variable-length quantity: the same lenient end of track
         tracks.append(ev)
     return float(division), tracks
 

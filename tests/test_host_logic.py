@@ -224,3 +224,24 @@ def test_constant_tables_of_product_and_oracle_are_the_same_extraction():
     a = open(os.path.join(ROOT, "openwurli_b200", "csrc", "ow_consts.inc"), "rb").read()
     b = open(os.path.join(ROOT, "oracle", "ow_consts.inc"), "rb").read()
     assert a == b
+
+
+def test_caller_buffers_are_checked_before_the_c_call():
+    """api.py: an undersized `out` (rows or columns) is refused in Python -- the C side sees only the stride -- and the two ow_consts.inc
+    copies (product / oracle, written from one extraction) are byte-identical."""
+    import openwurli_b200 as ow
+    jobs = [ow.bench_job(duration=0.01), ow.bench_job(duration=0.02)]
+    with pytest.raises(ValueError):
+        ow.render_bench(jobs, out=np.zeros((1, 882)))
+    with pytest.raises(ValueError):
+        ow.render_bench(jobs, out=np.zeros((2, 441)))
+    with pytest.raises(ValueError):
+        ow.render_voices([j.v for j in jobs], out=np.zeros((2, 100)))
+    with pytest.raises(ValueError):
+        ow.preamp_batch(np.zeros((2, 64)), 44100.0, out=np.zeros((2, 32)))
+    with pytest.raises(ValueError):
+        ow.power_amp_batch(np.zeros((2, 64)), out=np.zeros((1, 64)))
+    assert ow.release_caches() == 0      # nothing cached without a device
+    a = open(os.path.join(ROOT, "openwurli_b200", "csrc", "ow_consts.inc"), "rb").read()
+    b = open(os.path.join(ROOT, "oracle", "ow_consts.inc"), "rb").read()
+    assert a == b

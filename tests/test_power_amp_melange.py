@@ -208,3 +208,18 @@ def test_gpu_chain_batch_routes_caller_rows_through_the_melange_power_amp():
         assert L.owo_output_stage_melange(O.dptr(np.ascontiguousarray(x[i])), n, sr, vols[i], chars[i], 0, 1, O.dptr(ref)) == 0
         err, rel = _close(g[i], ref)
         assert err <= 1e-6 and rel <= 1e-7, (i, err, rel)
+
+
+@pytest.mark.gpu
+def test_gpu_release_caches_returns_the_staging_buffer_and_keeps_the_current_device():
+    """owg_release_caches: after a host-output render the per-device staging buffer is released (bytes > 0), the calling thread's CUDA
+    device is untouched, and the next render re-allocates and gives the same samples."""
+    import torch
+    import openwurli_b200 as ow
+    jobs = [ow.bench_job(note=60, velocity=90, duration=0.05), ow.bench_job(note=64, velocity=60, duration=0.05)]
+    a = ow.render_bench(jobs)
+    before = torch.cuda.current_device()
+    freed = ow.release_caches()
+    assert freed >= a.nbytes and torch.cuda.current_device() == before
+    assert ow.release_caches() == 0
+    assert np.array_equal(ow.render_bench(jobs), a)

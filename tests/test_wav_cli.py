@@ -144,6 +144,30 @@ def test_smf_parser_time_map_running_status_and_filters():
         smf.timed_events(b"RIFFxxxx")
 
 
+def test_smf_parser_edge_cases_follow_midly_non_strict():
+    """midly 0.5 as the reference builds it (no `strict` feature): meta and sysex events cancel running status, a system common / realtime
+    status byte or a truncated event ends the track and keeps what was read, no exception escapes."""
+    from openwurli_b200 import smf
+    eot = b"\x00\xFF\x2F\x00"
+    on = _vlq(0) + b"\x90\x3C\x64"
+    # a data byte after a meta event has no running status any more: the track ends there, the note before it is kept
+    t = on + _vlq(10) + b"\xFF\x01\x01\x41" + _vlq(0) + b"\x3E\x50" + _vlq(0) + b"\x90\x40\x64" + eot
+    assert [(k, n) for _, k, n, _ in smf.timed_events(_smf([t]))] == [("on", 60)]
+    # the same after a sysex
+    t = on + _vlq(0) + b"\xF0\x02\x01\xF7" + _vlq(0) + b"\x3E\x50" + eot
+    assert [(k, n) for _, k, n, _ in smf.timed_events(_smf([t]))] == [("on", 60)]
+    # F8 (timing clock) / F2 (song position) cannot occur in an SMF: end of track, not a channel message with two data bytes
+    for bad in (b"\xF8", b"\xF2\x01\x02"):
+        t = on + _vlq(0) + bad + _vlq(0) + b"\x90\x40\x64" + eot
+        assert [(k, n) for _, k, n, _ in smf.timed_events(_smf([t]))] == [("on", 60)]
+    # truncated in the middle of a channel message, of a delta and of a meta payload
+    for cut in (on + _vlq(0) + b"\x90\x40", on + b"\x81", on + _vlq(0) + b"\xFF\x51\x03\x07"):
+        assert [(k, n) for _, k, n, _ in smf.timed_events(_smf([cut]))] == [("on", 60)]
+    # a second, healthy track is unaffected by a broken first one
+    ev = smf.timed_events(_smf([on + _vlq(0) + b"\xF8", _vlq(480) + b"\x91\x30\x7F" + eot]))
+    assert [(k, n) for _, k, n, _ in ev] == [("on", 60), ("on", 48)]
+
+
 @pytest.mark.gpu
 def test_render_midi_cli_matches_oracle(tmp_path):
     """SMF file -> events -> render-midi voice manager + chain -> 24-bit WAV, against the oracle's restatement of cmd_render_midi."""
