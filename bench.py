@@ -463,6 +463,21 @@ def main():
                         vc, dtc = run_cpu(O, args.duration, args.tremolo_depth, max(2 * threads, 8), threads, 1)
                         entry["cpu_baseline"] = {"value": vc, "unit": UNIT, "cores": threads, "kind": "port"}
                     line["variants"][f"reference default build: {workload_name(args.duration, args.tremolo_depth, 'legacy8')}"] = entry
+        if not args.no_variants and world == 1 and model == 0:
+            # chain B with the melange 7-BJT power amplifier (`--no-default-features`): every 4th grid job x 0.5 s, a bounded
+            # slice (the amplifier costs far more per sample than the rest of the chain: pa_melange_kernel)
+            pj = grid_jobs(ow, 0.5, args.tremolo_depth)[::4]
+            outp = torch.empty((len(pj), int(0.5 * 44100.0)), dtype=torch.float64, device="cuda")
+            ow.render_bench(pj[:16], out=outp[:16], power_amp_model=ow.PA_MELANGE)   # settled amplifier state, module load
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ow.render_bench(pj, out=outp, power_amp_model=ow.PA_MELANGE)
+            torch.cuda.synchronize()
+            dtp = time.perf_counter() - t0
+            line.setdefault("variants", {})[f"melange power amplifier: {len(pj)} grid renders x 0.5 s, chain B with power_amp_model = melange (rail sag on)"] = {
+                "value": len(pj) * 0.5 / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "finite": bool(torch.isfinite(outp).all().item()),
+                "timing": "host clock around one call with device-resident output (includes the plan's H2D of the job records)"}
+            del outp
         if not args.no_cpu_baseline:
             import oracle_lib as O
             threads = O.lib().owo_hardware_threads() or os.cpu_count() or 1
