@@ -327,6 +327,10 @@ __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restric
     }
     const unsigned long long t_lo = (unsigned long long)(t_begin > 0 ? t_begin : 0);
     const unsigned long long t_hi = (t_end >= 0 && (unsigned long long)t_end < ns) ? (unsigned long long)t_end : ns;
+    // aligned pairs of output samples leave as one 16-byte store (st.global.v2.f64): the first sample of a pair is held for one iteration
+    const unsigned long long odd0 = ((unsigned long long)(uintptr_t)o >> 3) & 1ull;
+    double y_hold = 0.0;
+    bool held = false;
     for (unsigned long long t = t_lo; t < t_hi; t++) {
         // reed.rs:249-264 onset ramp
         double onset = 1.0;
@@ -394,7 +398,13 @@ __global__ void __launch_bounds__(32) voice_kernel(const OwgVoiceInit* __restric
         q = (q * (1.0 - alpha) + 2.0 * beta) / (1.0 + alpha);
         const double t2 = (q * omy - 1.0) * 1.8375;
         const double t3 = t2 * gain;
-        o[t] = t3;
+        if (held) {
+            *reinterpret_cast<double2*>(o + t - 1) = make_double2(y_hold, t3);
+            held = false;
+        } else if (((t + odd0) & 1ull) == 0ull && t + 1 < t_hi) {
+            y_hold = t3;
+            held = true;
+        } else o[t] = t3;
         if (TAPS && (int64_t)t >= w_begin && (int64_t)t < w_end) {
             const double ii = (double)((int64_t)t - w_begin);
             t1_peak = fmax(t1_peak, fabs(reed_x));

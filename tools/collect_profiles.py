@@ -47,4 +47,7 @@ if os.path.exists(f"{P}/{name}_chain_tile_kernel_sustain.json"):
     json.dump(d, open(f"{P}/chain_kernel_traffic.json", "w"), indent=1)  # bench.py reads roofline.traffic from here
 if os.path.exists(f"{G}/{tag}_racecheck_chain_tile.log"):
     shutil.copy(f"{G}/{tag}_racecheck_chain_tile.log", f"{P}/{name}_sanitizer_racecheck_chain_tile.log")
+for src, dst in (("racecheck_chain_split.log", "sanitizer_racecheck_chain_split.log"), ("pa_time.json", "pa_time.json")):
+    if os.path.exists(f"{G}/{tag}_{src}"):
+        shutil.copy(f"{G}/{tag}_{src}", f"{P}/{name}_{dst}")
 print("collected", sorted(x for x in os.listdir(P) if x.startswith(name)))

@@ -11,6 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
 ncu --set full --import-source on --clock-control none -k regex:chain_tile --launch-skip 0 -c 1 -o $O/${TAG}_tile_attack -f python tools/prof_run.py 0.5 1 0.5 > $O/${TAG}_ncu.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:chain_tile --launch-skip 2 -c 1 -o $O/${TAG}_tile_sustain -f python tools/prof_run.py 0.5 1 0.5 >> $O/${TAG}_ncu.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:tremolo_group_tile --launch-skip 2 -c 1 -o $O/${TAG}_osc -f python tools/trem_time.py >> $O/${TAG}_ncu.log 2>&1
+timeout 300 python tools/pa_time.py 8128 0.5 > $O/${TAG}_pa_time.json 2> $O/${TAG}_pa_time.err
 timeout 900 python tools/bench_configs.py > $O/${TAG}_bench_configs.json 2> $O/${TAG}_bench_configs.err
 timeout 600 compute-sanitizer --tool racecheck --kernel-name kns=chain_tile --log-file $O/${TAG}_racecheck_chain_tile.log python tools/racecheck_run.py > $O/${TAG}_racecheck_chain_tile.out 2>&1
 tail -3 $O/${TAG}_pytest.log
