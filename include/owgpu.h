@@ -146,7 +146,8 @@ void owg_default_opts(owg_opts* o);  /* device=-1, host output, f64 exact, melan
 
 /* Batch of Voice::render_note_with_scale (voice.rs:201-221) / Voice::note_on + render (chain V:
  * reed + attack noise + pickup + post-pickup gain).  out is [n][stride] f64; job i writes
- * (uint64)(duration_s*sample_rate) samples at out + i*stride. */
+ * (uint64)(duration_s*sample_rate) samples at out + i*stride; in a ragged batch the shorter rows are zero-filled up to the
+ * longest render of the call (columns beyond that are not touched).  The same holds for owg_render_bench. */
 int owg_render_voices(const owg_voice_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts);
 
 /* Batch of `preamp-bench render` (main.rs:371-496), chain B: voice -> [2x oversampler] ->

@@ -905,6 +905,15 @@ __global__ void __launch_bounds__(128) post_stage_metrics_kernel(const double* _
     mj[0] = m_peak; mj[1] = m_sq; mj[2] = m_re1; mj[3] = m_im1; mj[4] = m_re2; mj[5] = m_im2;
 }
 
+// ---- ragged batches: samples [n_samples[i], max_samples) of row i are silence (the render kernels write only the live part) ----
+__global__ void __launch_bounds__(128) zero_tails_kernel(double* __restrict__ out, int64_t stride, const unsigned long long* __restrict__ n_samples,
+                                                         int64_t n_rows, int64_t max_samples) {
+    const int64_t i = blockIdx.x;
+    if (i >= n_rows) return;
+    double* o = out + (size_t)i * stride;
+    for (int64_t t = (int64_t)n_samples[i] + threadIdx.x; t < max_samples; t += blockDim.x) o[t] = 0.0;
+}
+
 // ---- FP64 pipe micro-benchmark ------------------------------------------------------------------------
 template <bool FMA>
 __global__ void fp64_peak_kernel(double* sink, int iters, double a, double b) {

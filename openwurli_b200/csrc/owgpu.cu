@@ -584,6 +584,17 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
     } stage_return{pl->cache, borrowed_stage};
     int64_t launches = 0;
     CK(cudaEventRecord(pl->ev0, s));
+    auto zero_tails = [&]() -> int {  // ragged batch: rows shorter than the longest end in silence (defined output, whatever the staging buffer held)
+        bool ragged = false;
+        for (unsigned long long v : pl->n_samples) if (v != pl->max_samples) { ragged = true; break; }
+        if (ragged && pl->d_nsamp.p) {
+            zero_tails_kernel<<<(unsigned)pl->n, 128, 0, s>>>(dout, stride, pl->d_nsamp.p, pl->n, (int64_t)pl->max_samples);
+            CK(cudaGetLastError());
+            launches += 1;
+        }
+        return OWG_OK;
+    };
+    if (pl->kind != 2) { if (int rc = zero_tails()) return rc; }
     if (pl->collect_diag) CK(cudaMemsetAsync(pl->d_diag.p, 0, sizeof(DevDiag), s));
     // Tremolo groups: the Twin-T oscillator is one serial thread per group, so it is pipelined: it runs on its own stream in
     // chunks, and chunk c's LDR law + matrices + chain run on the main stream while the oscillator already produces chunk c+1.
@@ -624,6 +635,7 @@ int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_loca
         CK(cudaMemcpy2DAsync(dout, (size_t)stride * sizeof(double), pl->in_ptr, (size_t)pl->in_stride * sizeof(double),
                              (size_t)pl->max_samples * sizeof(double), (size_t)pl->n,
                              (pl->in_location < 0 ? out_location : pl->in_location) == OWG_OUT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+        if (int rc = zero_tails()) return rc;  // behind the input copy: what the caller's rows held beyond their length is not output
     } else {  // chain V for every job
         const int threads = 32;
         const int blocks = (int)((pl->n + threads - 1) / threads);
@@ -868,6 +880,17 @@ int fan_out_devices(const Job* jobs, int64_t n, double* out, int64_t stride, con
     }
     for (auto& t : th) t.join();
     for (int k = 0; k < nd; k++) if (rcs[k] != OWG_OK) return fail(rcs[k], "device " + std::to_string(devs[k]) + ": " + errs[k]);
+    {   // every GPU has written its rows up to ITS longest render; the call's contract is silence up to the longest render of the CALL
+        double gmax = 0.0;
+        for (int64_t i = 0; i < n; i++) gmax = std::max(gmax, std::floor((double)n_samples_of(jobs[i])));
+        for (int k = 0; k < nd; k++) {
+            double kmax = 0.0;
+            for (int64_t i = bounds[k]; i < bounds[k + 1]; i++) kmax = std::max(kmax, std::floor((double)n_samples_of(jobs[i])));
+            if (kmax < gmax)
+                for (int64_t i = bounds[k]; i < bounds[k + 1]; i++)
+                    std::memset(out + (size_t)i * (size_t)stride + (size_t)kmax, 0, (size_t)(gmax - kmax) * sizeof(double));
+        }
+    }
     if (o.collect_diag) {  // counters of a fanned-out call = sums over the GPUs
         owg_diag& d = g_last_diag;
         std::memset(&d, 0, sizeof(d));

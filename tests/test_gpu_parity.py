@@ -866,8 +866,12 @@ def test_in_call_multi_gpu_fan_out_is_bit_identical():
     devs = [0, 1] if n_dev >= 2 else [0, 1]  # bit 1 is ignored when the device does not exist
     jobs = [ow.bench_job(note=m, velocity=v, duration=d, tremolo_depth=t) for m, v, d, t in
             [(60, 100, 0.20, 0.5), (40, 127, 0.05, 0.5), (72, 80, 0.25, 0.5), (55, 60, 0.10, 0.5), (84, 64, 0.15, 0.0), (33, 127, 0.20, 0.0), (96, 1, 0.12, 0.0)]]
-    single = ow.render_bench(jobs)
-    multi = ow.render_bench(jobs, devices=devs, collect_diag=True)
+    single = ow.render_bench(jobs, out=np.full((len(jobs), int(0.25 * 44100.0)), 7.0))
+    # a ragged batch ends every shorter row in silence, whatever the caller's buffer or the library's staging buffer held before
+    for i, j in enumerate(jobs):
+        n_i = int(j.v.duration_s * j.v.sample_rate)
+        assert np.all(single[i, n_i:] == 0.0) and np.any(single[i, :n_i] != 0.0)
+    multi = ow.render_bench(jobs, devices=devs, collect_diag=True, out=np.full(single.shape, -3.0))
     assert np.array_equal(single, multi)
     d = ow.last_diag()
     assert sum(d.nr_iter_hist) > 0 and d.kernels_launched > 0
