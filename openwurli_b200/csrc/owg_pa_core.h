@@ -42,7 +42,18 @@
 enum { PA_IS, PA_VT, PA_BF, PA_BR, PA_NF, PA_NR, PA_ISE, PA_NE, PA_ISC, PA_NC, PA_SIGN, PA_VAF, PA_VAR, PA_IKF, PA_IKR, PA_VCRIT, PA_RB, PA_RC, PA_RE, PA_DEVF };
 // ... and the constant sub-expressions of bjt_evaluate, formed once on the host with the same IEEE operations the reference performs per call
 enum { PD_IS, PD_SIGN, PD_NF_VT, PD_NR_VT, PD_NE_VT, PD_NC_VT, PD_ISE, PD_ISC, PD_IS_BF, PD_IS_BR, PD_G_FWD, PD_G_REV, PD_G_LBE, PD_G_LBC,
-       PD_VAF, PD_VAR, PD_IKF, PD_IKR, PD_Q2F, PD_Q2R, PD_GCC_F, PD_GCC_R, PD_RB, PD_RC, PD_RE, PD_MAX_STEP, PD_VT, PD_VCRIT, PD_N };
+       PD_VAF, PD_VAR, PD_IKF, PD_IKR, PD_Q2F, PD_Q2R, PD_GCC_F, PD_GCC_R, PD_RB, PD_RC, PD_RE, PD_MAX_STEP, PD_VT, PD_VCRIT,
+       // device only: reciprocals of the eight model-constant divisors of bjt_evaluate, produced on the GPU by the first half of its own
+       // IEEE division sequence (owg_device.cuh recip_prepare) when the model is staged; see PA_DIV_CONST
+       PD_R_NF_VT, PD_R_NR_VT, PD_R_NE_VT, PD_R_NC_VT, PD_R_VAR, PD_R_VAF, PD_R_IKF, PD_R_IKR, PD_N };
+
+// a / d[IB] for a model-constant divisor.  Host: the plain IEEE division.  Device (owg_poweramp.cuh): the second half of the compiler's own
+// division sequence on the staged reciprocal d[IR] -- the same instructions `a / b` expands to, so the same bits, at a third of the cost.
+#if !defined(__CUDA_ARCH__)
+#define PA_DIV_CONST(a, d, IB, IR) ((a) / (d)[IB])
+#elif !defined(PA_DIV_CONST)
+#error "owg_poweramp.cuh defines PA_DIV_CONST for the device pass"
+#endif
 
 struct PaModel {  // one per sample rate; built by owg::pa_build_model (host_setup.cpp), read-only on the device
     double s[PA_N][PA_N], k[PA_M][PA_M], s_ni[PA_N][PA_M];
@@ -135,16 +146,17 @@ inline void pa_dev_derive(const double* r, double* d) {
     d[PD_Q2F] = is / (nf_vt * r[PA_IKF]); d[PD_Q2R] = is / (nr_vt * r[PA_IKR]);
     d[PD_GCC_F] = is / nf_vt; d[PD_GCC_R] = (-is) / nr_vt;
     d[PD_RB] = r[PA_RB]; d[PD_RC] = r[PA_RC]; d[PD_RE] = r[PA_RE]; d[PD_MAX_STEP] = 4.0 * vt; d[PD_VT] = vt; d[PD_VCRIT] = r[PA_VCRIT];
+    for (int k = PD_R_NF_VT; k < PD_N; k++) d[k] = 0.0;  // filled on the device when the model is staged
 }
 
 // bjt_evaluate, Gummel-Poon branch (gen_power_amp.rs:7990-8060; every device of this circuit has USE_GP = true)
 PA_HD void pa_bjt_evaluate(double vbe, double vbc, const double* d, double& ic, double& ib, double* jac) {
     const double sign = d[PD_SIGN], is = d[PD_IS];
     const double vbe_eff = sign * vbe, vbc_eff = sign * vbc;
-    const double exp_be = pa_exp(vbe_eff / d[PD_NF_VT]), exp_bc = pa_exp(vbc_eff / d[PD_NR_VT]);
+    const double exp_be = pa_exp(PA_DIV_CONST(vbe_eff, d, PD_NF_VT, PD_R_NF_VT)), exp_bc = pa_exp(PA_DIV_CONST(vbc_eff, d, PD_NR_VT, PD_R_NR_VT));
     const bool lbe = d[PD_ISE] > 0.0, lbc = d[PD_ISC] > 0.0;
-    const double exp_be_leak = lbe ? pa_exp(vbe_eff / d[PD_NE_VT]) : 0.0;
-    const double exp_bc_leak = lbc ? pa_exp(vbc_eff / d[PD_NC_VT]) : 0.0;
+    const double exp_be_leak = lbe ? pa_exp(PA_DIV_CONST(vbe_eff, d, PD_NE_VT, PD_R_NE_VT)) : 0.0;
+    const double exp_bc_leak = lbc ? pa_exp(PA_DIV_CONST(vbc_eff, d, PD_NC_VT, PD_R_NC_VT)) : 0.0;
     const double i_cc = is * (exp_be - exp_bc);
     const double ib_fwd = d[PD_IS_BF] * (exp_be - 1.0), ib_rev = d[PD_IS_BR] * (exp_bc - 1.0);
     const double ib_leak_be = lbe ? d[PD_ISE] * (exp_be_leak - 1.0) : 0.0;
@@ -152,15 +164,15 @@ PA_HD void pa_bjt_evaluate(double vbe, double vbc, const double* d, double& ic, 
     const double dib_fwd_dvbe = d[PD_G_FWD] * exp_be, dib_rev_dvbc = d[PD_G_REV] * exp_bc;
     const double dib_leak_dvbe = lbe ? d[PD_G_LBE] * exp_be_leak : 0.0;
     const double dib_leak_dvbc = lbc ? d[PD_G_LBC] * exp_bc_leak : 0.0;
-    const double q1_denom = (1.0 - vbe_eff / d[PD_VAR]) - vbc_eff / d[PD_VAF];
+    const double q1_denom = (1.0 - PA_DIV_CONST(vbe_eff, d, PD_VAR, PD_R_VAR)) - PA_DIV_CONST(vbc_eff, d, PD_VAF, PD_R_VAF);
     double q1 = 1.0, dq1_dvbe = 0.0, dq1_dvbc = 0.0;
     if (!(q1_denom <= 0.0 || fabs(q1_denom) < 1e-30)) {
         q1 = 1.0 / q1_denom;
-        dq1_dvbe = (q1 * q1) / d[PD_VAR];
-        dq1_dvbc = (q1 * q1) / d[PD_VAF];
+        dq1_dvbe = PA_DIV_CONST(q1 * q1, d, PD_VAR, PD_R_VAR);
+        dq1_dvbc = PA_DIV_CONST(q1 * q1, d, PD_VAF, PD_R_VAF);
     }
     const double cbe = is * (exp_be - 1.0), cbc = is * (exp_bc - 1.0);
-    const double q2 = cbe / d[PD_IKF] + cbc / d[PD_IKR];
+    const double q2 = PA_DIV_CONST(cbe, d, PD_IKF, PD_R_IKF) + PA_DIV_CONST(cbc, d, PD_IKR, PD_R_IKR);
     const double dq2_dvbe = d[PD_Q2F] * exp_be, dq2_dvbc = d[PD_Q2R] * exp_bc;
     const double disc = fmax(1.0 + 4.0 * q2, 0.0);
     const double dd = sqrt(disc);
@@ -247,15 +259,17 @@ PA_HD bool pa_tile_solve16(const T& t, PaScratch& sc) {
     for (int col = 0; col < PA_M; col++) {
         // pivot: largest |a[row][col]| over rows >= col, the lowest row on ties (the reference scans upwards with a strict `>`;
         // a NaN in a lower row is never selected, a NaN on the diagonal stays the pivot: it is entered as +inf and recognised below)
+        // The magnitudes are non-negative, so their bit patterns order like their values: a 64-bit maximum in two 32-bit reductions
+        // (redux.sync on the device), then the lowest lane that holds it.
         const double mine = fabs(sc.a[myrow][col]);
-        double mv = l < col ? -1.0 : (mine == mine ? mine : (l == col ? INFINITY : -1.0));
-        int mi = l;
-#pragma unroll
-        for (int off = 8; off >= 1; off >>= 1) {
-            const double ov = t.shfl_xor(mv, off);
-            const int oi = t.shfl_xor_i(mi, off);
-            if (ov > mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; }
-        }
+        const bool eligible = l >= col && (mine == mine || l == col);
+        const int64_t key = !eligible ? 0 : (mine == mine ? pa_bits(mine) : pa_bits(INFINITY));
+        const uint32_t hi = (uint32_t)((uint64_t)key >> 32), lo = (uint32_t)(uint64_t)key;
+        const uint32_t m_hi = t.max_u32(hi);
+        const bool cand = eligible && hi == m_hi;
+        const uint32_t m_lo = t.max_u32(cand ? lo : 0u);
+        const int mi = t.first_lane(cand && lo == m_lo);
+        const double mv = pa_from_bits((int64_t)(((uint64_t)m_hi << 32) | (uint64_t)m_lo));
         const double diag_abs = t.shfl(mine, col);
         const double max_val = mi == col ? diag_abs : mv;  // the reference's max_val (NaN when the diagonal is NaN and nothing beats it)
         singular = singular || max_val < 1e-15;

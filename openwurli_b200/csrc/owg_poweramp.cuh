@@ -4,6 +4,19 @@
 //   chain B's output stage: tools/preamp-bench/src/main.rs:478-496 (volume^2 -> PowerAmp::new() -> Speaker -> POST_SPEAKER_GAIN).
 #pragma once
 #include "owg_device.cuh"
+
+// a / b for a model-constant divisor b whose reciprocal r was staged by recip_prepare(): div_by() is the second half of the division
+// sequence the compiler emits for `a / b` (same instructions, same bits; operands outside its validated range take the full division)
+namespace owgd {
+__device__ __forceinline__ double pa_div_const(double a, double b, double r) {
+    Recip rc;
+    rc.r = r; rc.nb = -b; rc.b = b;
+    return div_by(a, rc);
+}
+}  // namespace owgd
+#if defined(__CUDA_ARCH__)
+#define PA_DIV_CONST(a, d, IB, IR) owgd::pa_div_const((a), (d)[IB], (d)[IR])
+#endif
 #include "owg_pa_core.h"
 
 namespace owgd {
@@ -20,7 +33,20 @@ struct PaCudaTile {
     __device__ __forceinline__ int shfl_xor_i(int x, int m) const { return __shfl_xor_sync(0xffffffffu, x, m, 16); }
     __device__ __forceinline__ bool any(bool p) const { return (__ballot_sync(0xffffffffu, p) & half) != 0u; }   // over the tile
     __device__ __forceinline__ bool warp_any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }           // over both tiles
+    __device__ __forceinline__ uint32_t max_u32(uint32_t x) const { return __reduce_max_sync(half, x); }          // redux.sync over the tile
+    __device__ __forceinline__ int first_lane(bool p) const { return (__ffs((int)(__ballot_sync(0xffffffffu, p) & half)) - 1) & 15; }
 };
+
+// reciprocals of the model-constant divisors (PA_DIV_CONST), one device per thread; the caller synchronises the CTA around it
+__device__ __forceinline__ void pa_stage_reciprocals(PaShared& sh) {
+    if (threadIdx.x < PA_NDEV) {
+        double* d = sh.dev[threadIdx.x];
+        d[PD_R_NF_VT] = recip_prepare(d[PD_NF_VT]).r; d[PD_R_NR_VT] = recip_prepare(d[PD_NR_VT]).r;
+        d[PD_R_NE_VT] = recip_prepare(d[PD_NE_VT]).r; d[PD_R_NC_VT] = recip_prepare(d[PD_NC_VT]).r;
+        d[PD_R_VAR] = recip_prepare(d[PD_VAR]).r; d[PD_R_VAF] = recip_prepare(d[PD_VAF]).r;
+        d[PD_R_IKF] = recip_prepare(d[PD_IKF]).r; d[PD_R_IKR] = recip_prepare(d[PD_IKR]).r;
+    }
+}
 
 #define OWG_PA_TILES_PER_CTA 8
 #define OWG_PA_THREADS (OWG_PA_TILES_PER_CTA * 16)
@@ -42,6 +68,8 @@ __global__ void __launch_bounds__(OWG_PA_THREADS, OWG_PA_CTAS_PER_SM) pa_melange
     __shared__ PaShared sh;
     __shared__ PaScratch sc[OWG_PA_TILES_PER_CTA];
     pa_stage_shared(*model, sh, threadIdx.x, blockDim.x);
+    __syncthreads();
+    pa_stage_reciprocals(sh);
     __syncthreads();
     const int tile_in_cta = threadIdx.x >> 4;
     const int64_t tile = (int64_t)blockIdx.x * OWG_PA_TILES_PER_CTA + tile_in_cta;
@@ -72,6 +100,8 @@ __global__ void __launch_bounds__(32) pa_settle_kernel(const PaModel* __restrict
     __shared__ PaShared sh;
     __shared__ PaScratch sc[2];
     pa_stage_shared(*model, sh, threadIdx.x, blockDim.x);
+    __syncthreads();
+    pa_stage_reciprocals(sh);
     __syncthreads();
     PaCudaTile t;
     t.lane = threadIdx.x & 15;

@@ -49,6 +49,16 @@ struct EmuTile {
         g_emu->barrier(); return r != 0;
     }
     bool warp_any(bool p) const { return any(p); }  // one tile per emulated warp
+    uint32_t max_u32(uint32_t x) const {
+        g_emu->slot_i[lane] = (int)x; g_emu->barrier();
+        uint32_t r = 0; for (int i = 0; i < L; i++) { const uint32_t v = (uint32_t)g_emu->slot_i[i]; if (v > r) r = v; }
+        g_emu->barrier(); return r;
+    }
+    int first_lane(bool p) const {
+        g_emu->slot_i[lane] = p ? 1 : 0; g_emu->barrier();
+        int r = L - 1; for (int i = L - 1; i >= 0; i--) if (g_emu->slot_i[i]) r = i;
+        g_emu->barrier(); return r;
+    }
 };
 struct Job {
     const PaModel* m; const PaShared* sh; PaScratch* sc; const PaSettled* settled; const double* x; double* y; int64_t n; double pre_gain;

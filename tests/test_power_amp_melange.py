@@ -223,3 +223,34 @@ def test_gpu_release_caches_returns_the_staging_buffer_and_keeps_the_current_dev
     assert freed >= a.nbytes and torch.cuda.current_device() == before
     assert ow.release_caches() == 0
     assert np.array_equal(ow.render_bench(jobs), a)
+
+
+@pytest.mark.gpu
+@needs_solver
+def test_gpu_power_amp_wide_batch_properties_and_sampled_rows():
+    """600 rows (75 CTAs, every SM busy) of chain-level material: outputs finite and inside the adapter's clamp, rows independent of their
+    neighbours (a row rendered alone is bit-identical), sampled rows equal to the oracle inside the north star's bound with equal reset counts."""
+    import openwurli_b200 as ow
+    sr, n, rows = 44100.0, 600, 600
+    t = np.arange(n) / sr
+    rng = np.random.default_rng(11)
+    amps = rng.uniform(0.002, 0.25, rows)[:, None]
+    freqs = (110.0 * 2 ** rng.uniform(0, 5, rows))[:, None]
+    x = np.ascontiguousarray(amps * np.sin(2 * np.pi * freqs * t) * np.exp(-3.0 * t) + 0.002 * rng.standard_normal((rows, n)))
+    y, rails, cnt = ow.power_amp_batch(x, sr, want_state=True)
+    assert np.isfinite(y).all() and np.abs(y).max() <= 1.0 and np.all(rails > 20.0) and np.all(rails <= 24.5 + 1e-9)
+    for i in (0, 1, 299, 598, 599):
+        yo, ro, resets = _oracle_amp(x[i], sr)
+        err, rel = _close(y[i], yo)
+        assert err <= 1e-6 and rel <= 1e-7 and int(cnt[i, 0]) == resets, (i, err, rel, cnt[i], resets)
+        assert np.array_equal(ow.power_amp_batch(np.ascontiguousarray(x[i:i + 1]), sr)[0], y[i])
+
+
+def test_row_per_lane_elimination_equals_the_sequential_one(tmp_path):
+    """pa_tile_solve16 on the lane emulator vs the reference's sequential partial-pivoting elimination: 400 random 16x16 systems (exact
+    pivot ties, zero columns, duplicated rows): solutions bit-identical, the same systems declared singular."""
+    exe = str(tmp_path / "pa_solve_check")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "tests"), "-o", exe,
+                    os.path.join(ROOT, "tests", "pa_solve_check.cpp"), os.path.join(ROOT, "openwurli_b200", "csrc", "host_pa_setup.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
+    assert out.startswith("bad=0 singular=") and int(out.split("=")[-1]) > 20, out
