@@ -66,7 +66,15 @@ def cmd_render(args):
     tremolo_depth = parse_flag(args, "--tremolo-depth", 0.0)
     sample_rate = parse_flag(args, "--sample-rate", BASE_SR)
     no_poweramp = has_flag(args, "--no-poweramp")
-    # --no-rail-sag is accepted and ignored: PowerAmp::set_rail_sag is a no-op on the behavioral path (power_amp.rs:255-257)
+    # The power amplifier is the crate's other compile-time choice (`legacy-power-amp`, in the default features): behavioural model or the
+    # melange 7-BJT solver.  Here it is a flag.  --no-rail-sag (main.rs:381, 481-483) is a no-op on the behavioural path
+    # (power_amp.rs:255-257) and selects ideal rails on the melange one.
+    no_rail_sag = has_flag(args, "--no-rail-sag")
+    pa_name = parse_flag_str(args, "--power-amp", "behavioral")
+    if pa_name not in ("behavioral", "melange"):
+        sys.stderr.write(f"Unknown --power-amp {pa_name} (behavioral | melange)\n")
+        return 1
+    pa_model = api.PA_BEHAVIORAL if pa_name == "behavioral" else (api.PA_MELANGE_IDEAL_RAILS if no_rail_sag else api.PA_MELANGE)
     no_preamp = has_flag(args, "--no-preamp")
     no_attack_noise = has_flag(args, "--no-attack-noise")
     no_mlp = has_flag(args, "--no-mlp")
@@ -86,7 +94,7 @@ def cmd_render(args):
     jobs = [api.bench_job(note=n, velocity=v, duration=duration, ldr=r_ldr, volume=volume, speaker=speaker_char,
                           tremolo_depth=tremolo_depth, sample_rate=sample_rate, no_poweramp=no_poweramp, no_preamp=no_preamp,
                           no_attack_noise=no_attack_noise, no_mlp=no_mlp, displacement_scale=disp_scale) for n, v in pairs]
-    out = api.render_bench(jobs, preamp_model=preamp_model)
+    out = api.render_bench(jobs, preamp_model=preamp_model, power_amp_model=pa_model)
     stem, ext = os.path.splitext(output_path)
     for k, (note, velocity) in enumerate(pairs):
         final_output = out[k]
@@ -359,7 +367,7 @@ USAGE = """Usage: preamp_bench <render|calibrate|sensitivity|render-midi|render-
   render-poly --notes a,b,c --velocities x,y,z --duration S --volume X --speaker C --ldr OHM --no-poweramp --normalize --output FILE
   render-midi --midi FILE --output FILE --volume X --speaker C --tail S --track N --tremolo-depth D --preamp-model M
   render     --note N --velocity V --duration S --ldr OHM --volume X --speaker C --tremolo-depth D --sample-rate HZ
-             --no-poweramp --no-rail-sag --no-preamp --no-attack-noise --no-mlp --normalize --displacement-scale DS --output FILE
+             --no-poweramp --no-rail-sag --power-amp behavioral|melange --no-preamp --no-attack-noise --no-mlp --normalize --displacement-scale DS --output FILE
              --preamp-model melange12|legacy8   (compile-time cargo feature in the reference)
   calibrate  --notes a,b,c --velocities x,y,z --ds-at-c4 D --ds-clamp-max M --volume X --speaker C --zero-trim --output FILE
 """

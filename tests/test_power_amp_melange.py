@@ -254,3 +254,29 @@ def test_row_per_lane_elimination_equals_the_sequential_one(tmp_path):
                     os.path.join(ROOT, "tests", "pa_solve_check.cpp"), os.path.join(ROOT, "openwurli_b200", "csrc", "host_pa_setup.cpp")], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
     assert out.startswith("bad=0 singular=") and int(out.split("=")[-1]) > 20, out
+
+
+def test_render_cli_rejects_an_unknown_power_amp(capsys):
+    from openwurli_b200.cli import preamp_bench
+    assert preamp_bench.main(["render", "--power-amp", "valve", "--duration", "0.01"]) == 1
+    assert "Unknown --power-amp" in capsys.readouterr().err
+
+
+@pytest.mark.gpu
+@needs_solver
+def test_gpu_render_cli_with_the_melange_power_amp_matches_the_oracle_wav(tmp_path):
+    """`preamp-bench render --power-amp melange [--no-rail-sag]` through the CLI mirror: the 24-bit file equals the oracle's chain-B preamp
+    tap -> owo_output_stage_melange -> the tool's rounding quantiser (+-1 LSB for a sample on a rounding boundary)."""
+    from openwurli_b200 import wav
+    from openwurli_b200.cli import preamp_bench
+    for extra, sag in (([], 1), (["--no-rail-sag"], 0)):
+        p = tmp_path / f"pa{sag}.wav"
+        assert preamp_bench.main(["render", "--note", "52", "--velocity", "110", "--duration", "0.2", "--volume", "0.8", "--speaker", "0.6",
+                                  "--power-amp", "melange", "--output", str(p)] + extra) == 0
+        q, sr = wav.read_wav_pcm24(str(p))
+        oj = O.bench_job(midi=52, vel=110, dur=0.2, volume=0.8, speaker=0.6)
+        pre = np.ascontiguousarray(O.render_bench_taps(oj)["preamp"])
+        ref = np.zeros(len(pre))
+        assert L.owo_output_stage_melange(O.dptr(pre), len(pre), 44100.0, 0.8, 0.6, 0, sag, O.dptr(ref)) == 0
+        assert sr == 44100 and q.size == ref.size
+        assert np.max(np.abs(q.astype(np.int64) - wav.pcm24_round(ref, wav.normalize_scale(ref, False)))) <= 1
