@@ -571,6 +571,9 @@ PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaSc
         s.dc_x = m.nan_out; s.dc_y = 0.0;
     } else pa_lane_load_settled(m, *settled, l, s);
     const bool adapter = settle == nullptr;
+    // what the caller is told about the row's end (a tile that keeps its longer neighbour company runs past its own last sample)
+    double end_rail_pos = s.rail_pos, end_rail_neg = s.rail_neg;
+    uint32_t end_resets = 0, end_be = 0, end_nan = 0, end_iters = 0;
     for (int64_t t0 = 0; t0 < n_steps; t0 += 16) {
         const int nb = n_steps - t0 < 16 ? (int)(n_steps - t0) : 16;
         const bool mine = valid && t0 + l < n;
@@ -609,6 +612,10 @@ PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaSc
                 out = post(out);
             }
             if (l == k) yout = out;
+            if (t0 + k + 1 == n) {
+                end_rail_pos = s.rail_pos; end_rail_neg = s.rail_neg;
+                end_resets = s.resets; end_be = s.be_fallbacks; end_nan = s.nan_resets; end_iters = s.last_iters;
+            }
         }
         if (adapter && y && mine) y[t0 + l] = yout;
     }
@@ -619,7 +626,7 @@ PA_HD void pa_tile_render(const T& t, const PaModel& m, const PaShared& sh, PaSc
         if (l == 0) { settle->dc_x = s.dc_x; settle->dc_y = s.dc_y; }
     }
     if (l == 0 && valid) {
-        if (rails_out) { rails_out[0] = rail_sag ? s.rail_pos : PA_RAIL_DC_BIAS; rails_out[1] = rail_sag ? s.rail_neg : PA_RAIL_DC_BIAS; }
-        if (counters_out) { counters_out[0] = s.resets; counters_out[1] = s.be_fallbacks; counters_out[2] = s.nan_resets; counters_out[3] = s.last_iters; }
+        if (rails_out) { rails_out[0] = rail_sag ? end_rail_pos : PA_RAIL_DC_BIAS; rails_out[1] = rail_sag ? end_rail_neg : PA_RAIL_DC_BIAS; }
+        if (counters_out) { counters_out[0] = end_resets; counters_out[1] = end_be; counters_out[2] = end_nan; counters_out[3] = end_iters; }
     }
 }

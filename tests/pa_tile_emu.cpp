@@ -12,77 +12,88 @@
 #include "../openwurli_b200/csrc/owg_pa_core.h"
 
 namespace {
-constexpr int L = 16;
+constexpr int L = 16;      // lanes per tile
+constexpr int LMAX = 32;   // one emulated warp: one or two tiles
 struct Emu {
-    ucontext_t main_ctx, ctx[L];
-    std::vector<char> stacks[L];
-    bool done[L];
+    ucontext_t main_ctx, ctx[LMAX];
+    std::vector<char> stacks[LMAX];
+    bool done[LMAX];
+    int nl = L;            // coroutines in this run (16: one tile, 32: two tiles in lock-step, as on the GPU)
     int cur = 0, arrived = 0;
     unsigned long gen = 0;
-    double slot_d[L];
-    int slot_i[L];
+    double slot_d[LMAX];
+    int slot_i[LMAX];
     void yield_next() {
         const int from = cur;
-        int nxt = (cur + 1) % L;
-        while (done[nxt] && nxt != from) nxt = (nxt + 1) % L;
+        int nxt = (cur + 1) % nl;
+        while (done[nxt] && nxt != from) nxt = (nxt + 1) % nl;
         if (nxt == from) return;
         cur = nxt;
         swapcontext(&ctx[from], &ctx[nxt]);
     }
+    // Every collective is a barrier over ALL lanes of the emulated warp, like a full-mask __shfl_sync / __syncwarp on the device: a tile
+    // that skipped a collective its neighbour executes would pair up different collectives and fail the comparison with the oracle.
     void barrier() {
         const unsigned long g = gen;
-        if (++arrived == L) { arrived = 0; gen++; return; }
+        if (++arrived == nl) { arrived = 0; gen++; return; }
         while (gen == g) yield_next();
     }
 };
 Emu* g_emu;
 struct EmuTile {
-    int lane;
+    int lane, base;  // lane within the tile, first lane of the tile in the warp
     void sync() const { g_emu->barrier(); }
-    double shfl(double x, int src) const { g_emu->slot_d[lane] = x; g_emu->barrier(); const double r = g_emu->slot_d[src]; g_emu->barrier(); return r; }
+    double shfl(double x, int src) const { g_emu->slot_d[base + lane] = x; g_emu->barrier(); const double r = g_emu->slot_d[base + src]; g_emu->barrier(); return r; }
     double shfl_xor(double x, int m) const { return shfl(x, lane ^ m); }
-    int shfl_i(int x, int src) const { g_emu->slot_i[lane] = x; g_emu->barrier(); const int r = g_emu->slot_i[src]; g_emu->barrier(); return r; }
+    int shfl_i(int x, int src) const { g_emu->slot_i[base + lane] = x; g_emu->barrier(); const int r = g_emu->slot_i[base + src]; g_emu->barrier(); return r; }
     int shfl_xor_i(int x, int m) const { return shfl_i(x, lane ^ m); }
-    bool any(bool p) const {
-        g_emu->slot_i[lane] = p ? 1 : 0; g_emu->barrier();
-        int r = 0; for (int i = 0; i < L; i++) r |= g_emu->slot_i[i];
+    bool any(bool p) const {  // over the tile
+        g_emu->slot_i[base + lane] = p ? 1 : 0; g_emu->barrier();
+        int r = 0; for (int i = 0; i < L; i++) r |= g_emu->slot_i[base + i];
         g_emu->barrier(); return r != 0;
     }
-    bool warp_any(bool p) const { return any(p); }  // one tile per emulated warp
+    bool warp_any(bool p) const {  // over both tiles
+        g_emu->slot_i[base + lane] = p ? 1 : 0; g_emu->barrier();
+        int r = 0; for (int i = 0; i < g_emu->nl; i++) r |= g_emu->slot_i[i];
+        g_emu->barrier(); return r != 0;
+    }
     uint32_t max_u32(uint32_t x) const {
-        g_emu->slot_i[lane] = (int)x; g_emu->barrier();
-        uint32_t r = 0; for (int i = 0; i < L; i++) { const uint32_t v = (uint32_t)g_emu->slot_i[i]; if (v > r) r = v; }
+        g_emu->slot_i[base + lane] = (int)x; g_emu->barrier();
+        uint32_t r = 0; for (int i = 0; i < L; i++) { const uint32_t v = (uint32_t)g_emu->slot_i[base + i]; if (v > r) r = v; }
         g_emu->barrier(); return r;
     }
     int first_lane(bool p) const {
-        g_emu->slot_i[lane] = p ? 1 : 0; g_emu->barrier();
-        int r = L - 1; for (int i = L - 1; i >= 0; i--) if (g_emu->slot_i[i]) r = i;
+        g_emu->slot_i[base + lane] = p ? 1 : 0; g_emu->barrier();
+        int r = L - 1; for (int i = L - 1; i >= 0; i--) if (g_emu->slot_i[base + i]) r = i;
         g_emu->barrier(); return r;
     }
 };
 struct Job {
     const PaModel* m; const PaShared* sh; PaScratch* sc; const PaSettled* settled; const double* x; double* y; int64_t n; double pre_gain;
-    bool rail_sag; PaSettled* settle; double* rails; uint32_t* counters;
+    bool rail_sag; PaSettled* settle; double* rails; uint32_t* counters; int64_t n_steps;
 };
-Job g_job;
-void lane_main(int lane) {
-    EmuTile t{lane};
+Job g_jobs[2];
+void lane_main(int idx) {
+    const Job& j = g_jobs[idx / L];
+    EmuTile t{idx % L, (idx / L) * L};
     PaNoPost post;
-    pa_tile_render(t, *g_job.m, *g_job.sh, *g_job.sc, g_job.settled, g_job.x, g_job.y, g_job.n, g_job.n, true, g_job.pre_gain, g_job.rail_sag, false,
-                   g_job.settle, g_job.rails, g_job.counters, post);
-    g_emu->done[lane] = true;
+    pa_tile_render(t, *j.m, *j.sh, *j.sc, j.settled, j.x, j.y, j.n, j.n_steps, true, j.pre_gain, j.rail_sag, false, j.settle, j.rails, j.counters, post);
+    g_emu->done[idx] = true;
     // hand over to a lane that is still running, or back to main when this was the last one
-    for (int i = 1; i <= L; i++) {
-        const int nxt = (lane + i) % L;
+    for (int i = 1; i <= g_emu->nl; i++) {
+        const int nxt = (idx + i) % g_emu->nl;
         if (!g_emu->done[nxt]) { g_emu->cur = nxt; setcontext(&g_emu->ctx[nxt]); }
     }
     setcontext(&g_emu->main_ctx);
 }
-void run_tile(const Job& job) {
+void run_tiles(const Job* jobs, int n_tiles) {
     Emu emu;
     g_emu = &emu;
-    g_job = job;
-    for (int i = 0; i < L; i++) {
+    emu.nl = n_tiles * L;
+    int64_t steps = 0;
+    for (int k = 0; k < n_tiles; k++) steps = jobs[k].n > steps ? jobs[k].n : steps;
+    for (int k = 0; k < n_tiles; k++) { g_jobs[k] = jobs[k]; g_jobs[k].n_steps = steps; }
+    for (int i = 0; i < emu.nl; i++) {
         emu.done[i] = false;
         emu.stacks[i].resize(1 << 20);
         getcontext(&emu.ctx[i]);
@@ -94,6 +105,7 @@ void run_tile(const Job& job) {
     emu.cur = 0;
     swapcontext(&emu.main_ctx, &emu.ctx[0]);
 }
+void run_tile(const Job& job) { run_tiles(&job, 1); }
 PaSettled g_settled;
 bool g_have_settled = false;
 }  // namespace
@@ -113,7 +125,7 @@ int paemu_render(double sample_rate, int rail_sag, const double* x, int64_t n, d
     if (!g_have_settled) {
         owg::pa_build_model(88200.0, &m0);
         pa_stage_shared(m0, sh, 0, 1);
-        run_tile(Job{&m0, &sh, &sc, nullptr, nullptr, nullptr, PA_SETTLE_SAMPLES, 1.0, false, &g_settled, nullptr, nullptr});
+        run_tile(Job{&m0, &sh, &sc, nullptr, nullptr, nullptr, PA_SETTLE_SAMPLES, 1.0, false, &g_settled, nullptr, nullptr, 0});
         g_have_settled = true;
         if (const char* cache = getenv("PAEMU_SETTLED_CACHE")) {
             if (FILE* f = fopen(cache, "wb")) { fwrite(&g_settled, sizeof(g_settled), 1, f); fclose(f); }
@@ -121,7 +133,22 @@ int paemu_render(double sample_rate, int rail_sag, const double* x, int64_t n, d
     }
     owg::pa_build_model(sample_rate, &m);
     pa_stage_shared(m, sh, 0, 1);
-    run_tile(Job{&m, &sh, &sc, &g_settled, x, y, n, pre_gain, rail_sag != 0, nullptr, rails2, counters4});
+    run_tile(Job{&m, &sh, &sc, &g_settled, x, y, n, pre_gain, rail_sag != 0, nullptr, rails2, counters4, 0});
+    return 0;
+}
+// Two rows on the two tiles of one emulated warp, in lock-step as on the GPU (rows of different length and difficulty: one tile converges or
+// ends while the other keeps iterating, retries with backward Euler, or resets).  Needs the settled state (paemu_render or paemu_set_settled).
+int paemu_render_pair(double sample_rate, int rail_sag, const double* x0, int64_t n0, const double* x1, int64_t n1, double* y0, double* y1,
+                      double* rails4, uint32_t* counters8) {
+    static PaModel m;
+    static PaShared sh;
+    static PaScratch sc[2];
+    if (!g_have_settled) return -1;
+    owg::pa_build_model(sample_rate, &m);
+    pa_stage_shared(m, sh, 0, 1);
+    Job jobs[2] = {Job{&m, &sh, &sc[0], &g_settled, x0, y0, n0, 1.0, rail_sag != 0, nullptr, rails4, counters8, 0},
+                   Job{&m, &sh, &sc[1], &g_settled, x1, y1, n1, 1.0, rail_sag != 0, nullptr, rails4 + 2, counters8 + 4, 0}};
+    run_tiles(jobs, 2);
     return 0;
 }
 // CircuitState::default() followed by n_extra silent samples of the raw solver (n_extra = 44100: compute_settled_state):
@@ -133,7 +160,7 @@ int paemu_settle(int64_t n_extra, double* out54) {
     PaSettled st;
     owg::pa_build_model(88200.0, &m0);
     pa_stage_shared(m0, sh, 0, 1);
-    run_tile(Job{&m0, &sh, &sc, nullptr, nullptr, nullptr, 50 + n_extra, 1.0, false, &st, nullptr, nullptr});
+    run_tile(Job{&m0, &sh, &sc, nullptr, nullptr, nullptr, 50 + n_extra, 1.0, false, &st, nullptr, nullptr, 0});
     memcpy(out54, &st, sizeof(st));
     return 0;
 }

@@ -54,6 +54,7 @@ def _emu():
     E.paemu_model.argtypes = [C.c_double, dp]
     E.paemu_settle.argtypes = [C.c_int64, dp]
     E.paemu_set_settled.argtypes = [dp]
+    E.paemu_render_pair.argtypes = [C.c_double, C.c_int, dp, C.c_int64, dp, C.c_int64, dp, dp, dp, C.POINTER(C.c_uint32)]
     return E
 
 
@@ -100,6 +101,31 @@ def test_lane_tiled_solver_source_is_bit_identical_to_the_oracle_on_the_lane_emu
     E.paemu_render(44100.0, 0, x.ctypes.data_as(dp), n, 1.0, y.ctypes.data_as(dp), rails.ctypes.data_as(dp), cnt.ctypes.data_as(cptr))
     yo, _, resets = _oracle_amp(x, 44100.0, rail_sag=False)
     assert np.array_equal(y, yo) and int(cnt[0]) == resets and tuple(rails) == (22.5, 22.5)   # ideal rails
+
+
+@needs_solver
+def test_two_tiles_of_a_warp_in_lock_step_on_the_lane_emulator():
+    """The GPU runs two instances per warp with full-warp collectives: a tile that has converged, ended, or does not need the
+    backward-Euler retry keeps executing its neighbour's collectives and commits nothing.  Here 32 coroutines emulate that warp (every
+    collective is a barrier over all 32 lanes): pairs of rows of different difficulty AND length -- silence beside a row that exhausts
+    both Newton loops and resets, a long row beside a short one -- each still bit-identical to the oracle."""
+    E = _emu()
+    ref = np.zeros(54)
+    assert L.owo_power_amp_settled(44100, O.dptr(ref)) == 0 and E.paemu_set_settled(ref.ctypes.data_as(dp)) == 0
+    sr = 44100.0
+    sig = _signals(sr, 36)
+    total_resets = 0
+    for a, na, b, nb in ((0, 36, 3, 36), (3, 20, 1, 36), (4, 36, 6, 7), (2, 36, 2, 36)):
+        x0, x1 = np.ascontiguousarray(sig[a][:na]), np.ascontiguousarray(sig[b][:nb])
+        y0, y1, rails, cnt = np.zeros(na), np.zeros(nb), np.zeros(4), np.zeros(8, np.uint32)
+        assert E.paemu_render_pair(sr, 1, x0.ctypes.data_as(dp), na, x1.ctypes.data_as(dp), nb, y0.ctypes.data_as(dp), y1.ctypes.data_as(dp),
+                                   rails.ctypes.data_as(dp), cnt.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+        for x, y, r, c in ((x0, y0, rails[:2], cnt[:4]), (x1, y1, rails[2:], cnt[4:])):
+            yo, ro, resets = _oracle_amp(x, sr)
+            assert np.array_equal(y.view(np.uint64), yo.view(np.uint64)), (a, b, float(np.abs(y - yo).max()))
+            assert np.array_equal(r, ro) and int(c[0]) == resets
+            total_resets += resets
+    assert total_resets > 0
 
 
 def test_power_amp_entry_point_refuses_without_a_device_and_rejects_bad_arguments():
