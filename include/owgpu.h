@@ -7,6 +7,9 @@
  * need).  There is NO CPU fallback: every render call fails with OWG_E_NO_DEVICE when no CUDA
  * device is usable.
  *
+ * Every entry point that selects a CUDA device (opts->device / device_mask, a plan's device) restores the calling thread's current
+ * device before it returns.
+ *
  * Numeric trouble is not an error: the reference's guards (NaN -> reset / zeros, BE fallback,
  * voltage damping) are reproduced on the device and reported through owg_last_diag().
  */

@@ -32,6 +32,14 @@ thread_local owg_diag g_last_diag;
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
+// Every entry point that selects a device leaves the calling thread's current CUDA device as it found it (a co-resident framework
+// such as torch assumes its own notion of "current device" survives a library call).
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 #define CK(expr)                                                                                   \
     do {                                                                                           \
         cudaError_t _e = (expr);                                                                   \
@@ -453,6 +461,7 @@ void owg_default_opts(owg_opts* o) {
 }
 
 int owg_plan_voices(const owg_voice_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan) {
+    DeviceRestore restore_device_;
     if (!plan || n < 0 || (n > 0 && !jobs)) return fail(OWG_E_BAD_ARG, "owg_plan_voices: bad argument");
     for (int64_t i = 0; i < n; i++) if (bad_voice_job(jobs[i])) return fail(OWG_E_BAD_ARG, "owg_plan_voices: job with invalid sample_rate/duration/velocity");
     owg_plan* pl = new owg_plan();
@@ -523,6 +532,7 @@ static int plan_bench_impl(const owg_bench_job* jobs, int64_t n, const owg_opts*
 }
 
 int owg_plan_bench(const owg_bench_job* jobs, int64_t n, const owg_opts* opts, owg_plan** plan) {
+    DeviceRestore restore_device_;
     return plan_bench_impl(jobs, n, opts, plan, nullptr);
 }
 
@@ -546,11 +556,13 @@ int owg_plan_last_timing(const owg_plan* pl, float* main_kernel_ms, float* total
 
 void owg_plan_destroy(owg_plan* pl) {
     if (!pl) return;
+    DeviceRestore restore_device_;
     cudaSetDevice(pl->device);
     delete pl;
 }
 
 int owg_plan_execute(owg_plan* pl, double* out, int64_t stride, int32_t out_location) {
+    DeviceRestore restore_device_;
     if (!pl) return fail(OWG_E_BAD_ARG, "null plan");
     if (pl->n == 0) return OWG_OK;
     if (!out) return fail(OWG_E_BAD_ARG, "null output");
@@ -906,6 +918,7 @@ int fan_out_devices(const Job* jobs, int64_t n, double* out, int64_t stride, con
 }  // extern "C++"
 
 int owg_render_voices(const owg_voice_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (opts && popcount32(opts->device_mask) >= 2 && n > 0 && jobs && out)
         return fan_out_devices(jobs, n, out, stride, *opts, [](const owg_voice_job& j) { const double x = j.duration_s * j.sample_rate; return x > 0.0 ? x : 0.0; },
                                [](const owg_voice_job* j, int64_t m, double* o, int64_t st, const owg_opts* op) { return owg_render_voices(j, m, o, st, op); });
@@ -1041,6 +1054,7 @@ int64_t owg_release_caches(int32_t device) {
 
 int owg_power_amp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double sample_rate, int32_t rail_sag, double* out,
                         int64_t out_stride, double* rails, uint32_t* counters, const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (n_inst < 0 || n_samp < 0 || !(sample_rate > 0.0) || !std::isfinite(sample_rate)) return fail(OWG_E_BAD_ARG, "owg_power_amp_batch: bad argument");
     if (n_inst == 0 || n_samp == 0) return OWG_OK;
     if (!in || !out || in_stride < n_samp || out_stride < n_samp) return fail(OWG_E_BAD_ARG, "owg_power_amp_batch: null buffer or stride < n_samp");
@@ -1074,6 +1088,7 @@ int owg_power_amp_batch(const double* in, int64_t in_stride, int64_t n_inst, int
 }
 
 int owg_render_bench(const owg_bench_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (opts && popcount32(opts->device_mask) >= 2 && n > 0 && jobs && out)
         return fan_out_devices(jobs, n, out, stride, *opts, [](const owg_bench_job& j) { const double x = j.v.duration_s * j.v.sample_rate; return x > 0.0 ? x : 0.0; },
                                [](const owg_bench_job* j, int64_t m, double* o, int64_t st, const owg_opts* op) { return owg_render_bench(j, m, o, st, op); });
@@ -1091,6 +1106,7 @@ int owg_render_bench(const owg_bench_job* jobs, int64_t n, double* out, int64_t 
 
 int owg_render_bench_metrics(const owg_bench_job* jobs, int64_t n, double window_start_s, double window_end_s, double* metrics,
                              const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (n < 0 || (n > 0 && (!jobs || !metrics)) || !(window_end_s > window_start_s) || !(window_start_s >= 0.0))
         return fail(OWG_E_BAD_ARG, "owg_render_bench_metrics: bad argument");
     if (n == 0) return OWG_OK;
@@ -1236,6 +1252,7 @@ void owg_default_calib_cfg(owg_calib_cfg* c) {
 
 int owg_render_calibrate(const owg_bench_job* jobs, int64_t n, const owg_calib_cfg* cfg_in, double window_start_s, double window_end_s,
                          double* rows, const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (n < 0 || (n > 0 && (!jobs || !rows)) || !(window_end_s > window_start_s) || !(window_start_s >= 0.0))
         return fail(OWG_E_BAD_ARG, "owg_render_calibrate: bad argument");
     if (n == 0) return OWG_OK;
@@ -1316,6 +1333,7 @@ int owg_render_calibrate(const owg_bench_job* jobs, int64_t n, const owg_calib_c
 }
 
 int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_t stride, const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (n < 0 || (n > 0 && (!jobs || !out))) return fail(OWG_E_BAD_ARG, "owg_render_engines: bad argument");
     if (n == 0) return OWG_OK;
     for (int64_t i = 0; i < n; i++) {
@@ -1705,6 +1723,7 @@ int owg_render_engines(const owg_engine_job* jobs, int64_t n, float* out, int64_
 
 int owg_preamp_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, double fs_base, int oversample,
                      double tremolo_depth, double r_ldr_static, double* out, int64_t out_stride, const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (n_inst < 0 || n_samp < 0 || !(fs_base > 0.0) || !std::isfinite(fs_base) || std::isnan(tremolo_depth))
         return fail(OWG_E_BAD_ARG, "owg_preamp_batch: bad argument");
     if (n_inst == 0 || n_samp == 0) return OWG_OK;
@@ -1822,6 +1841,7 @@ static int chain_batch_impl(const double* in, int in_location, int64_t in_stride
 
 int owg_chain_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t n_samp, const owg_bench_job* params, int32_t init_order,
                     double* out, int64_t out_stride, const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (n_inst < 0 || n_samp < 0 || (init_order != OWG_INIT_RESET_THEN_SET && init_order != OWG_INIT_SET_THEN_RESET))
         return fail(OWG_E_BAD_ARG, "owg_chain_batch: bad argument");
     if (n_inst == 0 || n_samp == 0) return OWG_OK;
@@ -1836,6 +1856,7 @@ int owg_chain_batch(const double* in, int64_t in_stride, int64_t n_inst, int64_t
 }
 
 int owg_render_midi(const owg_midi_job* jobs, int64_t n, double* out, int64_t stride, const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (n < 0 || (n > 0 && (!jobs || !out))) return fail(OWG_E_BAD_ARG, "owg_render_midi: bad argument");
     if (n == 0) return OWG_OK;
     const double SR = 44100.0;  // BASE_SR: the tool renders at 44.1 kHz only
@@ -1989,6 +2010,7 @@ int owg_last_diag(owg_diag* out) {
 }
 
 int owg_selftest_division(int64_t n_per_thread, uint64_t seed, uint64_t* mismatches, uint64_t* tested) {
+    DeviceRestore restore_device_;
     if (!mismatches || n_per_thread <= 0) return fail(OWG_E_BAD_ARG, "owg_selftest_division: bad argument");
     if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
     unsigned long long* d = nullptr;
@@ -2052,6 +2074,7 @@ static int alias_analyze_device(const void* d_rows, int32_t row_dtype, int64_t s
 
 int owg_alias_analyze(const void* rows, int32_t row_dtype, int64_t stride, int64_t n_rows, int64_t n_samples, double sample_rate,
                       double analyze_seconds, const double* nominal_f0, double* results, const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (!rows || !nominal_f0 || !results || n_rows < 0 || n_samples < 0 || stride < n_samples || (row_dtype != OWG_ROWS_F64 && row_dtype != OWG_ROWS_F32) ||
         !(sample_rate > 0.0) || !std::isfinite(sample_rate) || !(analyze_seconds > 0.0))
         return fail(OWG_E_BAD_ARG, "owg_alias_analyze: bad argument");
@@ -2071,6 +2094,7 @@ int owg_alias_analyze(const void* rows, int32_t row_dtype, int64_t stride, int64
 
 int owg_render_engines_alias(const owg_engine_job* jobs, int64_t n, double analyze_seconds, const double* nominal_f0, double* results,
                              const owg_opts* opts) {
+    DeviceRestore restore_device_;
     if (!jobs || !nominal_f0 || !results || n < 0) return fail(OWG_E_BAD_ARG, "owg_render_engines_alias: bad argument");
     if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
     if (n == 0) return OWG_OK;
@@ -2091,6 +2115,7 @@ int owg_render_engines_alias(const owg_engine_job* jobs, int64_t n, double analy
 }
 
 int owg_fp64_peak(int32_t device, int32_t fma_mode, float ms_target, double* tera_instr_per_s) {
+    DeviceRestore restore_device_;
     if (!tera_instr_per_s) return fail(OWG_E_BAD_ARG, "null result");
     if (usable_devices() <= 0) return fail(OWG_E_NO_DEVICE, "no usable CUDA device");
     if (device >= 0) CK(cudaSetDevice(device));

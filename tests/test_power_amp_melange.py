@@ -306,3 +306,22 @@ def test_gpu_render_cli_with_the_melange_power_amp_matches_the_oracle_wav(tmp_pa
         assert L.owo_output_stage_melange(O.dptr(pre), len(pre), 44100.0, 0.8, 0.6, 0, sag, O.dptr(ref)) == 0
         assert sr == 44100 and q.size == ref.size
         assert np.max(np.abs(q.astype(np.int64) - wav.pcm24_round(ref, wav.normalize_scale(ref, False)))) <= 1
+
+
+@pytest.mark.gpu
+def test_gpu_entry_points_leave_the_current_cuda_device_alone():
+    """A call that renders on device 0 while the caller's current device is another one (multi-GPU boxes) -- or simply any call on a
+    one-GPU box -- returns with the thread's current CUDA device unchanged."""
+    import torch
+    import openwurli_b200 as ow
+    cur = torch.cuda.device_count() - 1
+    torch.cuda.set_device(cur)
+    probe = torch.ones(4, device="cuda")
+    ow.render_bench([ow.bench_job(duration=0.02)], device=0)
+    ow.render_voices([ow.voice_job(60, 100, 44100.0, 0.02)], device=0)
+    ow.power_amp_batch(np.zeros((1, 32)), device=0)
+    pl = ow.Plan.bench([ow.bench_job(duration=0.02)], device=0)
+    pl.execute(np.zeros((1, 882)))
+    pl.close()
+    assert torch.cuda.current_device() == cur and float((probe + 1).sum().item()) == 8.0 and probe.device.index == cur
+    torch.cuda.set_device(0)
