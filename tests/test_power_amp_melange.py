@@ -96,6 +96,12 @@ def test_lane_tiled_solver_source_is_bit_identical_to_the_oracle_on_the_lane_emu
             assert np.array_equal(rails, ro) and int(cnt[0]) == resets, (sr, k)
             total_resets += resets
     assert total_resets > 0
+    # non-finite input samples (process_sample treats them as 0, gen_power_amp.rs:8839), inputs beyond the +-100 V clamp, a DC step
+    x = np.ascontiguousarray(np.array([0.0, 0.01, np.nan, 0.02, np.inf, -np.inf, 150.0, -150.0, 0.5, 0.5, 0.5, -0.5, 0.0, 0.0, 1e-300, -0.0] * 2))
+    y, rails, cnt = np.zeros(len(x)), np.zeros(2), np.zeros(4, np.uint32)
+    assert E.paemu_render(44100.0, 1, x.ctypes.data_as(dp), len(x), 1.0, y.ctypes.data_as(dp), rails.ctypes.data_as(dp), cnt.ctypes.data_as(cptr)) == 0
+    yo, ro, resets = _oracle_amp(x, 44100.0)
+    assert np.array_equal(y.view(np.uint64), yo.view(np.uint64)) and np.array_equal(rails, ro) and int(cnt[0]) == resets and np.isfinite(y).all()
     x = np.ascontiguousarray(_signals(44100.0, n)[3])
     y, rails, cnt = np.zeros(n), np.zeros(2), np.zeros(4, np.uint32)
     E.paemu_render(44100.0, 0, x.ctypes.data_as(dp), n, 1.0, y.ctypes.data_as(dp), rails.ctypes.data_as(dp), cnt.ctypes.data_as(cptr))
