@@ -182,6 +182,19 @@ extern "C" {
     /// `counters` `[n][4]` (resets, backward-Euler retries, NaN resets, last_nr_iterations) may be null.
     pub fn owg_power_amp_batch(input: *const f64, in_stride: i64, n_inst: i64, n_samp: i64, sample_rate: f64, rail_sag: i32, out: *mut f64,
                                out_stride: i64, rails: *mut f64, counters: *mut u32, opts: *const owg_opts) -> i32;
+    // ---- probes and self-tests (what the test-suite pins the host logic and the device arithmetic with) ----
+    /// Voice::note_on's init record (61 doubles) as the host computes it
+    pub fn owg_host_voice_init(job: *const owg_voice_job, out61: *mut f64) -> i32;
+    /// chain-B output-stage parameters of one job (18 doubles)
+    pub fn owg_host_chain_init(job: *const owg_bench_job, out18: *mut f64) -> i32;
+    /// the legacy 8-node preamp's plan-time record (188 doubles)
+    pub fn owg_host_legacy_group(preamp_sr: f64, r_static: f64, out188: *mut f64) -> i32;
+    /// FP64 pipe micro-benchmark (the roofline denominator): tera-instructions per second of DFMA (fma = 1) or unfused DADD/DMUL (fma = 0)
+    pub fn owg_fp64_peak(device: i32, fma: i32, ms_target: f32, tera_instr_per_s: *mut f64) -> i32;
+    /// profiling counters of the lane-tiled kernels (DIAG builds of a call)
+    pub fn owg_debug_counters(out: *mut u64, n: i32, reset: i32) -> i32;
+    /// shared-reciprocal division against the compiler's `/` on random operands, on the device
+    pub fn owg_selftest_division(n_per_thread: i64, seed: u64, mismatches: *mut u64, tested: *mut u64) -> i32;
     /// frees the grow-only device staging buffers no call is using (device = -1: every device); returns the bytes released
     pub fn owg_release_caches(device: i32) -> i64;
     pub fn owg_chain_batch(input: *const f64, in_stride: i64, n_inst: i64, n_samp: i64, params: *const owg_bench_job, init_order: i32,

@@ -245,3 +245,22 @@ def test_caller_buffers_are_checked_before_the_c_call():
     a = open(os.path.join(ROOT, "openwurli_b200", "csrc", "ow_consts.inc"), "rb").read()
     b = open(os.path.join(ROOT, "oracle", "ow_consts.inc"), "rb").read()
     assert a == b
+
+
+def test_rust_sys_crate_declares_exactly_the_header_functions():
+    """bindings/rust/owgpu-sys (uncompiled here: no Rust toolchain) must at least declare every function of include/owgpu.h and nothing
+    else, with the same number of parameters, and mirror the size-critical structs field for field in count."""
+    hdr = open(os.path.join(ROOT, "include", "owgpu.h")).read()
+    rs = open(os.path.join(ROOT, "bindings", "rust", "owgpu-sys", "src", "lib.rs")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    c_fns = {m.group(1): m.group(2) for m in re.finditer(r"\b(owg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr_nc)}
+    r_fns = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (owg_[a-z0-9_]+)\s*\(([^)]*)\)", rs)}
+    assert set(c_fns) == set(r_fns), (sorted(set(c_fns) - set(r_fns)), sorted(set(r_fns) - set(c_fns)))
+    for name, args in c_fns.items():
+        n_c = 0 if args.strip() in ("", "void") else args.count(",") + 1
+        n_r = len([a for a in r_fns[name].split(",") if a.strip()])
+        assert n_c == n_r, (name, n_c, n_r)
+    # owg_opts: same number of fields (the layout test against ctypes sizes is test_struct_sizes...)
+    c_opts = re.search(r"typedef struct owg_opts \{(.*?)\} owg_opts;", hdr_nc, re.S).group(1)
+    r_opts = re.search(r"pub struct owg_opts \{(.*?)\n\}", rs, re.S).group(1)
+    assert c_opts.count(";") == len(re.findall(r"pub \w+:", r_opts))
